@@ -1,0 +1,811 @@
+// C ABI implementation (include/fdtdx_b200.h): plan = constant tables + scratch; caller owns buffers.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fdtdx_b200.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "tensor_kernels.cuh"
+#include "yee_kernels.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(x)                                                                        \
+  do {                                                                                     \
+    cudaError_t _e = (x);                                                                  \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(FDTDX_ECUDA, std::string(#x) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+static const double kEta0 = (4e-7 * M_PI) * 299792458.0;
+#define MAX_IDX 64
+
+struct PmlHost {
+  int axis, dir, lo, hi, kappa_one;
+  std::vector<float> aE, bE, kE, aH, bH, kH;
+};
+struct SrcHost {
+  SrcDev d;
+  std::vector<uint8_t> on;
+};
+struct DetHost {
+  DetDev d;
+  std::vector<uint8_t> on;
+  int nvals;
+};
+
+struct FdtdxPlan {
+  int nx, ny, nz, xoff, nxg, T;
+  double courant, dt;
+  int eps_tier, mu_tier, sigE_tier, sigH_tier;
+  double inv_mu_scalar;
+  int wrap[3];
+  bool metric;
+  float* d_sB[3];
+  float* d_sF[3];
+  float* d_w[3];
+  std::vector<PmlHost> pmls;
+  std::vector<WallDev> walls;
+  std::vector<SrcHost> srcs;
+  SrcDev* d_srcs = nullptr;
+  std::vector<DetHost> dets;
+  // recorder
+  bool has_rec = false;
+  int rec_dtype = 0, rec_slots = 0;
+  std::vector<int32_t> slot_of_time, replay_a, replay_b;
+  std::vector<float> replay_w;
+  // dispersion
+  int n_poles = 0, coeff_tier = 1, has_c4 = 0;
+  int halo_lo = 0, halo_hi = 0;
+  void* slots[FDTDX_SLOT_COUNT][MAX_IDX];
+  std::vector<void*> owned;
+  bool finalized = false;
+  AxisPmlDev axis[3];
+  int p_parity = 0, e_parity = 0, h_parity = 0;
+  long long launches = 0;
+  int xchunk = 0, rows = 8;
+  float* d_K = nullptr;  // tensor path: curl scratch (3,N)
+};
+
+extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
+extern "C" int fdtdx_b200_version(void) { return 100; }
+
+template <typename T>
+static int to_device(FdtdxPlan* p, const T* host, size_t n, T** out) {
+  *out = nullptr;
+  if (n == 0) return FDTDX_OK;
+  CUDA_TRY(cudaMalloc((void**)out, n * sizeof(T)));
+  p->owned.push_back(*out);
+  if (host) CUDA_TRY(cudaMemcpy(*out, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  else CUDA_TRY(cudaMemset(*out, 0, n * sizeof(T)));
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_plan_create(FdtdxPlan** out, int nx, int ny, int nz, int x_offset, int nx_global,
+                                      double courant_number, double dt, int total_time_steps, int eps_tier,
+                                      int mu_tier, int sigma_e_tier, int sigma_h_tier, double inv_mu_scalar,
+                                      const int wrap[3], const float* const sB[3], const float* const sF[3],
+                                      const float* const widths[3]) {
+  if (!out || nx <= 0 || ny <= 0 || nz <= 0) return fail(FDTDX_EINVAL, "plan_create: bad dimensions");
+  if (!(eps_tier == 1 || eps_tier == 3 || eps_tier == 9)) return fail(FDTDX_EINVAL, "eps_tier must be 1, 3 or 9");
+  if (!(mu_tier == 0 || mu_tier == 1 || mu_tier == 3 || mu_tier == 9)) return fail(FDTDX_EINVAL, "mu_tier must be 0, 1, 3 or 9");
+  FdtdxPlan* p = new FdtdxPlan();
+  p->nx = nx; p->ny = ny; p->nz = nz; p->xoff = x_offset; p->nxg = nx_global; p->T = total_time_steps;
+  p->courant = courant_number; p->dt = dt;
+  p->eps_tier = eps_tier; p->mu_tier = mu_tier; p->sigE_tier = sigma_e_tier; p->sigH_tier = sigma_h_tier;
+  p->inv_mu_scalar = inv_mu_scalar;
+  for (int a = 0; a < 3; ++a) p->wrap[a] = wrap ? wrap[a] : 0;
+  memset(p->slots, 0, sizeof(p->slots));
+  p->metric = (sB != nullptr && sB[0] != nullptr);
+  const int n[3] = {nx, ny, nz};
+  const int ng[3] = {nx_global, ny, nz};
+  for (int a = 0; a < 3; ++a) {
+    p->d_sB[a] = p->d_sF[a] = p->d_w[a] = nullptr;
+    if (p->metric) {
+      int rc = to_device(p, sB[a], n[a], &p->d_sB[a]);
+      if (rc) return rc;
+      rc = to_device(p, sF[a], n[a], &p->d_sF[a]);
+      if (rc) return rc;
+    }
+    if (widths && widths[a]) {
+      int rc = to_device(p, widths[a], ng[a], &p->d_w[a]);
+      if (rc) return rc;
+    }
+  }
+  *out = p;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_plan_destroy(FdtdxPlan* p) {
+  if (!p) return FDTDX_OK;
+  for (void* q : p->owned) cudaFree(q);
+  delete p;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_plan_add_pml(FdtdxPlan* p, int axis, int direction, int lo, int hi, const float* a_E,
+                                       const float* b_E, const float* inv_kappa_E, const float* a_H,
+                                       const float* b_H, const float* inv_kappa_H, int kappa_is_one) {
+  if (!p || axis < 0 || axis > 2 || hi <= lo) return fail(FDTDX_EINVAL, "add_pml: bad arguments");
+  if ((int)p->pmls.size() >= FDTDX_MAX_PML) return fail(FDTDX_EINVAL, "add_pml: at most 6 slabs");
+  const int ng[3] = {p->nxg, p->ny, p->nz};
+  if (direction == 0 && lo != 0) return fail(FDTDX_EUNSUPPORTED, "add_pml: a '-' slab must start at index 0");
+  if (direction == 1 && hi != ng[axis]) return fail(FDTDX_EUNSUPPORTED, "add_pml: a '+' slab must end at the domain edge");
+  PmlHost h;
+  h.axis = axis; h.dir = direction; h.lo = lo; h.hi = hi; h.kappa_one = kappa_is_one;
+  const int L = hi - lo;
+  h.aE.assign(a_E, a_E + L); h.bE.assign(b_E, b_E + L);
+  h.aH.assign(a_H, a_H + L); h.bH.assign(b_H, b_H + L);
+  h.kE.resize(L); h.kH.resize(L);
+  for (int i = 0; i < L; ++i) {
+    h.kE[i] = inv_kappa_E[i] - 1.0f;
+    h.kH[i] = inv_kappa_H[i] - 1.0f;
+  }
+  p->pmls.push_back(h);
+  p->finalized = false;
+  return (int)p->pmls.size() - 1;
+}
+
+extern "C" int fdtdx_b200_plan_add_wall(FdtdxPlan* p, int kind, int axis, const int lo[3], const int hi[3]) {
+  if (!p || (int)p->walls.size() >= FDTDX_MAX_WALL) return fail(FDTDX_EINVAL, "add_wall: too many walls");
+  WallDev w;
+  w.kind = kind; w.axis = axis;
+  for (int a = 0; a < 3; ++a) { w.lo[a] = lo[a]; w.hi[a] = hi[a]; }
+  w.lo[0] -= p->xoff; w.hi[0] -= p->xoff;
+  p->walls.push_back(w);
+  return (int)p->walls.size() - 1;
+}
+
+static int fill_profile(FdtdxPlan* p, SrcDev& d, int profile_kind, const double* q, const float* signal, int signal_len) {
+  d.profile_kind = profile_kind;
+  for (int i = 0; i < 6; ++i) d.p[i] = 0.f;
+  if (profile_kind == FDTDX_PROFILE_CW) {
+    d.p[0] = (float)q[0]; d.p[1] = (float)q[1]; d.p[2] = (float)q[2]; d.p[3] = (float)q[3];
+    d.p[4] = (float)(2.0 * M_PI);
+  } else if (profile_kind == FDTDX_PROFILE_PULSE) {
+    d.p[0] = (float)q[0]; d.p[1] = (float)q[1]; d.p[2] = (float)q[2]; d.p[3] = (float)q[3];
+    d.p[5] = (float)q[4];
+  } else {
+    d.p[0] = (float)q[0]; d.p[1] = (float)q[1]; d.p[2] = (float)q[2]; d.p[3] = (float)q[3];
+  }
+  d.signal = nullptr; d.signal_len = signal_len;
+  if (signal && signal_len > 0) {
+    float* ds;
+    int rc = to_device(p, signal, signal_len, &ds);
+    if (rc) return rc;
+    d.signal = ds;
+  }
+  return FDTDX_OK;
+}
+
+static int fill_switch(FdtdxPlan* p, SrcHost& s, const uint8_t* on, const float* t_adj) {
+  s.d.on = nullptr; s.d.t_adj = nullptr;
+  if (on) {
+    s.on.assign(on, on + p->T);
+    uint8_t* d_on; float* d_t;
+    int rc = to_device(p, on, p->T, &d_on);
+    if (rc) return rc;
+    rc = to_device(p, t_adj, p->T, &d_t);
+    if (rc) return rc;
+    s.d.on = d_on; s.d.t_adj = d_t;
+  }
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_plan_add_plane_source(FdtdxPlan* p, const int lo[3], const int hi[3], int normal_axis,
+                                                int sign, const float* E_inc, const float* H_inc,
+                                                const float* toff_E, const float* toff_H, int profile_kind,
+                                                const double params[8], const float* signal, int signal_len,
+                                                double static_amplitude, double cE, double cH, const uint8_t* on,
+                                                const float* t_adj, const float* h_filter, int h_filter_len) {
+  if (!p || (int)p->srcs.size() >= FDTDX_MAX_SRC) return fail(FDTDX_EINVAL, "add_plane_source: too many sources");
+  SrcHost s;
+  memset(&s.d, 0, sizeof(SrcDev));
+  s.d.kind = 0;
+  // clip the plane to this rank's x-slab; the face arrays are sliced accordingly by the caller
+  for (int a = 0; a < 3; ++a) { s.d.lo[a] = lo[a]; s.d.hi[a] = hi[a]; }
+  s.d.lo[0] -= p->xoff; s.d.hi[0] -= p->xoff;
+  s.d.normal_axis = normal_axis;
+  s.d.sign = (float)sign;
+  s.d.static_amp = (float)static_amplitude;
+  s.d.cE = (float)cE; s.d.cH = (float)cH;
+  const size_t fn = (size_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  float *dE, *dH, *dtE, *dtH;
+  int rc;
+  if ((rc = to_device(p, E_inc, 3 * fn, &dE))) return rc;
+  if ((rc = to_device(p, H_inc, 3 * fn, &dH))) return rc;
+  if ((rc = to_device(p, toff_E, 3 * fn, &dtE))) return rc;
+  if ((rc = to_device(p, toff_H, 3 * fn, &dtH))) return rc;
+  s.d.Einc = dE; s.d.Hinc = dH; s.d.toffE = dtE; s.d.toffH = dtH;
+  if ((rc = fill_profile(p, s.d, profile_kind, params, signal, signal_len))) return rc;
+  if ((rc = fill_switch(p, s, on, t_adj))) return rc;
+  s.d.hfilter = nullptr; s.d.hfilter_len = 0;
+  if (h_filter && h_filter_len > 1) {
+    float* dh;
+    if ((rc = to_device(p, h_filter, h_filter_len, &dh))) return rc;
+    s.d.hfilter = dh; s.d.hfilter_len = h_filter_len;
+  }
+  p->srcs.push_back(s);
+  p->finalized = false;
+  return (int)p->srcs.size() - 1;
+}
+
+extern "C" int fdtdx_b200_plan_add_dipole(FdtdxPlan* p, const int cell[3], int polarization, int electric,
+                                          double scale, int profile_kind, const double params[8],
+                                          const float* signal, int signal_len, const uint8_t* on,
+                                          const float* t_adj) {
+  if (!p || (int)p->srcs.size() >= FDTDX_MAX_SRC) return fail(FDTDX_EINVAL, "add_dipole: too many sources");
+  SrcHost s;
+  memset(&s.d, 0, sizeof(SrcDev));
+  s.d.kind = 1;
+  for (int a = 0; a < 3; ++a) { s.d.lo[a] = cell[a]; s.d.hi[a] = cell[a] + 1; }
+  s.d.lo[0] -= p->xoff; s.d.hi[0] -= p->xoff;
+  s.d.pol = polarization; s.d.electric = electric; s.d.dip_scale = (float)scale;
+  int rc;
+  if ((rc = fill_profile(p, s.d, profile_kind, params, signal, signal_len))) return rc;
+  if ((rc = fill_switch(p, s, on, t_adj))) return rc;
+  p->srcs.push_back(s);
+  p->finalized = false;
+  return (int)p->srcs.size() - 1;
+}
+
+extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo[3], const int hi[3], int flags,
+                                            int comp_mask, int aux, const uint8_t* on, const int32_t* arr_idx,
+                                            const float* weights, int n_freq, const float* phasor_table,
+                                            const float* window, double scale, const int slice_idx[3]) {
+  if (!p || !on || !arr_idx) return fail(FDTDX_EINVAL, "add_detector: missing tables");
+  if (p->xoff != 0 || p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "detectors on x-sharded plans are not supported yet");
+  DetHost h;
+  memset(&h.d, 0, sizeof(DetDev));
+  DetDev& d = h.d;
+  d.kind = kind; d.flags = flags; d.comp_mask = comp_mask; d.aux = aux;
+  for (int a = 0; a < 3; ++a) { d.lo[a] = lo[a]; d.hi[a] = hi[a]; d.slice_idx[a] = slice_idx ? slice_idx[a] : 0; }
+  d.ncomp = 0;
+  for (int c = 0; c < 6; ++c) d.ncomp += (comp_mask >> c) & 1;
+  const size_t n = (size_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  h.on.assign(on, on + p->T);
+  int rc;
+  uint8_t* d_on; int32_t* d_idx;
+  if ((rc = to_device(p, on, p->T, &d_on))) return rc;
+  if ((rc = to_device(p, arr_idx, p->T, &d_idx))) return rc;
+  d.on = d_on; d.arr_idx = d_idx;
+  d.weights = nullptr; d.wsum = 1.0f;
+  const bool keep_all = (kind == FDTDX_DET_POYNTING) && (flags & DET_KEEP_ALL);
+  if (weights) {
+    const size_t wn = keep_all ? 3 * n : n;
+    float* dw;
+    if ((rc = to_device(p, weights, wn, &dw))) return rc;
+    d.weights = dw;
+    // jnp.sum(weights) in float32 (detector.py:108); pairwise order as numpy does it is close
+    // enough for a normalisation constant - computed in double and rounded once.
+    double acc = 0.0;
+    for (size_t i = 0; i < n; ++i) acc += (double)weights[i];
+    d.wsum = (float)acc;
+  }
+  d.nf = n_freq; d.scale = (float)scale;
+  if (kind == FDTDX_DET_PHASOR) {
+    if (!phasor_table || !window) return fail(FDTDX_EINVAL, "add_detector: phasor needs table and window");
+    float* dt; float* dw;
+    if ((rc = to_device(p, phasor_table, (size_t)2 * p->T * n_freq, &dt))) return rc;
+    if ((rc = to_device(p, window, p->T, &dw))) return rc;
+    d.ph_table = reinterpret_cast<const float2*>(dt);
+    d.window = dw;
+  }
+  if (flags & DET_EXACT) {
+    const size_t hn = (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+    if ((rc = to_device<float>(p, nullptr, hn, &d.hprev))) return rc;
+  }
+  h.nvals = 0;
+  const bool staged = (flags & DET_REDUCE) || ((flags & DET_SLICES) && (flags & DET_SLICE_MEAN));
+  if (staged) {
+    h.nvals = (kind == FDTDX_DET_FIELD || kind == FDTDX_DET_PHASOR) ? d.ncomp : (keep_all ? 3 : 1);
+    if ((rc = to_device<float>(p, nullptr, (size_t)h.nvals * n, &d.scratch))) return rc;
+  }
+  p->dets.push_back(h);
+  return (int)p->dets.size() - 1;
+}
+
+extern "C" int fdtdx_b200_plan_set_recorder(FdtdxPlan* p, int dtype, int n_slots, const int32_t* slot_of_time,
+                                            const int32_t* replay_a, const int32_t* replay_b, const float* replay_w) {
+  if (!p || !slot_of_time) return fail(FDTDX_EINVAL, "set_recorder: missing tables");
+  p->has_rec = true; p->rec_dtype = dtype; p->rec_slots = n_slots;
+  p->slot_of_time.assign(slot_of_time, slot_of_time + p->T);
+  p->replay_a.assign(replay_a, replay_a + p->T);
+  p->replay_b.assign(replay_b, replay_b + p->T);
+  p->replay_w.assign(replay_w, replay_w + p->T);
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_plan_set_dispersion(FdtdxPlan* p, int n_poles, int coeff_tier, int has_c4) {
+  if (!p || n_poles < 0 || !(coeff_tier == 1 || coeff_tier == 3)) return fail(FDTDX_EINVAL, "set_dispersion: bad arguments");
+  p->n_poles = n_poles; p->coeff_tier = coeff_tier; p->has_c4 = has_c4;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_halo_bind(FdtdxPlan* p, int has_lo, int has_hi) {
+  if (!p) return fail(FDTDX_EINVAL, "halo_bind: null plan");
+  p->halo_lo = has_lo; p->halo_hi = has_hi;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_bind(FdtdxPlan* p, int slot, int index, void* ptr) {
+  if (!p || slot < 0 || slot >= FDTDX_SLOT_COUNT || index < 0 || index >= MAX_IDX)
+    return fail(FDTDX_EINVAL, "bind: bad slot/index");
+  p->slots[slot][index] = ptr;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_get_parity(FdtdxPlan* p, int* pp, int* ep, int* hp) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  if (pp) *pp = p->p_parity;
+  if (ep) *ep = p->e_parity;
+  if (hp) *hp = p->h_parity;
+  return FDTDX_OK;
+}
+extern "C" int fdtdx_b200_set_parity(FdtdxPlan* p, int pp, int ep, int hp) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  p->p_parity = pp & 1; p->e_parity = ep & 1; p->h_parity = hp & 1;
+  return FDTDX_OK;
+}
+extern "C" long long fdtdx_b200_launch_count(FdtdxPlan* p) { return p ? p->launches : 0; }
+extern "C" int fdtdx_b200_set_tuning(FdtdxPlan* p, int xchunk, int rows) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  p->xchunk = xchunk;
+  if (rows > 0) p->rows = std::min(rows, 8);
+  return FDTDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int finalize(FdtdxPlan* p) {
+  if (p->finalized) return FDTDX_OK;
+  const int n[3] = {p->nx, p->ny, p->nz};
+  for (int a = 0; a < 3; ++a) {
+    AxisPmlDev& A = p->axis[a];
+    memset(&A, 0, sizeof(A));
+    A.lo_len = 0; A.hi_start = n[a]; A.hi_len = 0; A.kappa_one = 1;
+    std::vector<float> t[6];
+    for (auto& v : t) v.assign(n[a], 0.0f);
+    const int off = (a == 0) ? p->xoff : 0;
+    for (const PmlHost& h : p->pmls) {
+      if (h.axis != a) continue;
+      const int llo = std::max(h.lo - off, 0), lhi = std::min(h.hi - off, n[a]);
+      if (lhi <= llo) continue;
+      if (h.dir == 0) {
+        if (llo != 0) return fail(FDTDX_EUNSUPPORTED, "x-PML slab split across ranks away from the slab start");
+        A.lo_len = lhi;
+      } else {
+        if (lhi != n[a]) return fail(FDTDX_EUNSUPPORTED, "x-PML slab split across ranks away from the slab end");
+        A.hi_start = llo; A.hi_len = lhi - llo;
+      }
+      if (!h.kappa_one) A.kappa_one = 0;
+      for (int i = llo; i < lhi; ++i) {
+        const int q = i + off - h.lo;
+        t[0][i] = h.aE[q]; t[1][i] = h.bE[q]; t[2][i] = h.kE[q];
+        t[3][i] = h.aH[q]; t[4][i] = h.bH[q]; t[5][i] = h.kH[q];
+      }
+    }
+    float* d[6];
+    for (int q = 0; q < 6; ++q) {
+      int rc = to_device(p, t[q].data(), (size_t)n[a], &d[q]);
+      if (rc) return rc;
+    }
+    A.aE = d[0]; A.bE = d[1]; A.kE = d[2]; A.aH = d[3]; A.bH = d[4]; A.kH = d[5];
+  }
+  if (!p->srcs.empty()) {
+    std::vector<SrcDev> hs;
+    for (auto& s : p->srcs) hs.push_back(s.d);
+    int rc = to_device(p, hs.data(), hs.size(), &p->d_srcs);
+    if (rc) return rc;
+  }
+  p->finalized = true;
+  return FDTDX_OK;
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
+  memset(&P, 0, sizeof(P));
+  P.nx = p->nx; P.ny = p->ny; P.nz = p->nz;
+  const long long N = (long long)p->nx * p->ny * p->nz;
+  for (int a = 0; a < 3; ++a) P.wrap[a] = p->wrap[a];
+  P.x_lo_mode = p->halo_lo ? 2 : (p->wrap[0] ? 1 : 0);
+  P.x_hi_mode = p->halo_hi ? 2 : (p->wrap[0] ? 1 : 0);
+  P.cour = (float)p->courant; P.eta0 = (float)kEta0; P.inv_mu_scalar = (float)p->inv_mu_scalar; P.dt = (float)p->dt;
+  P.E = (float*)p->slots[FDTDX_SLOT_E][0];
+  P.H = (float*)p->slots[FDTDX_SLOT_H][0];
+  P.eps = (const float*)p->slots[FDTDX_SLOT_INV_EPS][0];
+  P.mu = (const float*)p->slots[FDTDX_SLOT_INV_MU][0];
+  P.sigE = (const float*)p->slots[FDTDX_SLOT_SIGMA_E][0];
+  P.sigH = (const float*)p->slots[FDTDX_SLOT_SIGMA_H][0];
+  if (!P.E || !P.H || !P.eps) return fail(FDTDX_EUNBOUND, "E, H and INV_EPS must be bound");
+  if (p->mu_tier > 0 && !P.mu) return fail(FDTDX_EUNBOUND, "INV_MU must be bound for mu_tier > 0");
+  if (p->sigE_tier > 0 && !P.sigE) return fail(FDTDX_EUNBOUND, "SIGMA_E must be bound");
+  if (p->sigH_tier > 0 && !P.sigH) return fail(FDTDX_EUNBOUND, "SIGMA_H must be bound");
+  P.eps_cs = (p->eps_tier == 1) ? 0 : N;
+  P.mu_cs = (p->mu_tier <= 1) ? 0 : N;
+  P.sigE_cs = (p->sigE_tier <= 1) ? 0 : N;
+  P.sigH_cs = (p->sigH_tier <= 1) ? 0 : N;
+  for (int a = 0; a < 3; ++a) { P.sB[a] = p->d_sB[a]; P.sF[a] = p->d_sF[a]; }
+  for (int a = 0; a < 3; ++a) P.pml[a] = p->axis[a];
+  for (size_t q = 0; q < p->pmls.size(); ++q) {
+    const PmlHost& h = p->pmls[q];
+    const int off = (h.axis == 0) ? p->xoff : 0;
+    const int n[3] = {p->nx, p->ny, p->nz};
+    if (std::min(h.hi - off, n[h.axis]) <= std::max(h.lo - off, 0)) continue;  // slab not on this rank
+    for (int w = 0; w < 2; ++w) {
+      float* pe = (float*)p->slots[FDTDX_SLOT_PSI_E][2 * q + w];
+      float* ph = (float*)p->slots[FDTDX_SLOT_PSI_H][2 * q + w];
+      if (!pe || !ph) return fail(FDTDX_EUNBOUND, "PSI_E / PSI_H must be bound for every PML slab");
+      P.pml[h.axis].psiE[h.dir][w] = pe;
+      P.pml[h.axis].psiH[h.dir][w] = ph;
+    }
+  }
+  P.simulate = simulate;
+  P.n_walls = (int)p->walls.size();
+  for (int w = 0; w < P.n_walls; ++w) P.walls[w] = p->walls[w];
+  P.n_src = (int)p->srcs.size();
+  P.src = p->d_srcs;
+  P.n_poles = p->n_poles; P.has_c4 = p->has_c4;
+  if (p->n_poles > 0) {
+    float* A = (float*)p->slots[FDTDX_SLOT_P_A][0];
+    float* B = (float*)p->slots[FDTDX_SLOT_P_B][0];
+    if (!A || !B) return fail(FDTDX_EUNBOUND, "P_A / P_B must be bound for dispersive runs");
+    P.P_cur = p->p_parity ? B : A;
+    P.P_new = p->p_parity ? A : B;
+    P.c1 = (const float*)p->slots[FDTDX_SLOT_C1][0];
+    P.c2 = (const float*)p->slots[FDTDX_SLOT_C2][0];
+    P.c3 = (const float*)p->slots[FDTDX_SLOT_C3][0];
+    P.c4 = (const float*)p->slots[FDTDX_SLOT_C4][0];
+    if (!P.c1 || !P.c2 || !P.c3 || (p->has_c4 && !P.c4)) return fail(FDTDX_EUNBOUND, "dispersive coefficients must be bound");
+    P.c_cs = (p->coeff_tier == 1) ? 0 : N;
+  }
+  P.haloH = (const float*)p->slots[FDTDX_SLOT_HALO_H_LO][0];
+  P.haloE = (const float*)p->slots[FDTDX_SLOT_HALO_E_HI][0];
+  if (p->halo_lo && !P.haloH) return fail(FDTDX_EUNBOUND, "HALO_H_LO must be bound");
+  if (p->halo_hi && !P.haloE) return fail(FDTDX_EUNBOUND, "HALO_E_HI must be bound");
+  int xc = p->xchunk;
+  if (xc <= 0) {
+    // enough CTAs for >= ~6 waves of 148 SMs x 8 resident CTAs, but chunks long enough that the
+    // one-plane re-read at each chunk start stays below ~3 % of the traffic
+    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + p->rows - 1) / p->rows);
+    long long want = (148LL * 8 * 6 + tiles - 1) / tiles;
+    xc = (int)std::max(8LL, std::min<long long>(64, p->nx / std::max(1LL, want)));
+  }
+  P.xchunk = std::min(xc, p->nx);
+  return FDTDX_OK;
+}
+
+static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
+  if (p->nz % 4 != 0) return false;
+  const void* ptrs[] = {P.E, P.H, P.eps, P.mu, P.haloH, P.haloE};
+  for (const void* q : ptrs)
+    if (q && !aligned16(q)) return false;
+  for (int a = 0; a < 2; ++a)
+    for (int s = 0; s < 2; ++s)
+      for (int w = 0; w < 2; ++w) {
+        if (P.pml[a].psiE[s][w] && !aligned16(P.pml[a].psiE[s][w])) return false;
+        if (P.pml[a].psiH[s][w] && !aligned16(P.pml[a].psiH[s][w])) return false;
+      }
+  return true;
+}
+
+template <int V, int TIER, bool REV>
+static void launch_E3(const StepParams& P, int t, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st) {
+#define GO(S, A, M) yee_E_kernel<V, TIER, REV, S, A, M><<<g, b, 0, st>>>(P, t)
+  if constexpr (REV) {
+    if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
+    else { if (met) GO(false, false, true); else GO(false, false, false); }
+  } else {
+    if (ade) {
+      if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
+      else { if (met) GO(false, true, true); else GO(false, true, false); }
+    } else {
+      if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
+      else { if (met) GO(false, false, true); else GO(false, false, false); }
+    }
+  }
+#undef GO
+}
+
+static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
+  const bool v4 = can_vec4(p, P);
+  const int V = v4 ? 4 : 1;
+  dim3 b(32, p->rows);
+  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
+  const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
+  if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
+  const int tier = p->eps_tier;
+#define DISP(VV, TT)                                                         \
+  do {                                                                       \
+    if (rev) launch_E3<VV, TT, true>(P, t, sig, ade, met, g, b, st);         \
+    else launch_E3<VV, TT, false>(P, t, sig, ade, met, g, b, st);            \
+  } while (0)
+  if (v4) { if (tier == 1) DISP(4, 1); else DISP(4, 3); }
+  else { if (tier == 1) DISP(1, 1); else DISP(1, 3); }
+#undef DISP
+  p->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
+template <int V, int MUT>
+static void launch_H2(const StepParams& P, int t, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st) {
+#define GO(R, S, M) yee_H_kernel<V, MUT, R, S, M><<<g, b, 0, st>>>(P, t)
+  if (rev) {
+    if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
+    else { if (met) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    if (sig) { if (met) GO(false, true, true); else GO(false, true, false); }
+    else { if (met) GO(false, false, true); else GO(false, false, false); }
+  }
+#undef GO
+}
+
+static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
+  const bool v4 = can_vec4(p, P);
+  const int V = v4 ? 4 : 1;
+  dim3 b(32, p->rows);
+  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
+  const bool sig = p->sigH_tier > 0, met = p->metric;
+  const int mt = p->mu_tier;
+  if (v4) {
+    if (mt == 0) launch_H2<4, 0>(P, t, rev, sig, met, g, b, st);
+    else if (mt == 1) launch_H2<4, 1>(P, t, rev, sig, met, g, b, st);
+    else launch_H2<4, 3>(P, t, rev, sig, met, g, b, st);
+  } else {
+    if (mt == 0) launch_H2<1, 0>(P, t, rev, sig, met, g, b, st);
+    else if (mt == 1) launch_H2<1, 1>(P, t, rev, sig, met, g, b, st);
+    else launch_H2<1, 3>(P, t, rev, sig, met, g, b, st);
+  }
+  p->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
+static void make_grid(const FdtdxPlan* p, GridDev& G) {
+  memset(&G, 0, sizeof(G));
+  G.nx = p->nx; G.ny = p->ny; G.nz = p->nz; G.x_offset = p->xoff;
+  const long long N = (long long)p->nx * p->ny * p->nz;
+  for (int a = 0; a < 3; ++a) { G.wrap[a] = p->wrap[a]; G.w[a] = p->d_w[a]; }
+  G.E = (const float*)p->slots[p->e_parity ? FDTDX_SLOT_E_ALT : FDTDX_SLOT_E][0];
+  G.H = (const float*)p->slots[p->h_parity ? FDTDX_SLOT_H_ALT : FDTDX_SLOT_H][0];
+  G.eps = (const float*)p->slots[FDTDX_SLOT_INV_EPS][0];
+  G.mu = (const float*)p->slots[FDTDX_SLOT_INV_MU][0];
+  G.eps_cs = (p->eps_tier == 1) ? 0 : N;
+  G.mu_cs = (p->mu_tier <= 1) ? 0 : N;
+  G.inv_mu_scalar = (float)p->inv_mu_scalar;
+}
+
+static int bind_det_state(FdtdxPlan* p, size_t di, DetDev& d) {
+  for (int k = 0; k < 4; ++k) d.state[k] = (float*)p->slots[FDTDX_SLOT_DET_STATE][4 * di + k];
+  if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
+  if (d.kind == FDTDX_DET_ENERGY && (d.flags & DET_SLICES) && (!d.state[1] || !d.state[2]))
+    return fail(FDTDX_EUNBOUND, "energy slice detector needs three state buffers");
+  return FDTDX_OK;
+}
+
+static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) {
+  GridDev G;
+  make_grid(p, G);
+  for (size_t di = 0; di < p->dets.size(); ++di) {
+    DetHost& h = p->dets[di];
+    if (((h.d.flags & DET_INVERSE) != 0) != inverse) continue;
+    if (!h.on[t] || !(h.d.flags & DET_EXACT)) continue;
+    const long long n = 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1) * (h.d.hi[2] - h.d.lo[2] + 1);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    det_gather_hprev_kernel<<<blocks, 256, 0, st>>>(G, h.d);
+    p->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
+static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) {
+  GridDev G;
+  make_grid(p, G);
+  for (size_t di = 0; di < p->dets.size(); ++di) {
+    DetHost& h = p->dets[di];
+    if (((h.d.flags & DET_INVERSE) != 0) != inverse) continue;
+    if (!h.on[t]) continue;
+    int rc = bind_det_state(p, di, h.d);
+    if (rc) return rc;
+    const long long n = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
+    det_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G, h.d, t);
+    p->launches++;
+    if (h.d.flags & DET_REDUCE) {
+      const int wpv = (h.d.kind == FDTDX_DET_POYNTING && (h.d.flags & DET_KEEP_ALL)) ? 1 : 0;
+      det_reduce_all_kernel<<<h.nvals, 1024, 0, st>>>(h.d, t, h.nvals, wpv);
+      p->launches++;
+    } else if ((h.d.flags & DET_SLICES) && (h.d.flags & DET_SLICE_MEAN)) {
+      const int dims[3] = {h.d.hi[0] - h.d.lo[0], h.d.hi[1] - h.d.lo[1], h.d.hi[2] - h.d.lo[2]};
+      for (int axis = 0; axis < 3; ++axis) {
+        const long long nout = n / dims[axis];
+        det_slice_mean_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(h.d, t, axis);
+        p->launches++;
+      }
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
+static int make_rec(FdtdxPlan* p, RecDev& R) {
+  memset(&R, 0, sizeof(R));
+  R.dtype = p->rec_dtype;
+  R.n_planes = 0;
+  for (size_t q = 0; q < p->pmls.size(); ++q) {
+    const PmlHost& h = p->pmls[q];
+    if (p->xoff != 0 || p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "recorder on x-sharded plans is not supported yet");
+    RecPlane& pl = R.planes[R.n_planes++];
+    const int n[3] = {p->nx, p->ny, p->nz};
+    for (int a = 0; a < 3; ++a) { pl.lo[a] = 0; pl.hi[a] = n[a]; }
+    if (h.dir == 1) { pl.lo[h.axis] = h.lo; pl.hi[h.axis] = h.lo + 1; }
+    else { pl.lo[h.axis] = h.hi - 1; pl.hi[h.axis] = h.hi; }
+    pl.data[0] = p->slots[FDTDX_SLOT_REC_DATA][2 * q + 0];
+    pl.data[1] = p->slots[FDTDX_SLOT_REC_DATA][2 * q + 1];
+    if (!pl.data[0] || !pl.data[1]) return fail(FDTDX_EUNBOUND, "REC_DATA must be bound for every PML slab");
+  }
+  return FDTDX_OK;
+}
+
+#include "tensor_launch.inl"
+
+static int step_E(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) {
+  if (p->eps_tier == 9 || p->sigE_tier == 9) return tensor_step(p, t, simulate, rev, /*is_E=*/true, st);
+  StepParams P;
+  int rc = make_params(p, P, simulate);
+  if (rc) return rc;
+  rc = launch_E(p, P, t, rev, st);
+  if (rc) return rc;
+  if (!rev && p->n_poles > 0) p->p_parity ^= 1;
+  return FDTDX_OK;
+}
+
+static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) {
+  if (p->mu_tier == 9 || p->sigH_tier == 9) return tensor_step(p, t, simulate, rev, /*is_E=*/false, st);
+  StepParams P;
+  int rc = make_params(p, P, simulate);
+  if (rc) return rc;
+  return launch_H(p, P, t, rev, st);
+}
+
+static int step_record(FdtdxPlan* p, int t, int record_detectors, int record_boundaries, cudaStream_t st) {
+  if (record_boundaries) {
+    if (!p->has_rec) return fail(FDTDX_EINVAL, "Need recorder to record boundaries");
+    const int slot = p->slot_of_time[t];
+    if (slot >= 0 && !p->pmls.empty()) {
+      RecDev R;
+      int rc = make_rec(p, R);
+      if (rc) return rc;
+      GridDev G;
+      make_grid(p, G);
+      long long fmax = 0;
+      for (int q = 0; q < R.n_planes; ++q) {
+        const RecPlane& pl = R.planes[q];
+        fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
+      }
+      dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
+      rec_record_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, slot);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  if (record_detectors) return detectors_sample(p, t, false, st);
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_run_forward_phase(FdtdxPlan* p, int t, int phase, int record_detectors,
+                                            int record_boundaries, int simulate_boundaries, void* stream) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "time step outside [0, T)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = finalize(p);
+  if (rc) return rc;
+  if (phase == 0) {
+    if (record_detectors && (rc = detectors_gather(p, t, false, st))) return rc;
+    return step_E(p, t, simulate_boundaries, false, st);
+  }
+  if (phase == 1) return step_H(p, t, simulate_boundaries, false, st);
+  return step_record(p, t, record_detectors, record_boundaries, st);
+}
+
+extern "C" int fdtdx_b200_run_forward(FdtdxPlan* p, int t0, int n, int record_detectors, int record_boundaries,
+                                      int simulate_boundaries, void* stream) {
+  for (int t = t0; t < t0 + n; ++t)
+    for (int phase = 0; phase < 3; ++phase) {
+      int rc = fdtdx_b200_run_forward_phase(p, t, phase, record_detectors, record_boundaries, simulate_boundaries, stream);
+      if (rc) return rc;
+    }
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int record_detectors, int reset_fields,
+                                      void* stream) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = finalize(p);
+  if (rc) return rc;
+  for (int t = t_from - 1; t > t_from - 1 - n; --t) {
+    if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "reverse time step outside [0, T)");
+    if (!p->has_rec) return fail(FDTDX_EINVAL, "Need recorder to record boundaries");
+    if (!p->pmls.empty()) {
+      RecDev R;
+      if ((rc = make_rec(p, R))) return rc;
+      GridDev G;
+      make_grid(p, G);
+      long long fmax = 0;
+      for (int q = 0; q < R.n_planes; ++q) {
+        const RecPlane& pl = R.planes[q];
+        fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
+      }
+      dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
+      rec_replay_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, p->replay_a[t],
+                                           p->replay_b[t], p->replay_w[t]);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (record_detectors && (rc = detectors_gather(p, t, true, st))) return rc;
+    if ((rc = step_H(p, t, 0, true, st))) return rc;
+    if ((rc = step_E(p, t, 0, true, st))) return rc;
+    if (reset_fields && !p->pmls.empty()) {
+      BoxList B;
+      B.n = 0;
+      long long nmax = 0;
+      const int nn[3] = {p->nx, p->ny, p->nz};
+      for (const PmlHost& h : p->pmls) {
+        for (int a = 0; a < 3; ++a) { B.lo[B.n][a] = 0; B.hi[B.n][a] = nn[a]; }
+        B.lo[B.n][h.axis] = h.lo; B.hi[B.n][h.axis] = h.hi;
+        nmax = std::max(nmax, (long long)(h.hi - h.lo) * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
+        B.n++;
+      }
+      GridDev G;
+      make_grid(p, G);
+      dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
+      reset_pml_kernel<<<g, 256, 0, st>>>(B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (record_detectors && (rc = detectors_sample(p, t, true, st))) return rc;
+  }
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* stream) {
+  (void)p; (void)t_from; (void)n; (void)stream;
+  return fail(FDTDX_EUNSUPPORTED, "run_adjoint: the fused VJP kernels are not built yet (SURVEY section 8 a18)");
+}
+
+extern "C" int fdtdx_b200_run_forward_host(FdtdxPlan* p, const float* h_E, const float* h_H, const float* h_inv_eps,
+                                           float* h_E_out, float* h_H_out, int t0, int n, int record_detectors,
+                                           void* stream, size_t* h2d_bytes, size_t* d2h_bytes) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)p->nx * p->ny * p->nz;
+  float* dE = (float*)p->slots[FDTDX_SLOT_E][0];
+  float* dH = (float*)p->slots[FDTDX_SLOT_H][0];
+  float* dEps = (float*)p->slots[FDTDX_SLOT_INV_EPS][0];
+  if (!dE || !dH || !dEps) return fail(FDTDX_EUNBOUND, "E, H and INV_EPS must be bound");
+  size_t up = 0, down = 0;
+  if (h_E) { CUDA_TRY(cudaMemcpyAsync(dE, h_E, 3 * N * 4, cudaMemcpyHostToDevice, st)); up += 3 * N * 4; }
+  if (h_H) { CUDA_TRY(cudaMemcpyAsync(dH, h_H, 3 * N * 4, cudaMemcpyHostToDevice, st)); up += 3 * N * 4; }
+  if (h_inv_eps) {
+    const size_t nb = (size_t)p->eps_tier * N * 4;
+    CUDA_TRY(cudaMemcpyAsync(dEps, h_inv_eps, nb, cudaMemcpyHostToDevice, st));
+    up += nb;
+  }
+  int rc = fdtdx_b200_run_forward(p, t0, n, record_detectors, 0, 1, stream);
+  if (rc) return rc;
+  if (h_E_out) { CUDA_TRY(cudaMemcpyAsync(h_E_out, dE, 3 * N * 4, cudaMemcpyDeviceToHost, st)); down += 3 * N * 4; }
+  if (h_H_out) { CUDA_TRY(cudaMemcpyAsync(h_H_out, dH, 3 * N * 4, cudaMemcpyDeviceToHost, st)); down += 3 * N * 4; }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = down;
+  return FDTDX_OK;
+}

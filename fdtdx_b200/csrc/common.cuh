@@ -1,0 +1,117 @@
+// Shared device-side descriptors for the Yee hot-path kernels (sm_100a).
+//
+// Arithmetic discipline: this translation unit is compiled with -fmad=false and IEEE division so
+// that every float32 expression rounds exactly like the reference's jnp expression evaluated
+// op-by-op; the kernels are HBM-bound, so un-fused FMUL+FADD is free.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define FDTDX_MAX_SRC 8
+#define FDTDX_MAX_WALL 12
+
+struct AxisPmlDev {
+  int lo_len;    // local cells [0, lo_len) belong to the '-' slab (0: none)
+  int hi_start;  // local cells [hi_start, n) belong to the '+' slab (n: none)
+  int hi_len;
+  int kappa_one; // both slabs have kappa == 1 (correction == psi, perfectly_matched_layer.py:184)
+  // per-cell coefficient tables along this axis, local length n; zero outside the slabs.
+  // k* = 1/kappa - 1.  E-side tables feed curl_H (E update), H-side feed curl_E (H update).
+  const float *aE, *bE, *kE, *aH, *bH, *kH;
+  float* psiE[2][2];  // [side: 0 lo, 1 hi][which: psi_1, psi_2]
+  float* psiH[2][2];
+};
+
+struct WallDev {
+  int kind;  // 0 PEC (E), 1 PMC (H)
+  int axis;
+  int lo[3], hi[3];
+};
+
+struct SrcDev {
+  int kind;  // 0 TFSF plane, 1 dipole
+  int lo[3], hi[3];
+  int normal_axis;
+  float sign;  // +1 / -1 (direction); negated for the reverse pass at launch
+  int profile_kind;
+  float p[6];  // profile params, float32-rounded exactly like the weak python scalars
+  float static_amp;
+  float cE, cH;
+  const float *Einc, *Hinc, *toffE, *toffH;  // (3, face)
+  const float* signal;
+  int signal_len;
+  const float* hfilter;
+  int hfilter_len;
+  const uint8_t* on;   // per-time-step gate or nullptr (default always-on switch)
+  const float* t_adj;  // remapped time step (source.py:44-49) or nullptr
+  // dipole
+  int pol, electric;
+  float dip_scale;
+};
+
+struct StepParams {
+  int nx, ny, nz;
+  int wrap[3];
+  int x_lo_mode, x_hi_mode;  // 0 zero halo, 1 local wrap, 2 neighbour halo buffer
+  float cour, eta0, inv_mu_scalar, dt;
+  float* E;
+  float* H;
+  const float* eps;
+  const float* mu;  // nullptr => scalar
+  const float* sigE;
+  const float* sigH;
+  long long eps_cs, mu_cs, sigE_cs, sigH_cs;  // component strides (0 for 1-component tiers)
+  const float* sB[3];
+  const float* sF[3];
+  AxisPmlDev pml[3];
+  int simulate;
+  int n_walls;
+  WallDev walls[FDTDX_MAX_WALL];
+  int n_src;
+  const SrcDev* src;  // device array
+  // ADE (update.py:316-350)
+  int n_poles, has_c4;
+  const float* P_cur;  // dispersive_P_curr
+  float* P_new;        // buffer that held dispersive_P_prev; receives the new P_curr
+  const float *c1, *c2, *c3, *c4;
+  long long c_cs;  // coefficient component stride (0: isotropic, N: per-axis)
+  const float* haloH;  // (2,ny,nz) Hy,Hz of plane x0-1
+  const float* haloE;  // (2,ny,nz) Ey,Ez of plane x1
+  int xchunk;
+};
+
+template <int V>
+struct Vec {
+  float v[V];
+};
+
+template <int V>
+__device__ __forceinline__ Vec<V> ldv(const float* __restrict__ p) {
+  Vec<V> r;
+  if constexpr (V == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) r.v[e] = p[e];
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void stv(float* __restrict__ p, const Vec<V>& r) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) p[e] = r.v[e];
+  }
+}
+template <int V>
+__device__ __forceinline__ Vec<V> zerov() {
+  Vec<V> r;
+#pragma unroll
+  for (int e = 0; e < V; ++e) r.v[e] = 0.f;
+  return r;
+}

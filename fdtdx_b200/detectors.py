@@ -1,0 +1,254 @@
+"""Detector descriptors and state layout.
+
+Mirrors ``fdtdx/objects/detectors/{detector,energy,field,poynting_flux,phasor,mode}.py`` as far
+as the time step reads them: region, gate table ``on[t]``,
+``arr_idx[t]``, interpolation flag, ``inverse`` flag, and the per-type reduction.  The per-step
+``update`` arithmetic itself lives in the CUDA kernels (``csrc/detector_kernels.cuh``) and,
+restated for checking, in ``oracle/yee.py``.  State arrays keep the reference's shapes/dtypes
+(``detector.py:231-244``).
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Literal, Sequence
+
+import numpy as np
+
+from fdtdx_b200.boundaries import SimulationObject
+from fdtdx_b200.switch import OnOffSwitch, WaveCharacter
+
+_f32 = np.float32
+COMPONENT_NAMES = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
+
+
+@dataclass
+class Detector(SimulationObject):
+    dtype: type = np.float32
+    exact_interpolation: bool = True
+    inverse: bool = False
+    switch: OnOffSwitch = field(default_factory=OnOffSwitch)
+    _num_time_steps_on: int | None = None
+    _is_on_at_time_step_arr: np.ndarray | None = None
+    _time_step_to_arr_idx: np.ndarray | None = None
+    _cached_cell_volume_weights: np.ndarray | None = None
+    _dt: float = 0.0
+
+    def _calculate_on_list(self, config) -> list[bool]:
+        return self.switch.calculate_on_list(config.time_steps_total, config.time_step_duration)
+
+    def _num_latent_time_steps(self) -> int:
+        return int(self._num_time_steps_on)
+
+    def place_on_grid(self, config):
+        """``detector.py:195-229``."""
+        self._dt = config.time_step_duration
+        on_list = self._calculate_on_list(config)
+        self._is_on_at_time_step_arr = np.asarray(on_list, dtype=bool)
+        self._num_time_steps_on = int(sum(on_list))
+        idx, counter = [-1] * len(on_list), 0
+        for t, on in enumerate(on_list):
+            if on:
+                idx[t] = counter
+                counter += 1
+        self._time_step_to_arr_idx = np.asarray(idx, dtype=np.int32)
+        grid = config.resolved_grid
+        if grid is not None:
+            self._cached_cell_volume_weights = grid.cell_volume(self.grid_slice_tuple)
+        else:
+            sp = config.uniform_spacing()
+            self._cached_cell_volume_weights = (np.ones(self.grid_shape, _f32) * _f32(sp**3)).astype(_f32)
+        return self
+
+    def _shape_dtype_single_time_step(self) -> dict[str, tuple[tuple[int, ...], type]]:
+        raise NotImplementedError
+
+    def init_state(self) -> dict[str, np.ndarray]:
+        n = self._num_latent_time_steps()
+        return {k: np.zeros((n, *shape), dtype=dt) for k, (shape, dt) in self._shape_dtype_single_time_step().items()}
+
+
+@dataclass
+class EnergyDetector(Detector):
+    """``energy.py``."""
+
+    as_slices: bool = False
+    reduce_volume: bool = False
+    x_slice: float | None = None
+    y_slice: float | None = None
+    z_slice: float | None = None
+    aggregate: str | None = None
+    _slice_indices: tuple[int, int, int] | None = None
+
+    @property
+    def use_mean(self) -> bool:
+        return self.aggregate == "mean" or any(s is None for s in (self.x_slice, self.y_slice, self.z_slice))
+
+    def place_on_grid(self, config):
+        super().place_on_grid(config)
+        idxs = []
+        for axis, pos in enumerate((self.x_slice, self.y_slice, self.z_slice)):
+            n = self.grid_shape[axis]
+            if pos is None:
+                idxs.append(n // 2)
+                continue
+            grid = config.resolved_grid
+            if grid is not None:
+                lo, hi = self.grid_slice_tuple[axis]
+                centers = grid.centers(axis)[lo:hi]
+                idxs.append(int(np.clip(np.argmin(np.abs(centers - pos)), 0, n - 1)))
+            else:
+                sp = config.uniform_spacing()
+                origin = self.grid_slice_tuple[axis][0] * sp
+                idxs.append(max(0, min(int((pos - origin) / sp), n - 1)))
+        self._slice_indices = tuple(idxs)
+        return self
+
+    def _shape_dtype_single_time_step(self):
+        if self.as_slices and self.reduce_volume:
+            raise Exception("Cannot both reduce volume and save slices!")
+        gs = self.grid_shape
+        if self.as_slices:
+            return {
+                "XY Plane": ((gs[0], gs[1]), self.dtype),
+                "XZ Plane": ((gs[0], gs[2]), self.dtype),
+                "YZ Plane": ((gs[1], gs[2]), self.dtype),
+            }
+        if self.reduce_volume:
+            return {"energy": ((1,), self.dtype)}
+        return {"energy": (gs, self.dtype)}
+
+
+@dataclass
+class FieldDetector(Detector):
+    """``field.py``."""
+
+    reduce_volume: bool = False
+    components: Sequence[str] = COMPONENT_NAMES
+
+    def _shape_dtype_single_time_step(self):
+        n = len(self.components)
+        return {"fields": ((n,) if self.reduce_volume else (n, *self.grid_shape), self.dtype)}
+
+
+@dataclass
+class PoyntingFluxDetector(Detector):
+    """``poynting_flux.py:68-195``."""
+
+    direction: Literal["+", "-"] = "+"
+    reduce_volume: bool = True
+    fixed_propagation_axis: int | None = None
+    keep_all_components: bool = False
+    _cached_face_area_weights: np.ndarray | None = None
+
+    @property
+    def propagation_axis(self) -> int:
+        if self.fixed_propagation_axis is not None:
+            if self.fixed_propagation_axis not in (0, 1, 2):
+                raise Exception(f"Invalid: {self.fixed_propagation_axis=}")
+            return self.fixed_propagation_axis
+        if sum(a == 1 for a in self.grid_shape) != 1:
+            raise Exception(f"Invalid poynting flux detector shape: {self.grid_shape}")
+        return self.grid_shape.index(1)
+
+    def place_on_grid(self, config):
+        super().place_on_grid(config)
+        grid = config.resolved_grid
+
+        def weights(axis):
+            if grid is not None:
+                return grid.face_area(self.grid_slice_tuple, axis)
+            sp = config.uniform_spacing()
+            return (np.ones(self.grid_shape, _f32) * _f32(sp) * _f32(sp)).astype(_f32)
+
+        if self.keep_all_components:
+            self._cached_face_area_weights = np.stack([weights(a) for a in range(3)])
+        else:
+            self._cached_face_area_weights = weights(self.propagation_axis if grid is not None else 0)
+        return self
+
+    def _shape_dtype_single_time_step(self):
+        if self.keep_all_components:
+            shape = (3,) if self.reduce_volume else (3, *self.grid_shape)
+        else:
+            shape = (1,) if self.reduce_volume else self.grid_shape
+        return {"poynting_flux": (shape, self.dtype)}
+
+
+@dataclass
+class PhasorDetector(Detector):
+    """Running DFT (``phasor.py:21-235``).  State ``phasor``: ``(1, nf, nc, *region)`` complex64."""
+
+    wave_characters: Sequence[WaveCharacter] = ()
+    reduce_volume: bool = False
+    components: Sequence[str] = COMPONENT_NAMES
+    dtype: type = np.complex64
+    scaling_mode: Literal["continuous", "pulse"] = "continuous"
+    dft_subsample: int | str = 1
+    _dft_stride: int = 1
+    _window_at_time_step_arr: np.ndarray | None = None
+    _window_sum: float | None = None
+
+    def __post_init__(self):
+        if self.dtype not in (np.complex64,):
+            raise Exception(f"Invalid dtype in PhasorDetector: {self.dtype} (complex64 only on this backend)")
+
+    @property
+    def _angular_frequencies(self) -> np.ndarray:
+        # 2 * jnp.pi * jnp.array(freqs): float32 array times the weak python scalar 2*pi
+        return _f32(2 * np.pi) * np.array([wc.get_frequency() for wc in self.wave_characters], dtype=_f32)
+
+    def _resolve_dft_stride(self, config) -> int:
+        sub = self.dft_subsample
+        if isinstance(sub, str):
+            if sub != "auto":
+                raise Exception(f"Invalid dft_subsample: {sub!r}")
+            dt = float(config.time_step_duration)
+            f_max = max((abs(float(wc.get_frequency())) for wc in self.wave_characters), default=0.0)
+            if f_max <= 0.0 or dt <= 0.0:
+                return 1
+            return max(1, math.floor(1.0 / (8.0 * f_max * dt)))
+        return max(1, int(sub))
+
+    def _calculate_on_list(self, config) -> list[bool]:
+        on_list = super()._calculate_on_list(config)
+        stride = self._resolve_dft_stride(config)
+        if stride <= 1:
+            return on_list
+        active = [t for t, on in enumerate(on_list) if on]
+        kept = [False] * len(on_list)
+        for t in active[::stride]:
+            kept[t] = True
+        return kept
+
+    def place_on_grid(self, config):
+        super().place_on_grid(config)
+        self._dft_stride = self._resolve_dft_stride(config)
+        window = self._is_on_at_time_step_arr.astype(_f32)
+        self._window_at_time_step_arr = window
+        self._window_sum = float(window.sum())
+        if not math.isfinite(self._window_sum) or self._window_sum <= 0.0:
+            raise Exception(f"Detector '{self.name}': the window sums to {self._window_sum}")
+        return self
+
+    def _static_scale(self) -> float | int:
+        if self.scaling_mode == "continuous":
+            return 2 / self._window_sum
+        if self.scaling_mode == "pulse":
+            return self._dft_stride
+        raise Exception(f"Invalid scaling mode: {self.scaling_mode=}")
+
+    def _num_latent_time_steps(self) -> int:
+        return 1
+
+    def _shape_dtype_single_time_step(self):
+        nf, nc = len(self.wave_characters), len(self.components)
+        gs = self.grid_shape if not self.reduce_volume else ()
+        return {"phasor": ((nf, nc, *gs), np.complex64)}
+
+
+@dataclass
+class ModeOverlapDetector(PhasorDetector):
+    """``mode.py:193-``: for the time step this *is* a ``PhasorDetector`` (all six components);
+    the overlap integral is post-processing and out of scope."""

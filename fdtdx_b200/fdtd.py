@@ -1,0 +1,199 @@
+"""Loop drivers with the reference's signatures, running on the sm_100a kernels.
+
+Mirrors ``fdtdx/fdtd/wrapper.py:14-63`` (``run_fdtd``), ``fdtdx/fdtd/fdtd.py:39-584``
+(``reversible_fdtd``, ``checkpointed_fdtd``, ``custom_fdtd_forward``),
+``fdtdx/fdtd/forward.py:83-156`` (``forward``) and ``fdtdx/fdtd/backward.py:18-135``
+(``full_backward``, ``backward``).  Arrays are CUDA ``torch.Tensor`` leaves of an
+``ArrayContainer``; like the reference under ``donate_argnames`` the field/state buffers are
+updated in place and the returned container aliases them.  There is no CPU path: without the
+CUDA extension every driver raises.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+from fdtdx_b200.config import SimulationConfig
+from fdtdx_b200.container import ArrayContainer, ObjectContainer, SimulationState
+from fdtdx_b200.plan import Plan
+
+
+def _require_cuda(arrays: ArrayContainer):
+    import torch
+
+    E = arrays.fields.E
+    if not isinstance(E, torch.Tensor) or not E.is_cuda:
+        raise RuntimeError(
+            "fdtdx_b200 runs on CUDA tensors only (no CPU fallback): move the container with arrays.to_torch('cuda')"
+        )
+
+
+def get_plan(arrays: ArrayContainer, objects: ObjectContainer, config: SimulationConfig) -> Plan:
+    """Plan cache on the ObjectContainer (plans hold only constant tables + scratch)."""
+    _require_cuda(arrays)
+    cache = objects.__dict__.setdefault("_plan_cache", {})
+    mu = arrays.inv_permeabilities
+    key = (
+        id(config),
+        arrays.fields.E.device.index,
+        tuple(arrays.inv_permittivities.shape),
+        tuple(mu.shape) if hasattr(mu, "shape") else float(mu),
+        None if arrays.electric_conductivity is None else tuple(arrays.electric_conductivity.shape),
+        None if arrays.magnetic_conductivity is None else tuple(arrays.magnetic_conductivity.shape),
+        None if arrays.dispersive_c1 is None else tuple(arrays.dispersive_c1.shape),
+        arrays.dispersive_c4 is not None,
+    )
+    plan = cache.get(key)
+    if plan is None:
+        plan = Plan(objects, config, arrays)
+        cache[key] = plan
+    plan.bind(arrays)
+    return plan
+
+
+def _progress(show_progress: bool, progress_callback, t: int, total: int):
+    if progress_callback is not None:
+        progress_callback(t, total)
+
+
+def _run_forward_loop(arrays, objects, config, start: int, end: int, record_detectors: bool, record_boundaries: bool, progress_callback=None):
+    plan = get_plan(arrays, objects, config)
+    n = int(end) - int(start)
+    if n > 0:
+        if progress_callback is None:
+            plan.run_forward(int(start), n, record_detectors, record_boundaries, True)
+        else:
+            chunk = max(1, n // 100)
+            t = int(start)
+            while t < end:
+                m = min(chunk, int(end) - t)
+                plan.run_forward(t, m, record_detectors, record_boundaries, True)
+                t += m
+                progress_callback(t, int(end))
+    return plan.finish(arrays)
+
+
+def checkpointed_fdtd(
+    arrays: ArrayContainer,
+    objects: ObjectContainer,
+    config: SimulationConfig,
+    key=None,
+    stopping_condition=None,
+    show_progress: bool = True,
+    progress_callback: Callable[[int, int], None] | None = None,
+) -> SimulationState:
+    """``fdtd.py:421-496``: reset, then ``forward`` until ``time_steps_total``.
+
+    Only the default ``TimeStepCondition`` is on the hot path."""
+    if stopping_condition is not None:
+        raise NotImplementedError("custom stopping conditions need a per-step global reduction (SURVEY section 8 f4)")
+    arrays = arrays.reset()
+    T = config.time_steps_total
+    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+    return T, arrays
+
+
+def custom_fdtd_forward(
+    arrays: ArrayContainer,
+    objects: ObjectContainer,
+    config: SimulationConfig,
+    key=None,
+    reset_container: bool = True,
+    record_detectors: bool = True,
+    start_time: int = 0,
+    end_time: int = 0,
+    show_progress: bool = True,
+    progress_callback: Callable[[int, int], None] | None = None,
+) -> SimulationState:
+    """``fdtd.py:499-584``."""
+    if reset_container:
+        arrays = arrays.reset()
+    end = max(int(end_time), int(start_time))
+    arrays = _run_forward_loop(arrays, objects, config, int(start_time), end, record_detectors, False, progress_callback)
+    return end, arrays
+
+
+def reversible_fdtd(
+    arrays: ArrayContainer,
+    objects: ObjectContainer,
+    config: SimulationConfig,
+    key=None,
+    show_progress: bool = True,
+    progress_callback: Callable[[int, int], None] | None = None,
+) -> SimulationState:
+    """``fdtd.py:39-418``: forward pass with boundary recording; the time-reversed backward pass
+    is available through :func:`full_backward`.  The fused adjoint (VJP) kernels behind
+    ``custom_vjp`` are the next row of SURVEY.md section 8 (a18) and are not built yet."""
+    if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
+        raise NotImplementedError(
+            "Dispersive time-reversible gradient computation under active development. "
+            "Use GradientConfig(method='checkpointed') instead."
+        )
+    num_ckpt = 0 if config.gradient_config is None else config.gradient_config.num_checkpoints_reversible
+    if num_ckpt > 0 and num_ckpt + 1 > config.time_steps_total:
+        raise Exception(
+            "num_checkpoints_reversible must be <= time_steps_total - 1 "
+            f"(got num_checkpoints_reversible={num_ckpt}, time_steps_total={config.time_steps_total})"
+        )
+    arrays = arrays.reset()
+    T = config.time_steps_total
+    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+    return T, arrays
+
+
+def run_fdtd(
+    arrays: ArrayContainer,
+    objects: ObjectContainer,
+    config: SimulationConfig,
+    key=None,
+    stopping_condition=None,
+    show_progress: bool = True,
+    progress_callback: Callable[[int, int], None] | None = None,
+) -> SimulationState:
+    """``wrapper.py:14-63`` dispatch rule."""
+    if config.gradient_config is None:
+        return checkpointed_fdtd(arrays, objects, config, key, stopping_condition, show_progress, progress_callback)
+    if stopping_condition is not None:
+        raise Exception("Custom stopping conditions are only supported for forward-only simulations")
+    if config.gradient_config.method == "reversible":
+        return reversible_fdtd(arrays, objects, config, key, show_progress, progress_callback)
+    if config.gradient_config.method == "checkpointed":
+        return checkpointed_fdtd(arrays, objects, config, key, None, show_progress, progress_callback)
+    raise Exception(f"Unknown gradient computation method: {config.gradient_config.method}")
+
+
+def forward(state: SimulationState, config, objects, key=None, record_detectors=True, record_boundaries=False, simulate_boundaries=True) -> SimulationState:
+    """One forward step (``forward.py:83-156``)."""
+    t, arrays = state
+    plan = get_plan(arrays, objects, config)
+    plan.run_forward(int(t), 1, record_detectors, record_boundaries, simulate_boundaries)
+    return int(t) + 1, plan.finish(arrays)
+
+
+def backward(state: SimulationState, config, objects, key=None, record_detectors=True, reset_fields=True, fields_to_reset=("E", "H")) -> SimulationState:
+    """One reverse step (``backward.py:62-135``)."""
+    if tuple(fields_to_reset) != ("E", "H"):
+        raise NotImplementedError("fields_to_reset other than ('E','H')")
+    t, arrays = state
+    plan = get_plan(arrays, objects, config)
+    plan.run_reverse(int(t), 1, record_detectors, reset_fields)
+    return int(t) - 1, plan.finish(arrays)
+
+
+def full_backward(state: SimulationState, objects, config, key=None, record_detectors=True, reset_fields=True, start_time_step: int = 0) -> SimulationState:
+    """``backward.py:18-59``."""
+    t, arrays = state
+    n = int(t) - int(start_time_step)
+    if n <= 0:
+        return state
+    plan = get_plan(arrays, objects, config)
+    plan.run_reverse(int(t), n, record_detectors, reset_fields)
+    return int(start_time_step), plan.finish(arrays)
+
+
+def apply_params(arrays, objects, params, key=None, **kwargs):
+    """``initialization.py:317-323`` stand-in: device parameter mapping is out of scope (SURVEY
+    section 8 f2); with no devices the arrays pass through unchanged."""
+    if params:
+        raise NotImplementedError("apply_params with device parameters is outside the hot-path scope")
+    return arrays, objects, {}

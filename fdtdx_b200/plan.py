@@ -1,0 +1,462 @@
+"""Plan compiler: lowers ``(ObjectContainer, SimulationConfig, ArrayContainer)`` to the POD tables
+the C ABI takes (``include/fdtdx_b200.h``) and binds the caller's device buffers.
+
+What it reads off each object is exactly the hook list of SURVEY.md section 8b: boundary
+axis/direction/slice/wrap flag and CPML tables; source arrays, profile and switch tables; detector
+region, gate/index tables and reduction flags; recorder slot tables.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from fdtdx_b200 import _lib
+from fdtdx_b200._lib import check
+from fdtdx_b200.boundaries import PerfectElectricConductor, PerfectMagneticConductor
+from fdtdx_b200.constants import c as c0
+from fdtdx_b200.detectors import (
+    COMPONENT_NAMES,
+    EnergyDetector,
+    FieldDetector,
+    PhasorDetector,
+    PoyntingFluxDetector,
+)
+from fdtdx_b200.profile import PROFILE_CW, PROFILE_PULSE, PROFILE_TABLE
+from fdtdx_b200.sources import PointDipoleSource, TFSFPlaneSource
+
+_f32 = np.float32
+
+
+def _fptr(a: np.ndarray | None):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _iarr(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def metric_scales(config, axis: int):
+    """(sB, sF) float32 per-cell scales of ``curl.py:10-39`` for one axis (global length)."""
+    grid = config.resolved_grid
+    w = grid.cell_widths(axis)
+    ref = c0 * config.time_step_duration / config.courant_number
+    prev = np.concatenate([w[:1], w[:-1]])
+    wb = _f32(0.5) * (w + prev)
+    return (_f32(ref) / wb).astype(_f32), (_f32(ref) / w).astype(_f32)
+
+
+def _profile_params(profile, wave_character):
+    p = [0.0] * 8
+    signal = None
+    if profile.kind == PROFILE_CW:
+        period = wave_character.get_period()
+        p[0], p[1], p[2], p[3] = period, wave_character.phase_shift, profile.phase_shift, profile.num_startup_periods * period
+    elif profile.kind == PROFILE_PULSE:
+        sw = profile.spectral_width.get_frequency()
+        fc = profile.center_wave.get_frequency()
+        sigma_t = 1.0 / (2 * np.pi * sw)
+        p[0], p[1], p[2], p[3], p[4] = 2 * np.pi * fc, wave_character.phase_shift, profile.center_wave.phase_shift, 6 * sigma_t, 2.0 * sigma_t**2
+    elif profile.kind == PROFILE_TABLE:
+        p[0], p[1], p[2], p[3] = profile.start_time, profile.time_step_duration, profile.outside_value, 1.0 if profile.interpolation == "nearest" else 0.0
+        signal = np.ascontiguousarray(profile.signal, dtype=_f32)
+    else:
+        raise NotImplementedError(type(profile))
+    return (C.c_double * 8)(*p), signal
+
+
+class Plan:
+    """Owns one ``FdtdxPlan*``.  ``x_range`` restricts the plan to an x-slab (multi-GPU)."""
+
+    def __init__(self, objects, config, arrays, x_range: tuple[int, int] | None = None, halo=(False, False)):
+        self.lib = _lib.lib()
+        self.objects, self.config = objects, config
+        shape = objects.volume.grid_shape
+        self.global_shape = shape
+        x0, x1 = x_range if x_range is not None else (0, shape[0])
+        self.x0, self.x1 = x0, x1
+        nx, ny, nz = x1 - x0, shape[1], shape[2]
+        self.local_shape = (nx, ny, nz)
+        self.T = max(int(config.time_steps_total), 1)
+        self._keep = []  # host arrays must stay alive until the C call returns; kept for safety
+
+        inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
+        self.eps_tier = int(inv_eps.shape[0])
+        self.mu_is_array = hasattr(inv_mu, "shape") and len(inv_mu.shape) > 0
+        self.mu_tier = int(inv_mu.shape[0]) if self.mu_is_array else 0
+        sE, sH = arrays.electric_conductivity, arrays.magnetic_conductivity
+        self.sigE_tier = 0 if sE is None else int(sE.shape[0])
+        self.sigH_tier = 0 if sH is None else int(sH.shape[0])
+        wrap = [False, False, False]
+        for b in objects.boundary_objects:
+            if b.uses_wrap_padding:
+                if getattr(b, "needs_complex_fields", False):
+                    raise NotImplementedError("Bloch boundaries with k != 0 need complex fields (out of scope)")
+                wrap[b.axis] = True
+        if any(s != 0 for s in config.symmetry):
+            raise NotImplementedError("config.symmetry is outside the hot-path scope (setup-time domain reduction)")
+        self.wrap = wrap
+        sB = sF = widths = None
+        if config.has_nonuniform_grid:
+            sB_l, sF_l, w_l = [], [], []
+            for a in range(3):
+                b_, f_ = metric_scales(config, a)
+                if a == 0:
+                    b_, f_ = b_[x0:x1], f_[x0:x1]
+                sB_l.append(np.ascontiguousarray(b_))
+                sF_l.append(np.ascontiguousarray(f_))
+                w_l.append(np.ascontiguousarray(config.resolved_grid.cell_widths(a), dtype=_f32))
+            self._keep += sB_l + sF_l + w_l
+            mk = lambda lst: (C.POINTER(C.c_float) * 3)(*[_fptr(x) for x in lst])
+            sB, sF, widths = mk(sB_l), mk(sF_l), mk(w_l)
+        h = C.c_void_p()
+        check(
+            self.lib.fdtdx_b200_plan_create(
+                C.byref(h), nx, ny, nz, x0, shape[0], config.courant_number, config.time_step_duration, self.T,
+                self.eps_tier, self.mu_tier, self.sigE_tier, self.sigH_tier,
+                float(inv_mu) if not self.mu_is_array else 1.0, _iarr(wrap), sB, sF, widths,
+            )
+        )
+        self.h = h
+        self._add_boundaries()
+        self._add_sources()
+        self._add_detectors()
+        self._set_recorder()
+        self.n_poles = 0
+        if arrays.dispersive_c1 is not None:
+            c1 = arrays.dispersive_c1
+            self.n_poles = int(c1.shape[0])
+            tiers = {int(x.shape[1]) for x in (arrays.dispersive_c1, arrays.dispersive_c2, arrays.dispersive_c3) if x is not None}
+            if arrays.dispersive_c4 is not None:
+                tiers.add(int(arrays.dispersive_c4.shape[1]))
+            if len(tiers) != 1 or next(iter(tiers)) not in (1, 3):
+                raise NotImplementedError(f"dispersive coefficient component tiers {tiers} (need one common tier of 1 or 3)")
+            check(self.lib.fdtdx_b200_plan_set_dispersion(self.h, self.n_poles, next(iter(tiers)), int(arrays.dispersive_c4 is not None)))
+        check(self.lib.fdtdx_b200_halo_bind(self.h, int(halo[0]), int(halo[1])))
+        self.halo = halo
+        self._bound = []
+
+    # ------------------------------------------------------------------ tables
+    def _add_boundaries(self):
+        self.pml_index = {}
+        order = [p.axis for p in self.objects.pml_objects]
+        if order != sorted(order):
+            raise NotImplementedError("PML objects must be listed in axis order (x, y, z) - the CPML corrections are applied in that order")
+        for pml in self.objects.pml_objects:
+            lo, hi = pml.grid_slice_tuple[pml.axis]
+            full = [(0, n) for n in self.global_shape]
+            full[pml.axis] = (lo, hi)
+            if tuple(full) != tuple(pml.grid_slice_tuple):
+                raise NotImplementedError("PML slabs must span the full cross-section")
+            t = [np.ascontiguousarray(x.reshape(-1), dtype=_f32) for x in (pml.pml_a_E, pml.pml_b_E, pml.inv_kappa_E, pml.pml_a_H, pml.pml_b_H, pml.inv_kappa_H)]
+            for i in (2, 5):
+                if t[i].size == 1:
+                    t[i] = np.full(hi - lo, t[i][0], _f32)
+            idx = check(
+                self.lib.fdtdx_b200_plan_add_pml(
+                    self.h, pml.axis, 1 if pml.direction == "+" else 0, lo, hi, *[_fptr(x) for x in t], int(pml.kappa_is_one)
+                )
+            )
+            self.pml_index[pml.name] = idx
+        for b in self.objects.boundary_objects:
+            if isinstance(b, (PerfectElectricConductor, PerfectMagneticConductor)):
+                kind = 0 if isinstance(b, PerfectElectricConductor) else 1
+                lo = [s[0] for s in b.grid_slice_tuple]
+                hi = [s[1] for s in b.grid_slice_tuple]
+                check(self.lib.fdtdx_b200_plan_add_wall(self.h, kind, b.axis, _iarr(lo), _iarr(hi)))
+
+    def _switch_tables(self, src):
+        if src.uses_default_switch:
+            return None, None
+        on = np.ascontiguousarray(src._is_on_at_time_step_arr, dtype=np.uint8)
+        t_adj = np.ascontiguousarray(src._time_step_to_on_idx, dtype=_f32)
+        on, t_adj = self._pad_T(on), self._pad_T(t_adj)
+        self._keep += [on, t_adj]
+        return on.ctypes.data_as(C.POINTER(C.c_uint8)), _fptr(t_adj)
+
+    def _pad_T(self, a):
+        if a.shape[0] >= self.T:
+            return np.ascontiguousarray(a[: self.T])
+        return np.ascontiguousarray(np.concatenate([a, np.zeros(self.T - a.shape[0], a.dtype)]))
+
+    def _add_sources(self):
+        cfg = self.config
+        for src in self.objects.sources:
+            params, signal = _profile_params(src.temporal_profile, src.wave_character)
+            on, t_adj = self._switch_tables(src)
+            sl = [list(s) for s in src.grid_slice_tuple]
+            if isinstance(src, TFSFPlaneSource):
+                if self.eps_tier == 9 or self.mu_tier == 9:
+                    pass  # tensor rows are handled by the tensor kernels with the same descriptor
+                xs = slice(max(sl[0][0], self.x0) - sl[0][0], min(sl[0][1], self.x1) - sl[0][0])
+                if xs.stop <= xs.start:
+                    continue
+                arrs = [np.ascontiguousarray(a[:, xs], dtype=_f32) for a in (src._E, src._H, src._time_offset_E, src._time_offset_H)]
+                lo = [max(sl[0][0], self.x0), sl[1][0], sl[2][0]]
+                hi = [min(sl[0][1], self.x1), sl[1][1], sl[2][1]]
+                cE = float(_f32(cfg.courant_number) * _f32(src.metric_scale_at_plane(cfg, "backward")))
+                cH = float(_f32(cfg.courant_number) * _f32(src.metric_scale_at_plane(cfg, "forward")))
+                hf = None if src._temporal_H_filter is None else np.ascontiguousarray(src._temporal_H_filter, dtype=_f32)
+                check(
+                    self.lib.fdtdx_b200_plan_add_plane_source(
+                        self.h, _iarr(lo), _iarr(hi), src.propagation_axis, 1 if src.direction == "+" else -1,
+                        *[_fptr(a) for a in arrs], src.temporal_profile.kind, params, _fptr(signal),
+                        0 if signal is None else signal.shape[0], float(src.static_amplitude_factor), cE, cH, on, t_adj,
+                        _fptr(hf), 0 if hf is None else hf.shape[0],
+                    )
+                )
+            elif isinstance(src, PointDipoleSource):
+                cell = [s[0] for s in sl]
+                if not (self.x0 <= cell[0] < self.x1):
+                    continue
+                scale = cfg.courant_number * src.amplitude * src.static_amplitude_factor
+                check(
+                    self.lib.fdtdx_b200_plan_add_dipole(
+                        self.h, _iarr(cell), src.polarization, int(src.source_type == "electric"), scale,
+                        src.temporal_profile.kind, params, _fptr(signal), 0 if signal is None else signal.shape[0], on, t_adj,
+                    )
+                )
+            else:
+                raise NotImplementedError(f"source type {type(src).__name__} is not on the hot path")
+
+    def _add_detectors(self):
+        cfg = self.config
+        self.det_index = {}
+        for det in self.objects.detectors:
+            flags = 0
+            if det.exact_interpolation:
+                flags |= _lib.DETF_EXACT
+            if det.inverse:
+                flags |= _lib.DETF_INVERSE
+            comp_mask, aux, weights, nf, table, window, scale, slice_idx = 0, 0, None, 0, None, None, 1.0, [0, 0, 0]
+            if isinstance(det, PhasorDetector):
+                kind = _lib.DET_PHASOR
+                comp_mask = sum(1 << i for i, n in enumerate(COMPONENT_NAMES) if n in det.components)
+                if det.reduce_volume:
+                    flags |= _lib.DETF_REDUCE
+                    weights = det._cached_cell_volume_weights
+                om = det._angular_frequencies
+                nf = om.shape[0]
+                tp = (np.arange(self.T, dtype=_f32) * _f32(cfg.time_step_duration)).astype(_f32)
+                ang = (om[None, :] * tp[:, None]).astype(_f32)
+                table = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], axis=-1), dtype=_f32)
+                window = self._pad_T(np.ascontiguousarray(det._window_at_time_step_arr, dtype=_f32))
+                scale = float(det._static_scale())
+            elif isinstance(det, FieldDetector):
+                kind = _lib.DET_FIELD
+                comp_mask = sum(1 << i for i, n in enumerate(COMPONENT_NAMES) if n in det.components)
+                if det.reduce_volume:
+                    flags |= _lib.DETF_REDUCE
+                    weights = det._cached_cell_volume_weights
+            elif isinstance(det, EnergyDetector):
+                kind = _lib.DET_ENERGY
+                if self.eps_tier == 9 or self.mu_tier == 9:
+                    raise NotImplementedError("EnergyDetector in full-tensor media is not on the hot path yet")
+                if det.as_slices:
+                    flags |= _lib.DETF_SLICES
+                    if det.use_mean:
+                        flags |= _lib.DETF_SLICE_MEAN
+                    slice_idx = list(det._slice_indices)
+                elif det.reduce_volume:
+                    flags |= _lib.DETF_REDUCE
+                    weights = det._cached_cell_volume_weights
+            elif isinstance(det, PoyntingFluxDetector):
+                kind = _lib.DET_POYNTING
+                if det.keep_all_components:
+                    flags |= _lib.DETF_KEEP_ALL
+                else:
+                    aux = det.propagation_axis
+                if det.direction == "-":
+                    flags |= _lib.DETF_NEGATIVE
+                if det.reduce_volume:
+                    flags |= _lib.DETF_REDUCE
+                    weights = det._cached_face_area_weights
+            else:
+                raise NotImplementedError(f"detector type {type(det).__name__} is not on the hot path")
+            lo = [s[0] for s in det.grid_slice_tuple]
+            hi = [s[1] for s in det.grid_slice_tuple]
+            on = self._pad_T(np.ascontiguousarray(det._is_on_at_time_step_arr, dtype=np.uint8))
+            idx = self._pad_T(np.ascontiguousarray(det._time_step_to_arr_idx, dtype=np.int32))
+            if isinstance(det, PhasorDetector):
+                idx = np.zeros_like(idx)
+            w = None if weights is None else np.ascontiguousarray(weights, dtype=_f32)
+            di = check(
+                self.lib.fdtdx_b200_plan_add_detector(
+                    self.h, kind, _iarr(lo), _iarr(hi), flags, comp_mask, aux,
+                    on.ctypes.data_as(C.POINTER(C.c_uint8)), idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                    _fptr(w), nf, _fptr(None if table is None else table.reshape(-1)), _fptr(window), scale, _iarr(slice_idx),
+                )
+            )
+            self.det_index[det.name] = di
+
+    def _set_recorder(self):
+        gc = self.config.gradient_config
+        self.recorder = None
+        if gc is None or gc.recorder is None:
+            return
+        rec = gc.recorder
+        if rec.slot_of_time is None or rec._max_time_steps != self.config.time_steps_total:
+            rec.init_tables(self.config.time_steps_total)
+        self.recorder = rec
+        i32 = lambda a: self._pad_T(np.ascontiguousarray(a, dtype=np.int32)).ctypes.data_as(C.POINTER(C.c_int32))
+        w = self._pad_T(np.ascontiguousarray(rec.replay_w, dtype=_f32))
+        check(
+            self.lib.fdtdx_b200_plan_set_recorder(
+                self.h, rec.dtype_code, rec._latent_array_size, i32(rec.slot_of_time), i32(rec.replay_a), i32(rec.replay_b), _fptr(w)
+            )
+        )
+
+    # ------------------------------------------------------------------ binding
+    def _bind(self, slot: int, index: int, t, dtype=None, shape=None):
+        import torch
+
+        if t is None:
+            check(self.lib.fdtdx_b200_bind(self.h, slot, index, None))
+            return
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("fdtdx_b200 buffers must be contiguous CUDA tensors")
+        if dtype is not None and t.dtype != dtype:
+            raise ValueError(f"buffer dtype {t.dtype} != expected {dtype}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"buffer shape {tuple(t.shape)} != expected {tuple(shape)}")
+        self._bound.append(t)
+        check(self.lib.fdtdx_b200_bind(self.h, slot, index, C.c_void_p(t.data_ptr())))
+
+    def bind(self, arrays):
+        import torch
+
+        f32 = torch.float32
+        self._bound = []
+        L = self.local_shape
+        self._bind(_lib.SLOT_E, 0, arrays.fields.E, f32, (3, *L))
+        self._bind(_lib.SLOT_H, 0, arrays.fields.H, f32, (3, *L))
+        self._bind(_lib.SLOT_INV_EPS, 0, arrays.inv_permittivities, f32, (self.eps_tier, *L))
+        if self.mu_is_array:
+            self._bind(_lib.SLOT_INV_MU, 0, arrays.inv_permeabilities, f32, (self.mu_tier, *L))
+        if self.sigE_tier:
+            self._bind(_lib.SLOT_SIGMA_E, 0, arrays.electric_conductivity, f32, (self.sigE_tier, *L))
+        if self.sigH_tier:
+            self._bind(_lib.SLOT_SIGMA_H, 0, arrays.magnetic_conductivity, f32, (self.sigH_tier, *L))
+        for pml in self.objects.pml_objects:
+            q = self.pml_index[pml.name]
+            if pml.name not in arrays.fields.psi_E:
+                continue  # slab lives on another rank
+            for w in range(2):
+                self._bind(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32)
+                self._bind(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32)
+        if self.n_poles:
+            self._bind(_lib.SLOT_P_A, 0, arrays.fields.dispersive_P_curr, f32, (self.n_poles, 3, *L))
+            self._bind(_lib.SLOT_P_B, 0, arrays.fields.dispersive_P_prev, f32, (self.n_poles, 3, *L))
+            self._bind(_lib.SLOT_C1, 0, arrays.dispersive_c1, f32)
+            self._bind(_lib.SLOT_C2, 0, arrays.dispersive_c2, f32)
+            self._bind(_lib.SLOT_C3, 0, arrays.dispersive_c3, f32)
+            if arrays.dispersive_c4 is not None:
+                self._bind(_lib.SLOT_C4, 0, arrays.dispersive_c4, f32)
+            check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
+        for det in self.objects.detectors:
+            di = self.det_index[det.name]
+            st = arrays.detector_states[det.name]
+            for k, key in enumerate(st.keys()):
+                self._bind(_lib.SLOT_DET_STATE, 4 * di + k, st[key])
+        if self.recorder is not None and arrays.recording_state is not None:
+            for pml in self.objects.pml_objects:
+                q = self.pml_index[pml.name]
+                for f, fs in enumerate(("E", "H")):
+                    self._bind(_lib.SLOT_REC_DATA, 2 * q + f, arrays.recording_state.data[f"{pml.name}_{fs}"], self.recorder.torch_dtype())
+        self._bind_tensor_path(arrays)
+
+    def _bind_tensor_path(self, arrays):
+        """Full-tensor tier: ping-pong buffers and precomputed A/B (``fdtd/misc.py:69-129``)."""
+        import torch
+
+        self.tensor_E = self.eps_tier == 9 or self.sigE_tier == 9
+        self.tensor_H = self.mu_tier == 9 or self.sigH_tier == 9
+        if not (self.tensor_E or self.tensor_H):
+            return
+        from fdtdx_b200.tensor_setup import update_matrices
+
+        dev = arrays.fields.E.device
+        if self.tensor_E:
+            self.E_alt = torch.zeros_like(arrays.fields.E)
+            self._bind(_lib.SLOT_E_ALT, 0, self.E_alt)
+            A, B, Ar, Br = update_matrices(arrays.inv_permittivities, arrays.electric_conductivity, self.config.courant_number, "E")
+            self.tE = (A, B, Ar, Br)
+        if self.tensor_H:
+            self.H_alt = torch.zeros_like(arrays.fields.H)
+            self._bind(_lib.SLOT_H_ALT, 0, self.H_alt)
+            A, B, Ar, Br = update_matrices(arrays.inv_permeabilities, arrays.magnetic_conductivity, self.config.courant_number, "H")
+            self.tH = (A, B, Ar, Br)
+        self.set_tensor_direction(reverse=False)
+        check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
+
+    def set_tensor_direction(self, reverse: bool):
+        if getattr(self, "tensor_E", False):
+            A, B, Ar, Br = self.tE
+            self._bind(_lib.SLOT_TENSOR_A_E, 0, Ar if reverse else A)
+            self._bind(_lib.SLOT_TENSOR_B_E, 0, Br if reverse else B)
+        if getattr(self, "tensor_H", False):
+            A, B, Ar, Br = self.tH
+            self._bind(_lib.SLOT_TENSOR_A_H, 0, Ar if reverse else A)
+            self._bind(_lib.SLOT_TENSOR_B_H, 0, Br if reverse else B)
+
+    # ------------------------------------------------------------------ execution
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run_forward(self, t0: int, n: int, record_detectors: bool, record_boundaries: bool, simulate_boundaries: bool = True):
+        self.set_tensor_direction(False)
+        check(self.lib.fdtdx_b200_run_forward(self.h, int(t0), int(n), int(record_detectors), int(record_boundaries), int(simulate_boundaries), self._stream()))
+
+    def run_forward_phase(self, t: int, phase: int, record_detectors: bool, record_boundaries: bool, simulate_boundaries: bool = True):
+        check(self.lib.fdtdx_b200_run_forward_phase(self.h, int(t), int(phase), int(record_detectors), int(record_boundaries), int(simulate_boundaries), self._stream()))
+
+    def run_reverse(self, t_from: int, n: int, record_detectors: bool, reset_fields: bool):
+        self.set_tensor_direction(True)
+        check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
+
+    def parity(self) -> tuple[int, int, int]:
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.fdtdx_b200_get_parity(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.fdtdx_b200_launch_count(self.h))
+
+    def set_tuning(self, xchunk: int = 0, rows: int = 0):
+        check(self.lib.fdtdx_b200_set_tuning(self.h, int(xchunk), int(rows)))
+
+    def finish(self, arrays):
+        """Return the container whose leaves hold the *current* state after ping-pong passes."""
+        pp, ep, hp = self.parity()
+        if self.n_poles and pp:
+            arrays = arrays.aset("fields->dispersive_P_curr", arrays.fields.dispersive_P_prev).aset(
+                "fields->dispersive_P_prev", arrays.fields.dispersive_P_curr
+            )
+        if getattr(self, "tensor_E", False) and ep:
+            arrays.fields.E.copy_(self.E_alt)
+        if getattr(self, "tensor_H", False) and hp:
+            arrays.fields.H.copy_(self.H_alt)
+        check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
+        if self.n_poles and pp:
+            # the swapped container is re-bound on the next call; nothing else to do
+            pass
+        return arrays
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fdtdx_b200_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
