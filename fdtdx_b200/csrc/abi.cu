@@ -10,7 +10,6 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "tensor_kernels.cuh"
-#include "yee_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -55,6 +54,7 @@ struct FdtdxPlan {
   std::vector<WallDev> walls;
   std::vector<SrcHost> srcs;
   SrcDev* d_srcs = nullptr;
+  WallDev* d_walls = nullptr;
   std::vector<DetHost> dets;
   // recorder
   bool has_rec = false;
@@ -160,6 +160,7 @@ extern "C" int fdtdx_b200_plan_add_wall(FdtdxPlan* p, int kind, int axis, const 
   for (int a = 0; a < 3; ++a) { w.lo[a] = lo[a]; w.hi[a] = hi[a]; }
   w.lo[0] -= p->xoff; w.hi[0] -= p->xoff;
   p->walls.push_back(w);
+  p->finalized = false;
   return (int)p->walls.size() - 1;
 }
 
@@ -404,6 +405,10 @@ static int finalize(FdtdxPlan* p) {
     int rc = to_device(p, hs.data(), hs.size(), &p->d_srcs);
     if (rc) return rc;
   }
+  if (!p->walls.empty()) {
+    int rc = to_device(p, p->walls.data(), p->walls.size(), &p->d_walls);
+    if (rc) return rc;
+  }
   p->finalized = true;
   return FDTDX_OK;
 }
@@ -449,7 +454,7 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   }
   P.simulate = simulate;
   P.n_walls = (int)p->walls.size();
-  for (int w = 0; w < P.n_walls; ++w) P.walls[w] = p->walls[w];
+  P.walls = p->d_walls;
   P.n_src = (int)p->srcs.size();
   P.src = p->d_srcs;
   P.n_poles = p->n_poles; P.has_c4 = p->has_c4;
@@ -496,23 +501,9 @@ static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
   return true;
 }
 
-template <int V, int TIER, bool REV>
-static void launch_E3(const StepParams& P, int t, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st) {
-#define GO(S, A, M) yee_E_kernel<V, TIER, REV, S, A, M><<<g, b, 0, st>>>(P, t)
-  if constexpr (REV) {
-    if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
-    else { if (met) GO(false, false, true); else GO(false, false, false); }
-  } else {
-    if (ade) {
-      if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
-      else { if (met) GO(false, true, true); else GO(false, true, false); }
-    } else {
-      if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
-      else { if (met) GO(false, false, true); else GO(false, false, false); }
-    }
-  }
-#undef GO
-}
+// kernel dispatchers live in yee_E.cu / yee_H.cu (separate translation units, built in parallel)
+void fdtdx_dispatch_E(const StepParams& P, int t, bool v4, int tier, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_H(const StepParams& P, int t, bool v4, int mu_tier, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
 
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
@@ -521,31 +512,10 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
-  const int tier = p->eps_tier;
-#define DISP(VV, TT)                                                         \
-  do {                                                                       \
-    if (rev) launch_E3<VV, TT, true>(P, t, sig, ade, met, g, b, st);         \
-    else launch_E3<VV, TT, false>(P, t, sig, ade, met, g, b, st);            \
-  } while (0)
-  if (v4) { if (tier == 1) DISP(4, 1); else DISP(4, 3); }
-  else { if (tier == 1) DISP(1, 1); else DISP(1, 3); }
-#undef DISP
+  fdtdx_dispatch_E(P, t, v4, p->eps_tier, rev, sig, ade, met, g, b, st);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
-}
-
-template <int V, int MUT>
-static void launch_H2(const StepParams& P, int t, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st) {
-#define GO(R, S, M) yee_H_kernel<V, MUT, R, S, M><<<g, b, 0, st>>>(P, t)
-  if (rev) {
-    if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
-    else { if (met) GO(true, false, true); else GO(true, false, false); }
-  } else {
-    if (sig) { if (met) GO(false, true, true); else GO(false, true, false); }
-    else { if (met) GO(false, false, true); else GO(false, false, false); }
-  }
-#undef GO
 }
 
 static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
@@ -553,17 +523,7 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   const int V = v4 ? 4 : 1;
   dim3 b(32, p->rows);
   dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
-  const bool sig = p->sigH_tier > 0, met = p->metric;
-  const int mt = p->mu_tier;
-  if (v4) {
-    if (mt == 0) launch_H2<4, 0>(P, t, rev, sig, met, g, b, st);
-    else if (mt == 1) launch_H2<4, 1>(P, t, rev, sig, met, g, b, st);
-    else launch_H2<4, 3>(P, t, rev, sig, met, g, b, st);
-  } else {
-    if (mt == 0) launch_H2<1, 0>(P, t, rev, sig, met, g, b, st);
-    else if (mt == 1) launch_H2<1, 1>(P, t, rev, sig, met, g, b, st);
-    else launch_H2<1, 3>(P, t, rev, sig, met, g, b, st);
-  }
+  fdtdx_dispatch_H(P, t, v4, p->mu_tier, rev, p->sigH_tier > 0, p->metric, g, b, st);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;

@@ -68,7 +68,7 @@ struct StepParams {
   AxisPmlDev pml[3];
   int simulate;
   int n_walls;
-  WallDev walls[FDTDX_MAX_WALL];
+  const WallDev* walls;  // device array
   int n_src;
   const SrcDev* src;  // device array
   // ADE (update.py:316-350)

@@ -21,7 +21,7 @@
 // temporal profiles (objects/sources/profile.py:263-273, 322-345, 412-439; core/window.py:16-30)
 // float32, same operation order as the reference; no FMA contraction (compiled with -fmad=false).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ float src_profile(const SrcDev& S, float time) {
+static __device__ __noinline__ float src_profile(const SrcDev& S, float time) {
   if (S.profile_kind == 0) {  // SingleFrequencyProfile
     float phase = ((S.p[4] * time) / S.p[0] + S.p[1]) + S.p[2];  // 2*pi*time/period + phase_shift + self.phase_shift
     float raw = cosf(phase);                                     // Re(exp(-i*phase))
@@ -63,12 +63,12 @@ __device__ __forceinline__ bool in_box(const int* lo, const int* hi, int i, int 
 }
 
 // E-side injection at one cell (tfsf.py:193-308 diagonal branch; dipole.py:195-232).
-__device__ __noinline__ void inject_E(const StepParams& P, int t, bool reverse, int i, int j, int k,
+static __device__ __noinline__ void inject_E(const SrcDev* __restrict__ srcs, int n_src, float dt, int t, bool reverse, int i, int j, int k,
                                        float ie0, float ie1, float ie2, float* e0, float* e1, float* e2) {
   float ie[3] = {ie0, ie1, ie2};
   float E[3] = {*e0, *e1, *e2};
-  for (int s = 0; s < P.n_src; ++s) {
-    const SrcDev& S = P.src[s];
+  for (int s = 0; s < n_src; ++s) {
+    const SrcDev& S = srcs[s];
     if (!in_box(S.lo, S.hi, i, j, k)) continue;
     float tf;
     if (!src_time(S, t, 0.0f, &tf)) continue;
@@ -80,8 +80,8 @@ __device__ __noinline__ void inject_E(const StepParams& P, int t, bool reverse, 
       float sign = reverse ? -S.sign : S.sign;
       float amp_a, amp_b;
       if (S.hfilter == nullptr) {
-        amp_a = src_profile(S, (tf + S.toffH[a * fn + f]) * P.dt) * S.static_amp;
-        amp_b = src_profile(S, (tf + S.toffH[b * fn + f]) * P.dt) * S.static_amp;
+        amp_a = src_profile(S, (tf + S.toffH[a * fn + f]) * dt) * S.static_amp;
+        amp_b = src_profile(S, (tf + S.toffH[b * fn + f]) * dt) * S.static_amp;
       } else {
         // jnp.interp(t + toff, arange(T), filter, left=0, right=0)   (tfsf.py:259-264)
         float amps[2];
@@ -107,7 +107,7 @@ __device__ __noinline__ void inject_E(const StepParams& P, int t, bool reverse, 
       E[a] = E[a] + sign * Hb;
       E[b] = E[b] + (-sign) * Ha;
     } else if (S.electric) {
-      float amp = src_profile(S, tf * P.dt);
+      float amp = src_profile(S, tf * dt);
       float sg = reverse ? 1.0f : -1.0f;
       float scale = S.dip_scale * amp;
       E[S.pol] = E[S.pol] + sg * (scale * ie[S.pol]);
@@ -117,12 +117,12 @@ __device__ __noinline__ void inject_E(const StepParams& P, int t, bool reverse, 
 }
 
 // H-side injection at one cell (tfsf.py:311-409 diagonal branch; dipole.py:236-277).
-__device__ __noinline__ void inject_H(const StepParams& P, int t, bool reverse, int i, int j, int k,
+static __device__ __noinline__ void inject_H(const SrcDev* __restrict__ srcs, int n_src, float dt, int t, bool reverse, int i, int j, int k,
                                        float im0, float im1, float im2, float* h0, float* h1, float* h2) {
   float im[3] = {im0, im1, im2};
   float H[3] = {*h0, *h1, *h2};
-  for (int s = 0; s < P.n_src; ++s) {
-    const SrcDev& S = P.src[s];
+  for (int s = 0; s < n_src; ++s) {
+    const SrcDev& S = srcs[s];
     if (!in_box(S.lo, S.hi, i, j, k)) continue;
     float tf;
     if (!src_time(S, t, 0.5f, &tf)) continue;
@@ -132,8 +132,8 @@ __device__ __noinline__ void inject_H(const StepParams& P, int t, bool reverse, 
       long long f = ((long long)(i - S.lo[0]) * fy + (j - S.lo[1])) * fz + (k - S.lo[2]);
       int a = (S.normal_axis + 1) % 3, b = (S.normal_axis + 2) % 3;
       float sign = reverse ? -S.sign : S.sign;
-      float amp_a = src_profile(S, (tf + S.toffE[a * fn + f]) * P.dt) * S.static_amp;
-      float amp_b = src_profile(S, (tf + S.toffE[b * fn + f]) * P.dt) * S.static_amp;
+      float amp_a = src_profile(S, (tf + S.toffE[a * fn + f]) * dt) * S.static_amp;
+      float amp_b = src_profile(S, (tf + S.toffE[b * fn + f]) * dt) * S.static_amp;
       float Ea = S.Einc[a * fn + f] * amp_a;
       float Eb = S.Einc[b * fn + f] * amp_b;
       Ea = (Ea * S.cH) * im[b];
@@ -141,7 +141,7 @@ __device__ __noinline__ void inject_H(const StepParams& P, int t, bool reverse, 
       H[b] = H[b] + sign * Ea;
       H[a] = H[a] + (-sign) * Eb;
     } else if (!S.electric) {
-      float amp = src_profile(S, tf * P.dt);
+      float amp = src_profile(S, tf * dt);
       float sg = reverse ? 1.0f : -1.0f;
       float scale = S.dip_scale * amp;
       H[S.pol] = H[S.pol] + sg * (scale * im[S.pol]);
@@ -150,9 +150,9 @@ __device__ __noinline__ void inject_H(const StepParams& P, int t, bool reverse, 
   *h0 = H[0]; *h1 = H[1]; *h2 = H[2];
 }
 
-__device__ __forceinline__ bool any_src_hits(const StepParams& P, int i, int j, int k0, int V) {
-  for (int s = 0; s < P.n_src; ++s) {
-    const SrcDev& S = P.src[s];
+__device__ __forceinline__ bool any_src_hits(const SrcDev* __restrict__ srcs, int n_src, int i, int j, int k0, int V) {
+  for (int s = 0; s < n_src; ++s) {
+    const SrcDev& S = srcs[s];
     if (i >= S.lo[0] && i < S.hi[0] && j >= S.lo[1] && j < S.hi[1] && k0 < S.hi[2] && k0 + V > S.lo[2]) return true;
   }
   return false;
@@ -179,6 +179,7 @@ __device__ __forceinline__ void cpml_cell(float a, float b, float km1, bool kapp
   }
 }
 
+#if !defined(FDTDX_BUILD_H)
 // ------------------------------------------------------------------------------------------------
 // E half-step
 // ------------------------------------------------------------------------------------------------
@@ -301,8 +302,8 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         const int side = (i >= px.hi_start) ? 1 : 0;
         const int il = side ? i - px.hi_start : i;
         const long long pidx = ((long long)il * ny + j) * nz + k0;
-        float* q1 = px.psiE[side][0] + pidx;
-        float* q2 = px.psiE[side][1] + pidx;
+        float* q1 = (side ? px.psiE[1][0] : px.psiE[0][0]) + pidx;
+        float* q2 = (side ? px.psiE[1][1] : px.psiE[0][1]) + pidx;
         Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = px.aE[i], b = px.bE[i], km1 = px.kE[i];
 #pragma unroll
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
       }
       if (in_y) {
         const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        float* q1 = py.psiE[yside][0] + pidx;
-        float* q2 = py.psiE[yside][1] + pidx;
+        float* q1 = (yside ? py.psiE[1][0] : py.psiE[0][0]) + pidx;
+        float* q2 = (yside ? py.psiE[1][1] : py.psiE[0][1]) + pidx;
         Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = py.aE[j], b = py.bE[j], km1 = py.kE[j];
 #pragma unroll
@@ -340,14 +341,14 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
             const long long pidx = ((long long)i * ny + j) * L + kl;
             float c1, c2;  // a=2: i=0(x), j=1(y); d1 = dzHy, d2 = dzHx
             cpml_cell(pz.aE[k], pz.bE[k], pz.kE[k], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e],
-                      pz.psiE[side][0] + pidx, pz.psiE[side][1] + pidx, &c1, &c2);
+                      (side ? pz.psiE[1][0] : pz.psiE[0][0]) + pidx, (side ? pz.psiE[1][1] : pz.psiE[0][1]) + pidx, &c1, &c2);
             Kx.v[e] = Kx.v[e] - c1;
             Ky.v[e] = Ky.v[e] + c2;
           }
         }
       }
       // material update
-      const bool src_hit = (P.n_src > 0) && any_src_hits(P, i, j, k0, V);
+      const bool src_hit = (P.n_src > 0) && any_src_hits(P.src, P.n_src, i, j, k0, V);
       Vec<V> oe[3];
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         float En[3];
         if (REV) {
           // update_E_reverse: sources first (inverse), then ((1+s)E - c K inv_eps) / (1-s)
-          if (src_hit) inject_E(P, t, true, i, j, k0 + e, ie[0], ie[1], ie[2], &Eo[0], &Eo[1], &Eo[2]);
+          if (src_hit) inject_E(P.src, P.n_src, P.dt, t, true, i, j, k0 + e, ie[0], ie[1], ie[2], &Eo[0], &Eo[1], &Eo[2]);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float Ec = Eo[c];
@@ -415,11 +416,11 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
             }
             En[c] = E1;
           }
-          if (src_hit) inject_E(P, t, false, i, j, k0 + e, ie[0], ie[1], ie[2], &En[0], &En[1], &En[2]);
+          if (src_hit) inject_E(P.src, P.n_src, P.dt, t, false, i, j, k0 + e, ie[0], ie[1], ie[2], &En[0], &En[1], &En[2]);
         }
         // PEC walls (pec.py:70-77)
         for (int w = 0; w < P.n_walls; ++w) {
-          const WallDev& W = P.walls[w];
+          const WallDev W = P.walls[w];
           if (W.kind == 0 && in_box(W.lo, W.hi, i, j, k0 + e)) {
             if (W.axis != 0) En[0] = 0.0f;
             if (W.axis != 1) En[1] = 0.0f;
@@ -437,6 +438,9 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
   }
 }
 
+#endif  // !FDTDX_BUILD_H
+
+#if !defined(FDTDX_BUILD_E)
 // ------------------------------------------------------------------------------------------------
 // H half-step
 // ------------------------------------------------------------------------------------------------
@@ -561,8 +565,8 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         const int side = (i >= px.hi_start) ? 1 : 0;
         const int il = side ? i - px.hi_start : i;
         const long long pidx = ((long long)il * ny + j) * nz + k0;
-        float* q1 = px.psiH[side][0] + pidx;
-        float* q2 = px.psiH[side][1] + pidx;
+        float* q1 = (side ? px.psiH[1][0] : px.psiH[0][0]) + pidx;
+        float* q2 = (side ? px.psiH[1][1] : px.psiH[0][1]) + pidx;
         Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = px.aH[i], b = px.bH[i], km1 = px.kH[i];
 #pragma unroll
@@ -576,8 +580,8 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
       }
       if (in_y) {
         const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        float* q1 = py.psiH[yside][0] + pidx;
-        float* q2 = py.psiH[yside][1] + pidx;
+        float* q1 = (yside ? py.psiH[1][0] : py.psiH[0][0]) + pidx;
+        float* q2 = (yside ? py.psiH[1][1] : py.psiH[0][1]) + pidx;
         Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = py.aH[j], b = py.bH[j], km1 = py.kH[j];
 #pragma unroll
@@ -600,13 +604,13 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
             const long long pidx = ((long long)i * ny + j) * L + kl;
             float c1, c2;
             cpml_cell(pz.aH[k], pz.bH[k], pz.kH[k], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e],
-                      pz.psiH[side][0] + pidx, pz.psiH[side][1] + pidx, &c1, &c2);
+                      (side ? pz.psiH[1][0] : pz.psiH[0][0]) + pidx, (side ? pz.psiH[1][1] : pz.psiH[0][1]) + pidx, &c1, &c2);
             Kx.v[e] = Kx.v[e] - c1;
             Ky.v[e] = Ky.v[e] + c2;
           }
         }
       }
-      const bool src_hit = (P.n_src > 0) && any_src_hits(P, i, j, k0, V);
+      const bool src_hit = (P.n_src > 0) && any_src_hits(P.src, P.n_src, i, j, k0, V);
       Vec<V> oh[3];
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         const long long cell = base + row + e;
         float Hn[3];
         if (REV) {
-          if (src_hit) inject_H(P, t, true, i, j, k0 + e, im[0], im[1], im[2], &Ho[0], &Ho[1], &Ho[2]);
+          if (src_hit) inject_H(P.src, P.n_src, P.dt, t, true, i, j, k0 + e, im[0], im[1], im[2], &Ho[0], &Ho[1], &Ho[2]);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float Hc = Ho[c];
@@ -643,10 +647,10 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
               Hn[c] = Ho[c] - (P.cour * K[c]) * im[c];
             }
           }
-          if (src_hit) inject_H(P, t, false, i, j, k0 + e, im[0], im[1], im[2], &Hn[0], &Hn[1], &Hn[2]);
+          if (src_hit) inject_H(P.src, P.n_src, P.dt, t, false, i, j, k0 + e, im[0], im[1], im[2], &Hn[0], &Hn[1], &Hn[2]);
         }
         for (int w = 0; w < P.n_walls; ++w) {
-          const WallDev& W = P.walls[w];
+          const WallDev W = P.walls[w];
           if (W.kind == 1 && in_box(W.lo, W.hi, i, j, k0 + e)) {
             if (W.axis != 0) Hn[0] = 0.0f;
             if (W.axis != 1) Hn[1] = 0.0f;
@@ -664,3 +668,4 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
     ez = ez_n;
   }
 }
+#endif  // !FDTDX_BUILD_E
