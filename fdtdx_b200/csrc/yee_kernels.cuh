@@ -158,6 +158,11 @@ __device__ __forceinline__ bool any_src_hits(const SrcDev* __restrict__ srcs, in
   return false;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#define FDTDX_PF_DIST 2
+
 // CPML for one axis at one cell (perfectly_matched_layer.py:138-190; curl.py:284-308, 371-394).
 // d1 = d_a F_j, d2 = d_a F_i; returns the corrections to subtract from K_i and add to K_j.
 __device__ __forceinline__ void cpml_cell(float a, float b, float km1, bool kappa_one, bool simulate,
@@ -263,6 +268,54 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         ie2 = ie0;
       }
     }
+    // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
+    // indices only), so their latency overlaps instead of serialising behind the curl.
+    const bool in_x = (i < px.lo_len || i >= px.hi_start);
+    Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
+    float psz1[V], psz2[V];
+    float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
+    if (active) {
+      if (in_x) {
+        const int side = (i >= px.hi_start) ? 1 : 0;
+        const int il = side ? i - px.hi_start : i;
+        const long long pidx = ((long long)il * ny + j) * nz + k0;
+        qx1 = (side ? px.psiE[1][0] : px.psiE[0][0]) + pidx;
+        qx2 = (side ? px.psiE[1][1] : px.psiE[0][1]) + pidx;
+        psx1 = ldv<V>(qx1);
+        psx2 = ldv<V>(qx2);
+      }
+      if (in_y) {
+        const long long pidx = ((long long)i * yL + jl) * nz + k0;
+        qy1 = (yside ? py.psiE[1][0] : py.psiE[0][0]) + pidx;
+        qy2 = (yside ? py.psiE[1][1] : py.psiE[0][1]) + pidx;
+        psy1 = ldv<V>(qy1);
+        psy2 = ldv<V>(qy2);
+      }
+      if (any_z) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int k = k0 + e;
+          psz1[e] = 0.0f;
+          psz2[e] = 0.0f;
+          if (k < pz.lo_len || k >= pz.hi_start) {
+            const int side = (k >= pz.hi_start) ? 1 : 0;
+            const int kl = side ? k - pz.hi_start : k;
+            const int L = side ? pz.hi_len : pz.lo_len;
+            const long long pidx = ((long long)i * ny + j) * L + kl;
+            psz1[e] = (side ? pz.psiE[1][0] : pz.psiE[0][0])[pidx];
+            psz2[e] = (side ? pz.psiE[1][1] : pz.psiE[0][1])[pidx];
+          }
+        }
+      }
+      // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
+      if (i + FDTDX_PF_DIST < ic1) {
+        const long long pb = base + FDTDX_PF_DIST * plane + row;
+        prefetch_l2(Hx + pb); prefetch_l2(Hy + pb); prefetch_l2(Hz + pb);
+        prefetch_l2(Ex + pb); prefetch_l2(Ey + pb); prefetch_l2(Ez + pb);
+        prefetch_l2(P.eps + pb);
+        if (TIER == 3) { prefetch_l2(P.eps + P.eps_cs + pb); prefetch_l2(P.eps + 2 * P.eps_cs + pb); }
+      }
+    }
     // z-neighbour (k-1) of the first element: last element of the previous lane
     float hx_l = __shfl_up_sync(0xffffffffu, hx.v[V - 1], 1);
     float hy_l = __shfl_up_sync(0xffffffffu, hy.v[V - 1], 1);
@@ -273,7 +326,6 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
     if (active) {
       float sBx = 1.0f;
       if (MET) sBx = P.sB[0][i];
-      const bool in_x = (i < px.lo_len || i >= px.hi_start);
       Vec<V> Kx, Ky, Kz;
       Vec<V> dxHz_v, dxHy_v, dyHx_v, dyHz_v, dzHy_v, dzHx_v;
 #pragma unroll
@@ -299,36 +351,26 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
       }
       // CPML corrections in the reference's object order: x slabs, y slabs, z slabs.
       if (in_x) {
-        const int side = (i >= px.hi_start) ? 1 : 0;
-        const int il = side ? i - px.hi_start : i;
-        const long long pidx = ((long long)il * ny + j) * nz + k0;
-        float* q1 = (side ? px.psiE[1][0] : px.psiE[0][0]) + pidx;
-        float* q2 = (side ? px.psiE[1][1] : px.psiE[0][1]) + pidx;
-        Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = px.aE[i], b = px.bE[i], km1 = px.kE[i];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          float c1, c2;  // a=0: i=1(y), j=2(z); d1 = dxHz, d2 = dxHy
-          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxHz_v.v[e], dxHy_v.v[e], &p1.v[e], &p2.v[e], &c1, &c2);
+          float c1, c2;  // axis 0: d1 = dx F_z, d2 = dx F_y; corrects K_y (-) and K_z (+)
+          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxHz_v.v[e], dxHy_v.v[e], &psx1.v[e], &psx2.v[e], &c1, &c2);
           Ky.v[e] = Ky.v[e] - c1;
           Kz.v[e] = Kz.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(q1, p1); stv<V>(q2, p2); }
+        if (P.simulate && !REV) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
       }
       if (in_y) {
-        const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        float* q1 = (yside ? py.psiE[1][0] : py.psiE[0][0]) + pidx;
-        float* q2 = (yside ? py.psiE[1][1] : py.psiE[0][1]) + pidx;
-        Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = py.aE[j], b = py.bE[j], km1 = py.kE[j];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          float c1, c2;  // a=1: i=2(z), j=0(x); d1 = dyHx, d2 = dyHz
-          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyHx_v.v[e], dyHz_v.v[e], &p1.v[e], &p2.v[e], &c1, &c2);
+          float c1, c2;  // axis 1: d1 = dy F_x, d2 = dy F_z; corrects K_z (-) and K_x (+)
+          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyHx_v.v[e], dyHz_v.v[e], &psy1.v[e], &psy2.v[e], &c1, &c2);
           Kz.v[e] = Kz.v[e] - c1;
           Kx.v[e] = Kx.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(q1, p1); stv<V>(q2, p2); }
+        if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
       if (any_z) {
 #pragma unroll
@@ -339,9 +381,13 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
             const int kl = side ? k - pz.hi_start : k;
             const int L = side ? pz.hi_len : pz.lo_len;
             const long long pidx = ((long long)i * ny + j) * L + kl;
-            float c1, c2;  // a=2: i=0(x), j=1(y); d1 = dzHy, d2 = dzHx
+            float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
             cpml_cell(pz.aE[k], pz.bE[k], pz.kE[k], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e],
-                      (side ? pz.psiE[1][0] : pz.psiE[0][0]) + pidx, (side ? pz.psiE[1][1] : pz.psiE[0][1]) + pidx, &c1, &c2);
+                      &psz1[e], &psz2[e], &c1, &c2);
+            if (P.simulate && !REV) {
+              (side ? pz.psiE[1][0] : pz.psiE[0][0])[pidx] = psz1[e];
+              (side ? pz.psiE[1][1] : pz.psiE[0][1])[pidx] = psz2[e];
+            }
             Kx.v[e] = Kx.v[e] - c1;
             Ky.v[e] = Ky.v[e] + c2;
           }
@@ -528,6 +574,54 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         }
       }
     }
+    // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
+    // indices only), so their latency overlaps instead of serialising behind the curl.
+    const bool in_x = (i < px.lo_len || i >= px.hi_start);
+    Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
+    float psz1[V], psz2[V];
+    float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
+    if (active) {
+      if (in_x) {
+        const int side = (i >= px.hi_start) ? 1 : 0;
+        const int il = side ? i - px.hi_start : i;
+        const long long pidx = ((long long)il * ny + j) * nz + k0;
+        qx1 = (side ? px.psiH[1][0] : px.psiH[0][0]) + pidx;
+        qx2 = (side ? px.psiH[1][1] : px.psiH[0][1]) + pidx;
+        psx1 = ldv<V>(qx1);
+        psx2 = ldv<V>(qx2);
+      }
+      if (in_y) {
+        const long long pidx = ((long long)i * yL + jl) * nz + k0;
+        qy1 = (yside ? py.psiH[1][0] : py.psiH[0][0]) + pidx;
+        qy2 = (yside ? py.psiH[1][1] : py.psiH[0][1]) + pidx;
+        psy1 = ldv<V>(qy1);
+        psy2 = ldv<V>(qy2);
+      }
+      if (any_z) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int k = k0 + e;
+          psz1[e] = 0.0f;
+          psz2[e] = 0.0f;
+          if (k < pz.lo_len || k >= pz.hi_start) {
+            const int side = (k >= pz.hi_start) ? 1 : 0;
+            const int kl = side ? k - pz.hi_start : k;
+            const int L = side ? pz.hi_len : pz.lo_len;
+            const long long pidx = ((long long)i * ny + j) * L + kl;
+            psz1[e] = (side ? pz.psiH[1][0] : pz.psiH[0][0])[pidx];
+            psz2[e] = (side ? pz.psiH[1][1] : pz.psiH[0][1])[pidx];
+          }
+        }
+      }
+      // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
+      if (i + FDTDX_PF_DIST < ic1) {
+        const long long pb = base + FDTDX_PF_DIST * plane + row;
+        prefetch_l2(Hx + pb); prefetch_l2(Hy + pb); prefetch_l2(Hz + pb);
+        prefetch_l2(Ex + pb); prefetch_l2(Ey + pb); prefetch_l2(Ez + pb);
+        if (MUT >= 1) prefetch_l2(P.mu + pb);
+        if (MUT == 3) { prefetch_l2(P.mu + P.mu_cs + pb); prefetch_l2(P.mu + 2 * P.mu_cs + pb); }
+      }
+    }
     float ex_r = __shfl_down_sync(0xffffffffu, ex.v[0], 1);
     float ey_r = __shfl_down_sync(0xffffffffu, ey.v[0], 1);
     if (last_lane) {
@@ -537,7 +631,6 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
     if (active) {
       float sFx = 1.0f;
       if (MET) sFx = P.sF[0][i];
-      const bool in_x = (i < px.lo_len || i >= px.hi_start);
       Vec<V> Kx, Ky, Kz;
       Vec<V> dxEz_v, dxEy_v, dyEx_v, dyEz_v, dzEy_v, dzEx_v;
 #pragma unroll
@@ -562,36 +655,26 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         dyEz_v.v[e] = dyEz; dzEy_v.v[e] = dzEy; dzEx_v.v[e] = dzEx;
       }
       if (in_x) {
-        const int side = (i >= px.hi_start) ? 1 : 0;
-        const int il = side ? i - px.hi_start : i;
-        const long long pidx = ((long long)il * ny + j) * nz + k0;
-        float* q1 = (side ? px.psiH[1][0] : px.psiH[0][0]) + pidx;
-        float* q2 = (side ? px.psiH[1][1] : px.psiH[0][1]) + pidx;
-        Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = px.aH[i], b = px.bH[i], km1 = px.kH[i];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          float c1, c2;
-          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxEz_v.v[e], dxEy_v.v[e], &p1.v[e], &p2.v[e], &c1, &c2);
+          float c1, c2;  // axis 0: d1 = dx F_z, d2 = dx F_y; corrects K_y (-) and K_z (+)
+          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxEz_v.v[e], dxEy_v.v[e], &psx1.v[e], &psx2.v[e], &c1, &c2);
           Ky.v[e] = Ky.v[e] - c1;
           Kz.v[e] = Kz.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(q1, p1); stv<V>(q2, p2); }
+        if (P.simulate && !REV) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
       }
       if (in_y) {
-        const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        float* q1 = (yside ? py.psiH[1][0] : py.psiH[0][0]) + pidx;
-        float* q2 = (yside ? py.psiH[1][1] : py.psiH[0][1]) + pidx;
-        Vec<V> p1 = ldv<V>(q1), p2 = ldv<V>(q2);
         const float a = py.aH[j], b = py.bH[j], km1 = py.kH[j];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          float c1, c2;
-          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyEx_v.v[e], dyEz_v.v[e], &p1.v[e], &p2.v[e], &c1, &c2);
+          float c1, c2;  // axis 1: d1 = dy F_x, d2 = dy F_z; corrects K_z (-) and K_x (+)
+          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyEx_v.v[e], dyEz_v.v[e], &psy1.v[e], &psy2.v[e], &c1, &c2);
           Kz.v[e] = Kz.v[e] - c1;
           Kx.v[e] = Kx.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(q1, p1); stv<V>(q2, p2); }
+        if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
       if (any_z) {
 #pragma unroll
@@ -602,9 +685,13 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
             const int kl = side ? k - pz.hi_start : k;
             const int L = side ? pz.hi_len : pz.lo_len;
             const long long pidx = ((long long)i * ny + j) * L + kl;
-            float c1, c2;
+            float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
             cpml_cell(pz.aH[k], pz.bH[k], pz.kH[k], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e],
-                      (side ? pz.psiH[1][0] : pz.psiH[0][0]) + pidx, (side ? pz.psiH[1][1] : pz.psiH[0][1]) + pidx, &c1, &c2);
+                      &psz1[e], &psz2[e], &c1, &c2);
+            if (P.simulate && !REV) {
+              (side ? pz.psiH[1][0] : pz.psiH[0][0])[pidx] = psz1[e];
+              (side ? pz.psiH[1][1] : pz.psiH[0][1])[pidx] = psz2[e];
+            }
             Kx.v[e] = Kx.v[e] - c1;
             Ky.v[e] = Ky.v[e] + c2;
           }
