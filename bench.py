@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py - Gcell-updates/s of the E+H Yee step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # CPU arm (oracle port, host cores)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full Yee step (E half-step + H half-step + detector accumulation) over the whole
+grid.  Default workload = BASELINE.json configs[1]: the directional-coupler scene of the reference's
+``performance/directional_coupler.py`` at cells-per-lambda 20, (1897, 291, 128) = 70.7 M cells,
+non-uniform grid, 12-cell CPML, mode plane source, three phasor detectors.  At N > 1 the same scene
+is chained N times along x, one coupler per rank (weak scaling, x-slab halo exchange).
+``--workload box`` is the C5 vacuum/dielectric box (``--box-n`` cube side; x-slab sharded).
+
+Timing: W >= 3 warm-up steps, then exactly K steps between CUDA events with a barrier and a
+synchronize on both sides, max over ranks.  Grids are >> L2 (126 MB), so no flush is needed.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(self.samples),
+        }
+
+
+def build_workload(args, device, rank, world):
+    from fdtdx_b200 import workloads as W
+    from fdtdx_b200.dist import slab_bounds
+
+    if args.workload == "coupler":
+        grid, nx1, _ = W.coupler_grid(args.cpl, world)
+        x_range = (rank * nx1, (rank + 1) * nx1)
+        objects, arrays, cfg = W.build_coupler(args.cpl, device=device, n_copies=world, x_range=x_range, with_detectors=not args.no_detectors)
+        name = f"C2 directional coupler cpl={args.cpl} ({nx1}x{grid.shape[1]}x{grid.shape[2]} per GPU, x{world} chained along x)"
+    else:
+        n = args.box_n
+        shape = (n * world, n, n) if args.scaling == "weak" else (n, n, n)
+        x_range = slab_bounds(shape[0], world, rank)
+        objects, arrays, cfg = W.build_box(shape, device=device, x_range=x_range)
+        name = f"C5 vacuum/dielectric box {shape[0]}x{shape[1]}x{shape[2]} + 10-cell CPML, x-slab sharded"
+    return objects, arrays, cfg, x_range, name
+
+
+def cpu_baseline(args, steps=None):
+    """Oracle (NumPy float32 restatement of the reference) on a bounded sample of the workload."""
+    from fdtdx_b200 import workloads as W
+    from oracle import yee
+
+    if args.workload == "coupler":
+        objects, arrays, cfg = W.build_coupler(args.cpu_cpl, device=None, with_detectors=not args.no_detectors)
+        sample = f"coupler scene at cpl={args.cpu_cpl}"
+    else:
+        objects, arrays, cfg = W.build_box((args.cpu_box_n,) * 3, device=None)
+        sample = f"box scene {args.cpu_box_n}^3"
+    shape = objects.volume.grid_shape
+    cells = float(np.prod(shape))
+    yee.custom_fdtd_forward(arrays, objects, cfg, None, True, True, 0, 1)  # warm
+    n = steps or args.cpu_steps
+    t0 = time.perf_counter()
+    yee.custom_fdtd_forward(arrays, objects, cfg, None, True, True, 0, n)
+    dt = time.perf_counter() - t0
+    return {
+        "value": cells * n / dt / 1e9,
+        "unit": "Gcell/s",
+        "cores": 1,
+        "kind": "port",
+        "sample": f"{sample}, grid {shape[0]}x{shape[1]}x{shape[2]} ({cells/1e6:.2f} Mcell), {n} steps, NumPy float32 oracle (restated reference algorithm, not fdtdx/JAX: jax is not installable here)",
+        "seconds": dt,
+    }
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    K, Wm = args.steps, args.warmup
+    from fdtdx_b200 import workloads as W
+    from oracle import yee
+
+    if args.workload == "coupler":
+        objects, arrays, cfg = W.build_coupler(args.cpu_cpl, device=None, with_detectors=not args.no_detectors)
+        sample = f"coupler scene at cpl={args.cpu_cpl}"
+    else:
+        objects, arrays, cfg = W.build_box((args.cpu_box_n,) * 3, device=None)
+        sample = f"box scene {args.cpu_box_n}^3"
+    shape = objects.volume.grid_shape
+    cells = float(np.prod(shape))
+    K = min(K, 20)  # bounded sample: each step is a full pass over the reduced grid
+    st = yee.custom_fdtd_forward(arrays, objects, cfg, None, True, True, 0, min(Wm, 3))
+    t0 = time.perf_counter()
+    yee.custom_fdtd_forward(st[1], objects, cfg, None, False, True, st[0], st[0] + K)
+    dt = time.perf_counter() - t0
+    val = cells * K / dt / 1e9
+    line = {
+        "impl": "reference",
+        "metric": "Gcell-updates/s (E+H Yee step)",
+        "value": val,
+        "unit": "Gcell/s",
+        "n_gpus": args.gpus,
+        "steps": K,
+        "warmup": min(Wm, 3),
+        "ms_per_step": dt / K * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{sample} (bounded CPU sample of the GPU workload), grid {shape[0]}x{shape[1]}x{shape[2]}"},
+        "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": 1, "kind": "port",
+                         "sample": f"{sample}: NumPy float32 oracle port of the reference algorithm; the reference's own JAX-CPU path cannot run here (no jax in the image, no network)"},
+        "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="coupler", choices=["coupler", "box"])
+    ap.add_argument("--cpl", type=int, default=20, help="cells per wavelength of the coupler scene (20 -> 70.7 Mcell)")
+    ap.add_argument("--box-n", type=int, default=1024)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-detectors", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--cpu-cpl", type=int, default=5)
+    ap.add_argument("--cpu-box-n", type=int, default=96)
+    ap.add_argument("--cpu-steps", type=int, default=30)
+    ap.add_argument("--xchunk", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 backend has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: WORLD_SIZE={world} but --gpus={args.gpus}; using WORLD_SIZE", file=sys.stderr)
+
+    from fdtdx_b200 import workloads as W
+    from fdtdx_b200.dist import SlabRunner
+    from fdtdx_b200.fdtd import get_plan
+
+    objects, arrays, cfg, x_range, wname = build_workload(args, device, rank, world)
+    local_shape = tuple(arrays.fields.E.shape[1:])
+    cells_local = float(np.prod(local_shape))
+    cells_total = cells_local * world
+    K, Wm = args.steps, args.warmup
+    if Wm + K + 2 > cfg.time_steps_total:
+        K = max(1, cfg.time_steps_total - Wm - 2)
+    record_det = not args.no_detectors
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world > 1:
+        runner = SlabRunner(objects, cfg, arrays, x_range, rank, world, overlap=not args.no_overlap)
+        plan = runner.plan
+        plan.set_tuning(args.xchunk, args.rows)
+        step_fn = lambda t0, n: runner.run(t0, n, record_det)
+    else:
+        plan = get_plan(arrays, objects, cfg)
+        plan.set_tuning(args.xchunk, args.rows)
+        step_fn = lambda t0, n: plan.run_forward(t0, n, record_det, False, True)
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    step_fn(0, Wm)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = plan.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    step_fn(Wm, K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = plan.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=device)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = cells_total * K / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel roofline: yee_E (the dominant kernel) timed live with CUDA events ----------
+    roofline = None
+    hbm_peak, peak_src = _peaks()
+    if world == 1:
+        nrep = min(K, 50)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nrep)]
+        t = Wm + K
+        if t + nrep >= cfg.time_steps_total:
+            t = Wm
+        for a, b, c in evs:
+            a.record()
+            plan.run_forward_phase(t, 0, False, False, True)
+            b.record()
+            plan.run_forward_phase(t, 1, False, False, True)
+            c.record()
+            t += 1
+        torch.cuda.synchronize()
+        ms_E = float(np.mean([a.elapsed_time(b) for a, b, _ in evs]))
+        ms_H = float(np.mean([b.elapsed_time(c) for _, b, c in evs]))
+        bpc = W.bytes_per_cell_step(objects, arrays, local_shape)
+        n_eps = int(arrays.inv_permittivities.shape[0])
+        psi_b = (bpc - (72 + 4 * n_eps)) / 2  # CPML psi bytes per cell per half-step
+        bytes_E = (12 + 12 + 12 + 4 * n_eps + psi_b) * cells_local
+        achieved = bytes_E / (ms_E * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm",
+            "kernel": "yee_E_kernel (E half-step: curl_H + CPML + material update + source + PEC)",
+            "achieved": achieved,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": achieved / hbm_peak,
+            "traffic": None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_E,
+            "ms_per_launch": ms_E,
+            "ms_per_launch_yee_H": ms_H,
+            "bytes_per_cell_step": bpc,
+            "whole_step_frac": bpc * value / hbm_peak,
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                with open(tr) as f:
+                    roofline["traffic"] = json.load(f).get(args.workload)
+            except Exception:
+                pass
+
+    # ---- end-to-end through the public API with HOST buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        import fdtdx_b200 as fx
+
+        n_e2e = K
+        host = {
+            "E": torch.zeros(arrays.fields.E.shape, dtype=torch.float32).pin_memory(),
+            "H": torch.zeros(arrays.fields.H.shape, dtype=torch.float32).pin_memory(),
+            "eps": arrays.inv_permittivities.cpu().pin_memory(),
+        }
+        out_E = torch.empty(arrays.fields.E.shape, dtype=torch.float32).pin_memory()
+        det_host = {k: {k2: torch.empty(v2.shape, dtype=v2.dtype).pin_memory() for k2, v2 in v.items()} for k, v in arrays.detector_states.items()}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        arrays.fields.E.copy_(host["E"], non_blocking=True)
+        arrays.fields.H.copy_(host["H"], non_blocking=True)
+        arrays.inv_permittivities.copy_(host["eps"], non_blocking=True)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        _, out = fx.custom_fdtd_forward(arrays, objects, cfg, None, reset_container=False, record_detectors=record_det, start_time=0, end_time=n_e2e, show_progress=False)
+        out_E.copy_(out.fields.E, non_blocking=True)
+        d2h = out_E.numel() * 4
+        for k, v in out.detector_states.items():
+            for k2, v2 in v.items():
+                det_host[k][k2].copy_(v2, non_blocking=True)
+                d2h += v2.numel() * v2.element_size()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {
+            "value": cells_total * n_e2e / dt / 1e9,
+            "unit": "Gcell/s",
+            "h2d_bytes_per_step": h2d / n_e2e,
+            "d2h_bytes_per_step": d2h / n_e2e,
+            "steps": n_e2e,
+            "note": "custom_fdtd_forward over the run: pinned-host E,H,inv_eps -> device, K steps, E + detector states -> host; copies amortised over the K steps of the run",
+        }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": "Gcell-updates/s (E+H Yee step)",
+            "value": value,
+            "unit": "Gcell/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": Wm,
+            "ms_per_step": ms / K,
+            "higher_is_better": True,
+            "scaling": args.scaling if args.workload == "box" else "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": wname,
+                "cells_total": cells_total,
+                "l2_policy": "inputs >> L2 (no flush needed)",
+                "detectors": record_det,
+                "halo_overlap": (not args.no_overlap) if world > 1 else None,
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

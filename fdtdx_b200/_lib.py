@@ -32,7 +32,7 @@ EXPORTS = [
     "fdtdx_b200_plan_set_dispersion", "fdtdx_b200_halo_bind", "fdtdx_b200_bind", "fdtdx_b200_run_forward",
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
     "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning",
-    "fdtdx_b200_run_forward_host",
+    "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
 ]
 
 _p = C.c_void_p
@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_bind.argtypes = [_p, _i, _i, _p]
     L.fdtdx_b200_run_forward.argtypes = [_p, _i, _i, _i, _i, _i, _p]
     L.fdtdx_b200_run_forward_phase.argtypes = [_p, _i, _i, _i, _i, _i, _p]
+    L.fdtdx_b200_run_half_range.argtypes = [_p, _i, _i, _i, _i, _i, _p]
+    L.fdtdx_b200_get_xchunk.argtypes = [_p]
     L.fdtdx_b200_run_reverse.argtypes = [_p, _i, _i, _i, _i, _p]
     L.fdtdx_b200_run_adjoint.argtypes = [_p, _i, _i, _p]
     L.fdtdx_b200_get_parity.argtypes = [_p, _ip, _ip, _ip]

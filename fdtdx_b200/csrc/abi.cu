@@ -262,12 +262,19 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
                                             const float* weights, int n_freq, const float* phasor_table,
                                             const float* window, double scale, const int slice_idx[3]) {
   if (!p || !on || !arr_idx) return fail(FDTDX_EINVAL, "add_detector: missing tables");
-  if (p->xoff != 0 || p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "detectors on x-sharded plans are not supported yet");
   DetHost h;
   memset(&h.d, 0, sizeof(DetDev));
   DetDev& d = h.d;
   d.kind = kind; d.flags = flags; d.comp_mask = comp_mask; d.aux = aux;
   for (int a = 0; a < 3; ++a) { d.lo[a] = lo[a]; d.hi[a] = hi[a]; d.slice_idx[a] = slice_idx ? slice_idx[a] : 0; }
+  d.lo[0] -= p->xoff; d.hi[0] -= p->xoff;  // local x coordinates of this rank's slab
+  if (p->nx != p->nxg) {
+    // x-sharded: the region and its co-location stencil (x-1) must lie inside this slab; detectors
+    // straddling a slab edge would need an extra E-plane exchange - not built yet.
+    const int need_lo = (flags & DET_EXACT) ? 1 : 0;
+    if (d.lo[0] < need_lo || d.hi[0] > p->nx)
+      return fail(FDTDX_EUNSUPPORTED, "detector region (plus stencil) must lie inside one x-slab");
+  }
   d.ncomp = 0;
   for (int c = 0; c < 6; ++c) d.ncomp += (comp_mask >> c) & 1;
   const size_t n = (size_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
@@ -480,10 +487,12 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     // enough CTAs for >= ~6 waves of 148 SMs x 8 resident CTAs, but chunks long enough that the
     // one-plane re-read at each chunk start stays below ~3 % of the traffic
     const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + p->rows - 1) / p->rows);
-    long long want = (148LL * 8 * 6 + tiles - 1) / tiles;
-    xc = (int)std::max(8LL, std::min<long long>(64, p->nx / std::max(1LL, want)));
+    long long want = (148LL * 2 * 8 + tiles - 1) / tiles;  // >= ~8 waves at 2 resident CTAs per SM
+    xc = (int)std::max(16LL, std::min<long long>(64, p->nx / std::max(1LL, want)));
   }
   P.xchunk = std::min(xc, p->nx);
+  P.x_begin = 0;
+  P.x_end = p->nx;
   return FDTDX_OK;
 }
 
@@ -509,7 +518,7 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   const bool v4 = can_vec4(p, P);
   const int V = v4 ? 4 : 1;
   dim3 b(32, p->rows);
-  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
+  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
   fdtdx_dispatch_E(P, t, v4, p->eps_tier, rev, sig, ade, met, g, b, st);
@@ -522,7 +531,7 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   const bool v4 = can_vec4(p, P);
   const int V = v4 ? 4 : 1;
   dim3 b(32, p->rows);
-  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (p->nx + P.xchunk - 1) / P.xchunk);
+  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
   fdtdx_dispatch_H(P, t, v4, p->mu_tier, rev, p->sigH_tier > 0, p->metric, g, b, st);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -673,7 +682,41 @@ extern "C" int fdtdx_b200_run_forward_phase(FdtdxPlan* p, int t, int phase, int 
     return step_E(p, t, simulate_boundaries, false, st);
   }
   if (phase == 1) return step_H(p, t, simulate_boundaries, false, st);
+  if (phase == 3) return record_detectors ? detectors_gather(p, t, false, st) : FDTDX_OK;
   return step_record(p, t, record_detectors, record_boundaries, st);
+}
+
+extern "C" int fdtdx_b200_run_half_range(FdtdxPlan* p, int t, int which, int x_begin, int x_end, int simulate_boundaries,
+                                         void* stream) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "time step outside [0, T)");
+  if (x_begin < 0 || x_end > p->nx || x_begin > x_end) return fail(FDTDX_EINVAL, "run_half_range: bad plane range");
+  if (x_begin == x_end) return FDTDX_OK;
+  if (p->eps_tier == 9 || p->mu_tier == 9 || p->sigE_tier == 9 || p->sigH_tier == 9)
+    return fail(FDTDX_EUNSUPPORTED, "run_half_range: full-tensor media are not supported on x-sharded plans");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = finalize(p);
+  if (rc) return rc;
+  StepParams P;
+  if ((rc = make_params(p, P, simulate_boundaries))) return rc;
+  P.x_begin = x_begin;
+  P.x_end = x_end;
+  if (which == 0) {
+    rc = launch_E(p, P, t, false, st);
+    // ADE ping-pong flips once per step: callers issue the range starting at plane 0 last
+    if (!rc && p->n_poles > 0 && x_begin == 0) p->p_parity ^= 1;
+    return rc;
+  }
+  return launch_H(p, P, t, false, st);
+}
+
+extern "C" int fdtdx_b200_get_xchunk(FdtdxPlan* p) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  StepParams P;
+  int rc = finalize(p);
+  if (rc) return rc;
+  if ((rc = make_params(p, P, 1))) return rc;
+  return P.xchunk;
 }
 
 extern "C" int fdtdx_b200_run_forward(FdtdxPlan* p, int t0, int n, int record_detectors, int record_boundaries,

@@ -80,6 +80,7 @@ struct StepParams {
   const float* haloH;  // (2,ny,nz) Hy,Hz of plane x0-1
   const float* haloE;  // (2,ny,nz) Ey,Ez of plane x1
   int xchunk;
+  int x_begin, x_end;  // plane range of this launch (sub-ranges let the halo exchange overlap)
 };
 
 template <int V>

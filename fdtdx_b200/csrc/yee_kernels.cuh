@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int ic0 = blockIdx.z * P.xchunk;
-  const int ic1 = min(ic0 + P.xchunk, P.nx);
+  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
+  const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const bool active = (k0 < P.nz) && (j < P.ny);
   const int nz = P.nz, ny = P.ny;
   const long long plane = (long long)ny * nz;
@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int ic0 = blockIdx.z * P.xchunk;
-  const int ic1 = min(ic0 + P.xchunk, P.nx);
+  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
+  const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const bool active = (k0 < P.nz) && (j < P.ny);
   const int nz = P.nz, ny = P.ny;
   const long long plane = (long long)ny * nz;

@@ -1,0 +1,135 @@
+"""x-slab multi-GPU runner: one process per GPU, one halo plane per half-step.
+
+The reference shards every ``(., Nx, Ny, Nz)`` array on x with a ``NamedSharding`` and lets XLA
+insert collective-permutes (``fdtd/initialization.py:598-611``, ``core/jax/sharding.py:160-176``).
+Here rank r owns planes ``[x0, x1)``; before the E half-step it needs ``Hy, Hz`` of plane ``x0-1``
+(backward difference, ``curl.py:360-361``) and before the H half-step ``Ey, Ez`` of plane ``x1``
+(forward difference, ``curl.py:273-274``): two tangential components of one plane, to/from one
+neighbour, per half-step.  There is no collective in the step.
+
+Overlap: the interior planes of a half-step do not depend on the halo, so each half-step is issued
+as ``interior`` (all x-chunks but the one touching the neighbour) while the halo plane travels on a
+side stream, then the ``edge`` chunk once it has landed.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+from fdtdx_b200 import _lib
+from fdtdx_b200._lib import check
+from fdtdx_b200.plan import Plan
+
+
+def slab_bounds(nx: int, world: int, rank: int) -> tuple[int, int]:
+    """Equal x-slabs; like the reference (``sharding.py:169-173``) ``nx`` must divide evenly."""
+    if nx % world != 0:
+        raise ValueError(f"Nx={nx} must be divisible by the number of ranks ({world})")
+    w = nx // world
+    return rank * w, (rank + 1) * w
+
+
+def neighbours(rank: int, world: int, periodic_x: bool) -> tuple[int | None, int | None]:
+    lo = rank - 1 if rank > 0 else (world - 1 if periodic_x and world > 1 else None)
+    hi = rank + 1 if rank < world - 1 else (0 if periodic_x and world > 1 else None)
+    return lo, hi
+
+
+class HaloExchange:
+    """Point-to-point exchange of one packed plane with the two x-neighbours over
+    ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests)."""
+
+    def __init__(self, rank: int, world: int, periodic_x: bool, group=None):
+        self.rank, self.world = rank, world
+        self.lo, self.hi = neighbours(rank, world, periodic_x)
+        self.group = group
+
+    def exchange(self, send_to_hi, recv_from_lo, send_to_lo, recv_from_hi):
+        """Any argument may be None.  Returns after the receives have completed (on the current
+        CUDA stream for NCCL)."""
+        import torch.distributed as dist
+
+        ops = []
+        if send_to_hi is not None and self.hi is not None:
+            ops.append(dist.P2POp(dist.isend, send_to_hi, self.hi, self.group))
+        if recv_from_lo is not None and self.lo is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_from_lo, self.lo, self.group))
+        if send_to_lo is not None and self.lo is not None:
+            ops.append(dist.P2POp(dist.isend, send_to_lo, self.lo, self.group))
+        if recv_from_hi is not None and self.hi is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_from_hi, self.hi, self.group))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class SlabRunner:
+    """Drives one rank's slab through the C ABI with halo exchange between the half-steps."""
+
+    def __init__(self, objects, config, arrays, x_range, rank: int, world: int, group=None, overlap: bool = True):
+        import torch
+
+        self.objects, self.config, self.arrays = objects, config, arrays
+        self.rank, self.world = rank, world
+        periodic_x = any(b.uses_wrap_padding and b.axis == 0 for b in objects.boundary_objects)
+        self.hx = HaloExchange(rank, world, periodic_x, group)
+        has_lo, has_hi = self.hx.lo is not None, self.hx.hi is not None
+        self.plan = Plan(objects, config, arrays, x_range=x_range, halo=(has_lo, has_hi))
+        self.plan.bind(arrays)
+        E, H = arrays.fields.E, arrays.fields.H
+        ny, nz = E.shape[2], E.shape[3]
+        mk = lambda: torch.zeros((2, ny, nz), dtype=torch.float32, device=E.device)
+        self.haloH, self.haloE, self.sendH, self.sendE = mk(), mk(), mk(), mk()
+        if has_lo:
+            self.plan._bind(_lib.SLOT_HALO_H_LO, 0, self.haloH)
+        if has_hi:
+            self.plan._bind(_lib.SLOT_HALO_E_HI, 0, self.haloE)
+        self.overlap = overlap and world > 1
+        self.side = torch.cuda.Stream(device=E.device) if (self.overlap and E.is_cuda) else None
+        self.nx = E.shape[1]
+
+    def _range(self, t, which, x_begin, x_end, simulate=True):
+        import torch
+
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self.plan.lib.fdtdx_b200_run_half_range(self.plan.h, int(t), int(which), int(x_begin), int(x_end), int(simulate), st))
+
+    def step(self, t: int, record_detectors: bool = False):
+        import torch
+
+        E, H = self.arrays.fields.E, self.arrays.fields.H
+        xc = self.plan.xchunk_hint()
+        if self.side is None:
+            self.sendH.copy_(H[1:3, -1])
+            self.hx.exchange(self.sendH, self.haloH, None, None)
+            self.plan.run_forward_phase(t, 0, record_detectors, False, True)
+            self.sendE.copy_(E[1:3, 0])
+            self.hx.exchange(None, None, self.sendE, self.haloE)
+            self.plan.run_forward_phase(t, 1, record_detectors, False, True)
+        else:
+            main = torch.cuda.current_stream()
+            # --- E half-step: needs Hy,Hz of x0-1 only in the first chunk
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.sendH.copy_(H[1:3, -1])
+                self.hx.exchange(self.sendH, self.haloH, None, None)
+            if record_detectors:
+                self.plan.run_forward_phase(t, 3, True, False, True)  # detector H_prev gather only
+            self._range(t, 0, xc, self.nx)
+            main.wait_stream(self.side)
+            self._range(t, 0, 0, xc)
+            # --- H half-step: needs Ey,Ez of x1 only in the last chunk
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.sendE.copy_(E[1:3, 0])
+                self.hx.exchange(None, None, self.sendE, self.haloE)
+            last = max(self.nx - xc, 0)
+            self._range(t, 1, 0, last)
+            main.wait_stream(self.side)
+            self._range(t, 1, last, self.nx)
+        self.plan.run_forward_phase(t, 2, record_detectors, False, True)
+
+    def run(self, t0: int, n: int, record_detectors: bool = False):
+        for t in range(t0, t0 + n):
+            self.step(t, record_detectors)

@@ -228,6 +228,9 @@ class Plan:
         cfg = self.config
         self.det_index = {}
         for det in self.objects.detectors:
+            dlo, dhi = det.grid_slice_tuple[0]
+            if dhi <= self.x0 or dlo >= self.x1:
+                continue  # lives on another rank's slab
             flags = 0
             if det.exact_interpolation:
                 flags |= _lib.DETF_EXACT
@@ -359,6 +362,8 @@ class Plan:
                 self._bind(_lib.SLOT_C4, 0, arrays.dispersive_c4, f32)
             check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
         for det in self.objects.detectors:
+            if det.name not in self.det_index:
+                continue
             di = self.det_index[det.name]
             st = arrays.detector_states[det.name]
             for k, key in enumerate(st.keys()):
@@ -426,6 +431,9 @@ class Plan:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         check(self.lib.fdtdx_b200_get_parity(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def xchunk_hint(self) -> int:
+        return check(self.lib.fdtdx_b200_get_xchunk(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.fdtdx_b200_launch_count(self.h))

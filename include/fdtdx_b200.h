@@ -167,6 +167,12 @@ int fdtdx_b200_run_forward(FdtdxPlan* plan, int t0, int n, int record_detectors,
  * phase 0 = update_E, phase 1 = update_H, phase 2 = record + detectors. */
 int fdtdx_b200_run_forward_phase(FdtdxPlan* plan, int t, int phase, int record_detectors,
                                  int record_boundaries, int simulate_boundaries, void* stream);
+/* One half-step restricted to the x planes [x_begin, x_end) of this rank's slab (which: 0 = E,
+ * 1 = H).  Lets an x-slab caller run the interior while the halo plane is in flight and the edge
+ * chunk afterwards.  Phase 3 of run_forward_phase = detector H_prev gather only. */
+int fdtdx_b200_run_half_range(FdtdxPlan* plan, int t, int which, int x_begin, int x_end,
+                              int simulate_boundaries, void* stream);
+int fdtdx_b200_get_xchunk(FdtdxPlan* plan);
 /* n reverse steps entered from state t_from (first step reconstructs t_from-1): body of `backward`
  * (fdtd/backward.py:62-135): add_interfaces (update.py:1181), update_H_reverse (:856),
  * update_E_reverse (:526), [apply_field_reset], [inverse detectors]. */
