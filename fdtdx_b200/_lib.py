@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from functools import lru_cache
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfdtdx_b200.so")
+LIB_PATH = os.environ.get("FDTDX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfdtdx_b200.so")
 
 # enum FdtdxSlot
 (

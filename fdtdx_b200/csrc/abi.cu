@@ -371,6 +371,8 @@ extern "C" int fdtdx_b200_set_tuning(FdtdxPlan* p, int xchunk, int rows) {
 }
 
 // ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
 static int finalize(FdtdxPlan* p) {
   if (p->finalized) return FDTDX_OK;
   const int n[3] = {p->nx, p->ny, p->nz};
@@ -420,8 +422,6 @@ static int finalize(FdtdxPlan* p) {
   return FDTDX_OK;
 }
 
-static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
-
 static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   memset(&P, 0, sizeof(P));
   P.nx = p->nx; P.ny = p->ny; P.nz = p->nz;
@@ -459,6 +459,19 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
       P.pml[h.axis].psiH[h.dir][w] = ph;
     }
   }
+  {
+    // z slabs can move psi as float2 halves when slab thickness, slab start and nz are even/4-aligned
+    // and no lane (4 cells) touches both slabs
+    AxisPmlDev& Z = P.pml[2];
+    bool ok = (p->nz % 4 == 0) && (Z.lo_len % 2 == 0) && (Z.hi_len % 2 == 0) && (Z.hi_start % 2 == 0) &&
+              (Z.lo_len + 4 <= Z.hi_start || Z.lo_len == 0 || Z.hi_len == 0);
+    for (int s = 0; s < 2; ++s)
+      for (int w = 0; w < 2; ++w) {
+        if (Z.psiE[s][w] && (reinterpret_cast<uintptr_t>(Z.psiE[s][w]) & 7u)) ok = false;
+        if (Z.psiH[s][w] && (reinterpret_cast<uintptr_t>(Z.psiH[s][w]) & 7u)) ok = false;
+      }
+    Z.vec_ok = ok ? 1 : 0;
+  }
   P.simulate = simulate;
   P.n_walls = (int)p->walls.size();
   P.walls = p->d_walls;
@@ -487,8 +500,8 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     // enough CTAs for >= ~6 waves of 148 SMs x 8 resident CTAs, but chunks long enough that the
     // one-plane re-read at each chunk start stays below ~3 % of the traffic
     const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + p->rows - 1) / p->rows);
-    long long want = (148LL * 2 * 8 + tiles - 1) / tiles;  // >= ~8 waves at 2 resident CTAs per SM
-    xc = (int)std::max(16LL, std::min<long long>(64, p->nx / std::max(1LL, want)));
+    long long want = (148LL * 2 * 16 + tiles - 1) / tiles;  // >= ~16 waves at 2 resident CTAs per SM
+    xc = (int)std::max(16LL, std::min<long long>(32, p->nx / std::max(1LL, want)));
   }
   P.xchunk = std::min(xc, p->nx);
   P.x_begin = 0;
@@ -511,8 +524,20 @@ static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
 }
 
 // kernel dispatchers live in yee_E.cu / yee_H.cu (separate translation units, built in parallel)
-void fdtdx_dispatch_E(const StepParams& P, int t, bool v4, int tier, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
-void fdtdx_dispatch_H(const StepParams& P, int t, bool v4, int mu_tier, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_E4(const StepParams& P, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_E1(const StepParams& P, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_H4(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_H1(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
+
+// 0: no CPML slab on this rank; 1: scalar z-slab accesses; 2: 128-bit z-slab accesses
+static int pml_mode(const FdtdxPlan* p, const StepParams& P) {
+  bool any = false;
+  const int n[3] = {p->nx, p->ny, p->nz};
+  for (int a = 0; a < 3; ++a)
+    if (P.pml[a].lo_len > 0 || P.pml[a].hi_start < n[a]) any = true;
+  if (!any) return 0;
+  return P.pml[2].vec_ok ? 2 : 1;
+}
 
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
@@ -521,7 +546,8 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
-  fdtdx_dispatch_E(P, t, v4, p->eps_tier, rev, sig, ade, met, g, b, st);
+  if (v4) fdtdx_dispatch_E4(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+  else fdtdx_dispatch_E1(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
@@ -532,7 +558,8 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   const int V = v4 ? 4 : 1;
   dim3 b(32, p->rows);
   dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
-  fdtdx_dispatch_H(P, t, v4, p->mu_tier, rev, p->sigH_tier > 0, p->metric, g, b, st);
+  if (v4) fdtdx_dispatch_H4(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+  else fdtdx_dispatch_H1(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;

@@ -17,6 +17,7 @@ struct AxisPmlDev {
   int hi_start;  // local cells [hi_start, n) belong to the '+' slab (n: none)
   int hi_len;
   int kappa_one; // both slabs have kappa == 1 (correction == psi, perfectly_matched_layer.py:184)
+  int vec_ok;    // z axis only: slab rows are 16-byte aligned (thickness % 4 == 0, psi pointers aligned)
   // per-cell coefficient tables along this axis, local length n; zero outside the slabs.
   // k* = 1/kappa - 1.  E-side tables feed curl_H (E update), H-side feed curl_E (H update).
   const float *aE, *bE, *kE, *aH, *bH, *kH;

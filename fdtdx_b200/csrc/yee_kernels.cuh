@@ -161,7 +161,15 @@ __device__ __forceinline__ bool any_src_hits(const SrcDev* __restrict__ srcs, in
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+#ifndef FDTDX_PF_DIST
 #define FDTDX_PF_DIST 2
+#endif
+#ifndef FDTDX_PF_L1
+#define FDTDX_PF_L1 0  // 1: additionally pull the next plane into L1
+#endif
 
 // CPML for one axis at one cell (perfectly_matched_layer.py:138-190; curl.py:284-308, 371-394).
 // d1 = d_a F_j, d2 = d_a F_i; returns the corrections to subtract from K_i and add to K_j.
@@ -188,7 +196,7 @@ __device__ __forceinline__ void cpml_cell(float a, float b, float km1, bool kapp
 // ------------------------------------------------------------------------------------------------
 // E half-step
 // ------------------------------------------------------------------------------------------------
-template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET>
+template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
 __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
@@ -220,13 +228,33 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
   const AxisPmlDev& px = P.pml[0];
   const AxisPmlDev& py = P.pml[1];
   const AxisPmlDev& pz = P.pml[2];
-  const bool in_y = active && (j < py.lo_len || j >= py.hi_start);
+  // PM: 0 = no CPML slab on this plan (all CPML code compiled out), 1 = scalar z-slab path, 2 = 128-bit z-slab path
+  const bool in_y = (PM > 0) && active && (j < py.lo_len || j >= py.hi_start);
   const int yside = (j >= py.hi_start) ? 1 : 0;
   const int jl = yside ? j - py.hi_start : j;
   const int yL = yside ? py.hi_len : py.lo_len;
-  const bool any_z = active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
+  const bool any_z = (PM > 0) && active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
+  // PM == 2 (V == 4, even slab thickness): the lane's four cells are two 64-bit halves, each either
+  // entirely inside or entirely outside a z slab, so psi moves as float2 with no per-cell branch.
+  const int zside = (k0 + V > pz.hi_start) ? 1 : 0;
+  const bool zvec = (PM == 2) && any_z;
+  const bool zh0 = zvec && (zside ? (k0 >= pz.hi_start) : (k0 < pz.lo_len));
+  const bool zh1 = zvec && (zside ? (k0 + 2 >= pz.hi_start) : (k0 + 2 < pz.lo_len));
+  const long long zstride = (long long)ny * (zside ? pz.hi_len : pz.lo_len);
+  const long long zoff = (long long)j * (zside ? pz.hi_len : pz.lo_len) + (zside ? k0 - pz.hi_start : k0);
+  float* const pz1 = zside ? pz.psiE[1][0] : pz.psiE[0][0];
+  float* const pz2 = zside ? pz.psiE[1][1] : pz.psiE[0][1];
+  Vec<V> az = zerov<V>(), bz = zerov<V>(), kz = zerov<V>();
+  if (zvec) { az = ldv<V>(pz.aE + k0); bz = ldv<V>(pz.bE + k0); kz = ldv<V>(pz.kE + k0); }
   float sBy = 1.0f;
-  if (MET && active) sBy = P.sB[1][j];
+  float sBzv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) sBzv[e] = 1.0f;
+  if (MET && active) {
+    sBy = P.sB[1][j];
+#pragma unroll
+    for (int e = 0; e < V; ++e) sBzv[e] = P.sB[2][k0 + e];
+  }
 
   // register queue: Hy, Hz of the previous x plane
   Vec<V> hy_im = zerov<V>(), hz_im = zerov<V>();
@@ -270,7 +298,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
     }
     // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
     // indices only), so their latency overlaps instead of serialising behind the curl.
-    const bool in_x = (i < px.lo_len || i >= px.hi_start);
+    const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);
     Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
     float psz1[V], psz2[V];
     float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
@@ -291,7 +319,22 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         psy1 = ldv<V>(qy1);
         psy2 = ldv<V>(qy2);
       }
-      if (any_z) {
+      if (zvec) {
+        if constexpr (V == 4) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) { psz1[e] = 0.0f; psz2[e] = 0.0f; }
+          const float* q1 = pz1 + i * zstride + zoff;
+          const float* q2 = pz2 + i * zstride + zoff;
+          if (zh0) {
+            const float2 t1 = *reinterpret_cast<const float2*>(q1), t2 = *reinterpret_cast<const float2*>(q2);
+            psz1[0] = t1.x; psz1[1] = t1.y; psz2[0] = t2.x; psz2[1] = t2.y;
+          }
+          if (zh1) {
+            const float2 t1 = *reinterpret_cast<const float2*>(q1 + 2), t2 = *reinterpret_cast<const float2*>(q2 + 2);
+            psz1[2] = t1.x; psz1[3] = t1.y; psz2[2] = t2.x; psz2[3] = t2.y;
+          }
+        }
+      } else if (any_z) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           const int k = k0 + e;
@@ -315,6 +358,12 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         prefetch_l2(P.eps + pb);
         if (TIER == 3) { prefetch_l2(P.eps + P.eps_cs + pb); prefetch_l2(P.eps + 2 * P.eps_cs + pb); }
       }
+      if (FDTDX_PF_L1 && i + 1 < ic1) {
+        const long long pb = base + plane + row;
+        prefetch_l1(Hx + pb); prefetch_l1(Hy + pb); prefetch_l1(Hz + pb);
+        prefetch_l1(Ex + pb); prefetch_l1(Ey + pb); prefetch_l1(Ez + pb);
+        prefetch_l1(P.eps + pb);
+      }
     }
     // z-neighbour (k-1) of the first element: last element of the previous lane
     float hx_l = __shfl_up_sync(0xffffffffu, hx.v[V - 1], 1);
@@ -332,8 +381,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
       for (int e = 0; e < V; ++e) {
         float hx_km = (e == 0) ? hx_l : hx.v[e == 0 ? 0 : e - 1];
         float hy_km = (e == 0) ? hy_l : hy.v[e == 0 ? 0 : e - 1];
-        float sBz = 1.0f;
-        if (MET) sBz = P.sB[2][k0 + e];
+        const float sBz = sBzv[e];
         float dyHz = hz.v[e] - hz_jm.v[e];
         float dzHy = hy.v[e] - hy_km;
         float dzHx = hx.v[e] - hx_km;
@@ -372,7 +420,31 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
         }
         if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
-      if (any_z) {
+      if (zvec) {
+        if constexpr (V == 4) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            if ((e < 2) ? zh0 : zh1) {
+              float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
+              cpml_cell(az.v[e], bz.v[e], kz.v[e], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e], &psz1[e], &psz2[e], &c1, &c2);
+              Kx.v[e] = Kx.v[e] - c1;
+              Ky.v[e] = Ky.v[e] + c2;
+            }
+          }
+          if (P.simulate && !REV) {
+            float* q1 = pz1 + i * zstride + zoff;
+            float* q2 = pz2 + i * zstride + zoff;
+            if (zh0) {
+              *reinterpret_cast<float2*>(q1) = make_float2(psz1[0], psz1[1]);
+              *reinterpret_cast<float2*>(q2) = make_float2(psz2[0], psz2[1]);
+            }
+            if (zh1) {
+              *reinterpret_cast<float2*>(q1 + 2) = make_float2(psz1[2], psz1[3]);
+              *reinterpret_cast<float2*>(q2 + 2) = make_float2(psz2[2], psz2[3]);
+            }
+          }
+        }
+      } else if (any_z) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           const int k = k0 + e;
@@ -490,7 +562,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
 // ------------------------------------------------------------------------------------------------
 // H half-step
 // ------------------------------------------------------------------------------------------------
-template <int V, int MUT, bool REV, bool SIG, bool MET>
+template <int V, int MUT, bool REV, bool SIG, bool MET, int PM>
 __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
@@ -522,13 +594,33 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
   const AxisPmlDev& px = P.pml[0];
   const AxisPmlDev& py = P.pml[1];
   const AxisPmlDev& pz = P.pml[2];
-  const bool in_y = active && (j < py.lo_len || j >= py.hi_start);
+  // PM: 0 = no CPML slab on this plan (all CPML code compiled out), 1 = scalar z-slab path, 2 = 128-bit z-slab path
+  const bool in_y = (PM > 0) && active && (j < py.lo_len || j >= py.hi_start);
   const int yside = (j >= py.hi_start) ? 1 : 0;
   const int jl = yside ? j - py.hi_start : j;
   const int yL = yside ? py.hi_len : py.lo_len;
-  const bool any_z = active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
+  const bool any_z = (PM > 0) && active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
+  // PM == 2 (V == 4, even slab thickness): the lane's four cells are two 64-bit halves, each either
+  // entirely inside or entirely outside a z slab, so psi moves as float2 with no per-cell branch.
+  const int zside = (k0 + V > pz.hi_start) ? 1 : 0;
+  const bool zvec = (PM == 2) && any_z;
+  const bool zh0 = zvec && (zside ? (k0 >= pz.hi_start) : (k0 < pz.lo_len));
+  const bool zh1 = zvec && (zside ? (k0 + 2 >= pz.hi_start) : (k0 + 2 < pz.lo_len));
+  const long long zstride = (long long)ny * (zside ? pz.hi_len : pz.lo_len);
+  const long long zoff = (long long)j * (zside ? pz.hi_len : pz.lo_len) + (zside ? k0 - pz.hi_start : k0);
+  float* const pz1 = zside ? pz.psiH[1][0] : pz.psiH[0][0];
+  float* const pz2 = zside ? pz.psiH[1][1] : pz.psiH[0][1];
+  Vec<V> az = zerov<V>(), bz = zerov<V>(), kz = zerov<V>();
+  if (zvec) { az = ldv<V>(pz.aH + k0); bz = ldv<V>(pz.bH + k0); kz = ldv<V>(pz.kH + k0); }
   float sFy = 1.0f;
-  if (MET && active) sFy = P.sF[1][j];
+  float sFzv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) sFzv[e] = 1.0f;
+  if (MET && active) {
+    sFy = P.sF[1][j];
+#pragma unroll
+    for (int e = 0; e < V; ++e) sFzv[e] = P.sF[2][k0 + e];
+  }
 
   // register queue: E of the current plane is the "next" plane loaded one step earlier
   Vec<V> ex = zerov<V>(), ey = zerov<V>(), ez = zerov<V>();
@@ -576,7 +668,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
     }
     // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
     // indices only), so their latency overlaps instead of serialising behind the curl.
-    const bool in_x = (i < px.lo_len || i >= px.hi_start);
+    const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);
     Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
     float psz1[V], psz2[V];
     float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
@@ -597,7 +689,22 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         psy1 = ldv<V>(qy1);
         psy2 = ldv<V>(qy2);
       }
-      if (any_z) {
+      if (zvec) {
+        if constexpr (V == 4) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) { psz1[e] = 0.0f; psz2[e] = 0.0f; }
+          const float* q1 = pz1 + i * zstride + zoff;
+          const float* q2 = pz2 + i * zstride + zoff;
+          if (zh0) {
+            const float2 t1 = *reinterpret_cast<const float2*>(q1), t2 = *reinterpret_cast<const float2*>(q2);
+            psz1[0] = t1.x; psz1[1] = t1.y; psz2[0] = t2.x; psz2[1] = t2.y;
+          }
+          if (zh1) {
+            const float2 t1 = *reinterpret_cast<const float2*>(q1 + 2), t2 = *reinterpret_cast<const float2*>(q2 + 2);
+            psz1[2] = t1.x; psz1[3] = t1.y; psz2[2] = t2.x; psz2[3] = t2.y;
+          }
+        }
+      } else if (any_z) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           const int k = k0 + e;
@@ -621,6 +728,12 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         if (MUT >= 1) prefetch_l2(P.mu + pb);
         if (MUT == 3) { prefetch_l2(P.mu + P.mu_cs + pb); prefetch_l2(P.mu + 2 * P.mu_cs + pb); }
       }
+      if (FDTDX_PF_L1 && i + 2 < ic1) {
+        const long long pb = base + 2 * plane + row;
+        prefetch_l1(Ex + pb); prefetch_l1(Ey + pb); prefetch_l1(Ez + pb);
+        const long long ph = base + plane + row;
+        prefetch_l1(Hx + ph); prefetch_l1(Hy + ph); prefetch_l1(Hz + ph);
+      }
     }
     float ex_r = __shfl_down_sync(0xffffffffu, ex.v[0], 1);
     float ey_r = __shfl_down_sync(0xffffffffu, ey.v[0], 1);
@@ -637,8 +750,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
       for (int e = 0; e < V; ++e) {
         float ex_kp = (e == V - 1) ? ex_r : ex.v[e == V - 1 ? e : e + 1];
         float ey_kp = (e == V - 1) ? ey_r : ey.v[e == V - 1 ? e : e + 1];
-        float sFz = 1.0f;
-        if (MET) sFz = P.sF[2][k0 + e];
+        const float sFz = sFzv[e];
         float dyEz = ez_jp.v[e] - ez.v[e];
         float dzEy = ey_kp - ey.v[e];
         float dzEx = ex_kp - ex.v[e];
@@ -676,7 +788,31 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
         }
         if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
-      if (any_z) {
+      if (zvec) {
+        if constexpr (V == 4) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            if ((e < 2) ? zh0 : zh1) {
+              float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
+              cpml_cell(az.v[e], bz.v[e], kz.v[e], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e], &psz1[e], &psz2[e], &c1, &c2);
+              Kx.v[e] = Kx.v[e] - c1;
+              Ky.v[e] = Ky.v[e] + c2;
+            }
+          }
+          if (P.simulate && !REV) {
+            float* q1 = pz1 + i * zstride + zoff;
+            float* q2 = pz2 + i * zstride + zoff;
+            if (zh0) {
+              *reinterpret_cast<float2*>(q1) = make_float2(psz1[0], psz1[1]);
+              *reinterpret_cast<float2*>(q2) = make_float2(psz2[0], psz2[1]);
+            }
+            if (zh1) {
+              *reinterpret_cast<float2*>(q1 + 2) = make_float2(psz1[2], psz1[3]);
+              *reinterpret_cast<float2*>(q2 + 2) = make_float2(psz2[2], psz2[3]);
+            }
+          }
+        }
+      } else if (any_z) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           const int k = k0 + e;
