@@ -430,8 +430,9 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   P.x_lo_mode = p->halo_lo ? 2 : (p->wrap[0] ? 1 : 0);
   P.x_hi_mode = p->halo_hi ? 2 : (p->wrap[0] ? 1 : 0);
   P.cour = (float)p->courant; P.eta0 = (float)kEta0; P.inv_mu_scalar = (float)p->inv_mu_scalar; P.dt = (float)p->dt;
-  P.E = (float*)p->slots[FDTDX_SLOT_E][0];
-  P.H = (float*)p->slots[FDTDX_SLOT_H][0];
+  // full-tensor tiers ping-pong their field between the primary and the ALT buffer
+  P.E = (float*)p->slots[p->e_parity ? FDTDX_SLOT_E_ALT : FDTDX_SLOT_E][0];
+  P.H = (float*)p->slots[p->h_parity ? FDTDX_SLOT_H_ALT : FDTDX_SLOT_H][0];
   P.eps = (const float*)p->slots[FDTDX_SLOT_INV_EPS][0];
   P.mu = (const float*)p->slots[FDTDX_SLOT_INV_MU][0];
   P.sigE = (const float*)p->slots[FDTDX_SLOT_SIGMA_E][0];

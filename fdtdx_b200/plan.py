@@ -390,11 +390,15 @@ class Plan:
             self.E_alt = torch.zeros_like(arrays.fields.E)
             self._bind(_lib.SLOT_E_ALT, 0, self.E_alt)
             A, B, Ar, Br = update_matrices(arrays.inv_permittivities, arrays.electric_conductivity, self.config.courant_number, "E")
+            if arrays.electric_conductivity is None:
+                A = Ar = None  # M1 = M2 = I: A is exactly the identity (fdtd/misc.py:88-96), not stored
             self.tE = (A, B, Ar, Br)
         if self.tensor_H:
             self.H_alt = torch.zeros_like(arrays.fields.H)
             self._bind(_lib.SLOT_H_ALT, 0, self.H_alt)
             A, B, Ar, Br = update_matrices(arrays.inv_permeabilities, arrays.magnetic_conductivity, self.config.courant_number, "H")
+            if arrays.magnetic_conductivity is None:
+                A = Ar = None
             self.tH = (A, B, Ar, Br)
         self.set_tensor_direction(reverse=False)
         check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))

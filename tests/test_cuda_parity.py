@@ -92,6 +92,56 @@ def test_seeded_step_parity(name):
     assert_fields_close(a_o, a_g)
 
 
+TENSOR_CASES = {
+    "eps9_pml": (dict(eps_tier=9), 8),
+    "eps9_periodic": (dict(eps_tier=9, boundaries="periodic"), 8),
+    "eps9_sigma9": (dict(eps_tier=9, sigma_E=9), 6),
+    "eps9_mu9": (dict(eps_tier=9, mu_tier=9), 6),
+    "mu9_only": (dict(mu_tier=9, eps_tier=3), 6),
+    "eps9_nonuniform": (dict(eps_tier=9, nonuniform=True), 6),
+    "eps9_pec": (dict(eps_tier=9, boundaries={"min_x": "pec", "max_x": "pmc", "min_y": "periodic", "max_y": "periodic", "min_z": "pml", "max_z": "pml"}), 6),
+    "eps9_ade": (dict(eps_tier=9, poles=2, coeff_tier=3), 6),
+    "eps9_odd_steps": (dict(eps_tier=9, mu_tier=9, shape=(7, 9, 11)), 5),
+}
+
+
+@pytest.mark.parametrize("name", list(TENSOR_CASES))
+def test_full_tensor_step_parity(name):
+    """Full-tensor tier (update.py:356-492, 752-822): two-phase curl-scratch + 3x3 apply kernels."""
+    kw, steps = TENSOR_CASES[name]
+    objects, arrays, cfg = build_scene(**kw)
+    a_o, a_g = run_both(objects, arrays, cfg, steps)
+    assert_fields_close(a_o, a_g)
+
+
+@pytest.mark.parametrize("src", ["plane_z", "plane_x", "dipole"])
+def test_full_tensor_sources_and_detectors(src):
+    """TFSF injection into all three rows under full anisotropy (tfsf.py:285-295, 384-391)."""
+    shape = (16, 10, 12) if src == "plane_x" else (12, 10, 16)
+    objects, arrays, cfg = build_scene(shape=shape, eps_tier=9, mu_tier=9 if src == "plane_z" else 0, source=src,
+                                       detectors=("field", "phasor", "poynting"), time=6e-15)
+    steps = min(cfg.time_steps_total, 40)
+    a_o, a_g = run_both(objects, arrays, cfg, steps, seed=False)
+    assert np.abs(a_o.fields.E).max() > 0
+    assert_fields_close(a_o, a_g)
+    assert_detectors_close(a_o, a_g)
+
+
+def test_full_tensor_reverse():
+    """C3b-style: forward with recording then reverse steps through the tensor reverse update
+    (update.py:610-681, 932-1002; A = M2^-1 M1)."""
+    rec = fx.Recorder(modules=[])
+    objects, arrays, cfg = build_scene(shape=(14, 12, 16), thickness=4, eps_tier=9, sigma_E=9, source="plane_z", recorder=rec, time=4e-15,
+                                       boundaries={"min_x": "periodic", "max_x": "periodic", "min_y": "periodic", "max_y": "periodic", "min_z": "pml", "max_z": "pml"})
+    T = cfg.time_steps_total
+    st_o = yee.checkpointed_fdtd(arrays, objects, cfg)
+    st_g = fx.run_fdtd(arrays.to_torch("cuda"), objects, cfg)
+    assert_fields_close(st_o[1], st_g[1])
+    st_o = yee.full_backward(st_o, objects, cfg, record_detectors=False, reset_fields=True, start_time_step=T - 7)
+    st_g = fx.full_backward(st_g, objects, cfg, record_detectors=False, reset_fields=True, start_time_step=T - 7)
+    assert_fields_close(st_o[1], st_g[1], tol=DET_TOL)
+
+
 @pytest.mark.parametrize("periodic", [True, False])
 def test_simulate_boundaries_false(periodic):
     objects, arrays, cfg = build_scene(boundaries="periodic" if periodic else "pml")
