@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "tensor_kernels.cuh"
+#include "adjoint_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -72,6 +73,7 @@ struct FdtdxPlan {
   long long launches = 0;
   int xchunk = 0, rows = 8;
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
+  float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
 };
 
 extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
@@ -474,6 +476,7 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     Z.vec_ok = ok ? 1 : 0;
   }
   P.simulate = simulate;
+  P.psi_store = 1;
   P.n_walls = (int)p->walls.size();
   P.walls = p->d_walls;
   P.n_src = (int)p->srcs.size();
@@ -808,9 +811,109 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
   return FDTDX_OK;
 }
 
+static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const float* F, const float* G, float* lamF, float* lamG,
+                        const float* lam_extra, cudaStream_t st) {
+  AdjParams A;
+  memset(&A, 0, sizeof(A));
+  const long long N = (long long)p->nx * p->ny * p->nz;
+  A.nx = p->nx; A.ny = p->ny; A.nz = p->nz;
+  for (int a = 0; a < 3; ++a) { A.wrap[a] = p->wrap[a]; A.pml[a] = S.pml[a]; A.sc[a] = is_E ? p->d_sB[a] : p->d_sF[a]; }
+  A.cour = S.cour; A.eta0 = S.eta0; A.mat_scalar = S.inv_mu_scalar; A.is_E = is_E ? 1 : 0;
+  A.F = F; A.G = G; A.lamF = lamF; A.lamG = lamG; A.lam_extra = lam_extra; A.ld = p->d_ld;
+  if (is_E) {
+    A.mat = S.eps; A.mat_tier = p->eps_tier; A.mat_cs = (p->eps_tier == 1) ? 0 : N;
+    A.sig = S.sigE; A.sig_cs = S.sigE_cs;
+    A.g_mat = (float*)p->slots[FDTDX_SLOT_GRAD_INV_EPS][0];
+  } else {
+    A.mat = S.mu; A.mat_tier = p->mu_tier; A.mat_cs = (p->mu_tier <= 1) ? 0 : N;
+    A.sig = S.sigH; A.sig_cs = S.sigH_cs;
+    A.g_mat = (p->mu_tier > 0) ? (float*)p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr;
+  }
+  for (size_t q = 0; q < p->pmls.size(); ++q) {
+    const PmlHost& h = p->pmls[q];
+    for (int w = 0; w < 2; ++w)
+      A.lam_psi[h.axis][h.dir][w] = (float*)p->slots[is_E ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H][2 * q + w];
+  }
+  A.n_walls = S.n_walls; A.walls = S.walls;
+  const unsigned blocks = (unsigned)((N + 255) / 256);
+  adj_local_kernel<<<blocks, 256, 0, st>>>(A);
+  adj_gather_kernel<<<blocks, 256, 0, st>>>(A);
+  p->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
 extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* stream) {
-  (void)p; (void)t_from; (void)n; (void)stream;
-  return fail(FDTDX_EUNSUPPORTED, "run_adjoint: the fused VJP kernels are not built yet (SURVEY section 8 a18)");
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = finalize(p);
+  if (rc) return rc;
+  if (p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "run_adjoint on x-sharded plans is not supported yet");
+  if (p->eps_tier == 9 || p->mu_tier == 9 || p->sigE_tier == 9 || p->sigH_tier == 9)
+    return fail(FDTDX_EUNSUPPORTED, "run_adjoint: full-tensor media are not supported yet");
+  if (p->n_poles > 0) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
+  const long long N = (long long)p->nx * p->ny * p->nz;
+  float* lamE = (float*)p->slots[FDTDX_SLOT_COT_E][0];
+  float* lamH = (float*)p->slots[FDTDX_SLOT_COT_H][0];
+  if (!lamE || !lamH || !p->slots[FDTDX_SLOT_GRAD_INV_EPS][0]) return fail(FDTDX_EUNBOUND, "COT_E, COT_H and GRAD_INV_EPS must be bound");
+  if (!p->d_Etmp) {
+    if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_Etmp))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_Htmp))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_lamHx))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)6 * N, &p->d_ld))) return rc;
+  }
+  for (int t = t_from - 1; t > t_from - 1 - n; --t) {
+    if (t < 0) break;  // the reference's extra t = -1 iteration (fdtd.py:253-260) starts from the zero state; skipped
+    // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False)
+    if ((rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
+    StepParams S;
+    if ((rc = make_params(p, S, 1))) return rc;
+    float* E = S.E;
+    float* H = S.H;
+    // (2) recompute E_{t+1}, H_{t+1} from the reconstructed state without touching psi
+    CUDA_TRY(cudaMemcpyAsync(p->d_Etmp, E, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+    StepParams F1 = S;
+    F1.psi_store = 0;
+    F1.E = p->d_Etmp;
+    if ((rc = launch_E(p, F1, t, false, st))) return rc;
+    StepParams F2 = F1;
+    F2.H = p->d_Htmp;
+    if ((rc = launch_H(p, F2, t, false, st))) return rc;
+    // (3) detector cotangents at step t
+    bool any_det = false;
+    for (size_t di = 0; di < p->dets.size(); ++di) {
+      DetHost& h = p->dets[di];
+      if ((h.d.flags & DET_INVERSE) || !h.on[t]) continue;
+      if (!p->slots[FDTDX_SLOT_COT_DET][4 * di]) continue;  // no cotangent for this detector
+      if (!any_det) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
+      any_det = true;
+      GridDev G;
+      make_grid(p, G);
+      G.E = p->d_Etmp;
+      G.H = H;  // H_prev gather reads the step's input H
+      if (h.d.flags & DET_EXACT) {
+        const long long hn = 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1) * (h.d.hi[2] - h.d.lo[2] + 1);
+        det_gather_hprev_kernel<<<(int)std::min<long long>((hn + 255) / 256, 148 * 16), 256, 0, st>>>(G, h.d);
+        p->launches++;
+      }
+      G.H = p->d_Htmp;
+      DetAdj A;
+      for (int k = 0; k < 4; ++k) A.cot[k] = (const float*)p->slots[FDTDX_SLOT_COT_DET][4 * di + k];
+      A.lamE = lamE; A.lamH = lamH; A.lamHprev = p->d_lamHx;
+      A.g_eps = (float*)p->slots[FDTDX_SLOT_GRAD_INV_EPS][0];
+      A.eps_tier = p->eps_tier;
+      const long long dn = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
+      det_adjoint_kernel<<<(unsigned)((dn + 127) / 128), 128, 0, st>>>(G, h.d, A, t);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    // (4) H half-step transpose: lambda_H' -> lambda_H_in, accumulates into lambda_E'
+    if ((rc = adjoint_half(p, S, false, H, p->d_Etmp, lamH, lamE, any_det ? p->d_lamHx : nullptr, st))) return rc;
+    // (5) E half-step transpose: lambda_E' -> lambda_E_in, accumulates into lambda_H_in
+    if ((rc = adjoint_half(p, S, true, E, H, lamE, lamH, nullptr, st))) return rc;
+  }
+  return FDTDX_OK;
 }
 
 extern "C" int fdtdx_b200_run_forward_host(FdtdxPlan* p, const float* h_E, const float* h_H, const float* h_inv_eps,

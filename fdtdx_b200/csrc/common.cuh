@@ -68,6 +68,7 @@ struct StepParams {
   const float* sF[3];
   AxisPmlDev pml[3];
   int simulate;
+  int psi_store;  // 0: compute psi' for the correction but leave the stored psi untouched (adjoint recompute)
   int n_walls;
   const WallDev* walls;  // device array
   int n_src;

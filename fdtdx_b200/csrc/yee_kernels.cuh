@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
           Ky.v[e] = Ky.v[e] - c1;
           Kz.v[e] = Kz.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
+        if (P.simulate && !REV && P.psi_store) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
       }
       if (in_y) {
         const float a = py.aE[j], b = py.bE[j], km1 = py.kE[j];
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
           Kz.v[e] = Kz.v[e] - c1;
           Kx.v[e] = Kx.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
+        if (P.simulate && !REV && P.psi_store) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
       if (zvec) {
         if constexpr (V == 4) {
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
               Ky.v[e] = Ky.v[e] + c2;
             }
           }
-          if (P.simulate && !REV) {
+          if (P.simulate && !REV && P.psi_store) {
             float* q1 = pz1 + i * zstride + zoff;
             float* q2 = pz2 + i * zstride + zoff;
             if (zh0) {
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
             float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
             cpml_cell(pz.aE[k], pz.bE[k], pz.kE[k], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e],
                       &psz1[e], &psz2[e], &c1, &c2);
-            if (P.simulate && !REV) {
+            if (P.simulate && !REV && P.psi_store) {
               (side ? pz.psiE[1][0] : pz.psiE[0][0])[pidx] = psz1[e];
               (side ? pz.psiE[1][1] : pz.psiE[0][1])[pidx] = psz2[e];
             }
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
           Ky.v[e] = Ky.v[e] - c1;
           Kz.v[e] = Kz.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
+        if (P.simulate && !REV && P.psi_store) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
       }
       if (in_y) {
         const float a = py.aH[j], b = py.bH[j], km1 = py.kH[j];
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
           Kz.v[e] = Kz.v[e] - c1;
           Kx.v[e] = Kx.v[e] + c2;
         }
-        if (P.simulate && !REV) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
+        if (P.simulate && !REV && P.psi_store) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
       }
       if (zvec) {
         if constexpr (V == 4) {
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
               Ky.v[e] = Ky.v[e] + c2;
             }
           }
-          if (P.simulate && !REV) {
+          if (P.simulate && !REV && P.psi_store) {
             float* q1 = pz1 + i * zstride + zoff;
             float* q2 = pz2 + i * zstride + zoff;
             if (zh0) {
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const in
             float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
             cpml_cell(pz.aH[k], pz.bH[k], pz.kH[k], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e],
                       &psz1[e], &psz2[e], &c1, &c2);
-            if (P.simulate && !REV) {
+            if (P.simulate && !REV && P.psi_store) {
               (side ? pz.psiH[1][0] : pz.psiH[0][0])[pidx] = psz1[e];
               (side ? pz.psiH[1][1] : pz.psiH[0][1])[pidx] = psz2[e];
             }

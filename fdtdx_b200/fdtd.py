@@ -113,6 +113,65 @@ def custom_fdtd_forward(
     return end, arrays
 
 
+class _ReversibleFunction:
+    """Built lazily so that importing this module does not import torch."""
+
+    _cls = None
+
+    @classmethod
+    def get(cls):
+        if cls._cls is not None:
+            return cls._cls
+        import torch
+
+        class ReversibleFDTD(torch.autograd.Function):
+            """custom_vjp of ``reversible_fdtd`` (``fdtd/fdtd.py:176-379``): differentiable w.r.t.
+            ``inv_permittivities`` / ``inv_permeabilities`` only (``:324-333``)."""
+
+            @staticmethod
+            def forward(ctx, inv_eps, inv_mu, holder):
+                arrays, objects, config, progress_callback = holder["arrays"], holder["objects"], holder["config"], holder["cb"]
+                T = config.time_steps_total
+                with torch.no_grad():
+                    arrays = arrays.aset("inv_permittivities", inv_eps.detach())
+                    if inv_mu is not None:
+                        arrays = arrays.aset("inv_permeabilities", inv_mu.detach())
+                    arrays = arrays.reset()
+                    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+                holder["out"] = arrays
+                ctx.holder = holder
+                ctx.set_materialize_grads(False)
+                names = [(d, k) for d, st in arrays.detector_states.items() for k in st]
+                holder["names"] = names
+                outs = (arrays.fields.E, arrays.fields.H, *[arrays.detector_states[d][k] for d, k in names])
+                return outs
+
+            @staticmethod
+            def backward(ctx, gE, gH, *gdet):
+                h = ctx.holder
+                arrays, objects, config = h["out"], h["objects"], h["config"]
+                if not config.invertible_optimization:
+                    raise Exception("Need recorder to record boundaries")
+                T = config.time_steps_total
+                # reconstruct on copies so that the user's final fields stay intact (JAX is functional)
+                work = arrays.aset("fields->E", arrays.fields.E.detach().clone()).aset("fields->H", arrays.fields.H.detach().clone())
+                cot_E = torch.zeros_like(work.fields.E) if gE is None else gE.detach().clone().contiguous()
+                cot_H = torch.zeros_like(work.fields.H) if gH is None else gH.detach().clone().contiguous()
+                cot_det = {}
+                for (d, k), g in zip(h["names"], gdet):
+                    if g is not None:
+                        cot_det.setdefault(d, {})[k] = g.detach().contiguous()
+                g_eps = torch.zeros_like(work.inv_permittivities)
+                mu = work.inv_permeabilities
+                g_mu = torch.zeros_like(mu) if isinstance(mu, torch.Tensor) else None
+                plan = get_plan(work, objects, config)
+                plan.run_adjoint(work, T, T, cot_E, cot_H, cot_det, g_eps, g_mu)
+                return g_eps, g_mu, None
+
+        cls._cls = ReversibleFDTD
+        return ReversibleFDTD
+
+
 def reversible_fdtd(
     arrays: ArrayContainer,
     objects: ObjectContainer,
@@ -121,9 +180,12 @@ def reversible_fdtd(
     show_progress: bool = True,
     progress_callback: Callable[[int, int], None] | None = None,
 ) -> SimulationState:
-    """``fdtd.py:39-418``: forward pass with boundary recording; the time-reversed backward pass
-    is available through :func:`full_backward`.  The fused adjoint (VJP) kernels behind
-    ``custom_vjp`` are the next row of SURVEY.md section 8 (a18) and are not built yet."""
+    """``fdtd.py:39-418``: forward pass with PML-interface recording; when ``inv_permittivities`` (or
+    ``inv_permeabilities``) requires grad, the result is wired into torch autograd and the backward
+    pass runs the time-reversed reconstruction + fused adjoint kernels (``fdtdx_b200_run_adjoint``),
+    returning gradients for the materials only, like the reference's ``custom_vjp``."""
+    import torch
+
     if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
         raise NotImplementedError(
             "Dispersive time-reversible gradient computation under active development. "
@@ -135,10 +197,23 @@ def reversible_fdtd(
             "num_checkpoints_reversible must be <= time_steps_total - 1 "
             f"(got num_checkpoints_reversible={num_ckpt}, time_steps_total={config.time_steps_total})"
         )
-    arrays = arrays.reset()
+    _require_cuda(arrays)
     T = config.time_steps_total
-    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
-    return T, arrays
+    inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
+    needs_grad = inv_eps.requires_grad or (isinstance(inv_mu, torch.Tensor) and inv_mu.requires_grad)
+    if not needs_grad or not torch.is_grad_enabled():
+        arrays = arrays.reset()
+        arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+        return T, arrays
+    holder = {"arrays": arrays, "objects": objects, "config": config, "cb": progress_callback}
+    outs = _ReversibleFunction.get().apply(inv_eps, inv_mu if isinstance(inv_mu, torch.Tensor) else None, holder)
+    out = holder["out"]
+    out = out.aset("fields->E", outs[0]).aset("fields->H", outs[1])
+    det = {d: dict(st) for d, st in out.detector_states.items()}
+    for (d, k), v in zip(holder["names"], outs[2:]):
+        det[d][k] = v
+    out = out.aset("detector_states", det).aset("inv_permittivities", inv_eps).aset("inv_permeabilities", inv_mu)
+    return T, out
 
 
 def run_fdtd(

@@ -431,6 +431,36 @@ class Plan:
         self.set_tensor_direction(True)
         check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
 
+    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None):
+        """``fdtd_bwd`` loop (``fdtd/fdtd.py:262-333``): n iterations of reverse step + VJP of one forward
+        step.  ``arrays`` holds the state at ``t_from`` (fields are reconstructed in place); ``cot_E`` /
+        ``cot_H`` carry the field cotangents in place; ``cot_det[name][key]`` are the detector-state
+        cotangents; gradients accumulate into ``grad_inv_eps`` / ``grad_inv_mu``."""
+        import torch
+
+        self.bind(arrays)
+        self._bind(_lib.SLOT_COT_E, 0, cot_E, torch.float32)
+        self._bind(_lib.SLOT_COT_H, 0, cot_H, torch.float32)
+        self._bind(_lib.SLOT_GRAD_INV_EPS, 0, grad_inv_eps, torch.float32)
+        self._bind(_lib.SLOT_GRAD_INV_MU, 0, grad_inv_mu)
+        self._cot_psi = []
+        for pml in self.objects.pml_objects:
+            q = self.pml_index[pml.name]
+            for w in range(2):
+                for slot, src in ((_lib.SLOT_COT_PSI_E, arrays.fields.psi_E), (_lib.SLOT_COT_PSI_H, arrays.fields.psi_H)):
+                    z = torch.zeros_like(src[pml.name][w])
+                    self._cot_psi.append(z)
+                    self._bind(slot, 2 * q + w, z)
+        for det in self.objects.detectors:
+            if det.name not in self.det_index:
+                continue
+            di = self.det_index[det.name]
+            keys = list(arrays.detector_states[det.name].keys())
+            for k in range(4):
+                g = cot_det.get(det.name, {}).get(keys[k]) if k < len(keys) else None
+                self._bind(_lib.SLOT_COT_DET, 4 * di + k, g)
+        check(self.lib.fdtdx_b200_run_adjoint(self.h, int(t_from), int(n), self._stream()))
+
     def parity(self) -> tuple[int, int, int]:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         check(self.lib.fdtdx_b200_get_parity(self.h, C.byref(a), C.byref(b), C.byref(c)))

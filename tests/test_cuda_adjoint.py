@@ -1,0 +1,106 @@
+"""reversible_fdtd gradients: the fused adjoint kernels vs the gradient of the
+differentiable CPU oracle (torch autograd through ``oracle/yee_torch.py`` in float64 - the
+"checkpointed" reference the reference's own test compares against, tests/simulation/fdtd/test_fdtd.py:440-498).
+Tolerance: BASELINE.json north_star, time-reversal gradients <= 1e-4 relative L2.
+
+Two oracles: (i) without CPML the reversible method is exact, so the product must match plain
+autograd of the forward run (the reference's own reversible-vs-checkpointed cross-check uses
+periodic scenes); (ii) with CPML the reference's method is approximate by design (psi frozen,
+slab fields not reconstructible, Poynting/energy detectors linearised at reconstructed fields -
+SURVEY Appendix C.1), so the product is compared with ``yee_torch.reversible_gradient``, the
+restatement of ``fdtd_bwd`` itself, on the cells outside the slabs (inside them rounding noise is
+amplified by the reverse pass and neither side is meaningful)."""
+
+import numpy as np
+import pytest
+import torch
+
+import fdtdx_b200 as fx
+from oracle import yee_torch
+from scenes import build_scene, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _loss(det, E=None):
+    loss = 0.0
+    for name, st in det.items():
+        for k, v in st.items():
+            if v.is_complex():
+                loss = loss + (v.real**2 + v.imag**2).sum() * 3.0 + v.real.sum() * 1e-3
+            elif "poynting" in k:
+                loss = loss + v.sum() * 1e19
+            elif "energy" in k or "Plane" in k:
+                loss = loss + v.sum() * 1e21 if v.numel() < 1000 else loss + (v * v).sum() * 1e3 + v.sum()
+            else:
+                loss = loss + (v * v).sum() + v.sum() * 1e-2
+    if E is not None:
+        loss = loss + (E * E).sum() * 0.1
+    return loss
+
+
+CASES = {
+    "periodic_field_phasor": (dict(boundaries="periodic", source="plane_z", detectors=("field", "phasor"), time=3e-15), None, True),
+    "pml_poynting_phasor": (dict(source="plane_z", detectors=("poynting", "phasor", "field_reduce"), time=4e-15, shape=(16, 14, 20), thickness=4), 5, False),
+    "pml_energy_sigma_diag": (dict(source="plane_z", detectors=("energy_reduce", "poynting_full", "energy_slices"), eps_tier=3, sigma_E=True, sigma_H=True, time=3e-15, shape=(16, 14, 20), thickness=4), 5, False),
+    "nonuniform_pec_dipole": (dict(source="dipole", detectors=("poynting_all", "phasor_reduce", "raw_field"), nonuniform=True, time=3e-15, shape=(14, 12, 16),
+                                   boundaries={"min_x": "pec", "max_x": "pmc", "min_y": "periodic", "max_y": "periodic", "min_z": "pec", "max_z": "pmc"}), None, True),
+    "mu_array_kappa": (dict(source="plane_z", detectors=("poynting", "field"), mu_tier=3, kappa=True, time=3e-15, shape=(16, 14, 20), thickness=4), 5, False),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reversible_gradient_matches_oracle(name):
+    from oracle import yee
+
+    kw, margin, final_E = CASES[name]
+    rec = fx.Recorder(modules=[])
+    objects, arrays, cfg = build_scene(recorder=rec, **kw)
+    T = cfg.time_steps_total
+    mu_np = arrays.inv_permeabilities
+    has_mu = isinstance(mu_np, np.ndarray)
+    loss_fn = lambda E, H, det: _loss(det, E if final_E else None)
+    if margin is None:
+        # exact case: float64 autograd through the restated forward run
+        ie = torch.tensor(arrays.inv_permittivities.astype(np.float64), requires_grad=True)
+        im = torch.tensor(mu_np.astype(np.float64), requires_grad=True) if has_mu else None
+        E, H, det = yee_torch.run_forward(arrays.reset(), objects, cfg, T, inv_eps=ie, inv_mu=im, dtype=torch.float64)
+        loss_ref = loss_fn(E, H, det)
+        loss_ref.backward()
+        g_ref, gm_ref = ie.grad.numpy(), (im.grad.numpy() if has_mu else None)
+    else:
+        st = yee.checkpointed_fdtd(arrays, objects, cfg)
+        S = yee_torch.Stepper(st[1], objects, cfg)
+        E, H, _, _, det = S.initial(st[1])
+        loss_ref = loss_fn(E, H, det)
+        g_ref, gm_ref = yee_torch.reversible_gradient(st[1], objects, cfg, loss_fn)
+        g_ref, gm_ref = g_ref.numpy(), (gm_ref.numpy() if gm_ref is not None else None)
+    # product: reversible_fdtd wired into torch autograd
+    dev = arrays.to_torch("cuda")
+    dev.inv_permittivities.requires_grad_(True)
+    if has_mu:
+        dev.inv_permeabilities.requires_grad_(True)
+    t_end, out = fx.run_fdtd(dev, objects, cfg)
+    assert t_end == T
+    loss = _loss(out.detector_states, out.fields.E if final_E else None)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    E_final = out.fields.E.detach().clone()
+    loss.backward()
+    assert torch.equal(out.fields.E.detach(), E_final), "backward must not disturb the returned fields"
+    g = dev.inv_permittivities.grad.cpu().numpy()
+    sl = (slice(None),) * 4 if margin is None else (slice(None), *(slice(margin, -margin),) * 3)
+    assert np.abs(g_ref[sl]).max() > 0
+    err = rel_l2(g[sl], g_ref[sl])
+    assert err <= 1e-4, f"d loss / d inv_eps rel-L2 {err}"
+    if has_mu:
+        gm = dev.inv_permeabilities.grad.cpu().numpy()
+        errm = rel_l2(gm[sl], gm_ref[sl])
+        assert errm <= 1e-4, f"d loss / d inv_mu rel-L2 {errm}"
+
+
+def test_reversible_needs_recorder_and_rejects_dispersion():
+    objects, arrays, cfg = build_scene(poles=1, recorder=fx.Recorder(modules=[]))
+    dev = arrays.to_torch("cuda")
+    dev.inv_permittivities.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        fx.reversible_fdtd(dev, objects, cfg)
