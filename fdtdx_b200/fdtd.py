@@ -137,7 +137,18 @@ class _ReversibleFunction:
                     if inv_mu is not None:
                         arrays = arrays.aset("inv_permeabilities", inv_mu.detach())
                     arrays = arrays.reset()
-                    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+                    # sliced reversible pass (fdtd.py:106-166): full FieldState checkpoints at the interior
+                    # slice boundaries s_1..s_{k-1}
+                    bounds = holder["bounds"]
+                    ckpts = []
+                    for seg in range(len(bounds) - 1):
+                        arrays = _run_forward_loop(arrays, objects, config, bounds[seg], bounds[seg + 1], True, config.invertible_optimization, progress_callback)
+                        if seg < len(bounds) - 2:
+                            f = arrays.fields
+                            ckpts.append(
+                                (f.E.clone(), f.H.clone(), {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_E.items()}, {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_H.items()})
+                            )
+                    holder["ckpts"] = ckpts
                 holder["out"] = arrays
                 ctx.holder = holder
                 ctx.set_materialize_grads(False)
@@ -165,7 +176,22 @@ class _ReversibleFunction:
                 mu = work.inv_permeabilities
                 g_mu = torch.zeros_like(mu) if isinstance(mu, torch.Tensor) else None
                 plan = get_plan(work, objects, config)
-                plan.run_adjoint(work, T, T, cot_E, cot_H, cot_det, g_eps, g_mu)
+                bounds, ckpts = h["bounds"], h["ckpts"]
+                if ckpts:
+                    # psi is restored together with the fields at each boundary, so work on copies of it too
+                    work = work.aset("fields->psi_E", {k: (a.clone(), b.clone()) for k, (a, b) in work.fields.psi_E.items()})
+                    work = work.aset("fields->psi_H", {k: (a.clone(), b.clone()) for k, (a, b) in work.fields.psi_H.items()})
+                for seg in range(len(bounds) - 2, -1, -1):
+                    plan.run_adjoint(work, bounds[seg + 1], bounds[seg + 1] - bounds[seg], cot_E, cot_H, cot_det, g_eps, g_mu, keep_cot_psi=(seg != len(bounds) - 2))
+                    if seg > 0:
+                        # reset the reconstructed primal state to the exact checkpoint at s_i (fdtd.py:300-313)
+                        cE, cH, cpE, cpH = ckpts[seg - 1]
+                        work.fields.E.copy_(cE)
+                        work.fields.H.copy_(cH)
+                        for k in cpE:
+                            for w in range(2):
+                                work.fields.psi_E[k][w].copy_(cpE[k][w])
+                                work.fields.psi_H[k][w].copy_(cpH[k][w])
                 return g_eps, g_mu, None
 
         cls._cls = ReversibleFDTD
@@ -205,7 +231,8 @@ def reversible_fdtd(
         arrays = arrays.reset()
         arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
         return T, arrays
-    holder = {"arrays": arrays, "objects": objects, "config": config, "cb": progress_callback}
+    bounds = [round(i * T / (num_ckpt + 1)) for i in range(num_ckpt + 2)]  # _reversible_slice_boundaries, fdtd.py:20-36
+    holder = {"arrays": arrays, "objects": objects, "config": config, "cb": progress_callback, "bounds": bounds}
     outs = _ReversibleFunction.get().apply(inv_eps, inv_mu if isinstance(inv_mu, torch.Tensor) else None, holder)
     out = holder["out"]
     out = out.aset("fields->E", outs[0]).aset("fields->H", outs[1])

@@ -431,7 +431,7 @@ class Plan:
         self.set_tensor_direction(True)
         check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
 
-    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None):
+    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False):
         """``fdtd_bwd`` loop (``fdtd/fdtd.py:262-333``): n iterations of reverse step + VJP of one forward
         step.  ``arrays`` holds the state at ``t_from`` (fields are reconstructed in place); ``cot_E`` /
         ``cot_H`` carry the field cotangents in place; ``cot_det[name][key]`` are the detector-state
@@ -443,14 +443,16 @@ class Plan:
         self._bind(_lib.SLOT_COT_H, 0, cot_H, torch.float32)
         self._bind(_lib.SLOT_GRAD_INV_EPS, 0, grad_inv_eps, torch.float32)
         self._bind(_lib.SLOT_GRAD_INV_MU, 0, grad_inv_mu)
-        self._cot_psi = []
+        if not keep_cot_psi or not getattr(self, "_cot_psi", None):
+            self._cot_psi = {}
         for pml in self.objects.pml_objects:
             q = self.pml_index[pml.name]
             for w in range(2):
                 for slot, src in ((_lib.SLOT_COT_PSI_E, arrays.fields.psi_E), (_lib.SLOT_COT_PSI_H, arrays.fields.psi_H)):
-                    z = torch.zeros_like(src[pml.name][w])
-                    self._cot_psi.append(z)
-                    self._bind(slot, 2 * q + w, z)
+                    key = (slot, q, w)
+                    if key not in self._cot_psi:
+                        self._cot_psi[key] = torch.zeros_like(src[pml.name][w])
+                    self._bind(slot, 2 * q + w, self._cot_psi[key])
         for det in self.objects.detectors:
             if det.name not in self.det_index:
                 continue

@@ -98,6 +98,22 @@ def test_reversible_gradient_matches_oracle(name):
         assert errm <= 1e-4, f"d loss / d inv_mu rel-L2 {errm}"
 
 
+def test_sliced_checkpoints_match_single_slice():
+    """num_checkpoints_reversible (fdtd.py:106-166, tests/simulation/fdtd/test_fdtd.py:618-700): exact
+    field checkpoints at the slice boundaries leave the (periodic, exactly reversible) gradient unchanged."""
+    grads = []
+    for nck in (0, 3):
+        rec = fx.Recorder(modules=[])
+        objects, arrays, cfg = build_scene(recorder=rec, boundaries="periodic", source="plane_z", detectors=("field", "phasor"), time=3e-15, sigma_E=True)
+        cfg = cfg.aset("gradient_config", fx.GradientConfig(method="reversible", recorder=rec, num_checkpoints_reversible=nck))
+        dev = arrays.to_torch("cuda")
+        dev.inv_permittivities.requires_grad_(True)
+        _, out = fx.run_fdtd(dev, objects, cfg)
+        _loss(out.detector_states, out.fields.E).backward()
+        grads.append(dev.inv_permittivities.grad.cpu().numpy())
+    assert rel_l2(grads[1], grads[0]) <= 1e-4
+
+
 def test_reversible_needs_recorder_and_rejects_dispersion():
     objects, arrays, cfg = build_scene(poles=1, recorder=fx.Recorder(modules=[]))
     dev = arrays.to_torch("cuda")
