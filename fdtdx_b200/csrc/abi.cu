@@ -57,6 +57,10 @@ struct FdtdxPlan {
   SrcDev* d_srcs = nullptr;
   WallDev* d_walls = nullptr;
   std::vector<DetHost> dets;
+  std::vector<DetDev> h_dets;
+  DetDev* d_dets = nullptr;   // device copy of the detector descriptors (batched launches)
+  bool dets_dirty = true;
+  long long det_max_cells = 0, det_max_halo = 0;
   // recorder
   bool has_rec = false;
   int rec_dtype = 0, rec_slots = 0;
@@ -71,7 +75,7 @@ struct FdtdxPlan {
   AxisPmlDev axis[3];
   int p_parity = 0, e_parity = 0, h_parity = 0;
   long long launches = 0;
-  int xchunk = 0, rows = 8;
+  int xchunk = 0, rows = 4;
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
 };
@@ -319,6 +323,7 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
     if ((rc = to_device<float>(p, nullptr, (size_t)h.nvals * n, &d.scratch))) return rc;
   }
   p->dets.push_back(h);
+  p->dets_dirty = true;
   return (int)p->dets.size() - 1;
 }
 
@@ -583,52 +588,92 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
   G.inv_mu_scalar = (float)p->inv_mu_scalar;
 }
 
-static int bind_det_state(FdtdxPlan* p, size_t di, DetDev& d) {
-  for (int k = 0; k < 4; ++k) d.state[k] = (float*)p->slots[FDTDX_SLOT_DET_STATE][4 * di + k];
-  if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
-  if (d.kind == FDTDX_DET_ENERGY && (d.flags & DET_SLICES) && (!d.state[1] || !d.state[2]))
-    return fail(FDTDX_EUNBOUND, "energy slice detector needs three state buffers");
+// Upload the detector descriptors (with the currently bound state pointers) for the batched launches.
+static int sync_dets(FdtdxPlan* p, cudaStream_t st) {
+  if (p->dets.empty()) return FDTDX_OK;
+  bool changed = p->dets_dirty;
+  for (size_t di = 0; di < p->dets.size(); ++di) {
+    DetDev& d = p->dets[di].d;
+    float* st[4];
+    for (int k = 0; k < 4; ++k) st[k] = (float*)p->slots[FDTDX_SLOT_DET_STATE][4 * di + k];
+    for (int k = 0; k < 4; ++k)
+      if (st[k] != d.state[k]) { d.state[k] = st[k]; changed = true; }
+    if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
+    if (d.kind == FDTDX_DET_ENERGY && (d.flags & DET_SLICES) && (!d.state[1] || !d.state[2]))
+      return fail(FDTDX_EUNBOUND, "energy slice detector needs three state buffers");
+  }
+  if (!changed) return FDTDX_OK;
+  std::vector<DetDev>& h = p->h_dets;
+  h.clear();
+  p->det_max_cells = p->det_max_halo = 0;
+  for (auto& d : p->dets) {
+    h.push_back(d.d);
+    const long long n = (long long)(d.d.hi[0] - d.d.lo[0]) * (d.d.hi[1] - d.d.lo[1]) * (d.d.hi[2] - d.d.lo[2]);
+    const long long hn = 3LL * (d.d.hi[0] - d.d.lo[0] + 1) * (d.d.hi[1] - d.d.lo[1] + 1) * (d.d.hi[2] - d.d.lo[2] + 1);
+    p->det_max_cells = std::max(p->det_max_cells, n);
+    p->det_max_halo = std::max(p->det_max_halo, hn);
+  }
+  if (!p->d_dets) {
+    int rc = to_device(p, h.data(), h.size(), &p->d_dets);
+    if (rc) return rc;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(p->d_dets, h.data(), h.size() * sizeof(DetDev), cudaMemcpyHostToDevice, st));
+  }
+  p->dets_dirty = false;
   return FDTDX_OK;
 }
 
+static bool any_det_on(const FdtdxPlan* p, int t, bool inverse, bool need_exact, bool* any_post) {
+  bool any = false;
+  if (any_post) *any_post = false;
+  for (const DetHost& h : p->dets) {
+    if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t]) continue;
+    if (need_exact && !(h.d.flags & DET_EXACT)) continue;
+    any = true;
+    if (any_post && ((h.d.flags & DET_REDUCE) || ((h.d.flags & DET_SLICES) && (h.d.flags & DET_SLICE_MEAN)))) *any_post = true;
+  }
+  return any;
+}
+
 static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) {
+  if (!any_det_on(p, t, inverse, true, nullptr)) return FDTDX_OK;
+  int rc = sync_dets(p, st);
+  if (rc) return rc;
   GridDev G;
   make_grid(p, G);
-  for (size_t di = 0; di < p->dets.size(); ++di) {
-    DetHost& h = p->dets[di];
-    if (((h.d.flags & DET_INVERSE) != 0) != inverse) continue;
-    if (!h.on[t] || !(h.d.flags & DET_EXACT)) continue;
-    const long long n = 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1) * (h.d.hi[2] - h.d.lo[2] + 1);
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    det_gather_hprev_kernel<<<blocks, 256, 0, st>>>(G, h.d);
-    p->launches++;
-  }
+  dim3 g((unsigned)std::min<long long>((p->det_max_halo + 255) / 256, 148 * 8), (unsigned)p->dets.size());
+  det_gather_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+  p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
 }
 
 static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) {
+  bool any_post = false;
+  if (!any_det_on(p, t, inverse, false, &any_post)) return FDTDX_OK;
+  int rc = sync_dets(p, st);
+  if (rc) return rc;
   GridDev G;
   make_grid(p, G);
-  for (size_t di = 0; di < p->dets.size(); ++di) {
-    DetHost& h = p->dets[di];
-    if (((h.d.flags & DET_INVERSE) != 0) != inverse) continue;
-    if (!h.on[t]) continue;
-    int rc = bind_det_state(p, di, h.d);
-    if (rc) return rc;
-    const long long n = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
-    det_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G, h.d, t);
-    p->launches++;
-    if (h.d.flags & DET_REDUCE) {
-      const int wpv = (h.d.kind == FDTDX_DET_POYNTING && (h.d.flags & DET_KEEP_ALL)) ? 1 : 0;
-      det_reduce_all_kernel<<<h.nvals, 1024, 0, st>>>(h.d, t, h.nvals, wpv);
-      p->launches++;
-    } else if ((h.d.flags & DET_SLICES) && (h.d.flags & DET_SLICE_MEAN)) {
-      const int dims[3] = {h.d.hi[0] - h.d.lo[0], h.d.hi[1] - h.d.lo[1], h.d.hi[2] - h.d.lo[2]};
-      for (int axis = 0; axis < 3; ++axis) {
-        const long long nout = n / dims[axis];
-        det_slice_mean_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(h.d, t, axis);
+  dim3 g((unsigned)std::min<long long>((p->det_max_cells + 255) / 256, 148 * 8), (unsigned)p->dets.size());
+  det_sample_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+  p->launches++;
+  if (any_post) {
+    for (size_t di = 0; di < p->dets.size(); ++di) {
+      DetHost& h = p->dets[di];
+      if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t]) continue;
+      const long long n = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
+      if (h.d.flags & DET_REDUCE) {
+        const int wpv = (h.d.kind == FDTDX_DET_POYNTING && (h.d.flags & DET_KEEP_ALL)) ? 1 : 0;
+        det_reduce_all_kernel<<<h.nvals, 1024, 0, st>>>(h.d, t, h.nvals, wpv);
         p->launches++;
+      } else if ((h.d.flags & DET_SLICES) && (h.d.flags & DET_SLICE_MEAN)) {
+        const int dims[3] = {h.d.hi[0] - h.d.lo[0], h.d.hi[1] - h.d.lo[1], h.d.hi[2] - h.d.lo[2]};
+        for (int axis = 0; axis < 3; ++axis) {
+          const long long nout = n / dims[axis];
+          det_slice_mean_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(h.d, t, axis);
+          p->launches++;
+        }
       }
     }
   }

@@ -75,7 +75,15 @@ __device__ __forceinline__ float bea(const GridDev& G, float cur, float prev, in
 }
 
 // Copy H (region + one-cell halo on the low x/y side, +1 on the high z side) before the H update.
-__global__ void det_gather_hprev_kernel(const GridDev G, const DetDev D) {
+__device__ __forceinline__ void det_gather_body(const GridDev& G, const DetDev& D);
+__global__ void det_gather_hprev_kernel(const GridDev G, const DetDev D) { det_gather_body(G, D); }
+// batched: one launch for all detectors (blockIdx.y = detector), gated on the device by on[t]
+__global__ void det_gather_batch_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
+  const DetDev& D = dets[blockIdx.y];
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_EXACT)) return;
+  det_gather_body(G, D);
+}
+__device__ __forceinline__ void det_gather_body(const GridDev& G, const DetDev& D) {
   const int sx = D.hi[0] - D.lo[0] + 1, sy = D.hi[1] - D.lo[1] + 1, sz = D.hi[2] - D.lo[2] + 1;
   const long long n = (long long)sx * sy * sz;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < 3 * n; idx += (long long)gridDim.x * blockDim.x) {
@@ -124,11 +132,23 @@ __device__ __forceinline__ void colocate(const GridDev& G, const DetDev& D, int 
 }
 
 // One thread per region cell: sample, then write the per-type result (or stage it for a reduction).
+__device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& D, const int t, const long long cell);
 __global__ void det_sample_kernel(const GridDev G, const DetDev D, const int t) {
-  const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
-  const long long n = (long long)ex * ey * ez;
+  const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
   const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (cell >= n) return;
+  det_sample_body(G, D, t, cell);
+}
+__global__ void det_sample_batch_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
+  const DetDev& D = dets[blockIdx.y];
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t]) return;
+  const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
+  for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < n; cell += (long long)gridDim.x * blockDim.x)
+    det_sample_body(G, D, t, cell);
+}
+__device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& D, const int t, const long long cell) {
+  const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
+  const long long n = (long long)ex * ey * ez;
   const int rz = (int)(cell % ez);
   const int ry = (int)((cell / ez) % ey);
   const int rx = (int)(cell / ((long long)ez * ey));

@@ -73,6 +73,12 @@ struct StepParams {
   const WallDev* walls;  // device array
   int n_src;
   const SrcDev* src;  // device array
+  // hot-loop copies in kernel-parameter (constant) space: wall boxes, source bounding boxes and the
+  // union x-range of all sources (a CTA-uniform test that keeps the injection path cold)
+  WallDev wallp[FDTDX_MAX_WALL];
+  int src_lo[FDTDX_MAX_SRC][3], src_hi[FDTDX_MAX_SRC][3];
+  int src_x0, src_x1;
+  int wall_x0[2], wall_x1[2];  // union x-range of the PEC [0] / PMC [1] walls
   // ADE (update.py:316-350)
   int n_poles, has_c4;
   const float* P_cur;  // dispersive_P_curr
