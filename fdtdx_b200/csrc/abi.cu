@@ -486,6 +486,20 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   P.walls = p->d_walls;
   P.n_src = (int)p->srcs.size();
   P.src = p->d_srcs;
+  P.src_x0 = p->nx; P.src_x1 = 0;
+  for (int s = 0; s < P.n_src; ++s) {
+    const SrcDev& d = p->srcs[s].d;
+    for (int a = 0; a < 3; ++a) { P.src_lo[s][a] = d.lo[a]; P.src_hi[s][a] = d.hi[a]; }
+    P.src_x0 = std::min(P.src_x0, d.lo[0]);
+    P.src_x1 = std::max(P.src_x1, d.hi[0]);
+  }
+  for (int k = 0; k < 2; ++k) { P.wall_x0[k] = p->nx; P.wall_x1[k] = 0; }
+  for (int w = 0; w < P.n_walls; ++w) {
+    const WallDev& W = p->walls[w];
+    P.wallp[w] = W;
+    P.wall_x0[W.kind] = std::min(P.wall_x0[W.kind], W.lo[0]);
+    P.wall_x1[W.kind] = std::max(P.wall_x1[W.kind], W.hi[0]);
+  }
   P.n_poles = p->n_poles; P.has_c4 = p->has_c4;
   if (p->n_poles > 0) {
     float* A = (float*)p->slots[FDTDX_SLOT_P_A][0];

@@ -150,410 +150,507 @@ static __device__ __noinline__ void inject_H(const SrcDev* __restrict__ srcs, in
   *h0 = H[0]; *h1 = H[1]; *h2 = H[2];
 }
 
-__device__ __forceinline__ bool any_src_hits(const SrcDev* __restrict__ srcs, int n_src, int i, int j, int k0, int V) {
-  for (int s = 0; s < n_src; ++s) {
-    const SrcDev& S = srcs[s];
-    if (i >= S.lo[0] && i < S.hi[0] && j >= S.lo[1] && j < S.hi[1] && k0 < S.hi[2] && k0 + V > S.lo[2]) return true;
-  }
-  return false;
-}
-
+// ------------------------------------------------------------------------------------------------
+// Hot-loop helpers.  Everything the marching loop touches per plane lives in registers or in kernel
+// parameter (constant) space; source injection and wall masking are kept out of line so that the
+// common cell costs no local-memory traffic and no descriptor loads.
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 #ifndef FDTDX_PF_DIST
 #define FDTDX_PF_DIST 2
 #endif
-#ifndef FDTDX_PF_L1
-#define FDTDX_PF_L1 0  // 1: additionally pull the next plane into L1
+#ifndef FDTDX_MIN_CTAS
+#define FDTDX_MIN_CTAS 2
 #endif
 
-// CPML for one axis at one cell (perfectly_matched_layer.py:138-190; curl.py:284-308, 371-394).
-// d1 = d_a F_j, d2 = d_a F_i; returns the corrections to subtract from K_i and add to K_j.
-__device__ __forceinline__ void cpml_cell(float a, float b, float km1, bool kappa_one, bool simulate,
-                                          float d1, float d2, float* psi1, float* psi2,
-                                          float* corr1, float* corr2) {
-  float p1 = *psi1, p2 = *psi2;
-  if (simulate) {
-    p1 = b * p1 + a * d1;
-    p2 = b * p2 + a * d2;
-    *psi1 = p1;
-    *psi2 = p2;
+// Does any source box intersect cells (i, j, k0..k0+V-1)?  Boxes come from parameter space.
+__device__ __forceinline__ bool src_hits(const StepParams& P, int i, int j, int k0, int V) {
+  if (i < P.src_x0 || i >= P.src_x1) return false;  // CTA-uniform: almost every plane stops here
+  for (int s = 0; s < P.n_src; ++s) {
+    if (i >= P.src_lo[s][0] && i < P.src_hi[s][0] && j >= P.src_lo[s][1] && j < P.src_hi[s][1] && k0 < P.src_hi[s][2] &&
+        k0 + V > P.src_lo[s][2])
+      return true;
   }
-  if (kappa_one) {
-    *corr1 = p1;
-    *corr2 = p2;
-  } else {
-    *corr1 = km1 * d1 + p1;
-    *corr2 = km1 * d2 + p2;
+  return false;
+}
+
+// Cold path, outside the marching loop: inject the sources into this thread's cells of planes
+// [ic0, ic1) in global memory.  Forward: after the loop (the cell already holds the updated field;
+// the wall mask is re-applied because the reference masks after the injection).  Reverse: before the
+// loop (update_E_reverse undoes the injection first).  Same arithmetic as a fused epilogue; a thread
+// only touches cells it owns, so no other thread's data is involved.
+template <int V, int TIER>
+static __device__ __noinline__ void src_pass_E(const StepParams& P, int t, bool reverse, int ic0, int ic1, int j, int k0) {
+  const long long plane = (long long)P.ny * P.nz;
+  const long long N = plane * P.nx;
+  for (int i = max(ic0, P.src_x0); i < min(ic1, P.src_x1); ++i) {
+    if (!src_hits(P, i, j, k0, V)) continue;
+    const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
+    for (int e = 0; e < V; ++e) {
+      const long long cell = cell0 + e;
+      float e0 = P.E[cell], e1 = P.E[N + cell], e2 = P.E[2 * N + cell];
+      const float i0 = P.eps[cell];
+      const float i1 = (TIER == 3) ? P.eps[P.eps_cs + cell] : i0;
+      const float i2 = (TIER == 3) ? P.eps[2 * P.eps_cs + cell] : i0;
+      inject_E(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e, i0, i1, i2, &e0, &e1, &e2);
+      if (!reverse) {
+        for (int w = 0; w < P.n_walls; ++w) {
+          const WallDev& W = P.wallp[w];
+          if (W.kind == 0 && in_box(W.lo, W.hi, i, j, k0 + e)) {
+            if (W.axis != 0) e0 = 0.0f;
+            if (W.axis != 1) e1 = 0.0f;
+            if (W.axis != 2) e2 = 0.0f;
+          }
+        }
+      }
+      P.E[cell] = e0; P.E[N + cell] = e1; P.E[2 * N + cell] = e2;
+    }
   }
 }
+template <int V, int MUT>
+static __device__ __noinline__ void src_pass_H(const StepParams& P, int t, bool reverse, int ic0, int ic1, int j, int k0) {
+  const long long plane = (long long)P.ny * P.nz;
+  const long long N = plane * P.nx;
+  for (int i = max(ic0, P.src_x0); i < min(ic1, P.src_x1); ++i) {
+    if (!src_hits(P, i, j, k0, V)) continue;
+    const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
+    for (int e = 0; e < V; ++e) {
+      const long long cell = cell0 + e;
+      float h0 = P.H[cell], h1 = P.H[N + cell], h2 = P.H[2 * N + cell];
+      float m0 = P.inv_mu_scalar, m1 = m0, m2 = m0;
+      if (MUT >= 1) {
+        m0 = P.mu[cell];
+        m1 = (MUT == 3) ? P.mu[P.mu_cs + cell] : m0;
+        m2 = (MUT == 3) ? P.mu[2 * P.mu_cs + cell] : m0;
+      }
+      inject_H(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e, m0, m1, m2, &h0, &h1, &h2);
+      if (!reverse) {
+        for (int w = 0; w < P.n_walls; ++w) {
+          const WallDev& W = P.wallp[w];
+          if (W.kind == 1 && in_box(W.lo, W.hi, i, j, k0 + e)) {
+            if (W.axis != 0) h0 = 0.0f;
+            if (W.axis != 1) h1 = 0.0f;
+            if (W.axis != 2) h2 = 0.0f;
+          }
+        }
+      }
+      P.H[cell] = h0; P.H[N + cell] = h1; P.H[2 * N + cell] = h2;
+    }
+  }
+}
+
+// PEC (kind 0) / PMC (kind 1) tangential zeroing of V freshly computed cells (pec.py:70-77, pmc.py:63-76).
+template <int V>
+__device__ __forceinline__ void wall_mask(const StepParams& P, int kind, int i, int j, int k0, Vec<V>& o0, Vec<V>& o1, Vec<V>& o2) {
+  for (int w = 0; w < P.n_walls; ++w) {
+    const WallDev& W = P.wallp[w];
+    if (W.kind != kind || i < W.lo[0] || i >= W.hi[0] || j < W.lo[1] || j >= W.hi[1]) continue;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (k0 + e >= W.lo[2] && k0 + e < W.hi[2]) {
+        if (W.axis != 0) o0.v[e] = 0.0f;
+        if (W.axis != 1) o1.v[e] = 0.0f;
+        if (W.axis != 2) o2.v[e] = 0.0f;
+      }
+    }
+  }
+}
+
+// CPML for one axis on V cells (perfectly_matched_layer.py:138-190; curl.py:284-308, 371-394).
+// d1 = d_a F_j, d2 = d_a F_i; psi' = b psi + a d (UPD), correction = (1/kappa - 1) d + psi' (K1: kappa == 1,
+// correction = psi'); Km -= corr_1, Kp += corr_2.
+template <int V, bool UPD, bool K1>
+__device__ __forceinline__ void cpml_axis(const float a, const float b, const float km1, const Vec<V>& d1, const Vec<V>& d2,
+                                          Vec<V>& p1, Vec<V>& p2, Vec<V>& Km, Vec<V>& Kp) {
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    float q1 = p1.v[e], q2 = p2.v[e];
+    if (UPD) {
+      q1 = b * q1 + a * d1.v[e];
+      q2 = b * q2 + a * d2.v[e];
+      p1.v[e] = q1;
+      p2.v[e] = q2;
+    }
+    float c1 = q1, c2 = q2;
+    if (!K1) {
+      c1 = km1 * d1.v[e] + q1;
+      c2 = km1 * d2.v[e] + q2;
+    }
+    Km.v[e] = Km.v[e] - c1;
+    Kp.v[e] = Kp.v[e] + c2;
+  }
+}
+// vector coefficients (z axis: one coefficient per cell), elements [E0, E1)
+template <int V, int E0, int E1, bool UPD, bool K1>
+__device__ __forceinline__ void cpml_axis_v(const Vec<V>& a, const Vec<V>& b, const Vec<V>& km1, const Vec<V>& d1, const Vec<V>& d2,
+                                            Vec<V>& p1, Vec<V>& p2, Vec<V>& Km, Vec<V>& Kp) {
+#pragma unroll
+  for (int e = E0; e < E1; ++e) {
+    float q1 = p1.v[e], q2 = p2.v[e];
+    if (UPD) {
+      q1 = b.v[e] * q1 + a.v[e] * d1.v[e];
+      q2 = b.v[e] * q2 + a.v[e] * d2.v[e];
+      p1.v[e] = q1;
+      p2.v[e] = q2;
+    }
+    float c1 = q1, c2 = q2;
+    if (!K1) {
+      c1 = km1.v[e] * d1.v[e] + q1;
+      c2 = km1.v[e] * d2.v[e] + q2;
+    }
+    Km.v[e] = Km.v[e] - c1;
+    Kp.v[e] = Kp.v[e] + c2;
+  }
+}
+
+// Per-thread, loop-invariant description of the y / z CPML slabs this thread's cells belong to.
+template <int V>
+struct PmlLane {
+  bool in_y, any_z, zvec, zh0, zh1;
+  long long ystride, yoff;  // psi index of plane i: i * ystride + yoff
+  long long zstride, zoff;
+  float ay, by, ky;
+  Vec<V> az, bz, kz;
+};
+
+// The CPML block shared by both half-steps.  PSI selects the E-side (psiE, aE..) or H-side tables.
+// dX* are the six derivative vectors of this plane; K* the curl components to correct.
+// Object order of the reference: x slabs, y slabs, z slabs.
+#define FDTDX_CPML_BLOCK(PSI, AT, BT, KT)                                                                              \
+  if (PM > 0) {                                                                                                        \
+    if (in_x) {                                                                                                        \
+      float a = px.AT[i], b = px.BT[i];                                                                                \
+      const float km1 = px.KT[i];                                                                                      \
+      if (!P.simulate) { a = 0.0f; b = 1.0f; }                                                                         \
+      if (px.kappa_one) cpml_axis<V, !REV, true>(a, b, km1, dxFz, dxFy, psx1, psx2, Ky, Kz);                           \
+      else cpml_axis<V, !REV, false>(a, b, km1, dxFz, dxFy, psx1, psx2, Ky, Kz);                                       \
+      if (!REV && psi_st) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }                                                    \
+    }                                                                                                                  \
+    if (L.in_y) {                                                                                                      \
+      if (py.kappa_one) cpml_axis<V, !REV, true>(L.ay, L.by, L.ky, dyFx, dyFz, psy1, psy2, Kz, Kx);                    \
+      else cpml_axis<V, !REV, false>(L.ay, L.by, L.ky, dyFx, dyFz, psy1, psy2, Kz, Kx);                                \
+      if (!REV && psi_st) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }                                                    \
+    }                                                                                                                  \
+    if (PM == 2) {                                                                                                     \
+      if constexpr (V == 4) {                                                                                          \
+        if (L.zh0) {                                                                                                   \
+          if (pz.kappa_one) cpml_axis_v<V, 0, 2, !REV, true>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);        \
+          else cpml_axis_v<V, 0, 2, !REV, false>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);                    \
+          if (!REV && psi_st) {                                                                                        \
+            *reinterpret_cast<float2*>(qz1) = make_float2(psz1.v[0], psz1.v[1]);                                       \
+            *reinterpret_cast<float2*>(qz2) = make_float2(psz2.v[0], psz2.v[1]);                                       \
+          }                                                                                                            \
+        }                                                                                                              \
+        if (L.zh1) {                                                                                                   \
+          if (pz.kappa_one) cpml_axis_v<V, 2, 4, !REV, true>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);        \
+          else cpml_axis_v<V, 2, 4, !REV, false>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);                    \
+          if (!REV && psi_st) {                                                                                        \
+            *reinterpret_cast<float2*>(qz1 + 2) = make_float2(psz1.v[2], psz1.v[3]);                                   \
+            *reinterpret_cast<float2*>(qz2 + 2) = make_float2(psz2.v[2], psz2.v[3]);                                   \
+          }                                                                                                            \
+        }                                                                                                              \
+      }                                                                                                                \
+    } else if (L.any_z) {                                                                                              \
+      _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
+        const int k = k0 + e;                                                                                          \
+        if (k < pz.lo_len || k >= pz.hi_start) {                                                                       \
+          const int side = (k >= pz.hi_start) ? 1 : 0;                                                                 \
+          const int kl = side ? k - pz.hi_start : k;                                                                   \
+          const int Lz = side ? pz.hi_len : pz.lo_len;                                                                 \
+          const long long pidx = ((long long)i * ny + j) * Lz + kl;                                                    \
+          float* s1 = pz.PSI[side][0] + pidx;                                                                          \
+          float* s2 = pz.PSI[side][1] + pidx;                                                                          \
+          float q1 = *s1, q2 = *s2;                                                                                    \
+          if (!REV && P.simulate) {                                                                                    \
+            q1 = pz.BT[k] * q1 + pz.AT[k] * dzFy.v[e];                                                                 \
+            q2 = pz.BT[k] * q2 + pz.AT[k] * dzFx.v[e];                                                                 \
+            if (psi_st) { *s1 = q1; *s2 = q2; }                                                                        \
+          }                                                                                                            \
+          float c1 = q1, c2 = q2;                                                                                      \
+          if (!pz.kappa_one) { c1 = pz.KT[k] * dzFy.v[e] + q1; c2 = pz.KT[k] * dzFx.v[e] + q2; }                       \
+          Kx.v[e] = Kx.v[e] - c1;                                                                                      \
+          Ky.v[e] = Ky.v[e] + c2;                                                                                      \
+        }                                                                                                              \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }
+
+// Loads of the CPML auxiliary fields of plane i (issued together with the field loads: their
+// addresses depend on indices only, so the latencies overlap).
+#define FDTDX_CPML_LOADS(PSI)                                                                                          \
+  const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);                                                   \
+  Vec<V> psx1, psx2, psy1, psy2, psz1, psz2;                                                                           \
+  float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr, *qz1 = nullptr, *qz2 = nullptr;                \
+  if (PM > 0) {                                                                                                        \
+    if (in_x) {                                                                                                        \
+      const int side = (i >= px.hi_start) ? 1 : 0;                                                                     \
+      const long long pidx = (long long)(side ? i - px.hi_start : i) * plane + row;                                    \
+      qx1 = px.PSI[side][0] + pidx;                                                                                    \
+      qx2 = px.PSI[side][1] + pidx;                                                                                    \
+      psx1 = ldv<V>(qx1);                                                                                              \
+      psx2 = ldv<V>(qx2);                                                                                              \
+    }                                                                                                                  \
+    if (L.in_y) {                                                                                                      \
+      const long long pidx = (long long)i * L.ystride + L.yoff;                                                        \
+      qy1 = py1 + pidx;                                                                                                \
+      qy2 = py2 + pidx;                                                                                                \
+      psy1 = ldv<V>(qy1);                                                                                              \
+      psy2 = ldv<V>(qy2);                                                                                              \
+    }                                                                                                                  \
+    if (PM == 2) {                                                                                                     \
+      if constexpr (V == 4) {                                                                                          \
+        if (L.zvec) {                                                                                                  \
+          const long long pidx = (long long)i * L.zstride + L.zoff;                                                    \
+          qz1 = pz1 + pidx;                                                                                            \
+          qz2 = pz2 + pidx;                                                                                            \
+          if (L.zh0) {                                                                                                 \
+            const float2 t1 = *reinterpret_cast<const float2*>(qz1), t2 = *reinterpret_cast<const float2*>(qz2);       \
+            psz1.v[0] = t1.x; psz1.v[1] = t1.y; psz2.v[0] = t2.x; psz2.v[1] = t2.y;                                    \
+          }                                                                                                            \
+          if (L.zh1) {                                                                                                 \
+            const float2 t1 = *reinterpret_cast<const float2*>(qz1 + 2), t2 = *reinterpret_cast<const float2*>(qz2 + 2); \
+            psz1.v[2] = t1.x; psz1.v[3] = t1.y; psz2.v[2] = t2.x; psz2.v[3] = t2.y;                                    \
+          }                                                                                                            \
+        }                                                                                                              \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }
+
+// Loop-invariant slab membership of this thread (y: warp-uniform, z: per lane).
+#define FDTDX_CPML_SETUP(PSI, AT, BT, KT)                                                                              \
+  const AxisPmlDev& px = P.pml[0];                                                                                     \
+  const AxisPmlDev& py = P.pml[1];                                                                                     \
+  const AxisPmlDev& pz = P.pml[2];                                                                                     \
+  PmlLane<V> L;                                                                                                        \
+  L.in_y = false; L.any_z = false; L.zvec = false; L.zh0 = false; L.zh1 = false;                                       \
+  float *py1 = nullptr, *py2 = nullptr, *pz1 = nullptr, *pz2 = nullptr;                                                \
+  if (PM > 0) {                                                                                                        \
+    L.in_y = (j < py.lo_len || j >= py.hi_start);                                                                      \
+    if (L.in_y) {                                                                                                      \
+      const int yside = (j >= py.hi_start) ? 1 : 0;                                                                    \
+      const int yL = yside ? py.hi_len : py.lo_len;                                                                    \
+      L.ystride = (long long)yL * nz;                                                                                  \
+      L.yoff = (long long)(yside ? j - py.hi_start : j) * nz + k0;                                                     \
+      py1 = py.PSI[yside][0];                                                                                          \
+      py2 = py.PSI[yside][1];                                                                                          \
+      L.ay = py.AT[j]; L.by = py.BT[j]; L.ky = py.KT[j];                                                               \
+      if (!P.simulate) { L.ay = 0.0f; L.by = 1.0f; }                                                                   \
+    }                                                                                                                  \
+    L.any_z = (k0 < pz.lo_len || k0 + V > pz.hi_start);                                                                \
+    if (PM == 2 && L.any_z) {                                                                                          \
+      const int zside = (k0 + V > pz.hi_start) ? 1 : 0;                                                                \
+      const int zL = zside ? pz.hi_len : pz.lo_len;                                                                    \
+      L.zvec = true;                                                                                                   \
+      L.zh0 = zside ? (k0 >= pz.hi_start) : (k0 < pz.lo_len);                                                          \
+      L.zh1 = zside ? (k0 + 2 >= pz.hi_start) : (k0 + 2 < pz.lo_len);                                                  \
+      L.zstride = (long long)ny * zL;                                                                                  \
+      L.zoff = (long long)j * zL + (zside ? k0 - pz.hi_start : k0);                                                    \
+      pz1 = pz.PSI[zside][0];                                                                                          \
+      pz2 = pz.PSI[zside][1];                                                                                          \
+      L.az = ldv<V>(pz.AT + k0); L.bz = ldv<V>(pz.BT + k0); L.kz = ldv<V>(pz.KT + k0);                                 \
+      if (!P.simulate) {                                                                                               \
+        _Pragma("unroll") for (int e = 0; e < V; ++e) { L.az.v[e] = 0.0f; L.bz.v[e] = 1.0f; }                          \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }                                                                                                                    \
+  const bool psi_st = P.simulate && P.psi_store;
 
 #if !defined(FDTDX_BUILD_H)
 // ------------------------------------------------------------------------------------------------
 // E half-step
 // ------------------------------------------------------------------------------------------------
 template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
-__global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const int t) {
+__global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int nz = P.nz, ny = P.ny;
+  const bool active = (k0 < nz) && (j < ny);
+  const unsigned wmask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;  // the shuffles below run under wmask
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
-  const bool active = (k0 < P.nz) && (j < P.ny);
-  const int nz = P.nz, ny = P.ny;
   const long long plane = (long long)ny * nz;
   const long long N = plane * P.nx;
-  const float* __restrict__ Hx = P.H;
-  const float* __restrict__ Hy = P.H + N;
-  const float* __restrict__ Hz = P.H + 2 * N;
-  float* __restrict__ Ex = P.E;
-  float* __restrict__ Ey = P.E + N;
-  float* __restrict__ Ez = P.E + 2 * N;
-
   const long long row = (long long)j * nz + k0;
-  int jm = j - 1;
-  bool jm_ok = true;
-  if (jm < 0) { if (P.wrap[1]) jm = ny - 1; else jm_ok = false; }
-  const long long rowm = (long long)jm * nz + k0;
-  int km = k0 - 1;
-  bool km_ok = true;
-  if (km < 0) { if (P.wrap[2]) km = nz - 1; else km_ok = false; }
-  const long long rowk = (long long)j * nz + km;
 
-  // y / z PML membership of this thread's cells (x membership is per marching step)
-  const AxisPmlDev& px = P.pml[0];
-  const AxisPmlDev& py = P.pml[1];
-  const AxisPmlDev& pz = P.pml[2];
-  // PM: 0 = no CPML slab on this plan (all CPML code compiled out), 1 = scalar z-slab path, 2 = 128-bit z-slab path
-  const bool in_y = (PM > 0) && active && (j < py.lo_len || j >= py.hi_start);
-  const int yside = (j >= py.hi_start) ? 1 : 0;
-  const int jl = yside ? j - py.hi_start : j;
-  const int yL = yside ? py.hi_len : py.lo_len;
-  const bool any_z = (PM > 0) && active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
-  // PM == 2 (V == 4, even slab thickness): the lane's four cells are two 64-bit halves, each either
-  // entirely inside or entirely outside a z slab, so psi moves as float2 with no per-cell branch.
-  const int zside = (k0 + V > pz.hi_start) ? 1 : 0;
-  const bool zvec = (PM == 2) && any_z;
-  const bool zh0 = zvec && (zside ? (k0 >= pz.hi_start) : (k0 < pz.lo_len));
-  const bool zh1 = zvec && (zside ? (k0 + 2 >= pz.hi_start) : (k0 + 2 < pz.lo_len));
-  const long long zstride = (long long)ny * (zside ? pz.hi_len : pz.lo_len);
-  const long long zoff = (long long)j * (zside ? pz.hi_len : pz.lo_len) + (zside ? k0 - pz.hi_start : k0);
-  float* const pz1 = zside ? pz.psiE[1][0] : pz.psiE[0][0];
-  float* const pz2 = zside ? pz.psiE[1][1] : pz.psiE[0][1];
-  Vec<V> az = zerov<V>(), bz = zerov<V>(), kz = zerov<V>();
-  if (zvec) { az = ldv<V>(pz.aE + k0); bz = ldv<V>(pz.bE + k0); kz = ldv<V>(pz.kE + k0); }
+  // neighbour offsets (in elements) relative to this thread's first cell; *_ok false = zero halo
+  bool jm_ok = true, km_ok = true;
+  long long djm = -(long long)nz;
+  if (j == 0) { if (P.wrap[1]) djm = (long long)(ny - 1) * nz; else jm_ok = false; }
+  int dkm = -1;
+  if (k0 == 0) { if (P.wrap[2]) dkm = nz - 1; else km_ok = false; }
+
+  FDTDX_CPML_SETUP(psiE, aE, bE, kE)
+
   float sBy = 1.0f;
-  float sBzv[V];
-#pragma unroll
-  for (int e = 0; e < V; ++e) sBzv[e] = 1.0f;
-  if (MET && active) {
+  Vec<V> sBz;
+  if (MET) {
     sBy = P.sB[1][j];
-#pragma unroll
-    for (int e = 0; e < V; ++e) sBzv[e] = P.sB[2][k0 + e];
+    sBz = ldv<V>(P.sB[2] + k0);
   }
+
+  const float* pH = P.H + (long long)ic0 * plane + row;  // Hx of (ic0, j, k0); Hy, Hz at +N, +2N
+  float* pE = P.E + (long long)ic0 * plane + row;
+  const float* pEps = P.eps + (long long)ic0 * plane + row;
 
   // register queue: Hy, Hz of the previous x plane
-  Vec<V> hy_im = zerov<V>(), hz_im = zerov<V>();
-  if (active) {
-    if (ic0 > 0) {
-      hy_im = ldv<V>(Hy + (long long)(ic0 - 1) * plane + row);
-      hz_im = ldv<V>(Hz + (long long)(ic0 - 1) * plane + row);
-    } else if (P.x_lo_mode == 1) {
-      hy_im = ldv<V>(Hy + (long long)(P.nx - 1) * plane + row);
-      hz_im = ldv<V>(Hz + (long long)(P.nx - 1) * plane + row);
-    } else if (P.x_lo_mode == 2) {
-      hy_im = ldv<V>(P.haloH + row);
-      hz_im = ldv<V>(P.haloH + plane + row);
-    }
+  Vec<V> hy_im, hz_im;
+  if (ic0 > 0) {
+    hy_im = ldv<V>(pH + N - plane);
+    hz_im = ldv<V>(pH + 2 * N - plane);
+  } else if (P.x_lo_mode == 1) {
+    hy_im = ldv<V>(P.H + N + (long long)(P.nx - 1) * plane + row);
+    hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row);
+  } else if (P.x_lo_mode == 2) {
+    hy_im = ldv<V>(P.haloH + row);
+    hz_im = ldv<V>(P.haloH + plane + row);
+  } else {
+    hy_im = zerov<V>();
+    hz_im = zerov<V>();
   }
 
+  if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
-    const long long base = (long long)i * plane;
-    Vec<V> hx = zerov<V>(), hy = zerov<V>(), hz = zerov<V>();
-    Vec<V> hx_jm = zerov<V>(), hz_jm = zerov<V>();
-    Vec<V> ex, ey, ez, ie0, ie1, ie2;
-    if (active) {
-      hx = ldv<V>(Hx + base + row);
-      hy = ldv<V>(Hy + base + row);
-      hz = ldv<V>(Hz + base + row);
-      if (jm_ok) {
-        hx_jm = ldv<V>(Hx + base + rowm);
-        hz_jm = ldv<V>(Hz + base + rowm);
-      }
-      ex = ldv<V>(Ex + base + row);
-      ey = ldv<V>(Ey + base + row);
-      ez = ldv<V>(Ez + base + row);
-      ie0 = ldv<V>(P.eps + base + row);
-      if (TIER == 3) {
-        ie1 = ldv<V>(P.eps + P.eps_cs + base + row);
-        ie2 = ldv<V>(P.eps + 2 * P.eps_cs + base + row);
-      } else {
-        ie1 = ie0;
-        ie2 = ie0;
-      }
+    const Vec<V> hx = ldv<V>(pH), hy = ldv<V>(pH + N), hz = ldv<V>(pH + 2 * N);
+    Vec<V> hx_jm, hz_jm;
+    if (jm_ok) {
+      hx_jm = ldv<V>(pH + djm);
+      hz_jm = ldv<V>(pH + 2 * N + djm);
+    } else {
+      hx_jm = zerov<V>();
+      hz_jm = zerov<V>();
     }
-    // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
-    // indices only), so their latency overlaps instead of serialising behind the curl.
-    const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);
-    Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
-    float psz1[V], psz2[V];
-    float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
-    if (active) {
-      if (in_x) {
-        const int side = (i >= px.hi_start) ? 1 : 0;
-        const int il = side ? i - px.hi_start : i;
-        const long long pidx = ((long long)il * ny + j) * nz + k0;
-        qx1 = (side ? px.psiE[1][0] : px.psiE[0][0]) + pidx;
-        qx2 = (side ? px.psiE[1][1] : px.psiE[0][1]) + pidx;
-        psx1 = ldv<V>(qx1);
-        psx2 = ldv<V>(qx2);
-      }
-      if (in_y) {
-        const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        qy1 = (yside ? py.psiE[1][0] : py.psiE[0][0]) + pidx;
-        qy2 = (yside ? py.psiE[1][1] : py.psiE[0][1]) + pidx;
-        psy1 = ldv<V>(qy1);
-        psy2 = ldv<V>(qy2);
-      }
-      if (zvec) {
-        if constexpr (V == 4) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) { psz1[e] = 0.0f; psz2[e] = 0.0f; }
-          const float* q1 = pz1 + i * zstride + zoff;
-          const float* q2 = pz2 + i * zstride + zoff;
-          if (zh0) {
-            const float2 t1 = *reinterpret_cast<const float2*>(q1), t2 = *reinterpret_cast<const float2*>(q2);
-            psz1[0] = t1.x; psz1[1] = t1.y; psz2[0] = t2.x; psz2[1] = t2.y;
-          }
-          if (zh1) {
-            const float2 t1 = *reinterpret_cast<const float2*>(q1 + 2), t2 = *reinterpret_cast<const float2*>(q2 + 2);
-            psz1[2] = t1.x; psz1[3] = t1.y; psz2[2] = t2.x; psz2[3] = t2.y;
-          }
-        }
-      } else if (any_z) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int k = k0 + e;
-          psz1[e] = 0.0f;
-          psz2[e] = 0.0f;
-          if (k < pz.lo_len || k >= pz.hi_start) {
-            const int side = (k >= pz.hi_start) ? 1 : 0;
-            const int kl = side ? k - pz.hi_start : k;
-            const int L = side ? pz.hi_len : pz.lo_len;
-            const long long pidx = ((long long)i * ny + j) * L + kl;
-            psz1[e] = (side ? pz.psiE[1][0] : pz.psiE[0][0])[pidx];
-            psz2[e] = (side ? pz.psiE[1][1] : pz.psiE[0][1])[pidx];
-          }
-        }
-      }
-      // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
-      if (i + FDTDX_PF_DIST < ic1) {
-        const long long pb = base + FDTDX_PF_DIST * plane + row;
-        prefetch_l2(Hx + pb); prefetch_l2(Hy + pb); prefetch_l2(Hz + pb);
-        prefetch_l2(Ex + pb); prefetch_l2(Ey + pb); prefetch_l2(Ez + pb);
-        prefetch_l2(P.eps + pb);
-        if (TIER == 3) { prefetch_l2(P.eps + P.eps_cs + pb); prefetch_l2(P.eps + 2 * P.eps_cs + pb); }
-      }
-      if (FDTDX_PF_L1 && i + 1 < ic1) {
-        const long long pb = base + plane + row;
-        prefetch_l1(Hx + pb); prefetch_l1(Hy + pb); prefetch_l1(Hz + pb);
-        prefetch_l1(Ex + pb); prefetch_l1(Ey + pb); prefetch_l1(Ez + pb);
-        prefetch_l1(P.eps + pb);
-      }
+    const Vec<V> ex = ldv<V>(pE), ey = ldv<V>(pE + N), ez = ldv<V>(pE + 2 * N);
+    const Vec<V> ie0 = ldv<V>(pEps);
+    Vec<V> ie1, ie2;
+    if (TIER == 3) {
+      ie1 = ldv<V>(pEps + P.eps_cs);
+      ie2 = ldv<V>(pEps + 2 * P.eps_cs);
+    } else {
+      ie1 = ie0;
+      ie2 = ie0;
+    }
+    FDTDX_CPML_LOADS(psiE)
+    // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
+    if (i + FDTDX_PF_DIST < ic1) {
+      const long long pb = FDTDX_PF_DIST * plane;
+      prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb);
+      prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
+      prefetch_l2(pEps + pb);
+      if (TIER == 3) { prefetch_l2(pEps + P.eps_cs + pb); prefetch_l2(pEps + 2 * P.eps_cs + pb); }
     }
     // z-neighbour (k-1) of the first element: last element of the previous lane
-    float hx_l = __shfl_up_sync(0xffffffffu, hx.v[V - 1], 1);
-    float hy_l = __shfl_up_sync(0xffffffffu, hy.v[V - 1], 1);
+    float hx_l = __shfl_up_sync(wmask, hx.v[V - 1], 1);
+    float hy_l = __shfl_up_sync(wmask, hy.v[V - 1], 1);
     if (lane == 0) {
-      hx_l = (active && km_ok) ? Hx[base + rowk] : 0.0f;
-      hy_l = (active && km_ok) ? Hy[base + rowk] : 0.0f;
+      hx_l = km_ok ? pH[dkm] : 0.0f;
+      hy_l = km_ok ? pH[N + dkm] : 0.0f;
     }
-    if (active) {
-      float sBx = 1.0f;
-      if (MET) sBx = P.sB[0][i];
-      Vec<V> Kx, Ky, Kz;
-      Vec<V> dxHz_v, dxHy_v, dyHx_v, dyHz_v, dzHy_v, dzHx_v;
+    float sBx = 1.0f;
+    if (MET) sBx = P.sB[0][i];
+    Vec<V> Kx, Ky, Kz;
+    Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float hx_km = (e == 0) ? hx_l : hx.v[e == 0 ? 0 : e - 1];
-        float hy_km = (e == 0) ? hy_l : hy.v[e == 0 ? 0 : e - 1];
-        const float sBz = sBzv[e];
-        float dyHz = hz.v[e] - hz_jm.v[e];
-        float dzHy = hy.v[e] - hy_km;
-        float dzHx = hx.v[e] - hx_km;
-        float dxHz = hz.v[e] - hz_im.v[e];
-        float dxHy = hy.v[e] - hy_im.v[e];
-        float dyHx = hx.v[e] - hx_jm.v[e];
-        if (MET) {
-          dyHz *= sBy; dzHy *= sBz; dzHx *= sBz; dxHz *= sBx; dxHy *= sBx; dyHx *= sBy;
-        }
-        Kx.v[e] = dyHz - dzHy;
-        Ky.v[e] = dzHx - dxHz;
-        Kz.v[e] = dxHy - dyHx;
-        dxHz_v.v[e] = dxHz; dxHy_v.v[e] = dxHy; dyHx_v.v[e] = dyHx;
-        dyHz_v.v[e] = dyHz; dzHy_v.v[e] = dzHy; dzHx_v.v[e] = dzHx;
+    for (int e = 0; e < V; ++e) {
+      const float hx_km = (e == 0) ? hx_l : hx.v[e == 0 ? 0 : e - 1];
+      const float hy_km = (e == 0) ? hy_l : hy.v[e == 0 ? 0 : e - 1];
+      float dyHz = hz.v[e] - hz_jm.v[e];
+      float dzHy = hy.v[e] - hy_km;
+      float dzHx = hx.v[e] - hx_km;
+      float dxHz = hz.v[e] - hz_im.v[e];
+      float dxHy = hy.v[e] - hy_im.v[e];
+      float dyHx = hx.v[e] - hx_jm.v[e];
+      if (MET) {
+        dyHz *= sBy; dzHy *= sBz.v[e]; dzHx *= sBz.v[e]; dxHz *= sBx; dxHy *= sBx; dyHx *= sBy;
       }
-      // CPML corrections in the reference's object order: x slabs, y slabs, z slabs.
-      if (in_x) {
-        const float a = px.aE[i], b = px.bE[i], km1 = px.kE[i];
+      Kx.v[e] = dyHz - dzHy;
+      Ky.v[e] = dzHx - dxHz;
+      Kz.v[e] = dxHy - dyHx;
+      dxFz.v[e] = dxHz; dxFy.v[e] = dxHy; dyFx.v[e] = dyHx;
+      dyFz.v[e] = dyHz; dzFy.v[e] = dzHy; dzFx.v[e] = dzHx;
+    }
+    FDTDX_CPML_BLOCK(psiE, aE, bE, kE)
+    // material update
+    Vec<V> o0, o1, o2;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          float c1, c2;  // axis 0: d1 = dx F_z, d2 = dx F_y; corrects K_y (-) and K_z (+)
-          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxHz_v.v[e], dxHy_v.v[e], &psx1.v[e], &psx2.v[e], &c1, &c2);
-          Ky.v[e] = Ky.v[e] - c1;
-          Kz.v[e] = Kz.v[e] + c2;
-        }
-        if (P.simulate && !REV && P.psi_store) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
-      }
-      if (in_y) {
-        const float a = py.aE[j], b = py.bE[j], km1 = py.kE[j];
+    for (int e = 0; e < V; ++e) {
+      const float Eo[3] = {ex.v[e], ey.v[e], ez.v[e]};
+      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
+      const float ie[3] = {ie0.v[e], ie1.v[e], ie2.v[e]};
+      float En[3];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          float c1, c2;  // axis 1: d1 = dy F_x, d2 = dy F_z; corrects K_z (-) and K_x (+)
-          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyHx_v.v[e], dyHz_v.v[e], &psy1.v[e], &psy2.v[e], &c1, &c2);
-          Kz.v[e] = Kz.v[e] - c1;
-          Kx.v[e] = Kx.v[e] + c2;
-        }
-        if (P.simulate && !REV && P.psi_store) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
-      }
-      if (zvec) {
-        if constexpr (V == 4) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            if ((e < 2) ? zh0 : zh1) {
-              float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
-              cpml_cell(az.v[e], bz.v[e], kz.v[e], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e], &psz1[e], &psz2[e], &c1, &c2);
-              Kx.v[e] = Kx.v[e] - c1;
-              Ky.v[e] = Ky.v[e] + c2;
-            }
-          }
-          if (P.simulate && !REV && P.psi_store) {
-            float* q1 = pz1 + i * zstride + zoff;
-            float* q2 = pz2 + i * zstride + zoff;
-            if (zh0) {
-              *reinterpret_cast<float2*>(q1) = make_float2(psz1[0], psz1[1]);
-              *reinterpret_cast<float2*>(q2) = make_float2(psz2[0], psz2[1]);
-            }
-            if (zh1) {
-              *reinterpret_cast<float2*>(q1 + 2) = make_float2(psz1[2], psz1[3]);
-              *reinterpret_cast<float2*>(q2 + 2) = make_float2(psz2[2], psz2[3]);
-            }
-          }
-        }
-      } else if (any_z) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int k = k0 + e;
-          if (k < pz.lo_len || k >= pz.hi_start) {
-            const int side = (k >= pz.hi_start) ? 1 : 0;
-            const int kl = side ? k - pz.hi_start : k;
-            const int L = side ? pz.hi_len : pz.lo_len;
-            const long long pidx = ((long long)i * ny + j) * L + kl;
-            float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
-            cpml_cell(pz.aE[k], pz.bE[k], pz.kE[k], pz.kappa_one, P.simulate && !REV, dzHy_v.v[e], dzHx_v.v[e],
-                      &psz1[e], &psz2[e], &c1, &c2);
-            if (P.simulate && !REV && P.psi_store) {
-              (side ? pz.psiE[1][0] : pz.psiE[0][0])[pidx] = psz1[e];
-              (side ? pz.psiE[1][1] : pz.psiE[0][1])[pidx] = psz2[e];
-            }
-            Kx.v[e] = Kx.v[e] - c1;
-            Ky.v[e] = Ky.v[e] + c2;
-          }
-        }
-      }
-      // material update
-      const bool src_hit = (P.n_src > 0) && any_src_hits(P.src, P.n_src, i, j, k0, V);
-      Vec<V> oe[3];
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float Eo[3] = {ex.v[e], ey.v[e], ez.v[e]};
-        const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-        const float ie[3] = {ie0.v[e], ie1.v[e], ie2.v[e]};
-        const long long cell = base + row + e;
-        float En[3];
+      for (int c = 0; c < 3; ++c) {
         if (REV) {
-          // update_E_reverse: sources first (inverse), then ((1+s)E - c K inv_eps) / (1-s)
-          if (src_hit) inject_E(P.src, P.n_src, P.dt, t, true, i, j, k0 + e, ie[0], ie[1], ie[2], &Eo[0], &Eo[1], &Eo[2]);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float Ec = Eo[c];
-            if (SIG) {
-              float sg = P.sigE[c * P.sigE_cs + cell];
-              float s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-              Ec = Ec * (1.0f + s);
-              En[c] = (Ec - (P.cour * K[c]) * ie[c]) / (1.0f - s);
-            } else {
-              En[c] = Ec - (P.cour * K[c]) * ie[c];
-            }
+          // update_E_reverse: ((1+s)E - c K inv_eps) / (1-s)
+          if (SIG) {
+            const float sg = P.sigE[c * P.sigE_cs + (pE - P.E) + e];
+            const float s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
+            const float Ec = Eo[c] * (1.0f + s);
+            En[c] = (Ec - (P.cour * K[c]) * ie[c]) / (1.0f - s);
+          } else {
+            En[c] = Eo[c] - (P.cour * K[c]) * ie[c];
           }
         } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float s = 0.0f;
-            float E1;
-            if (SIG) {
-              float sg = P.sigE[c * P.sigE_cs + cell];
-              s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-              E1 = (1.0f - s) * Eo[c] + (P.cour * K[c]) * ie[c];
-            } else {
-              E1 = Eo[c] + (P.cour * K[c]) * ie[c];
+          float s = 0.0f;
+          float E1;
+          if (SIG) {
+            const float sg = P.sigE[c * P.sigE_cs + (pE - P.E) + e];
+            s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
+            E1 = (1.0f - s) * Eo[c] + (P.cour * K[c]) * ie[c];
+          } else {
+            E1 = Eo[c] + (P.cour * K[c]) * ie[c];
+          }
+          if (ADE) {
+            // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
+            const long long cell = (pE - P.E) + e;
+            const long long pstride = 3 * N;
+            float delta = 0.0f, c4sum = 0.0f;
+            for (int p = 0; p < P.n_poles; ++p) {
+              const long long pi = p * pstride + c * N + cell;
+              const long long ci = (long long)p * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
+              const float Pc = P.P_cur[pi], Pp = P.P_new[pi];
+              const float Phat = (P.c1[ci] * Pc + P.c2[ci] * Pp) + P.c3[ci] * Eo[c];
+              const float dd = Pc - Phat;
+              delta = (p == 0) ? dd : delta + dd;
+              if (P.has_c4) c4sum = (p == 0) ? P.c4[ci] : c4sum + P.c4[ci];
+              P.P_new[pi] = Phat;
             }
-            if (ADE) {
-              // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
-              const long long pstride = 3 * N;
-              float delta = 0.0f, c4sum = 0.0f;
+            E1 = E1 + ie[c] * delta;
+            if (P.has_c4) {
+              float divisor = 1.0f + ie[c] * c4sum;
+              if (SIG) divisor = divisor + s;
+              E1 = E1 / divisor;
               for (int p = 0; p < P.n_poles; ++p) {
                 const long long pi = p * pstride + c * N + cell;
                 const long long ci = (long long)p * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-                float Pc = P.P_cur[pi], Pp = P.P_new[pi];
-                float Phat = (P.c1[ci] * Pc + P.c2[ci] * Pp) + P.c3[ci] * Eo[c];
-                float dd = Pc - Phat;
-                delta = (p == 0) ? dd : delta + dd;
-                if (P.has_c4) c4sum = (p == 0) ? P.c4[ci] : c4sum + P.c4[ci];
-                P.P_new[pi] = Phat;
-              }
-              E1 = E1 + ie[c] * delta;
-              if (P.has_c4) {
-                float divisor = 1.0f + ie[c] * c4sum;
-                if (SIG) divisor = divisor + s;
-                E1 = E1 / divisor;
-                for (int p = 0; p < P.n_poles; ++p) {
-                  const long long pi = p * pstride + c * N + cell;
-                  const long long ci = (long long)p * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-                  P.P_new[pi] = P.P_new[pi] + P.c4[ci] * E1;
-                }
-              } else if (SIG) {
-                E1 = E1 / (1.0f + s);
+                P.P_new[pi] = P.P_new[pi] + P.c4[ci] * E1;
               }
             } else if (SIG) {
               E1 = E1 / (1.0f + s);
             }
-            En[c] = E1;
+          } else if (SIG) {
+            E1 = E1 / (1.0f + s);
           }
-          if (src_hit) inject_E(P.src, P.n_src, P.dt, t, false, i, j, k0 + e, ie[0], ie[1], ie[2], &En[0], &En[1], &En[2]);
+          En[c] = E1;
         }
-        // PEC walls (pec.py:70-77)
-        for (int w = 0; w < P.n_walls; ++w) {
-          const WallDev W = P.walls[w];
-          if (W.kind == 0 && in_box(W.lo, W.hi, i, j, k0 + e)) {
-            if (W.axis != 0) En[0] = 0.0f;
-            if (W.axis != 1) En[1] = 0.0f;
-            if (W.axis != 2) En[2] = 0.0f;
-          }
-        }
-        oe[0].v[e] = En[0]; oe[1].v[e] = En[1]; oe[2].v[e] = En[2];
       }
-      stv<V>(Ex + base + row, oe[0]);
-      stv<V>(Ey + base + row, oe[1]);
-      stv<V>(Ez + base + row, oe[2]);
+      o0.v[e] = En[0]; o1.v[e] = En[1]; o2.v[e] = En[2];
     }
+    // PEC walls (pec.py:70-77)
+    if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
+    stv<V>(pE, o0);
+    stv<V>(pE + N, o1);
+    stv<V>(pE + 2 * N, o2);
     hy_im = hy;
     hz_im = hz;
+    pH += plane;
+    pE += plane;
+    pEps += plane;
   }
+  if (!REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
 }
 
 #endif  // !FDTDX_BUILD_H
@@ -563,332 +660,158 @@ __global__ void __launch_bounds__(256) yee_E_kernel(const StepParams P, const in
 // H half-step
 // ------------------------------------------------------------------------------------------------
 template <int V, int MUT, bool REV, bool SIG, bool MET, int PM>
-__global__ void __launch_bounds__(256) yee_H_kernel(const StepParams P, const int t) {
+__global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int nz = P.nz, ny = P.ny;
+  const bool active = (k0 < nz) && (j < ny);
+  const unsigned wmask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
-  const bool active = (k0 < P.nz) && (j < P.ny);
-  const int nz = P.nz, ny = P.ny;
   const long long plane = (long long)ny * nz;
   const long long N = plane * P.nx;
-  const float* __restrict__ Ex = P.E;
-  const float* __restrict__ Ey = P.E + N;
-  const float* __restrict__ Ez = P.E + 2 * N;
-  float* __restrict__ Hx = P.H;
-  float* __restrict__ Hy = P.H + N;
-  float* __restrict__ Hz = P.H + 2 * N;
-
   const long long row = (long long)j * nz + k0;
-  int jp = j + 1;
-  bool jp_ok = true;
-  if (jp >= ny) { if (P.wrap[1]) jp = 0; else jp_ok = false; }
-  const long long rowp = (long long)jp * nz + k0;
-  int kp = k0 + V;  // first cell after this thread's vector
-  bool kp_ok = true;
-  if (kp >= nz) { if (P.wrap[2]) kp = 0; else kp_ok = false; }
-  const long long rowk = (long long)j * nz + kp;
+
+  bool jp_ok = true, kp_ok = true;
+  long long djp = nz;
+  if (j == ny - 1) { if (P.wrap[1]) djp = -(long long)(ny - 1) * nz; else jp_ok = false; }
+  int dkp = V;  // first cell after this thread's vector
+  if (k0 + V >= nz) { if (P.wrap[2]) dkp = -k0; else kp_ok = false; }
   const bool last_lane = (lane == 31) || (k0 + V >= nz);
 
-  const AxisPmlDev& px = P.pml[0];
-  const AxisPmlDev& py = P.pml[1];
-  const AxisPmlDev& pz = P.pml[2];
-  // PM: 0 = no CPML slab on this plan (all CPML code compiled out), 1 = scalar z-slab path, 2 = 128-bit z-slab path
-  const bool in_y = (PM > 0) && active && (j < py.lo_len || j >= py.hi_start);
-  const int yside = (j >= py.hi_start) ? 1 : 0;
-  const int jl = yside ? j - py.hi_start : j;
-  const int yL = yside ? py.hi_len : py.lo_len;
-  const bool any_z = (PM > 0) && active && (k0 < pz.lo_len || k0 + V > pz.hi_start);
-  // PM == 2 (V == 4, even slab thickness): the lane's four cells are two 64-bit halves, each either
-  // entirely inside or entirely outside a z slab, so psi moves as float2 with no per-cell branch.
-  const int zside = (k0 + V > pz.hi_start) ? 1 : 0;
-  const bool zvec = (PM == 2) && any_z;
-  const bool zh0 = zvec && (zside ? (k0 >= pz.hi_start) : (k0 < pz.lo_len));
-  const bool zh1 = zvec && (zside ? (k0 + 2 >= pz.hi_start) : (k0 + 2 < pz.lo_len));
-  const long long zstride = (long long)ny * (zside ? pz.hi_len : pz.lo_len);
-  const long long zoff = (long long)j * (zside ? pz.hi_len : pz.lo_len) + (zside ? k0 - pz.hi_start : k0);
-  float* const pz1 = zside ? pz.psiH[1][0] : pz.psiH[0][0];
-  float* const pz2 = zside ? pz.psiH[1][1] : pz.psiH[0][1];
-  Vec<V> az = zerov<V>(), bz = zerov<V>(), kz = zerov<V>();
-  if (zvec) { az = ldv<V>(pz.aH + k0); bz = ldv<V>(pz.bH + k0); kz = ldv<V>(pz.kH + k0); }
+  FDTDX_CPML_SETUP(psiH, aH, bH, kH)
+
   float sFy = 1.0f;
-  float sFzv[V];
-#pragma unroll
-  for (int e = 0; e < V; ++e) sFzv[e] = 1.0f;
-  if (MET && active) {
+  Vec<V> sFz;
+  if (MET) {
     sFy = P.sF[1][j];
-#pragma unroll
-    for (int e = 0; e < V; ++e) sFzv[e] = P.sF[2][k0 + e];
+    sFz = ldv<V>(P.sF[2] + k0);
   }
+
+  const float* pE = P.E + (long long)ic0 * plane + row;
+  float* pH = P.H + (long long)ic0 * plane + row;
+  const float* pMu = (MUT >= 1) ? P.mu + (long long)ic0 * plane + row : nullptr;
 
   // register queue: E of the current plane is the "next" plane loaded one step earlier
-  Vec<V> ex = zerov<V>(), ey = zerov<V>(), ez = zerov<V>();
-  if (active) {
-    ex = ldv<V>(Ex + (long long)ic0 * plane + row);
-    ey = ldv<V>(Ey + (long long)ic0 * plane + row);
-    ez = ldv<V>(Ez + (long long)ic0 * plane + row);
-  }
+  Vec<V> ex = ldv<V>(pE), ey = ldv<V>(pE + N), ez = ldv<V>(pE + 2 * N);
 
+  if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
-    const long long base = (long long)i * plane;
-    Vec<V> ex_n = zerov<V>(), ey_n = zerov<V>(), ez_n = zerov<V>();
-    Vec<V> ex_jp = zerov<V>(), ez_jp = zerov<V>();
-    Vec<V> hx, hy, hz, im0, im1, im2;
-    if (active) {
-      if (i + 1 < P.nx) {
-        const long long bn = base + plane;
-        ey_n = ldv<V>(Ey + bn + row);
-        ez_n = ldv<V>(Ez + bn + row);
-        if (i + 1 < ic1) ex_n = ldv<V>(Ex + bn + row);
-      } else if (P.x_hi_mode == 1) {
-        ey_n = ldv<V>(Ey + row);
-        ez_n = ldv<V>(Ez + row);
-      } else if (P.x_hi_mode == 2) {
-        ey_n = ldv<V>(P.haloE + row);
-        ez_n = ldv<V>(P.haloE + plane + row);
-      }
-      if (jp_ok) {
-        ex_jp = ldv<V>(Ex + base + rowp);
-        ez_jp = ldv<V>(Ez + base + rowp);
-      }
-      hx = ldv<V>(Hx + base + row);
-      hy = ldv<V>(Hy + base + row);
-      hz = ldv<V>(Hz + base + row);
-      if (MUT >= 1) {
-        im0 = ldv<V>(P.mu + base + row);
-        if (MUT == 3) {
-          im1 = ldv<V>(P.mu + P.mu_cs + base + row);
-          im2 = ldv<V>(P.mu + 2 * P.mu_cs + base + row);
-        } else {
-          im1 = im0;
-          im2 = im0;
-        }
+    Vec<V> ex_n, ey_n, ez_n;
+    if (i + 1 < P.nx) {
+      ey_n = ldv<V>(pE + N + plane);
+      ez_n = ldv<V>(pE + 2 * N + plane);
+      if (i + 1 < ic1) ex_n = ldv<V>(pE + plane);
+    } else if (P.x_hi_mode == 1) {
+      ey_n = ldv<V>(P.E + N + row);
+      ez_n = ldv<V>(P.E + 2 * N + row);
+    } else if (P.x_hi_mode == 2) {
+      ey_n = ldv<V>(P.haloE + row);
+      ez_n = ldv<V>(P.haloE + plane + row);
+    } else {
+      ey_n = zerov<V>();
+      ez_n = zerov<V>();
+    }
+    Vec<V> ex_jp, ez_jp;
+    if (jp_ok) {
+      ex_jp = ldv<V>(pE + djp);
+      ez_jp = ldv<V>(pE + 2 * N + djp);
+    } else {
+      ex_jp = zerov<V>();
+      ez_jp = zerov<V>();
+    }
+    const Vec<V> hx = ldv<V>(pH), hy = ldv<V>(pH + N), hz = ldv<V>(pH + 2 * N);
+    Vec<V> im0, im1, im2;
+    if (MUT >= 1) {
+      im0 = ldv<V>(pMu);
+      if (MUT == 3) {
+        im1 = ldv<V>(pMu + P.mu_cs);
+        im2 = ldv<V>(pMu + 2 * P.mu_cs);
+      } else {
+        im1 = im0;
+        im2 = im0;
       }
     }
-    // CPML auxiliary fields are fetched together with the field loads (their addresses depend on
-    // indices only), so their latency overlaps instead of serialising behind the curl.
-    const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);
-    Vec<V> psx1 = zerov<V>(), psx2 = zerov<V>(), psy1 = zerov<V>(), psy2 = zerov<V>();
-    float psz1[V], psz2[V];
-    float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr;
-    if (active) {
-      if (in_x) {
-        const int side = (i >= px.hi_start) ? 1 : 0;
-        const int il = side ? i - px.hi_start : i;
-        const long long pidx = ((long long)il * ny + j) * nz + k0;
-        qx1 = (side ? px.psiH[1][0] : px.psiH[0][0]) + pidx;
-        qx2 = (side ? px.psiH[1][1] : px.psiH[0][1]) + pidx;
-        psx1 = ldv<V>(qx1);
-        psx2 = ldv<V>(qx2);
-      }
-      if (in_y) {
-        const long long pidx = ((long long)i * yL + jl) * nz + k0;
-        qy1 = (yside ? py.psiH[1][0] : py.psiH[0][0]) + pidx;
-        qy2 = (yside ? py.psiH[1][1] : py.psiH[0][1]) + pidx;
-        psy1 = ldv<V>(qy1);
-        psy2 = ldv<V>(qy2);
-      }
-      if (zvec) {
-        if constexpr (V == 4) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) { psz1[e] = 0.0f; psz2[e] = 0.0f; }
-          const float* q1 = pz1 + i * zstride + zoff;
-          const float* q2 = pz2 + i * zstride + zoff;
-          if (zh0) {
-            const float2 t1 = *reinterpret_cast<const float2*>(q1), t2 = *reinterpret_cast<const float2*>(q2);
-            psz1[0] = t1.x; psz1[1] = t1.y; psz2[0] = t2.x; psz2[1] = t2.y;
-          }
-          if (zh1) {
-            const float2 t1 = *reinterpret_cast<const float2*>(q1 + 2), t2 = *reinterpret_cast<const float2*>(q2 + 2);
-            psz1[2] = t1.x; psz1[3] = t1.y; psz2[2] = t2.x; psz2[3] = t2.y;
-          }
-        }
-      } else if (any_z) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int k = k0 + e;
-          psz1[e] = 0.0f;
-          psz2[e] = 0.0f;
-          if (k < pz.lo_len || k >= pz.hi_start) {
-            const int side = (k >= pz.hi_start) ? 1 : 0;
-            const int kl = side ? k - pz.hi_start : k;
-            const int L = side ? pz.hi_len : pz.lo_len;
-            const long long pidx = ((long long)i * ny + j) * L + kl;
-            psz1[e] = (side ? pz.psiH[1][0] : pz.psiH[0][0])[pidx];
-            psz2[e] = (side ? pz.psiH[1][1] : pz.psiH[0][1])[pidx];
-          }
-        }
-      }
-      // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
-      if (i + FDTDX_PF_DIST < ic1) {
-        const long long pb = base + FDTDX_PF_DIST * plane + row;
-        prefetch_l2(Hx + pb); prefetch_l2(Hy + pb); prefetch_l2(Hz + pb);
-        prefetch_l2(Ex + pb); prefetch_l2(Ey + pb); prefetch_l2(Ez + pb);
-        if (MUT >= 1) prefetch_l2(P.mu + pb);
-        if (MUT == 3) { prefetch_l2(P.mu + P.mu_cs + pb); prefetch_l2(P.mu + 2 * P.mu_cs + pb); }
-      }
-      if (FDTDX_PF_L1 && i + 2 < ic1) {
-        const long long pb = base + 2 * plane + row;
-        prefetch_l1(Ex + pb); prefetch_l1(Ey + pb); prefetch_l1(Ez + pb);
-        const long long ph = base + plane + row;
-        prefetch_l1(Hx + ph); prefetch_l1(Hy + ph); prefetch_l1(Hz + ph);
-      }
+    FDTDX_CPML_LOADS(psiH)
+    if (i + FDTDX_PF_DIST < ic1) {
+      const long long pb = FDTDX_PF_DIST * plane;
+      prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb);
+      prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
+      if (MUT >= 1) prefetch_l2(pMu + pb);
+      if (MUT == 3) { prefetch_l2(pMu + P.mu_cs + pb); prefetch_l2(pMu + 2 * P.mu_cs + pb); }
     }
-    float ex_r = __shfl_down_sync(0xffffffffu, ex.v[0], 1);
-    float ey_r = __shfl_down_sync(0xffffffffu, ey.v[0], 1);
+    float ex_r = __shfl_down_sync(wmask, ex.v[0], 1);
+    float ey_r = __shfl_down_sync(wmask, ey.v[0], 1);
     if (last_lane) {
-      ex_r = (active && kp_ok) ? Ex[base + rowk] : 0.0f;
-      ey_r = (active && kp_ok) ? Ey[base + rowk] : 0.0f;
+      ex_r = kp_ok ? pE[dkp] : 0.0f;
+      ey_r = kp_ok ? pE[N + dkp] : 0.0f;
     }
-    if (active) {
-      float sFx = 1.0f;
-      if (MET) sFx = P.sF[0][i];
-      Vec<V> Kx, Ky, Kz;
-      Vec<V> dxEz_v, dxEy_v, dyEx_v, dyEz_v, dzEy_v, dzEx_v;
+    float sFx = 1.0f;
+    if (MET) sFx = P.sF[0][i];
+    Vec<V> Kx, Ky, Kz;
+    Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float ex_kp = (e == V - 1) ? ex_r : ex.v[e == V - 1 ? e : e + 1];
-        float ey_kp = (e == V - 1) ? ey_r : ey.v[e == V - 1 ? e : e + 1];
-        const float sFz = sFzv[e];
-        float dyEz = ez_jp.v[e] - ez.v[e];
-        float dzEy = ey_kp - ey.v[e];
-        float dzEx = ex_kp - ex.v[e];
-        float dxEz = ez_n.v[e] - ez.v[e];
-        float dxEy = ey_n.v[e] - ey.v[e];
-        float dyEx = ex_jp.v[e] - ex.v[e];
-        if (MET) {
-          dyEz *= sFy; dzEy *= sFz; dzEx *= sFz; dxEz *= sFx; dxEy *= sFx; dyEx *= sFy;
-        }
-        Kx.v[e] = dyEz - dzEy;
-        Ky.v[e] = dzEx - dxEz;
-        Kz.v[e] = dxEy - dyEx;
-        dxEz_v.v[e] = dxEz; dxEy_v.v[e] = dxEy; dyEx_v.v[e] = dyEx;
-        dyEz_v.v[e] = dyEz; dzEy_v.v[e] = dzEy; dzEx_v.v[e] = dzEx;
+    for (int e = 0; e < V; ++e) {
+      const float ex_kp = (e == V - 1) ? ex_r : ex.v[e == V - 1 ? e : e + 1];
+      const float ey_kp = (e == V - 1) ? ey_r : ey.v[e == V - 1 ? e : e + 1];
+      float dyEz = ez_jp.v[e] - ez.v[e];
+      float dzEy = ey_kp - ey.v[e];
+      float dzEx = ex_kp - ex.v[e];
+      float dxEz = ez_n.v[e] - ez.v[e];
+      float dxEy = ey_n.v[e] - ey.v[e];
+      float dyEx = ex_jp.v[e] - ex.v[e];
+      if (MET) {
+        dyEz *= sFy; dzEy *= sFz.v[e]; dzEx *= sFz.v[e]; dxEz *= sFx; dxEy *= sFx; dyEx *= sFy;
       }
-      if (in_x) {
-        const float a = px.aH[i], b = px.bH[i], km1 = px.kH[i];
+      Kx.v[e] = dyEz - dzEy;
+      Ky.v[e] = dzEx - dxEz;
+      Kz.v[e] = dxEy - dyEx;
+      dxFz.v[e] = dxEz; dxFy.v[e] = dxEy; dyFx.v[e] = dyEx;
+      dyFz.v[e] = dyEz; dzFy.v[e] = dzEy; dzFx.v[e] = dzEx;
+    }
+    FDTDX_CPML_BLOCK(psiH, aH, bH, kH)
+    Vec<V> o0, o1, o2;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          float c1, c2;  // axis 0: d1 = dx F_z, d2 = dx F_y; corrects K_y (-) and K_z (+)
-          cpml_cell(a, b, km1, px.kappa_one, P.simulate && !REV, dxEz_v.v[e], dxEy_v.v[e], &psx1.v[e], &psx2.v[e], &c1, &c2);
-          Ky.v[e] = Ky.v[e] - c1;
-          Kz.v[e] = Kz.v[e] + c2;
-        }
-        if (P.simulate && !REV && P.psi_store) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }
-      }
-      if (in_y) {
-        const float a = py.aH[j], b = py.bH[j], km1 = py.kH[j];
+    for (int e = 0; e < V; ++e) {
+      const float Ho[3] = {hx.v[e], hy.v[e], hz.v[e]};
+      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
+      float im[3];
+      if (MUT >= 1) { im[0] = im0.v[e]; im[1] = im1.v[e]; im[2] = im2.v[e]; }
+      else { im[0] = im[1] = im[2] = P.inv_mu_scalar; }
+      float Hn[3];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          float c1, c2;  // axis 1: d1 = dy F_x, d2 = dy F_z; corrects K_z (-) and K_x (+)
-          cpml_cell(a, b, km1, py.kappa_one, P.simulate && !REV, dyEx_v.v[e], dyEz_v.v[e], &psy1.v[e], &psy2.v[e], &c1, &c2);
-          Kz.v[e] = Kz.v[e] - c1;
-          Kx.v[e] = Kx.v[e] + c2;
-        }
-        if (P.simulate && !REV && P.psi_store) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }
-      }
-      if (zvec) {
-        if constexpr (V == 4) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            if ((e < 2) ? zh0 : zh1) {
-              float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
-              cpml_cell(az.v[e], bz.v[e], kz.v[e], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e], &psz1[e], &psz2[e], &c1, &c2);
-              Kx.v[e] = Kx.v[e] - c1;
-              Ky.v[e] = Ky.v[e] + c2;
-            }
+      for (int c = 0; c < 3; ++c) {
+        if (SIG) {
+          const float sg = P.sigH[c * P.sigH_cs + (pH - P.H) + e];
+          const float s = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
+          if (REV) {
+            const float Hc = Ho[c] * (1.0f + s);
+            Hn[c] = (Hc + (P.cour * K[c]) * im[c]) / (1.0f - s);
+          } else {
+            const float H1 = (1.0f - s) * Ho[c] - (P.cour * K[c]) * im[c];
+            Hn[c] = H1 / (1.0f + s);
           }
-          if (P.simulate && !REV && P.psi_store) {
-            float* q1 = pz1 + i * zstride + zoff;
-            float* q2 = pz2 + i * zstride + zoff;
-            if (zh0) {
-              *reinterpret_cast<float2*>(q1) = make_float2(psz1[0], psz1[1]);
-              *reinterpret_cast<float2*>(q2) = make_float2(psz2[0], psz2[1]);
-            }
-            if (zh1) {
-              *reinterpret_cast<float2*>(q1 + 2) = make_float2(psz1[2], psz1[3]);
-              *reinterpret_cast<float2*>(q2 + 2) = make_float2(psz2[2], psz2[3]);
-            }
-          }
-        }
-      } else if (any_z) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int k = k0 + e;
-          if (k < pz.lo_len || k >= pz.hi_start) {
-            const int side = (k >= pz.hi_start) ? 1 : 0;
-            const int kl = side ? k - pz.hi_start : k;
-            const int L = side ? pz.hi_len : pz.lo_len;
-            const long long pidx = ((long long)i * ny + j) * L + kl;
-            float c1, c2;  // axis 2: d1 = dz F_y, d2 = dz F_x; corrects K_x (-) and K_y (+)
-            cpml_cell(pz.aH[k], pz.bH[k], pz.kH[k], pz.kappa_one, P.simulate && !REV, dzEy_v.v[e], dzEx_v.v[e],
-                      &psz1[e], &psz2[e], &c1, &c2);
-            if (P.simulate && !REV && P.psi_store) {
-              (side ? pz.psiH[1][0] : pz.psiH[0][0])[pidx] = psz1[e];
-              (side ? pz.psiH[1][1] : pz.psiH[0][1])[pidx] = psz2[e];
-            }
-            Kx.v[e] = Kx.v[e] - c1;
-            Ky.v[e] = Ky.v[e] + c2;
-          }
-        }
-      }
-      const bool src_hit = (P.n_src > 0) && any_src_hits(P.src, P.n_src, i, j, k0, V);
-      Vec<V> oh[3];
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float Ho[3] = {hx.v[e], hy.v[e], hz.v[e]};
-        const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-        float im[3];
-        if (MUT >= 1) { im[0] = im0.v[e]; im[1] = im1.v[e]; im[2] = im2.v[e]; }
-        else { im[0] = im[1] = im[2] = P.inv_mu_scalar; }
-        const long long cell = base + row + e;
-        float Hn[3];
-        if (REV) {
-          if (src_hit) inject_H(P.src, P.n_src, P.dt, t, true, i, j, k0 + e, im[0], im[1], im[2], &Ho[0], &Ho[1], &Ho[2]);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float Hc = Ho[c];
-            if (SIG) {
-              float sg = P.sigH[c * P.sigH_cs + cell];
-              float s = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
-              Hc = Hc * (1.0f + s);
-              Hn[c] = (Hc + (P.cour * K[c]) * im[c]) / (1.0f - s);
-            } else {
-              Hn[c] = Hc + (P.cour * K[c]) * im[c];
-            }
-          }
+        } else if (REV) {
+          Hn[c] = Ho[c] + (P.cour * K[c]) * im[c];
         } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            if (SIG) {
-              float sg = P.sigH[c * P.sigH_cs + cell];
-              float s = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
-              float H1 = (1.0f - s) * Ho[c] - (P.cour * K[c]) * im[c];
-              Hn[c] = H1 / (1.0f + s);
-            } else {
-              Hn[c] = Ho[c] - (P.cour * K[c]) * im[c];
-            }
-          }
-          if (src_hit) inject_H(P.src, P.n_src, P.dt, t, false, i, j, k0 + e, im[0], im[1], im[2], &Hn[0], &Hn[1], &Hn[2]);
+          Hn[c] = Ho[c] - (P.cour * K[c]) * im[c];
         }
-        for (int w = 0; w < P.n_walls; ++w) {
-          const WallDev W = P.walls[w];
-          if (W.kind == 1 && in_box(W.lo, W.hi, i, j, k0 + e)) {
-            if (W.axis != 0) Hn[0] = 0.0f;
-            if (W.axis != 1) Hn[1] = 0.0f;
-            if (W.axis != 2) Hn[2] = 0.0f;
-          }
-        }
-        oh[0].v[e] = Hn[0]; oh[1].v[e] = Hn[1]; oh[2].v[e] = Hn[2];
       }
-      stv<V>(Hx + base + row, oh[0]);
-      stv<V>(Hy + base + row, oh[1]);
-      stv<V>(Hz + base + row, oh[2]);
+      o0.v[e] = Hn[0]; o1.v[e] = Hn[1]; o2.v[e] = Hn[2];
     }
+    if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
+    stv<V>(pH, o0);
+    stv<V>(pH + N, o1);
+    stv<V>(pH + 2 * N, o2);
     ex = ex_n;
     ey = ey_n;
     ez = ez_n;
+    pE += plane;
+    pH += plane;
+    if (MUT >= 1) pMu += plane;
   }
+  if (!REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
 }
 #endif  // !FDTDX_BUILD_E
