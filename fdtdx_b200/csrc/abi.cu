@@ -6,7 +6,13 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
 #include "../../include/fdtdx_b200.h"
+#include "tma_cfg.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "tensor_kernels.cuh"
@@ -76,6 +82,9 @@ struct FdtdxPlan {
   int p_parity = 0, e_parity = 0, h_parity = 0;
   long long launches = 0;
   int xchunk = 0, rows = 4;
+  int use_tma = -1;     // -1: decide from the environment (FDTDX_B200_TMA=0 disables), 0 / 1: forced
+  int xchunk_tma = 0;   // planes per CTA of the TMA-staged kernels (0: heuristic)
+  std::map<std::tuple<const void*, int, int>, CUtensorMap> tmaps;  // (base, components, box kind) -> map
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
 };
@@ -370,6 +379,12 @@ extern "C" int fdtdx_b200_set_parity(FdtdxPlan* p, int pp, int ep, int hp) {
   return FDTDX_OK;
 }
 extern "C" long long fdtdx_b200_launch_count(FdtdxPlan* p) { return p ? p->launches : 0; }
+extern "C" int fdtdx_b200_set_tma(FdtdxPlan* p, int enable, int xchunk_tma) {
+  if (!p) return fail(FDTDX_EINVAL, "set_tma: null plan");
+  p->use_tma = enable;
+  p->xchunk_tma = xchunk_tma;
+  return FDTDX_OK;
+}
 extern "C" int fdtdx_b200_set_tuning(FdtdxPlan* p, int xchunk, int rows) {
   if (!p) return fail(FDTDX_EINVAL, "null plan");
   p->xchunk = xchunk;
@@ -546,11 +561,17 @@ static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
   return true;
 }
 
-// kernel dispatchers live in yee_E.cu / yee_H.cu (separate translation units, built in parallel)
+// kernel dispatchers live in yee_E*.cu / yee_H*.cu (separate translation units, built in parallel)
 void fdtdx_dispatch_E4(const StepParams& P, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
 void fdtdx_dispatch_E1(const StepParams& P, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
 void fdtdx_dispatch_H4(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
 void fdtdx_dispatch_H1(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
+struct alignas(64) TmaSet {
+  CUtensorMap fld_halo, fld_plain, mat_plain, xhalo;
+};
+cudaError_t fdtdx_dispatch_E4_tma(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
+                                  cudaStream_t st);
+cudaError_t fdtdx_dispatch_H4_tma(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
 
 // 0: no CPML slab on this rank; 1: scalar z-slab accesses; 2: 128-bit z-slab accesses
 static int pml_mode(const FdtdxPlan* p, const StepParams& P) {
@@ -562,15 +583,99 @@ static int pml_mode(const FdtdxPlan* p, const StepParams& P) {
   return P.pml[2].vec_ok ? 2 : 1;
 }
 
+// ---- TMA-staged path (yee_tma.cuh) --------------------------------------------------------------
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)q;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// kind 0: halo box (TZ+4, R+1), kind 1: plain box (TZ, R).  Arrays are (C, nx, ny, nz) float32.
+static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind, CUtensorMap* out) {
+  auto key = std::make_tuple(base, comps * 4 + (nx == p->nx ? 0 : 1), kind);
+  auto it = p->tmaps.find(key);
+  if (it != p->tmaps.end()) { *out = it->second; return FDTDX_OK; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)p->nz, (cuuint64_t)p->ny, (cuuint64_t)nx, (cuuint64_t)comps};
+  const cuuint64_t strides[3] = {(cuuint64_t)p->nz * 4, (cuuint64_t)p->nz * p->ny * 4, (cuuint64_t)p->nz * p->ny * nx * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)(kind == 0 ? 128 + 4 : 128), (cuuint32_t)(kind == 0 ? FDTDX_TMA_R + 1 : FDTDX_TMA_R), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  p->tmaps[key] = m;
+  *out = m;
+  return FDTDX_OK;
+}
+
+static bool tma_wanted(const FdtdxPlan* p) {
+  if (p->use_tma >= 0) return p->use_tma != 0;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("FDTDX_B200_TMA");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env != 0;
+}
+// The staged kernels cover 128-bit-capable grids whose y / z halos are zero (PML, PEC, PMC faces).
+static bool can_tma(const FdtdxPlan* p, const StepParams& P, bool v4) {
+  if (!v4 || !tma_wanted(p) || p->wrap[1] || p->wrap[2]) return false;
+  if ((long long)p->nz * p->ny * 4 >= (1LL << 40) || p->ny < 1) return false;
+  return encode_tiled_fn() != nullptr;
+}
+static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
+  int xc = p->xchunk_tma;
+  if (xc <= 0) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("FDTDX_B200_TMA_XCHUNK"); env = e ? atoi(e) : 0; }
+    xc = env;
+  }
+  if (xc <= 0) {
+    // >= ~8 waves of 148 SMs x 2 resident CTAs, chunks of at least 32 planes (ring fill is ~3 planes)
+    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R);
+    const long long want = (148LL * 2 * 8 + tiles - 1) / tiles;
+    xc = (int)std::max<long long>(32, (P.x_end - P.x_begin) / std::max(1LL, want));
+  }
+  return std::max(1, std::min(xc, P.x_end - P.x_begin));
+}
+
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
   const int V = v4 ? 4 : 1;
-  dim3 b(32, p->rows);
-  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
-  if (v4) fdtdx_dispatch_E4(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
-  else fdtdx_dispatch_E1(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+  if (can_tma(p, P, v4)) {
+    TmaSet M;
+    memset(&M, 0, sizeof(M));
+    int rc;
+    if ((rc = get_tmap(p, P.H, 3, p->nx, 0, &M.fld_halo))) return rc;
+    if ((rc = get_tmap(p, P.E, 3, p->nx, 1, &M.fld_plain))) return rc;
+    if ((rc = get_tmap(p, P.eps, p->eps_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain))) return rc;
+    M.xhalo = M.fld_halo;
+    StepParams Q = P;
+    Q.xchunk = tma_chunk(p, P);
+    dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
+  } else {
+    dim3 b(32, p->rows);
+    dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
+    if (v4) fdtdx_dispatch_E4(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+    else fdtdx_dispatch_E1(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+  }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
@@ -579,10 +684,26 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
 static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
   const int V = v4 ? 4 : 1;
-  dim3 b(32, p->rows);
-  dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
-  if (v4) fdtdx_dispatch_H4(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
-  else fdtdx_dispatch_H1(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+  if (can_tma(p, P, v4)) {
+    TmaSet M;
+    memset(&M, 0, sizeof(M));
+    int rc;
+    if ((rc = get_tmap(p, P.E, 3, p->nx, 0, &M.fld_halo))) return rc;
+    if ((rc = get_tmap(p, P.H, 3, p->nx, 1, &M.fld_plain))) return rc;
+    M.mat_plain = M.fld_plain;
+    if (p->mu_tier > 0 && (rc = get_tmap(p, P.mu, p->mu_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain))) return rc;
+    M.xhalo = M.fld_halo;
+    if (P.x_hi_mode == 2 && (rc = get_tmap(p, P.haloE, 1, 2, 0, &M.xhalo))) return rc;
+    StepParams Q = P;
+    Q.xchunk = tma_chunk(p, P);
+    dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
+  } else {
+    dim3 b(32, p->rows);
+    dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
+    if (v4) fdtdx_dispatch_H4(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+    else fdtdx_dispatch_H1(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+  }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;

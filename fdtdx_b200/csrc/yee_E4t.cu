@@ -1,0 +1,52 @@
+// TMA-staged E half-step: instantiations + dispatch (see yee_tma.cuh).
+#define FDTDX_BUILD_E 1
+#include "yee_tma.cuh"
+#include "tma_cfg.h"
+
+template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
+static cudaError_t go_E(const StepParams& P, const TmaSet& M, int t, dim3 g, cudaStream_t st) {
+  constexpr int R = FDTDX_TMA_R, S = FDTDX_TMA_S;
+  constexpr int smem = tma_smem_bytes<R, TIER, S>();
+  auto k = yee_E_tma<TIER, REV, SIG, ADE, MET, PM, R, S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k<<<g, dim3(32, R), smem, st>>>(P, M, t);
+  return cudaSuccess;
+}
+
+template <int TIER, bool REV, int PM>
+static cudaError_t launch_E3(const StepParams& P, const TmaSet& M, int t, bool sig, bool ade, bool met, dim3 g, cudaStream_t st) {
+#define GO(S_, A_, M_) return go_E<TIER, REV, S_, A_, M_, PM>(P, M, t, g, st)
+  if constexpr (REV) {
+    if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
+    else { if (met) GO(false, false, true); else GO(false, false, false); }
+  } else {
+    if (ade) {
+      if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
+      else { if (met) GO(false, true, true); else GO(false, true, false); }
+    } else {
+      if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
+      else { if (met) GO(false, false, true); else GO(false, false, false); }
+    }
+  }
+#undef GO
+}
+
+template <int TIER, bool REV>
+static cudaError_t launch_E2(const StepParams& P, const TmaSet& M, int t, int pm, bool sig, bool ade, bool met, dim3 g, cudaStream_t st) {
+  if (pm == 0) return launch_E3<TIER, REV, 0>(P, M, t, sig, ade, met, g, st);
+  if (pm == 1) return launch_E3<TIER, REV, 1>(P, M, t, sig, ade, met, g, st);
+  return launch_E3<TIER, REV, 2>(P, M, t, sig, ade, met, g, st);
+}
+
+cudaError_t fdtdx_dispatch_E4_tma(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
+                                  cudaStream_t st) {
+  if (tier == 1) return rev ? launch_E2<1, true>(P, M, t, pm, sig, ade, met, g, st) : launch_E2<1, false>(P, M, t, pm, sig, ade, met, g, st);
+  return rev ? launch_E2<3, true>(P, M, t, pm, sig, ade, met, g, st) : launch_E2<3, false>(P, M, t, pm, sig, ade, met, g, st);
+}

@@ -1,0 +1,47 @@
+// TMA-staged H half-step: instantiations + dispatch (see yee_tma.cuh).
+#define FDTDX_BUILD_H 1
+#include "yee_tma.cuh"
+#include "tma_cfg.h"
+
+template <int MUT, bool REV, bool SIG, bool MET, int PM>
+static cudaError_t go_H(const StepParams& P, const TmaSet& M, int t, dim3 g, cudaStream_t st) {
+  constexpr int R = FDTDX_TMA_R, S = FDTDX_TMA_S;
+  constexpr int smem = tma_smem_bytes<R, MUT, S>();
+  auto k = yee_H_tma<MUT, REV, SIG, MET, PM, R, S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k<<<g, dim3(32, R), smem, st>>>(P, M, t);
+  return cudaSuccess;
+}
+
+template <int MUT, int PM>
+static cudaError_t launch_H3(const StepParams& P, const TmaSet& M, int t, bool rev, bool sig, bool met, dim3 g, cudaStream_t st) {
+#define GO(R_, S_, M_) return go_H<MUT, R_, S_, M_, PM>(P, M, t, g, st)
+  if (rev) {
+    if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
+    else { if (met) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    if (sig) { if (met) GO(false, true, true); else GO(false, true, false); }
+    else { if (met) GO(false, false, true); else GO(false, false, false); }
+  }
+#undef GO
+}
+
+template <int MUT>
+static cudaError_t launch_H2(const StepParams& P, const TmaSet& M, int t, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st) {
+  if (pm == 0) return launch_H3<MUT, 0>(P, M, t, rev, sig, met, g, st);
+  if (pm == 1) return launch_H3<MUT, 1>(P, M, t, rev, sig, met, g, st);
+  return launch_H3<MUT, 2>(P, M, t, rev, sig, met, g, st);
+}
+
+cudaError_t fdtdx_dispatch_H4_tma(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st) {
+  if (mt == 0) return launch_H2<0>(P, M, t, pm, rev, sig, met, g, st);
+  if (mt == 1) return launch_H2<1>(P, M, t, pm, rev, sig, met, g, st);
+  return launch_H2<3>(P, M, t, pm, rev, sig, met, g, st);
+}

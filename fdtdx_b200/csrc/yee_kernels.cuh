@@ -380,7 +380,7 @@ struct PmlLane {
 // Loads of the CPML auxiliary fields of plane i (issued together with the field loads: their
 // addresses depend on indices only, so the latencies overlap).
 #define FDTDX_CPML_LOADS(PSI)                                                                                          \
-  const bool in_x = (PM > 0) && (i < px.lo_len || i >= px.hi_start);                                                   \
+  const bool in_x = (PM > 0) && lane_ok && (i < px.lo_len || i >= px.hi_start);                                        \
   Vec<V> psx1, psx2, psy1, psy2, psz1, psz2;                                                                           \
   float *qx1 = nullptr, *qx2 = nullptr, *qy1 = nullptr, *qy2 = nullptr, *qz1 = nullptr, *qz2 = nullptr;                \
   if (PM > 0) {                                                                                                        \
@@ -426,7 +426,7 @@ struct PmlLane {
   PmlLane<V> L;                                                                                                        \
   L.in_y = false; L.any_z = false; L.zvec = false; L.zh0 = false; L.zh1 = false;                                       \
   float *py1 = nullptr, *py2 = nullptr, *pz1 = nullptr, *pz2 = nullptr;                                                \
-  if (PM > 0) {                                                                                                        \
+  if (PM > 0 && lane_ok) {                                                                                                        \
     L.in_y = (j < py.lo_len || j >= py.hi_start);                                                                      \
     if (L.in_y) {                                                                                                      \
       const int yside = (j >= py.hi_start) ? 1 : 0;                                                                    \
@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
   int dkm = -1;
   if (k0 == 0) { if (P.wrap[2]) dkm = nz - 1; else km_ok = false; }
 
+  const bool lane_ok = true;  // inactive lanes have already left
   FDTDX_CPML_SETUP(psiE, aE, bE, kE)
 
   float sBy = 1.0f;
@@ -681,6 +682,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
   if (k0 + V >= nz) { if (P.wrap[2]) dkp = -k0; else kp_ok = false; }
   const bool last_lane = (lane == 31) || (k0 + V >= nz);
 
+  const bool lane_ok = true;
   FDTDX_CPML_SETUP(psiH, aH, bH, kH)
 
   float sFy = 1.0f;

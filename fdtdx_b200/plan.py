@@ -477,6 +477,10 @@ class Plan:
     def set_tuning(self, xchunk: int = 0, rows: int = 0):
         check(self.lib.fdtdx_b200_set_tuning(self.h, int(xchunk), int(rows)))
 
+    def set_tma(self, enable: int = -1, xchunk_tma: int = 0):
+        """Select the TMA-staged (1) or register-marching (0) half-step kernels; -1 follows FDTDX_B200_TMA."""
+        check(self.lib.fdtdx_b200_set_tma(self.h, int(enable), int(xchunk_tma)))
+
     def finish(self, arrays):
         """Return the container whose leaves hold the *current* state after ping-pong passes."""
         pp, ep, hp = self.parity()

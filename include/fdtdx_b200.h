@@ -192,6 +192,11 @@ int fdtdx_b200_set_parity(FdtdxPlan* plan, int p_parity, int e_parity, int h_par
 long long fdtdx_b200_launch_count(FdtdxPlan* plan);
 /* Tuning knob: x-chunk length of the marching kernels (0 = auto). */
 int fdtdx_b200_set_tuning(FdtdxPlan* plan, int xchunk, int rows_per_block);
+/* Kernel-path selection for the E/H half-steps.  enable: 1 = TMA-staged shared-memory pipeline (default
+ * where applicable: Nz % 4 == 0, 16-byte aligned buffers, non-periodic y/z), 0 = register-marching kernels,
+ * -1 = follow the FDTDX_B200_TMA environment variable.  xchunk_tma: x planes per CTA (0 = heuristic).
+ * Pure tuning: results are bit-identical on both paths.  (No reference counterpart: XLA picks its own fusion.) */
+int fdtdx_b200_set_tma(FdtdxPlan* plan, int enable, int xchunk_tma);
 
 /* Host-buffer convenience used for end-to-end timing: copies E,H,inv_eps from HOST memory into the
  * bound device buffers, runs n forward steps, copies E,H back.  Sizes in bytes are returned. */
