@@ -292,7 +292,7 @@ def main():
         achieved = bytes_E / (ms_E * 1e-3) / 1e9
         roofline = {
             "bound": "hbm",
-            "kernel": "yee_E_kernel (E half-step: curl_H + CPML + material update + source + PEC)",
+            "kernel": "yee_E_tma (E half-step: TMA-staged curl_H + CPML + material update + PEC; sources in a cold pass)",
             "achieved": achieved,
             "peak": hbm_peak,
             "unit": "GB/s",

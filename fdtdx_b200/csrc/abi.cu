@@ -624,12 +624,8 @@ static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind,
 
 static bool tma_wanted(const FdtdxPlan* p) {
   if (p->use_tma >= 0) return p->use_tma != 0;
-  static int env = -1;
-  if (env < 0) {
-    const char* e = getenv("FDTDX_B200_TMA");
-    env = (e && e[0] == '0') ? 0 : 1;
-  }
-  return env != 0;
+  const char* e = getenv("FDTDX_B200_TMA");  // read per launch: tests flip it between plans
+  return !(e && e[0] == '0');
 }
 // The staged kernels cover 128-bit-capable grids whose y / z halos are zero (PML, PEC, PMC faces).
 static bool can_tma(const FdtdxPlan* p, const StepParams& P, bool v4) {
@@ -640,17 +636,16 @@ static bool can_tma(const FdtdxPlan* p, const StepParams& P, bool v4) {
 static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
   int xc = p->xchunk_tma;
   if (xc <= 0) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("FDTDX_B200_TMA_XCHUNK"); env = e ? atoi(e) : 0; }
-    xc = env;
+    const char* e = getenv("FDTDX_B200_TMA_XCHUNK");
+    xc = e ? atoi(e) : 0;
   }
   if (xc <= 0) {
-    // >= ~8 waves of 148 SMs x 2 resident CTAs, chunks of at least 32 planes (ring fill is ~3 planes)
-    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R);
-    const long long want = (148LL * 2 * 8 + tiles - 1) / tiles;
-    xc = (int)std::max<long long>(32, (P.x_end - P.x_begin) / std::max(1LL, want));
+    // Measured on B200 (scripts/sweep_tma.sh): 6-10 planes per CTA is the optimum on 512^3 and on the
+    // coupler grid.  Short chunks keep the ~300 resident CTAs inside one narrow x window (same DRAM
+    // pages, halo rows shared through L2); the 3-plane ring fill costs less than the drift of long chunks.
+    xc = 8;
   }
-  return std::max(1, std::min(xc, P.x_end - P.x_begin));
+  return std::max(1, std::min(std::min(xc, 64), P.x_end - P.x_begin));  // 64 = FDTDX_TMA_XC_MAX
 }
 
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {

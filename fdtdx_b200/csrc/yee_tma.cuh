@@ -21,6 +21,12 @@
 
 #define FDTDX_TMA_TZ 128                 // z cells per tile: one warp x float4
 #define FDTDX_TMA_HZ (FDTDX_TMA_TZ + 4)  // halo tile width: one 16-byte pad column group
+#define FDTDX_TMA_XC_MAX 64              // longest x chunk (planes per CTA) the per-plane scalar table holds
+// tail of the dynamic shared memory, in floats: [full barriers 2*S <= 16][arrivals <= 8][pad][ztab 3*128][xs XC_MAX]
+#define FDTDX_TMA_TAIL_ARR 16
+#define FDTDX_TMA_TAIL_ZTAB 32
+#define FDTDX_TMA_TAIL_XS (FDTDX_TMA_TAIL_ZTAB + 3 * FDTDX_TMA_TZ)
+#define FDTDX_TMA_TAIL_F (FDTDX_TMA_TAIL_XS + FDTDX_TMA_XC_MAX)
 #ifndef FDTDX_TMA_MAXREG
 #define FDTDX_TMA_MAXREG 128  // R * 32 = 256 threads x 128 registers: two CTAs per SM
 #endif
@@ -41,7 +47,8 @@ struct TmaGeom {
 };
 template <int R, int NMAT, int S>
 constexpr int tma_smem_bytes() {
-  return S * (3 * TmaGeom<R>::HALO_B + (3 + NMAT) * TmaGeom<R>::PLAIN_B) + S * 8 + S * 4;  // stages, full barriers, arrival counters
+  // stages, full barriers, arrival counters (padded to 16 B), z-slab coefficient tables, per-plane x scale
+  return S * (3 * TmaGeom<R>::HALO_B + (3 + NMAT) * TmaGeom<R>::PLAIN_B) + FDTDX_TMA_TAIL_F * 4;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -173,11 +180,8 @@ struct PmlT {
     }                                                                                                                  \
     if (PM == 2) {                                                                                                     \
       if (L.zh0 || L.zh1) {                                                                                            \
-        Vec<V> az = ldv<V>(pz.AT + k0), bz = ldv<V>(pz.BT + k0), kz = zerov<V>();                                      \
-        if (!pz.kappa_one) kz = ldv<V>(pz.KT + k0);                                                                    \
-        if (!P.simulate) {                                                                                             \
-          _Pragma("unroll") for (int e = 0; e < V; ++e) { az.v[e] = 0.0f; bz.v[e] = 1.0f; }                            \
-        }                                                                                                              \
+        const Vec<V> az = lds4(ztab + lane * V), bz = lds4(ztab + FDTDX_TMA_TZ + lane * V);                            \
+        const Vec<V> kz = lds4(ztab + 2 * FDTDX_TMA_TZ + lane * V);                                                    \
         float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                          \
         float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                          \
         if (L.zh0) {                                                                                                   \
@@ -268,13 +272,28 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   const int n_act = min(R, ny - j0);  // warps that own a row (the others leave before the loop)
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
-  int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + 2 * S);
+  int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
+  float* const ztab = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ZTAB;  // a, b, 1/kappa-1 of this tile's z cells
+  float* const xs = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_XS;      // metric x scale of this chunk's planes
 
   // reverse pass: update_E_reverse undoes the injection first; it must land in global memory before
   // the first tile load reads it (generic -> async proxy)
   if (REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
+  for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
+    const int tb = q / TZ, k = kt0 + (q - tb * TZ);
+    float v = 0.0f;
+    if (PM > 0 && k < nz) {
+      v = (tb == 0) ? P.pml[2].aE[k] : (tb == 1) ? P.pml[2].bE[k] : P.pml[2].kE[k];
+      if (!P.simulate && tb < 2) v = (tb == 0) ? 0.0f : 1.0f;
+    }
+    ztab[q] = v;
+  }
+  if (MET) {
+    for (int q = warp * 32 + lane; q < ic1 - ic0; q += R * 32) xs[q] = P.sB[0][ic0 + q];
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -340,7 +359,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       hy_l = sHy[-1];
     }
     float sBx = 1.0f;
-    if (MET) sBx = P.sB[0][i];
+    if (MET) sBx = xs[i - ic0];
     Vec<V> Kx, Ky, Kz;
     Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
@@ -518,11 +537,26 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   const int n_act = min(R, ny - j0);
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
-  int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + 2 * S);
+  int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
+  float* const ztab = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ZTAB;  // a, b, 1/kappa-1 of this tile's z cells
+  float* const xs = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_XS;      // metric x scale of this chunk's planes
 
   if (REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
+  for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
+    const int tb = q / TZ, k = kt0 + (q - tb * TZ);
+    float v = 0.0f;
+    if (PM > 0 && k < nz) {
+      v = (tb == 0) ? P.pml[2].aH[k] : (tb == 1) ? P.pml[2].bH[k] : P.pml[2].kH[k];
+      if (!P.simulate && tb < 2) v = (tb == 0) ? 0.0f : 1.0f;
+    }
+    ztab[q] = v;
+  }
+  if (MET) {
+    for (int q = warp * 32 + lane; q < ic1 - ic0; q += R * 32) xs[q] = P.sF[0][ic0 + q];
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -579,7 +613,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     const float* sbn = fdtdx_tma_smem + sn * STAGE_F;
     const Vec<V> ey_n = lds4(sbn + G::HALO_F + oh), ez_n = lds4(sbn + 2 * G::HALO_F + oh);
     float sFx = 1.0f;
-    if (MET) sFx = P.sF[0][i];
+    if (MET) sFx = xs[i - ic0];
     Vec<V> Kx, Ky, Kz;
     Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
