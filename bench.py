@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N>1: read neighbour planes in place over NVLink (peer) or exchange packed planes with NCCL send/recv")
     ap.add_argument("--cpu-cpl", type=int, default=5)
     ap.add_argument("--cpu-box-n", type=int, default=96)
     ap.add_argument("--cpu-steps", type=int, default=30)
@@ -232,7 +233,7 @@ def main():
         torch.cuda.synchronize()
 
     if world > 1:
-        runner = SlabRunner(objects, cfg, arrays, x_range, rank, world, overlap=not args.no_overlap)
+        runner = SlabRunner(objects, cfg, arrays, x_range, rank, world, overlap=not args.no_overlap, halo=args.halo)
         plan = runner.plan
         plan.set_tuning(args.xchunk, args.rows)
         step_fn = lambda t0, n: runner.run(t0, n, record_det)
@@ -373,7 +374,7 @@ def main():
                 "cells_total": cells_total,
                 "l2_policy": "inputs >> L2 (no flush needed)",
                 "detectors": record_det,
-                "halo_overlap": (not args.no_overlap) if world > 1 else None,
+                "halo": (("peer-memory reads over NVLink (CUDA IPC), no exchange" if runner.peer else f"NCCL send/recv, overlap={not args.no_overlap}") if world > 1 else None),
             },
             "clocks": clocks,
             "e2e": e2e,

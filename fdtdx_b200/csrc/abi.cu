@@ -82,6 +82,16 @@ struct FdtdxPlan {
   int p_parity = 0, e_parity = 0, h_parity = 0;
   long long launches = 0;
   int xchunk = 0, rows = 4;
+  // peer-memory halo (NVLink): neighbour field arrays + progress flags mapped through CUDA IPC
+  struct PeerLink {
+    float* field = nullptr;  // lo: neighbour's H (3,nx_peer,ny,nz); hi: neighbour's E
+    int* flags = nullptr;    // neighbour's {doneE, doneH} counters
+    int nx = 0;
+  } peer[2];
+  int* d_flags = nullptr;          // this rank's {doneE, doneH}
+  unsigned seqE = 0, seqH = 0;     // half-steps issued so far (identical on every rank)
+  bool peer_mode = false;
+  std::vector<std::pair<std::string, void*>> ipc_open;  // handle bytes -> mapped base
   int use_tma = -1;     // -1: decide from the environment (FDTDX_B200_TMA=0 disables), 0 / 1: forced
   int xchunk_tma = 0;   // planes per CTA of the TMA-staged kernels (0: heuristic)
   std::map<std::tuple<const void*, int, int>, CUtensorMap> tmaps;  // (base, components, box kind) -> map
@@ -139,6 +149,7 @@ extern "C" int fdtdx_b200_plan_create(FdtdxPlan** out, int nx, int ny, int nz, i
 }
 
 extern "C" int fdtdx_b200_plan_destroy(FdtdxPlan* p) {
+  if (p) for (auto& kv : p->ipc_open) cudaIpcCloseMemHandle(kv.second);
   if (!p) return FDTDX_OK;
   for (void* q : p->owned) cudaFree(q);
   delete p;
@@ -531,6 +542,21 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   }
   P.haloH = (const float*)p->slots[FDTDX_SLOT_HALO_H_LO][0];
   P.haloE = (const float*)p->slots[FDTDX_SLOT_HALO_E_HI][0];
+  P.haloH_cs = P.haloE_cs = (long long)p->ny * p->nz;
+  if (p->peer_mode) {
+    // read the neighbour's boundary plane in place: Hy of its last plane / Ey of its first plane
+    const long long plane = (long long)p->ny * p->nz;
+    if (p->halo_lo) {
+      const long long Np = plane * p->peer[0].nx;
+      P.haloH = p->peer[0].field + Np + (long long)(p->peer[0].nx - 1) * plane;
+      P.haloH_cs = Np;
+    }
+    if (p->halo_hi) {
+      const long long Np = plane * p->peer[1].nx;
+      P.haloE = p->peer[1].field + Np;
+      P.haloE_cs = Np;
+    }
+  }
   if (p->halo_lo && !P.haloH) return fail(FDTDX_EUNBOUND, "HALO_H_LO must be bound");
   if (p->halo_hi && !P.haloE) return fail(FDTDX_EUNBOUND, "HALO_E_HI must be bound");
   int xc = p->xchunk;
@@ -622,6 +648,26 @@ static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind,
   return FDTDX_OK;
 }
 
+// (2, ny, nz)-shaped view with an arbitrary component stride (packed staging buffer or a peer field array)
+static int get_xhalo_tmap(FdtdxPlan* p, const void* base, long long comp_stride, CUtensorMap* out) {
+  auto key = std::make_tuple(base, (int)(comp_stride % 2147483647LL), 2);
+  auto it = p->tmaps.find(key);
+  if (it != p->tmaps.end()) { *out = it->second; return FDTDX_OK; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)p->nz, (cuuint64_t)p->ny, 2, 1};
+  const cuuint64_t strides[3] = {(cuuint64_t)p->nz * 4, (cuuint64_t)comp_stride * 4, (cuuint64_t)comp_stride * 8};
+  const cuuint32_t box[4] = {128 + 4, FDTDX_TMA_R + 1, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled (x halo) failed (" + std::to_string((int)r) + ")");
+  p->tmaps[key] = m;
+  *out = m;
+  return FDTDX_OK;
+}
+
 static bool tma_wanted(const FdtdxPlan* p) {
   if (p->use_tma >= 0) return p->use_tma != 0;
   const char* e = getenv("FDTDX_B200_TMA");  // read per launch: tests flip it between plans
@@ -688,7 +734,7 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     M.mat_plain = M.fld_plain;
     if (p->mu_tier > 0 && (rc = get_tmap(p, P.mu, p->mu_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain))) return rc;
     M.xhalo = M.fld_halo;
-    if (P.x_hi_mode == 2 && (rc = get_tmap(p, P.haloE, 1, 2, 0, &M.xhalo))) return rc;
+    if (P.x_hi_mode == 2 && (rc = get_xhalo_tmap(p, P.haloE, P.haloE_cs, &M.xhalo))) return rc;
     StepParams Q = P;
     Q.xchunk = tma_chunk(p, P);
     dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
@@ -832,13 +878,41 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
 
 #include "tensor_launch.inl"
 
+// ---- peer-memory halo: stream-ordered progress flags ----------------------------------------------
+// A half-step that reads a neighbour's boundary plane in place must not start before the neighbour
+// has finished the half-step that produced it, and must finish before the neighbour overwrites it.
+// Both orders reduce to one rule per half-step: E waits for the low
+// neighbour's doneH == (H half-steps issued so far), H waits for the high neighbour's
+// doneE == (E half-steps issued so far).  The waits / signals are one-thread kernels on the caller's
+// stream, so the whole multi-step run stays a single asynchronous submission per rank.
+__global__ void peer_wait_kernel(const int* flag, int target) {
+  unsigned ns = 32;
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v - target >= 0) break;
+    __nanosleep(ns);
+    if (ns < 1024) ns *= 2;
+  }
+}
+__global__ void peer_signal_kernel(int* flag, int value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
 static int step_E(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) {
   if (p->eps_tier == 9 || p->sigE_tier == 9) return tensor_step(p, t, simulate, rev, /*is_E=*/true, st);
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
+  if (p->peer_mode && p->halo_lo) peer_wait_kernel<<<1, 1, 0, st>>>(p->peer[0].flags + 1, (int)p->seqH);
   rc = launch_E(p, P, t, rev, st);
   if (rc) return rc;
+  if (p->peer_mode) {
+    p->seqE++;
+    peer_signal_kernel<<<1, 1, 0, st>>>(p->d_flags, (int)p->seqE);
+    CUDA_TRY(cudaGetLastError());
+  }
   if (!rev && p->n_poles > 0) p->p_parity ^= 1;
   return FDTDX_OK;
 }
@@ -848,7 +922,89 @@ static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
-  return launch_H(p, P, t, rev, st);
+  if (p->peer_mode && p->halo_hi) peer_wait_kernel<<<1, 1, 0, st>>>(p->peer[1].flags, (int)p->seqE);
+  rc = launch_H(p, P, t, rev, st);
+  if (rc) return rc;
+  if (p->peer_mode) {
+    p->seqH++;
+    peer_signal_kernel<<<1, 1, 0, st>>>(p->d_flags + 1, (int)p->seqH);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return FDTDX_OK;
+}
+
+// ---- peer-memory halo: CUDA IPC plumbing -----------------------------------------------------------
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+static GetAddressRangeFn address_range_fn() {
+  static GetAddressRangeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (GetAddressRangeFn)q;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+extern "C" int fdtdx_b200_peer_export(FdtdxPlan* p, int what, unsigned char* handle64, long long* offset) {
+  if (!p || !handle64 || !offset) return fail(FDTDX_EINVAL, "peer_export: null argument");
+  void* ptr = nullptr;
+  if (what == 0) ptr = p->slots[FDTDX_SLOT_E][0];
+  else if (what == 1) ptr = p->slots[FDTDX_SLOT_H][0];
+  else if (what == 2) {
+    if (!p->d_flags) {
+      CUDA_TRY(cudaMalloc((void**)&p->d_flags, 256));
+      CUDA_TRY(cudaMemset(p->d_flags, 0, 256));
+      p->owned.push_back(p->d_flags);
+    }
+    ptr = p->d_flags;
+  } else return fail(FDTDX_EINVAL, "peer_export: what must be 0 (E), 1 (H) or 2 (flags)");
+  if (!ptr) return fail(FDTDX_EUNBOUND, "peer_export: E / H must be bound first");
+  GetAddressRangeFn gar = address_range_fn();
+  if (!gar) return fail(FDTDX_ECUDA, "cuMemGetAddressRange is not available from this driver");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (gar(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) return fail(FDTDX_ECUDA, "cuMemGetAddressRange failed");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, (void*)base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset = (long long)((CUdeviceptr)ptr - base);
+  return FDTDX_OK;
+}
+
+static int ipc_open(FdtdxPlan* p, const unsigned char* handle64, void** base) {
+  std::string key((const char*)handle64, 64);
+  for (auto& kv : p->ipc_open)
+    if (kv.first == key) { *base = kv.second; return FDTDX_OK; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* q = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+  p->ipc_open.emplace_back(key, q);
+  *base = q;
+  return FDTDX_OK;
+}
+
+// side 0: low-x neighbour (its H array + flags), side 1: high-x neighbour (its E array + flags)
+extern "C" int fdtdx_b200_peer_attach(FdtdxPlan* p, int side, const unsigned char* field_handle64, long long field_offset,
+                                      const unsigned char* flags_handle64, long long flags_offset, int nx_peer) {
+  if (!p || side < 0 || side > 1 || !field_handle64 || !flags_handle64 || nx_peer < 1) return fail(FDTDX_EINVAL, "peer_attach: bad argument");
+  if ((side == 0 && !p->halo_lo) || (side == 1 && !p->halo_hi)) return fail(FDTDX_EINVAL, "peer_attach: plan has no neighbour on that side (halo_bind)");
+  if (!p->d_flags) return fail(FDTDX_EINVAL, "peer_attach: export this rank's flags first");
+  void *fb = nullptr, *gb = nullptr;
+  int rc;
+  if ((rc = ipc_open(p, field_handle64, &fb))) return rc;
+  if ((rc = ipc_open(p, flags_handle64, &gb))) return rc;
+  p->peer[side].field = (float*)((char*)fb + field_offset);
+  p->peer[side].flags = (int*)((char*)gb + flags_offset);
+  p->peer[side].nx = nx_peer;
+  p->peer_mode = (!p->halo_lo || p->peer[0].field) && (!p->halo_hi || p->peer[1].field);
+  p->tmaps.clear();
+  return FDTDX_OK;
 }
 
 static int step_record(FdtdxPlan* p, int t, int record_detectors, int record_boundaries, cudaStream_t st) {

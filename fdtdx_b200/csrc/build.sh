@@ -4,7 +4,7 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="${FDTDX_OUT:-$HERE/../libfdtdx_b200.so}"
-OBJ="${FDTDX_OBJ:-$HERE/../../build/obj}"
+OBJ="${FDTDX_OBJ:-${TMPDIR:-/tmp}/fdtdx_b200_obj}"  # objects stay out of the tree (the tree is what travels to the GPU box)
 mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC ${FDTDX_NVCC_EXTRA:-}"

@@ -85,8 +85,12 @@ struct StepParams {
   float* P_new;        // buffer that held dispersive_P_prev; receives the new P_curr
   const float *c1, *c2, *c3, *c4;
   long long c_cs;  // coefficient component stride (0: isotropic, N: per-axis)
-  const float* haloH;  // (2,ny,nz) Hy,Hz of plane x0-1
-  const float* haloE;  // (2,ny,nz) Ey,Ez of plane x1
+  // x-slab neighbours (x_lo_mode / x_hi_mode == 2): Hy,Hz of plane x0-1 and Ey,Ez of plane x1.  Either a
+  // packed (2,ny,nz) staging buffer filled by an exchange (component stride = ny*nz), or the
+  // neighbour rank's own field array mapped over NVLink (component stride = that rank's Nx*ny*nz).
+  const float* haloH;
+  const float* haloE;
+  long long haloH_cs, haloE_cs;
   int xchunk;
   int x_begin, x_end;  // plane range of this launch (sub-ranges let the halo exchange overlap)
 };

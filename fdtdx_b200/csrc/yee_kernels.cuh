@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
     hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row);
   } else if (P.x_lo_mode == 2) {
     hy_im = ldv<V>(P.haloH + row);
-    hz_im = ldv<V>(P.haloH + plane + row);
+    hz_im = ldv<V>(P.haloH + P.haloH_cs + row);
   } else {
     hy_im = zerov<V>();
     hz_im = zerov<V>();
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
       ez_n = ldv<V>(P.E + 2 * N + row);
     } else if (P.x_hi_mode == 2) {
       ey_n = ldv<V>(P.haloE + row);
-      ez_n = ldv<V>(P.haloE + plane + row);
+      ez_n = ldv<V>(P.haloE + P.haloE_cs + row);
     } else {
       ey_n = zerov<V>();
       ez_n = zerov<V>();

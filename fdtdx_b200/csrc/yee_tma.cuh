@@ -334,7 +334,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row);
     } else if (P.x_lo_mode == 2) {
       hy_im = ldv<V>(P.haloH + row);
-      hz_im = ldv<V>(P.haloH + plane + row);
+      hz_im = ldv<V>(P.haloH + P.haloH_cs + row);
     }
   }
   const int oh = (warp + 1) * HZ + 4 + lane * V;  // own cells inside a halo tile

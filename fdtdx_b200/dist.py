@@ -7,9 +7,18 @@ Here rank r owns planes ``[x0, x1)``; before the E half-step it needs ``Hy, Hz``
 (forward difference, ``curl.py:273-274``): two tangential components of one plane, to/from one
 neighbour, per half-step.  There is no collective in the step.
 
-Overlap: the interior planes of a half-step do not depend on the halo, so each half-step is issued
-as ``interior`` (all x-chunks but the one touching the neighbour) while the halo plane travels on a
-side stream, then the ``edge`` chunk once it has landed.
+Two transports:
+
+* ``halo="peer"`` (default on CUDA): nothing is exchanged.  Every rank maps its neighbours' own E / H
+  arrays through CUDA IPC over NVLink and the half-step kernels read the boundary plane in place
+  (TMA tile loads for the H half-step, 128-bit loads for the E half-step's register queue); two
+  stream-ordered progress counters per rank keep producer/consumer order (``csrc/abi.cu``:
+  ``peer_wait_kernel`` / ``peer_signal_kernel``).  A whole multi-step run is ONE asynchronous call
+  into the C ABI per rank; ``torch.distributed`` is only used to ship the 64-byte IPC handles.
+* ``halo="nccl"``: packed planes over ``torch.distributed`` send/recv (NCCL on GPUs, gloo in the CPU
+  tests).  The interior planes of a half-step do not depend on the halo, so each half-step is issued
+  as ``interior`` (all x-chunks but the one touching the neighbour) while the halo plane travels on a
+  side stream, then the ``edge`` chunk once it has landed.
 """
 
 from __future__ import annotations
@@ -67,7 +76,9 @@ class HaloExchange:
 class SlabRunner:
     """Drives one rank's slab through the C ABI with halo exchange between the half-steps."""
 
-    def __init__(self, objects, config, arrays, x_range, rank: int, world: int, group=None, overlap: bool = True):
+    def __init__(self, objects, config, arrays, x_range, rank: int, world: int, group=None, overlap: bool = True, halo: str | None = None):
+        import os
+
         import torch
 
         self.objects, self.config, self.arrays = objects, config, arrays
@@ -86,8 +97,33 @@ class SlabRunner:
         if has_hi:
             self.plan._bind(_lib.SLOT_HALO_E_HI, 0, self.haloE)
         self.overlap = overlap and world > 1
-        self.side = torch.cuda.Stream(device=E.device) if (self.overlap and E.is_cuda) else None
         self.nx = E.shape[1]
+        halo = halo or os.environ.get("FDTDX_B200_HALO", "peer")
+        self.peer = bool(halo == "peer" and E.is_cuda and world > 1 and (has_lo or has_hi))
+        if self.peer:
+            self._attach_peers(group)
+        self.side = torch.cuda.Stream(device=E.device) if (self.overlap and E.is_cuda and not self.peer) else None
+
+    def _attach_peers(self, group):
+        """Ship this rank's IPC handles (E, H, progress flags) to everybody, attach the two neighbours'."""
+        import torch.distributed as dist
+
+        lib, h = self.plan.lib, self.plan.h
+        mine = {"nx": int(self.nx)}
+        for what, name in ((0, "E"), (1, "H"), (2, "flags")):
+            buf = C.create_string_buffer(64)
+            off = C.c_longlong(0)
+            check(lib.fdtdx_b200_peer_export(h, what, buf, C.byref(off)))
+            mine[name] = (bytes(buf.raw), int(off.value))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        if self.hx.lo is not None:
+            q = everyone[self.hx.lo]
+            check(lib.fdtdx_b200_peer_attach(h, 0, q["H"][0], q["H"][1], q["flags"][0], q["flags"][1], q["nx"]))
+        if self.hx.hi is not None:
+            q = everyone[self.hx.hi]
+            check(lib.fdtdx_b200_peer_attach(h, 1, q["E"][0], q["E"][1], q["flags"][0], q["flags"][1], q["nx"]))
+        dist.barrier(group=group)  # nobody starts stepping before every mapping exists
 
     def _range(self, t, which, x_begin, x_end, simulate=True):
         import torch
@@ -99,6 +135,10 @@ class SlabRunner:
         import torch
 
         E, H = self.arrays.fields.E, self.arrays.fields.H
+        if self.peer:
+            for phase in range(3):
+                self.plan.run_forward_phase(t, phase, record_detectors, False, True)
+            return
         xc = self.plan.xchunk_hint()
         if self.side is None:
             self.sendH.copy_(H[1:3, -1])
@@ -131,5 +171,8 @@ class SlabRunner:
         self.plan.run_forward_phase(t, 2, record_detectors, False, True)
 
     def run(self, t0: int, n: int, record_detectors: bool = False):
+        if self.peer:  # one asynchronous submission for the whole run
+            self.plan.run_forward(t0, n, record_detectors, False, True)
+            return
         for t in range(t0, t0 + n):
             self.step(t, record_detectors)

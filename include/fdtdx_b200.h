@@ -198,6 +198,23 @@ int fdtdx_b200_set_tuning(FdtdxPlan* plan, int xchunk, int rows_per_block);
  * Pure tuning: results are bit-identical on both paths.  (No reference counterpart: XLA picks its own fusion.) */
 int fdtdx_b200_set_tma(FdtdxPlan* plan, int enable, int xchunk_tma);
 
+/* ---- peer-memory halo over NVLink (replaces the XLA collective-permute of the x-sharded arrays,
+ * fdtd/initialization.py:598-611, core/jax/sharding.py:160-176) -----------------------------------------
+ * Instead of exchanging packed planes, a rank's half-step kernels read the neighbour's boundary plane in
+ * place: Hy,Hz of the low neighbour's last x plane (E half-step, curl.py:360-361) and Ey,Ez of the high
+ * neighbour's first x plane (H half-step, curl.py:273-274), through CUDA-IPC mappings of the neighbour's
+ * own E / H arrays.  Ordering is kept by two stream-ordered progress counters per rank.
+ *   peer_export: what = 0 (bound E array), 1 (bound H array), 2 (this rank's progress flags; allocated on
+ *                first use).  Writes the 64-byte cudaIpcMemHandle_t of the enclosing allocation and the byte
+ *                offset of the buffer inside it; the caller ships both to the neighbour process.
+ *   peer_attach: side = 0 (low-x neighbour: pass ITS H export + flags export), 1 (high-x neighbour: ITS E
+ *                export + flags export); nx_peer = the neighbour's local Nx.  Requires halo_bind for that
+ *                side.  Once every bound side is attached, run_forward / run_forward_phase use the peer path
+ *                and need no HALO_* buffers.  All ranks must issue the same sequence of half-steps. */
+int fdtdx_b200_peer_export(FdtdxPlan* plan, int what, unsigned char* handle64, long long* offset);
+int fdtdx_b200_peer_attach(FdtdxPlan* plan, int side, const unsigned char* field_handle64, long long field_offset,
+                           const unsigned char* flags_handle64, long long flags_offset, int nx_peer);
+
 /* Host-buffer convenience used for end-to-end timing: copies E,H,inv_eps from HOST memory into the
  * bound device buffers, runs n forward steps, copies E,H back.  Sizes in bytes are returned. */
 int fdtdx_b200_run_forward_host(FdtdxPlan* plan, const float* h_E, const float* h_H, const float* h_inv_eps,

@@ -19,12 +19,13 @@ for name, build, steps in (
 ):
     objects, arrays_full, cfg = build(None)
     nx = objects.volume.grid_shape[0]
-    for overlap in (False, True):
+    for overlap, halo in ((False, "nccl"), (True, "nccl"), (False, "peer")):
         x0, x1 = slab_bounds(nx, world, rank)
         objects_s, arrays, cfg_s = build((x0, x1))
-        runner = SlabRunner(objects_s, cfg_s, arrays, (x0, x1), rank, world, overlap=overlap)
+        runner = SlabRunner(objects_s, cfg_s, arrays, (x0, x1), rank, world, overlap=overlap, halo=halo)
         runner.run(0, steps, record_detectors=True)
         torch.cuda.synchronize()
+        dist.barrier()  # peer mode: neighbours read this rank's arrays in place until they are done too
         # single-GPU reference on every rank
         objects_f, arrays_f, cfg_f = build(None)
         plan = get_plan(arrays_f, objects_f, cfg_f)
@@ -39,7 +40,7 @@ for name, build, steps in (
                 ddet = max(ddet, float((v2 - arrays_f.detector_states[k][k2]).abs().max()))
         good = dE == 0.0 and dH == 0.0 and ddet == 0.0 and mx > 0
         ok = ok and good
-        print(f"[rank {rank}] {name} overlap={overlap}: max|dE|={dE:.3e} max|dH|={dH:.3e} det={ddet:.3e} (|E|max={mx:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
+        print(f"[rank {rank}] {name} halo={halo} overlap={overlap}: max|dE|={dE:.3e} max|dH|={dH:.3e} det={ddet:.3e} (|E|max={mx:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
         objects_f.__dict__.pop("_plan_cache", None)
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
