@@ -31,7 +31,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 static const double kEta0 = (4e-7 * M_PI) * 299792458.0;
-#define MAX_IDX 64
+#define MAX_IDX 512
 
 struct PmlHost {
   int axis, dir, lo, hi, kappa_one;
