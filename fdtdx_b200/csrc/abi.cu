@@ -696,7 +696,6 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
 
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
-  const int V = v4 ? 4 : 1;
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
   if (can_tma(p, P, v4)) {
@@ -712,10 +711,12 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
     CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
   } else {
+    // register-marching kernels, four cells per thread: 128-bit accesses (E4) or, on ragged rows, four
+    // predicated 32-bit accesses (E1)
     dim3 b(32, p->rows);
-    dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
+    dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
     if (v4) fdtdx_dispatch_E4(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
-    else fdtdx_dispatch_E1(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+    else fdtdx_dispatch_E1(P, t, p->eps_tier, std::min(pml_mode(p, P), 1), rev, sig, ade, met, g, b, st);
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -724,7 +725,6 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
 
 static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
-  const int V = v4 ? 4 : 1;
   if (can_tma(p, P, v4)) {
     TmaSet M;
     memset(&M, 0, sizeof(M));
@@ -741,9 +741,9 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
   } else {
     dim3 b(32, p->rows);
-    dim3 g((p->nz + 32 * V - 1) / (32 * V), (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
+    dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
     if (v4) fdtdx_dispatch_H4(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
-    else fdtdx_dispatch_H1(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+    else fdtdx_dispatch_H1(P, t, p->mu_tier, std::min(pml_mode(p, P), 1), rev, p->sigH_tier > 0, p->metric, g, b, st);
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());

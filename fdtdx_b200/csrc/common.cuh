@@ -100,25 +100,37 @@ struct Vec {
   float v[V];
 };
 
+// FDTDX_RAGGED (per translation unit): the 4-cells-per-thread marching kernels on grids whose rows
+// are not 16-byte aligned (Nz % 4 != 0 or unaligned buffers).  A warp still owns 128 consecutive z
+// cells of a row, but INTERLEAVED: lane l holds cells l, l+32, l+64, l+96 of the tile (element stride
+// FDTDX_ES = 32), so every 32-bit access of the warp is one fully coalesced 128-byte line and all
+// per-thread bookkeeping is still amortised over four cells.  nv = valid elements of this thread;
+// cells beyond the row read as 0 and are never written.
+#ifndef FDTDX_RAGGED
+#define FDTDX_RAGGED 0
+#endif
+#define FDTDX_ES (FDTDX_RAGGED ? 32 : 1)
+
 template <int V>
-__device__ __forceinline__ Vec<V> ldv(const float* __restrict__ p) {
+__device__ __forceinline__ Vec<V> ldv(const float* __restrict__ p, const int nv = V) {
   Vec<V> r;
-  if constexpr (V == 4) {
+  if constexpr (V == 4 && !FDTDX_RAGGED) {
     float4 t = *reinterpret_cast<const float4*>(p);
     r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
   } else {
 #pragma unroll
-    for (int e = 0; e < V; ++e) r.v[e] = p[e];
+    for (int e = 0; e < V; ++e) r.v[e] = (e < nv) ? p[e * FDTDX_ES] : 0.0f;
   }
   return r;
 }
 template <int V>
-__device__ __forceinline__ void stv(float* __restrict__ p, const Vec<V>& r) {
-  if constexpr (V == 4) {
+__device__ __forceinline__ void stv(float* __restrict__ p, const Vec<V>& r, const int nv = V) {
+  if constexpr (V == 4 && !FDTDX_RAGGED) {
     *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   } else {
 #pragma unroll
-    for (int e = 0; e < V; ++e) p[e] = r.v[e];
+    for (int e = 0; e < V; ++e)
+      if (e < nv) p[e * FDTDX_ES] = r.v[e];
   }
 }
 template <int V>

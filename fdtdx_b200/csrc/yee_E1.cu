@@ -1,10 +1,12 @@
-// E half-step kernel instantiations + dispatch for V = 1 (see yee_kernels.cuh).
+// E half-step kernel instantiations + dispatch for ragged rows (Nz % 4 != 0 or unaligned buffers):
+// four cells per thread moved as predicated 32-bit accesses (FDTDX_RAGGED, see common.cuh / yee_kernels.cuh).
+#define FDTDX_RAGGED 1
 #define FDTDX_BUILD_E 1
 #include "yee_kernels.cuh"
 
 template <int TIER, bool REV, int PM>
 static void launch_E3(const StepParams& P, int t, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st) {
-#define GO(S, A, M) yee_E_kernel<1, TIER, REV, S, A, M, PM><<<g, b, 0, st>>>(P, t)
+#define GO(S, A, M) yee_E_kernel<4, TIER, REV, S, A, M, PM><<<g, b, 0, st>>>(P, t)
   if constexpr (REV) {
     if (sig) { if (met) GO(true, false, true); else GO(true, false, false); }
     else { if (met) GO(false, false, true); else GO(false, false, false); }

@@ -1,10 +1,12 @@
-// H half-step kernel instantiations + dispatch for V = 1 (see yee_kernels.cuh).
+// H half-step kernel instantiations + dispatch for ragged rows (Nz % 4 != 0 or unaligned buffers):
+// four cells per thread moved as predicated 32-bit accesses (FDTDX_RAGGED, see common.cuh / yee_kernels.cuh).
+#define FDTDX_RAGGED 1
 #define FDTDX_BUILD_H 1
 #include "yee_kernels.cuh"
 
 template <int MUT, int PM>
 static void launch_H3(const StepParams& P, int t, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st) {
-#define GO(R, S, M) yee_H_kernel<1, MUT, R, S, M, PM><<<g, b, 0, st>>>(P, t)
+#define GO(R, S, M) yee_H_kernel<4, MUT, R, S, M, PM><<<g, b, 0, st>>>(P, t)
   if (rev) {
     if (sig) { if (met) GO(true, true, true); else GO(true, true, false); }
     else { if (met) GO(true, false, true); else GO(true, false, false); }

@@ -170,7 +170,7 @@ __device__ __forceinline__ bool src_hits(const StepParams& P, int i, int j, int 
   if (i < P.src_x0 || i >= P.src_x1) return false;  // CTA-uniform: almost every plane stops here
   for (int s = 0; s < P.n_src; ++s) {
     if (i >= P.src_lo[s][0] && i < P.src_hi[s][0] && j >= P.src_lo[s][1] && j < P.src_hi[s][1] && k0 < P.src_hi[s][2] &&
-        k0 + V > P.src_lo[s][2])
+        k0 + (V - 1) * FDTDX_ES + 1 > P.src_lo[s][2])
       return true;
   }
   return false;
@@ -188,17 +188,17 @@ static __device__ __noinline__ void src_pass_E(const StepParams& P, int t, bool 
   for (int i = max(ic0, P.src_x0); i < min(ic1, P.src_x1); ++i) {
     if (!src_hits(P, i, j, k0, V)) continue;
     const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
-    for (int e = 0; e < V; ++e) {
-      const long long cell = cell0 + e;
+    for (int e = 0; e < V && k0 + e * FDTDX_ES < P.nz; ++e) {
+      const long long cell = cell0 + e * FDTDX_ES;
       float e0 = P.E[cell], e1 = P.E[N + cell], e2 = P.E[2 * N + cell];
       const float i0 = P.eps[cell];
       const float i1 = (TIER == 3) ? P.eps[P.eps_cs + cell] : i0;
       const float i2 = (TIER == 3) ? P.eps[2 * P.eps_cs + cell] : i0;
-      inject_E(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e, i0, i1, i2, &e0, &e1, &e2);
+      inject_E(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e * FDTDX_ES, i0, i1, i2, &e0, &e1, &e2);
       if (!reverse) {
         for (int w = 0; w < P.n_walls; ++w) {
           const WallDev& W = P.wallp[w];
-          if (W.kind == 0 && in_box(W.lo, W.hi, i, j, k0 + e)) {
+          if (W.kind == 0 && in_box(W.lo, W.hi, i, j, k0 + e * FDTDX_ES)) {
             if (W.axis != 0) e0 = 0.0f;
             if (W.axis != 1) e1 = 0.0f;
             if (W.axis != 2) e2 = 0.0f;
@@ -216,8 +216,8 @@ static __device__ __noinline__ void src_pass_H(const StepParams& P, int t, bool 
   for (int i = max(ic0, P.src_x0); i < min(ic1, P.src_x1); ++i) {
     if (!src_hits(P, i, j, k0, V)) continue;
     const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
-    for (int e = 0; e < V; ++e) {
-      const long long cell = cell0 + e;
+    for (int e = 0; e < V && k0 + e * FDTDX_ES < P.nz; ++e) {
+      const long long cell = cell0 + e * FDTDX_ES;
       float h0 = P.H[cell], h1 = P.H[N + cell], h2 = P.H[2 * N + cell];
       float m0 = P.inv_mu_scalar, m1 = m0, m2 = m0;
       if (MUT >= 1) {
@@ -225,11 +225,11 @@ static __device__ __noinline__ void src_pass_H(const StepParams& P, int t, bool 
         m1 = (MUT == 3) ? P.mu[P.mu_cs + cell] : m0;
         m2 = (MUT == 3) ? P.mu[2 * P.mu_cs + cell] : m0;
       }
-      inject_H(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e, m0, m1, m2, &h0, &h1, &h2);
+      inject_H(P.src, P.n_src, P.dt, t, reverse, i, j, k0 + e * FDTDX_ES, m0, m1, m2, &h0, &h1, &h2);
       if (!reverse) {
         for (int w = 0; w < P.n_walls; ++w) {
           const WallDev& W = P.wallp[w];
-          if (W.kind == 1 && in_box(W.lo, W.hi, i, j, k0 + e)) {
+          if (W.kind == 1 && in_box(W.lo, W.hi, i, j, k0 + e * FDTDX_ES)) {
             if (W.axis != 0) h0 = 0.0f;
             if (W.axis != 1) h1 = 0.0f;
             if (W.axis != 2) h2 = 0.0f;
@@ -249,7 +249,7 @@ __device__ __forceinline__ void wall_mask(const StepParams& P, int kind, int i, 
     if (W.kind != kind || i < W.lo[0] || i >= W.hi[0] || j < W.lo[1] || j >= W.hi[1]) continue;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      if (k0 + e >= W.lo[2] && k0 + e < W.hi[2]) {
+      if (k0 + e * FDTDX_ES >= W.lo[2] && k0 + e * FDTDX_ES < W.hi[2]) {
         if (W.axis != 0) o0.v[e] = 0.0f;
         if (W.axis != 1) o1.v[e] = 0.0f;
         if (W.axis != 2) o2.v[e] = 0.0f;
@@ -326,12 +326,12 @@ struct PmlLane {
       if (!P.simulate) { a = 0.0f; b = 1.0f; }                                                                         \
       if (px.kappa_one) cpml_axis<V, !REV, true>(a, b, km1, dxFz, dxFy, psx1, psx2, Ky, Kz);                           \
       else cpml_axis<V, !REV, false>(a, b, km1, dxFz, dxFy, psx1, psx2, Ky, Kz);                                       \
-      if (!REV && psi_st) { stv<V>(qx1, psx1); stv<V>(qx2, psx2); }                                                    \
+      if (!REV && psi_st) { stv<V>(qx1, psx1, nv); stv<V>(qx2, psx2, nv); }                                                    \
     }                                                                                                                  \
     if (L.in_y) {                                                                                                      \
       if (py.kappa_one) cpml_axis<V, !REV, true>(L.ay, L.by, L.ky, dyFx, dyFz, psy1, psy2, Kz, Kx);                    \
       else cpml_axis<V, !REV, false>(L.ay, L.by, L.ky, dyFx, dyFz, psy1, psy2, Kz, Kx);                                \
-      if (!REV && psi_st) { stv<V>(qy1, psy1); stv<V>(qy2, psy2); }                                                    \
+      if (!REV && psi_st) { stv<V>(qy1, psy1, nv); stv<V>(qy2, psy2, nv); }                                                    \
     }                                                                                                                  \
     if (PM == 2) {                                                                                                     \
       if constexpr (V == 4) {                                                                                          \
@@ -354,8 +354,8 @@ struct PmlLane {
       }                                                                                                                \
     } else if (L.any_z) {                                                                                              \
       _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
-        const int k = k0 + e;                                                                                          \
-        if (k < pz.lo_len || k >= pz.hi_start) {                                                                       \
+        const int k = k0 + e * FDTDX_ES;                                                                               \
+        if (k < nz && (k < pz.lo_len || k >= pz.hi_start)) {                                                           \
           const int side = (k >= pz.hi_start) ? 1 : 0;                                                                 \
           const int kl = side ? k - pz.hi_start : k;                                                                   \
           const int Lz = side ? pz.hi_len : pz.lo_len;                                                                 \
@@ -389,15 +389,15 @@ struct PmlLane {
       const long long pidx = (long long)(side ? i - px.hi_start : i) * plane + row;                                    \
       qx1 = px.PSI[side][0] + pidx;                                                                                    \
       qx2 = px.PSI[side][1] + pidx;                                                                                    \
-      psx1 = ldv<V>(qx1);                                                                                              \
-      psx2 = ldv<V>(qx2);                                                                                              \
+      psx1 = ldv<V>(qx1, nv);                                                                                              \
+      psx2 = ldv<V>(qx2, nv);                                                                                              \
     }                                                                                                                  \
     if (L.in_y) {                                                                                                      \
       const long long pidx = (long long)i * L.ystride + L.yoff;                                                        \
       qy1 = py1 + pidx;                                                                                                \
       qy2 = py2 + pidx;                                                                                                \
-      psy1 = ldv<V>(qy1);                                                                                              \
-      psy2 = ldv<V>(qy2);                                                                                              \
+      psy1 = ldv<V>(qy1, nv);                                                                                              \
+      psy2 = ldv<V>(qy2, nv);                                                                                              \
     }                                                                                                                  \
     if (PM == 2) {                                                                                                     \
       if constexpr (V == 4) {                                                                                          \
@@ -438,7 +438,10 @@ struct PmlLane {
       L.ay = py.AT[j]; L.by = py.BT[j]; L.ky = py.KT[j];                                                               \
       if (!P.simulate) { L.ay = 0.0f; L.by = 1.0f; }                                                                   \
     }                                                                                                                  \
-    L.any_z = (k0 < pz.lo_len || k0 + V > pz.hi_start);                                                                \
+    _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                    \
+      const int k = k0 + e * FDTDX_ES;                                                                                 \
+      if (k < nz && (k < pz.lo_len || k >= pz.hi_start)) L.any_z = true;                                               \
+    }                                                                                                                  \
     if (PM == 2 && L.any_z) {                                                                                          \
       const int zside = (k0 + V > pz.hi_start) ? 1 : 0;                                                                \
       const int zL = zside ? pz.hi_len : pz.lo_len;                                                                    \
@@ -449,7 +452,7 @@ struct PmlLane {
       L.zoff = (long long)j * zL + (zside ? k0 - pz.hi_start : k0);                                                    \
       pz1 = pz.PSI[zside][0];                                                                                          \
       pz2 = pz.PSI[zside][1];                                                                                          \
-      L.az = ldv<V>(pz.AT + k0); L.bz = ldv<V>(pz.BT + k0); L.kz = ldv<V>(pz.KT + k0);                                 \
+      L.az = ldv<V>(pz.AT + k0, nv); L.bz = ldv<V>(pz.BT + k0, nv); L.kz = ldv<V>(pz.KT + k0, nv);                                 \
       if (!P.simulate) {                                                                                               \
         _Pragma("unroll") for (int e = 0; e < V; ++e) { L.az.v[e] = 0.0f; L.bz.v[e] = 1.0f; }                          \
       }                                                                                                                \
@@ -462,14 +465,15 @@ struct PmlLane {
 // E half-step
 // ------------------------------------------------------------------------------------------------
 template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
-__global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid_constant__ StepParams P, const int t) {
+static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
-  const int k0 = (blockIdx.x * 32 + lane) * V;
+  const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int nz = P.nz, ny = P.ny;
   const bool active = (k0 < nz) && (j < ny);
   const unsigned wmask = __ballot_sync(0xffffffffu, active);
   if (!active) return;  // the shuffles below run under wmask
+  const int nv = FDTDX_RAGGED ? min(V, (nz - k0 + FDTDX_ES - 1) / FDTDX_ES) : V;  // valid elements of this thread
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const long long plane = (long long)ny * nz;
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
   Vec<V> sBz;
   if (MET) {
     sBy = P.sB[1][j];
-    sBz = ldv<V>(P.sB[2] + k0);
+    sBz = ldv<V>(P.sB[2] + k0, nv);
   }
 
   const float* pH = P.H + (long long)ic0 * plane + row;  // Hx of (ic0, j, k0); Hy, Hz at +N, +2N
@@ -500,14 +504,14 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
   // register queue: Hy, Hz of the previous x plane
   Vec<V> hy_im, hz_im;
   if (ic0 > 0) {
-    hy_im = ldv<V>(pH + N - plane);
-    hz_im = ldv<V>(pH + 2 * N - plane);
+    hy_im = ldv<V>(pH + N - plane, nv);
+    hz_im = ldv<V>(pH + 2 * N - plane, nv);
   } else if (P.x_lo_mode == 1) {
-    hy_im = ldv<V>(P.H + N + (long long)(P.nx - 1) * plane + row);
-    hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row);
+    hy_im = ldv<V>(P.H + N + (long long)(P.nx - 1) * plane + row, nv);
+    hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row, nv);
   } else if (P.x_lo_mode == 2) {
-    hy_im = ldv<V>(P.haloH + row);
-    hz_im = ldv<V>(P.haloH + P.haloH_cs + row);
+    hy_im = ldv<V>(P.haloH + row, nv);
+    hz_im = ldv<V>(P.haloH + P.haloH_cs + row, nv);
   } else {
     hy_im = zerov<V>();
     hz_im = zerov<V>();
@@ -515,21 +519,21 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
 
   if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
-    const Vec<V> hx = ldv<V>(pH), hy = ldv<V>(pH + N), hz = ldv<V>(pH + 2 * N);
+    const Vec<V> hx = ldv<V>(pH, nv), hy = ldv<V>(pH + N, nv), hz = ldv<V>(pH + 2 * N, nv);
     Vec<V> hx_jm, hz_jm;
     if (jm_ok) {
-      hx_jm = ldv<V>(pH + djm);
-      hz_jm = ldv<V>(pH + 2 * N + djm);
+      hx_jm = ldv<V>(pH + djm, nv);
+      hz_jm = ldv<V>(pH + 2 * N + djm, nv);
     } else {
       hx_jm = zerov<V>();
       hz_jm = zerov<V>();
     }
-    const Vec<V> ex = ldv<V>(pE), ey = ldv<V>(pE + N), ez = ldv<V>(pE + 2 * N);
-    const Vec<V> ie0 = ldv<V>(pEps);
+    const Vec<V> ex = ldv<V>(pE, nv), ey = ldv<V>(pE + N, nv), ez = ldv<V>(pE + 2 * N, nv);
+    const Vec<V> ie0 = ldv<V>(pEps, nv);
     Vec<V> ie1, ie2;
     if (TIER == 3) {
-      ie1 = ldv<V>(pEps + P.eps_cs);
-      ie2 = ldv<V>(pEps + 2 * P.eps_cs);
+      ie1 = ldv<V>(pEps + P.eps_cs, nv);
+      ie2 = ldv<V>(pEps + 2 * P.eps_cs, nv);
     } else {
       ie1 = ie0;
       ie2 = ie0;
@@ -544,11 +548,34 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
       if (TIER == 3) { prefetch_l2(pEps + P.eps_cs + pb); prefetch_l2(pEps + 2 * P.eps_cs + pb); }
     }
     // z-neighbour (k-1) of the first element: last element of the previous lane
-    float hx_l = __shfl_up_sync(wmask, hx.v[V - 1], 1);
-    float hy_l = __shfl_up_sync(wmask, hy.v[V - 1], 1);
-    if (lane == 0) {
-      hx_l = km_ok ? pH[dkm] : 0.0f;
-      hy_l = km_ok ? pH[N + dkm] : 0.0f;
+    Vec<V> hx_kmv, hy_kmv;
+    if constexpr (FDTDX_RAGGED) {
+      // interleaved cells: k-1 of (element e, lane l) is (e, l-1); for lane 0 it is (e-1, lane 31)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        hx_kmv.v[e] = __shfl_up_sync(wmask, hx.v[e], 1);
+        hy_kmv.v[e] = __shfl_up_sync(wmask, hy.v[e], 1);
+        if (e > 0) {
+          const float tx = __shfl_sync(wmask, hx.v[e - 1], 31), ty = __shfl_sync(wmask, hy.v[e - 1], 31);
+          if (lane == 0) { hx_kmv.v[e] = tx; hy_kmv.v[e] = ty; }
+        }
+      }
+      if (lane == 0) {
+        hx_kmv.v[0] = km_ok ? pH[dkm] : 0.0f;
+        hy_kmv.v[0] = km_ok ? pH[N + dkm] : 0.0f;
+      }
+    } else {
+      float hx_l = __shfl_up_sync(wmask, hx.v[V - 1], 1);
+      float hy_l = __shfl_up_sync(wmask, hy.v[V - 1], 1);
+      if (lane == 0) {
+        hx_l = km_ok ? pH[dkm] : 0.0f;
+        hy_l = km_ok ? pH[N + dkm] : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        hx_kmv.v[e] = (e == 0) ? hx_l : hx.v[e == 0 ? 0 : e - 1];
+        hy_kmv.v[e] = (e == 0) ? hy_l : hy.v[e == 0 ? 0 : e - 1];
+      }
     }
     float sBx = 1.0f;
     if (MET) sBx = P.sB[0][i];
@@ -556,8 +583,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
     Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const float hx_km = (e == 0) ? hx_l : hx.v[e == 0 ? 0 : e - 1];
-      const float hy_km = (e == 0) ? hy_l : hy.v[e == 0 ? 0 : e - 1];
+      const float hx_km = hx_kmv.v[e], hy_km = hy_kmv.v[e];
       float dyHz = hz.v[e] - hz_jm.v[e];
       float dzHy = hy.v[e] - hy_km;
       float dzHx = hx.v[e] - hx_km;
@@ -587,7 +613,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
         if (REV) {
           // update_E_reverse: ((1+s)E - c K inv_eps) / (1-s)
           if (SIG) {
-            const float sg = P.sigE[c * P.sigE_cs + (pE - P.E) + e];
+            const float sg = (e < nv) ? P.sigE[c * P.sigE_cs + (pE - P.E) + e * FDTDX_ES] : 0.0f;
             const float s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
             const float Ec = Eo[c] * (1.0f + s);
             En[c] = (Ec - (P.cour * K[c]) * ie[c]) / (1.0f - s);
@@ -598,15 +624,15 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
           float s = 0.0f;
           float E1;
           if (SIG) {
-            const float sg = P.sigE[c * P.sigE_cs + (pE - P.E) + e];
+            const float sg = (e < nv) ? P.sigE[c * P.sigE_cs + (pE - P.E) + e * FDTDX_ES] : 0.0f;
             s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
             E1 = (1.0f - s) * Eo[c] + (P.cour * K[c]) * ie[c];
           } else {
             E1 = Eo[c] + (P.cour * K[c]) * ie[c];
           }
-          if (ADE) {
+          if (ADE && e < nv) {
             // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
-            const long long cell = (pE - P.E) + e;
+            const long long cell = (pE - P.E) + e * FDTDX_ES;
             const long long pstride = 3 * N;
             float delta = 0.0f, c4sum = 0.0f;
             for (int p = 0; p < P.n_poles; ++p) {
@@ -642,9 +668,9 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
     }
     // PEC walls (pec.py:70-77)
     if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
-    stv<V>(pE, o0);
-    stv<V>(pE + N, o1);
-    stv<V>(pE + 2 * N, o2);
+    stv<V>(pE, o0, nv);
+    stv<V>(pE + N, o1, nv);
+    stv<V>(pE + 2 * N, o2, nv);
     hy_im = hy;
     hz_im = hz;
     pH += plane;
@@ -661,14 +687,15 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid
 // H half-step
 // ------------------------------------------------------------------------------------------------
 template <int V, int MUT, bool REV, bool SIG, bool MET, int PM>
-__global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid_constant__ StepParams P, const int t) {
+static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
-  const int k0 = (blockIdx.x * 32 + lane) * V;
+  const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int nz = P.nz, ny = P.ny;
   const bool active = (k0 < nz) && (j < ny);
   const unsigned wmask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
+  const int nv = FDTDX_RAGGED ? min(V, (nz - k0 + FDTDX_ES - 1) / FDTDX_ES) : V;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const long long plane = (long long)ny * nz;
@@ -689,7 +716,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
   Vec<V> sFz;
   if (MET) {
     sFy = P.sF[1][j];
-    sFz = ldv<V>(P.sF[2] + k0);
+    sFz = ldv<V>(P.sF[2] + k0, nv);
   }
 
   const float* pE = P.E + (long long)ic0 * plane + row;
@@ -697,40 +724,40 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
   const float* pMu = (MUT >= 1) ? P.mu + (long long)ic0 * plane + row : nullptr;
 
   // register queue: E of the current plane is the "next" plane loaded one step earlier
-  Vec<V> ex = ldv<V>(pE), ey = ldv<V>(pE + N), ez = ldv<V>(pE + 2 * N);
+  Vec<V> ex = ldv<V>(pE, nv), ey = ldv<V>(pE + N, nv), ez = ldv<V>(pE + 2 * N, nv);
 
   if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
     Vec<V> ex_n, ey_n, ez_n;
     if (i + 1 < P.nx) {
-      ey_n = ldv<V>(pE + N + plane);
-      ez_n = ldv<V>(pE + 2 * N + plane);
-      if (i + 1 < ic1) ex_n = ldv<V>(pE + plane);
+      ey_n = ldv<V>(pE + N + plane, nv);
+      ez_n = ldv<V>(pE + 2 * N + plane, nv);
+      if (i + 1 < ic1) ex_n = ldv<V>(pE + plane, nv);
     } else if (P.x_hi_mode == 1) {
-      ey_n = ldv<V>(P.E + N + row);
-      ez_n = ldv<V>(P.E + 2 * N + row);
+      ey_n = ldv<V>(P.E + N + row, nv);
+      ez_n = ldv<V>(P.E + 2 * N + row, nv);
     } else if (P.x_hi_mode == 2) {
-      ey_n = ldv<V>(P.haloE + row);
-      ez_n = ldv<V>(P.haloE + P.haloE_cs + row);
+      ey_n = ldv<V>(P.haloE + row, nv);
+      ez_n = ldv<V>(P.haloE + P.haloE_cs + row, nv);
     } else {
       ey_n = zerov<V>();
       ez_n = zerov<V>();
     }
     Vec<V> ex_jp, ez_jp;
     if (jp_ok) {
-      ex_jp = ldv<V>(pE + djp);
-      ez_jp = ldv<V>(pE + 2 * N + djp);
+      ex_jp = ldv<V>(pE + djp, nv);
+      ez_jp = ldv<V>(pE + 2 * N + djp, nv);
     } else {
       ex_jp = zerov<V>();
       ez_jp = zerov<V>();
     }
-    const Vec<V> hx = ldv<V>(pH), hy = ldv<V>(pH + N), hz = ldv<V>(pH + 2 * N);
+    const Vec<V> hx = ldv<V>(pH, nv), hy = ldv<V>(pH + N, nv), hz = ldv<V>(pH + 2 * N, nv);
     Vec<V> im0, im1, im2;
     if (MUT >= 1) {
-      im0 = ldv<V>(pMu);
+      im0 = ldv<V>(pMu, nv);
       if (MUT == 3) {
-        im1 = ldv<V>(pMu + P.mu_cs);
-        im2 = ldv<V>(pMu + 2 * P.mu_cs);
+        im1 = ldv<V>(pMu + P.mu_cs, nv);
+        im2 = ldv<V>(pMu + 2 * P.mu_cs, nv);
       } else {
         im1 = im0;
         im2 = im0;
@@ -744,11 +771,39 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
       if (MUT >= 1) prefetch_l2(pMu + pb);
       if (MUT == 3) { prefetch_l2(pMu + P.mu_cs + pb); prefetch_l2(pMu + 2 * P.mu_cs + pb); }
     }
-    float ex_r = __shfl_down_sync(wmask, ex.v[0], 1);
-    float ey_r = __shfl_down_sync(wmask, ey.v[0], 1);
-    if (last_lane) {
-      ex_r = kp_ok ? pE[dkp] : 0.0f;
-      ey_r = kp_ok ? pE[N + dkp] : 0.0f;
+    Vec<V> ex_kpv, ey_kpv;
+    if constexpr (FDTDX_RAGGED) {
+      // interleaved cells: k+1 of (element e, lane l) is (e, l+1); for lane 31 it is (e+1, lane 0);
+      // past the row end it is the z halo (zero, or the row's first cell on a periodic axis)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        ex_kpv.v[e] = __shfl_down_sync(wmask, ex.v[e], 1);
+        ey_kpv.v[e] = __shfl_down_sync(wmask, ey.v[e], 1);
+        if (e + 1 < V) {
+          const float tx = __shfl_sync(wmask, ex.v[e + 1], 0), ty = __shfl_sync(wmask, ey.v[e + 1], 0);
+          if (lane == 31) { ex_kpv.v[e] = tx; ey_kpv.v[e] = ty; }
+        }
+        const int kn = k0 + e * FDTDX_ES + 1;
+        if (kn >= nz) {
+          ex_kpv.v[e] = P.wrap[2] ? pE[-k0] : 0.0f;
+          ey_kpv.v[e] = P.wrap[2] ? pE[N - k0] : 0.0f;
+        } else if (e == V - 1 && lane == 31) {
+          ex_kpv.v[e] = pE[kn - k0];
+          ey_kpv.v[e] = pE[N + kn - k0];
+        }
+      }
+    } else {
+      float ex_r = __shfl_down_sync(wmask, ex.v[0], 1);
+      float ey_r = __shfl_down_sync(wmask, ey.v[0], 1);
+      if (last_lane) {
+        ex_r = kp_ok ? pE[dkp] : 0.0f;
+        ey_r = kp_ok ? pE[N + dkp] : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        ex_kpv.v[e] = (e == V - 1) ? ex_r : ex.v[e == V - 1 ? e : e + 1];
+        ey_kpv.v[e] = (e == V - 1) ? ey_r : ey.v[e == V - 1 ? e : e + 1];
+      }
     }
     float sFx = 1.0f;
     if (MET) sFx = P.sF[0][i];
@@ -756,8 +811,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
     Vec<V> dxFz, dxFy, dyFx, dyFz, dzFy, dzFx;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const float ex_kp = (e == V - 1) ? ex_r : ex.v[e == V - 1 ? e : e + 1];
-      const float ey_kp = (e == V - 1) ? ey_r : ey.v[e == V - 1 ? e : e + 1];
+      const float ex_kp = ex_kpv.v[e], ey_kp = ey_kpv.v[e];
       float dyEz = ez_jp.v[e] - ez.v[e];
       float dzEy = ey_kp - ey.v[e];
       float dzEx = ex_kp - ex.v[e];
@@ -786,7 +840,7 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (SIG) {
-          const float sg = P.sigH[c * P.sigH_cs + (pH - P.H) + e];
+          const float sg = (e < nv) ? P.sigH[c * P.sigH_cs + (pH - P.H) + e * FDTDX_ES] : 0.0f;
           const float s = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
           if (REV) {
             const float Hc = Ho[c] * (1.0f + s);
@@ -804,9 +858,9 @@ __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid
       o0.v[e] = Hn[0]; o1.v[e] = Hn[1]; o2.v[e] = Hn[2];
     }
     if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
-    stv<V>(pH, o0);
-    stv<V>(pH + N, o1);
-    stv<V>(pH + 2 * N, o2);
+    stv<V>(pH, o0, nv);
+    stv<V>(pH + N, o1, nv);
+    stv<V>(pH + 2 * N, o2, nv);
     ex = ex_n;
     ey = ey_n;
     ez = ez_n;

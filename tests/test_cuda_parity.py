@@ -76,6 +76,13 @@ CASES = {
     "nonuniform": (dict(nonuniform=True), 10),
     "nonuniform_all": (dict(nonuniform=True, eps_tier=3, sigma_E=True, mu_tier=1, sigma_H=True), 8),
     "scalar_path_odd_nz": (dict(shape=(9, 7, 13)), 8),
+    # ragged rows (Nz % 4 != 0): four cells per thread, predicated 32-bit accesses, partial last lane
+    "ragged_nz65_metric": (dict(shape=(10, 11, 65), thickness=4, nonuniform=True, eps_tier=3), 6),
+    "ragged_nz3": (dict(shape=(6, 5, 3), thickness=1, boundaries={"min_x": "pml", "max_x": "pml", "min_y": "pml", "max_y": "pml", "min_z": "pec", "max_z": "pmc"}), 6),
+    "ragged_periodic_nz13": (dict(shape=(5, 6, 13), boundaries="periodic"), 8),
+    "ragged_periodic_z_nz134": (dict(shape=(4, 5, 134), thickness=2, boundaries={"min_x": "pml", "max_x": "pml", "min_y": "pml", "max_y": "pml", "min_z": "periodic", "max_z": "periodic"}), 6),
+    "ragged_all_tiers_nz18": (dict(shape=(6, 7, 18), nonuniform=True, eps_tier=3, sigma_E=True, mu_tier=3, sigma_H=True, kappa=True), 6),
+    "ragged_ade_nz10": (dict(shape=(6, 6, 10), poles=2, c4=True, eps_tier=3, coeff_tier=3), 6),
     "wide_z": (dict(shape=(6, 9, 260), thickness=2), 6),
     "multi_chunk": (dict(shape=(70, 9, 8), thickness=2), 6),
     "ade_1pole": (dict(poles=1), 8),
@@ -158,6 +165,8 @@ SRC_CASES = {
     "table": dict(source="table"),
     "dipole": dict(source="dipole"),
     "plane_nonuniform": dict(source="plane_z", nonuniform=True, eps_tier=3),
+    "plane_z_ragged": dict(source="plane_z", shape=(12, 10, 15)),
+    "plane_x_ragged": dict(source="plane_x", shape=(16, 10, 13)),
     "plane_periodic": dict(source="plane_z", boundaries={"min_x": "periodic", "max_x": "periodic", "min_y": "periodic", "max_y": "periodic", "min_z": "pml", "max_z": "pml"}),
 }
 
