@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tensor_kernels.cuh"
 #include "adjoint_kernels.cuh"
+#include "source_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -434,6 +435,8 @@ static int finalize(FdtdxPlan* p) {
         t[3][i] = h.aH[q]; t[4][i] = h.bH[q]; t[5][i] = h.kH[q];
       }
     }
+    if (A.lo_len > A.hi_start)
+      return fail(FDTDX_EUNSUPPORTED, "the '-' and '+' CPML slabs of one axis overlap (grid thinner than twice the PML thickness)");
     float* d[6];
     for (int q = 0; q < 6; ++q) {
       int rc = to_device(p, t[q].data(), (size_t)n[a], &d[q]);
@@ -518,6 +521,13 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     for (int a = 0; a < 3; ++a) { P.src_lo[s][a] = d.lo[a]; P.src_hi[s][a] = d.hi[a]; }
     P.src_x0 = std::min(P.src_x0, d.lo[0]);
     P.src_x1 = std::max(P.src_x1, d.hi[0]);
+  }
+  // x-normal planes and dipoles are injected inside the half-step kernels; sources that cross many x
+  // planes (y / z-normal planes, volumes) by src_apply_kernel (source_kernels.cuh)
+  P.src_inline = (P.src_x1 - P.src_x0 <= 2) ? 1 : 0;
+  {
+    const char* e = getenv("FDTDX_B200_SRC_INLINE");
+    if (e) P.src_inline = (e[0] != '0');
   }
   for (int k = 0; k < 2; ++k) { P.wall_x0[k] = p->nx; P.wall_x1[k] = 0; }
   for (int w = 0; w < P.n_walls; ++w) {
@@ -694,10 +704,34 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
   return std::max(1, std::min(std::min(xc, 64), P.x_end - P.x_begin));  // 64 = FDTDX_TMA_XC_MAX
 }
 
+static int launch_sources(FdtdxPlan* p, const StepParams& P, int t, bool is_E, bool rev, cudaStream_t st) {
+  if (P.n_src == 0 || P.src_inline) return FDTDX_OK;
+  long long mx = 0;
+  for (int s = 0; s < P.n_src; ++s) {
+    const long long d0 = std::min(P.src_hi[s][0], P.x_end) - std::max(P.src_lo[s][0], P.x_begin);
+    if (d0 <= 0) continue;
+    mx = std::max(mx, d0 * (P.src_hi[s][1] - P.src_lo[s][1]) * (long long)(P.src_hi[s][2] - P.src_lo[s][2]));
+  }
+  if (mx <= 0) return FDTDX_OK;
+  dim3 g((unsigned)std::min<long long>((mx + 255) / 256, 148 * 8), (unsigned)P.n_src);
+  const int te = p->eps_tier == 1 ? 1 : 3, tm = p->mu_tier;
+#define GO(A, B) src_apply_kernel<A, B><<<g, 256, 0, st>>>(P, t, is_E ? 1 : 0, rev ? 1 : 0)
+  if (te == 1) { if (tm == 0) GO(1, 0); else if (tm == 1) GO(1, 1); else GO(1, 3); }
+  else { if (tm == 0) GO(3, 0); else if (tm == 1) GO(3, 1); else GO(3, 3); }
+#undef GO
+  p->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
 static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
   const bool sig = p->sigE_tier > 0, ade = p->n_poles > 0, met = p->metric;
   if (rev && ade) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
+  if (rev) {  // update_E_reverse undoes the injection before the update
+    int rs = launch_sources(p, P, t, true, true, st);
+    if (rs) return rs;
+  }
   if (can_tma(p, P, v4)) {
     TmaSet M;
     memset(&M, 0, sizeof(M));
@@ -720,11 +754,15 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
-  return FDTDX_OK;
+  return rev ? FDTDX_OK : launch_sources(p, P, t, true, false, st);
 }
 
 static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStream_t st) {
   const bool v4 = can_vec4(p, P);
+  if (rev) {
+    int rs = launch_sources(p, P, t, false, true, st);
+    if (rs) return rs;
+  }
   if (can_tma(p, P, v4)) {
     TmaSet M;
     memset(&M, 0, sizeof(M));
@@ -747,7 +785,7 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
-  return FDTDX_OK;
+  return rev ? FDTDX_OK : launch_sources(p, P, t, false, false, st);
 }
 
 static void make_grid(const FdtdxPlan* p, GridDev& G) {

@@ -78,6 +78,7 @@ struct StepParams {
   WallDev wallp[FDTDX_MAX_WALL];
   int src_lo[FDTDX_MAX_SRC][3], src_hi[FDTDX_MAX_SRC][3];
   int src_x0, src_x1;
+  int src_inline;  // 1: the half-step kernels inject in their cold pass; 0: src_apply_kernel does (broad sources)
   int wall_x0[2], wall_x1[2];  // union x-range of the PEC [0] / PMC [1] walls
   // ADE (update.py:316-350)
   int n_poles, has_c4;

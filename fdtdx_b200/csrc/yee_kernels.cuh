@@ -517,7 +517,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     hz_im = zerov<V>();
   }
 
-  if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
+  if (REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
     const Vec<V> hx = ldv<V>(pH, nv), hy = ldv<V>(pH + N, nv), hz = ldv<V>(pH + 2 * N, nv);
     Vec<V> hx_jm, hz_jm;
@@ -677,7 +677,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     pE += plane;
     pEps += plane;
   }
-  if (!REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (!REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
 }
 
 #endif  // !FDTDX_BUILD_H
@@ -726,7 +726,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
   // register queue: E of the current plane is the "next" plane loaded one step earlier
   Vec<V> ex = ldv<V>(pE, nv), ey = ldv<V>(pE + N, nv), ez = ldv<V>(pE + 2 * N, nv);
 
-  if (REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
+  if (REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
     Vec<V> ex_n, ey_n, ez_n;
     if (i + 1 < P.nx) {
@@ -868,6 +868,6 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     pH += plane;
     if (MUT >= 1) pMu += plane;
   }
-  if (!REV && P.n_src > 0 && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (!REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
 }
 #endif  // !FDTDX_BUILD_E

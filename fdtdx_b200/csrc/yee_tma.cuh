@@ -278,7 +278,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 
   // reverse pass: update_E_reverse undoes the injection first; it must land in global memory before
   // the first tile load reads it (generic -> async proxy)
-  if (REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -481,7 +481,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     pE += plane;
   }
-  if (!REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
 }
 #endif  // !FDTDX_BUILD_H
 
@@ -541,7 +541,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   float* const ztab = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ZTAB;  // a, b, 1/kappa-1 of this tile's z cells
   float* const xs = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_XS;      // metric x scale of this chunk's planes
 
-  if (REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -698,6 +698,6 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     pH += plane;
   }
   // the extra Ey,Ez stage was consumed as the "next plane" of the last iteration; nothing to release
-  if (!REV && P.n_src > 0 && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
 }
 #endif  // !FDTDX_BUILD_E
