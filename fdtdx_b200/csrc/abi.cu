@@ -1204,9 +1204,20 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
       A.lam_psi[h.axis][h.dir][w] = (float*)p->slots[is_E ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H][2 * q + w];
   }
   A.n_walls = S.n_walls; A.walls = S.walls;
-  const unsigned blocks = (unsigned)((N + 255) / 256);
-  adj_local_kernel<<<blocks, 256, 0, st>>>(A);
-  adj_gather_kernel<<<blocks, 256, 0, st>>>(A);
+  // 128-bit form when every (., N)-shaped operand is 16-byte aligned and rows are multiples of 4 cells
+  bool v4 = (p->nz % 4 == 0);
+  const void* ptrs[] = {F, G, lamF, lamG, lam_extra, A.ld, A.mat, A.sig, A.g_mat, A.sc[2]};
+  for (const void* q : ptrs)
+    if (q && !aligned16(q)) v4 = false;
+  if (v4) {
+    dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, p->nx);
+    if (is_E) { adj_local4_kernel<true><<<g, b, 0, st>>>(A); adj_gather4_kernel<true><<<g, b, 0, st>>>(A); }
+    else { adj_local4_kernel<false><<<g, b, 0, st>>>(A); adj_gather4_kernel<false><<<g, b, 0, st>>>(A); }
+  } else {
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    adj_local_kernel<<<blocks, 256, 0, st>>>(A);
+    adj_gather_kernel<<<blocks, 256, 0, st>>>(A);
+  }
   p->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;

@@ -52,33 +52,22 @@ __device__ __forceinline__ float a_at(const AdjParams& P, const float* F, int c,
   return F[c * N + ((long long)x * P.ny + y) * P.nz + z];
 }
 
-__global__ void adj_local_kernel(const AdjParams P) {
-  const long long N = (long long)P.nx * P.ny * P.nz;
-  const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (cell >= N) return;
-  const int z = (int)(cell % P.nz);
-  const int y = (int)((cell / P.nz) % P.ny);
-  const int x = (int)(cell / ((long long)P.nz * P.ny));
+// Per-cell body shared by the scalar and the 4-cells-per-thread kernels: everything after the six
+// primal derivatives d[a][c] = d_a G_c (c != a) are known.  Reads lam (cotangent of the updated field),
+// F, the material, psi / lambda_psi of the slabs the cell belongs to; writes lam_in[3], ld[6] and the
+// material-gradient contributions (gq[c] per component; the caller accumulates them).
+template <bool IS_E>
+__device__ __forceinline__ void adj_local_body(const AdjParams& P, const int x, const int y, const int z, const long long cell, const long long N,
+                                               float d[3][3], float lam[3], const float Fv[3], const float mv[3], const float sgv[3],
+                                               const float extra[3], float lam_in[3], float ldv6[6], float gq[3]) {
   const int pos[3] = {x, y, z};
-  // ---- primal derivatives and curl at this cell (same arithmetic as the forward kernels) ----
-  float d[3][3];
-  const int s = P.is_E ? -1 : +1;
-  for (int a = 0; a < 3; ++a) {
-    const int ex = (a == 0) ? s : 0, ey = (a == 1) ? s : 0, ez = (a == 2) ? s : 0;
-    for (int c = 0; c < 3; ++c) {
-      if (c == a) continue;
-      const float here = a_at(P, P.G, c, x, y, z), there = a_at(P, P.G, c, x + ex, y + ey, z + ez);
-      float v = P.is_E ? (here - there) : (there - here);
-      if (P.sc[a]) v = v * P.sc[a][pos[a]];
-      d[a][c] = v;
-    }
-  }
   float K[3] = {d[1][2] - d[2][1], d[2][0] - d[0][2], d[0][1] - d[1][0]};
   // CPML state of this cell per axis
   bool inp[3];
   float ca[3], cb[3], ck[3];
   long long pidx[3];
   int side[3];
+#pragma unroll
   for (int a = 0; a < 3; ++a) {
     const AxisPmlDev& A = P.pml[a];
     const int idx = pos[a];
@@ -87,56 +76,54 @@ __global__ void adj_local_kernel(const AdjParams P) {
     ca[a] = cb[a] = ck[a] = 0.0f;
     pidx[a] = 0;
     if (!inp[a]) continue;
-    ca[a] = P.is_E ? A.aE[idx] : A.aH[idx];
-    cb[a] = P.is_E ? A.bE[idx] : A.bH[idx];
-    ck[a] = A.kappa_one ? 0.0f : (P.is_E ? A.kE[idx] : A.kH[idx]);
+    ca[a] = IS_E ? A.aE[idx] : A.aH[idx];
+    cb[a] = IS_E ? A.bE[idx] : A.bH[idx];
+    ck[a] = A.kappa_one ? 0.0f : (IS_E ? A.kE[idx] : A.kH[idx]);
     if (a == 0) pidx[a] = ((long long)(side[a] ? x - A.hi_start : x) * P.ny + y) * P.nz + z;
     else if (a == 1) pidx[a] = ((long long)x * (side[a] ? A.hi_len : A.lo_len) + (side[a] ? y - A.hi_start : y)) * P.nz + z;
     else pidx[a] = ((long long)x * P.ny + y) * (side[a] ? A.hi_len : A.lo_len) + (side[a] ? z - A.hi_start : z);
     const int i = (a + 1) % 3, j = (a + 2) % 3;
-    const float* q1 = P.is_E ? (side[a] ? A.psiE[1][0] : A.psiE[0][0]) : (side[a] ? A.psiH[1][0] : A.psiH[0][0]);
-    const float* q2 = P.is_E ? (side[a] ? A.psiE[1][1] : A.psiE[0][1]) : (side[a] ? A.psiH[1][1] : A.psiH[0][1]);
+    const float* q1 = IS_E ? (side[a] ? A.psiE[1][0] : A.psiE[0][0]) : (side[a] ? A.psiH[1][0] : A.psiH[0][0]);
+    const float* q2 = IS_E ? (side[a] ? A.psiE[1][1] : A.psiE[0][1]) : (side[a] ? A.psiH[1][1] : A.psiH[0][1]);
     const float p1 = cb[a] * q1[pidx[a]] + ca[a] * d[a][j];
     const float p2 = cb[a] * q2[pidx[a]] + ca[a] * d[a][i];
     K[i] = K[i] - (ck[a] * d[a][j] + p1);
     K[j] = K[j] + (ck[a] * d[a][i] + p2);
   }
   // ---- transpose of the material update ----
-  float lam[3] = {P.lamF[cell], P.lamF[N + cell], P.lamF[2 * N + cell]};
   for (int w = 0; w < P.n_walls; ++w) {
     const WallDev W = P.walls[w];
-    if (W.kind == (P.is_E ? 0 : 1) && x >= W.lo[0] && x < W.hi[0] && y >= W.lo[1] && y < W.hi[1] && z >= W.lo[2] && z < W.hi[2]) {
+    if (W.kind == (IS_E ? 0 : 1) && x >= W.lo[0] && x < W.hi[0] && y >= W.lo[1] && y < W.hi[1] && z >= W.lo[2] && z < W.hi[2]) {
       if (W.axis != 0) lam[0] = 0.0f;
       if (W.axis != 1) lam[1] = 0.0f;
       if (W.axis != 2) lam[2] = 0.0f;
     }
   }
   float lamK[3];
-  float gacc = 0.0f;
+#pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float m = P.mat_tier == 0 ? P.mat_scalar : P.mat[(long long)(P.mat_tier == 1 ? 0 : c) * P.mat_cs + cell];
-    float alpha = 0.0f;
-    if (P.sig) {
-      const float sg = P.sig[c * P.sig_cs + cell];
-      alpha = P.is_E ? ((P.cour * sg) * P.eta0) / 2.0f : ((P.cour * sg) / P.eta0) / 2.0f;
-    }
-    const float sv = alpha * m;
-    const float u = lam[c] / (1.0f + sv);
-    const float Fc = P.F[c * N + cell];
+    const float m = mv[c];
+    const float Fc = Fv[c];
     const float cK = P.cour * K[c];
-    const float Fpre = P.is_E ? ((1.0f - sv) * Fc + cK * m) / (1.0f + sv) : ((1.0f - sv) * Fc - cK * m) / (1.0f + sv);
-    const float g = P.is_E ? u * (cK - alpha * Fc - alpha * Fpre) : u * (-cK - alpha * Fc - alpha * Fpre);
-    if (P.g_mat) {
-      if (P.mat_tier == 3) P.g_mat[c * N + cell] += g;
-      else gacc += g;
+    float alpha = 0.0f, sv = 0.0f, u, Fpre;
+    if (P.sig) {
+      const float sg = sgv[c];
+      alpha = IS_E ? ((P.cour * sg) * P.eta0) / 2.0f : ((P.cour * sg) / P.eta0) / 2.0f;
+      sv = alpha * m;
+      u = lam[c] / (1.0f + sv);
+      Fpre = IS_E ? ((1.0f - sv) * Fc + cK * m) / (1.0f + sv) : ((1.0f - sv) * Fc - cK * m) / (1.0f + sv);
+    } else {  // sv == 0: the divisions by 1 and the (1 - 0) factors are exact identities
+      u = lam[c];
+      Fpre = IS_E ? Fc + cK * m : Fc - cK * m;
     }
+    gq[c] = IS_E ? u * (cK - alpha * Fc - alpha * Fpre) : u * (-cK - alpha * Fc - alpha * Fpre);
     float lin = (1.0f - sv) * u;
-    if (P.lam_extra) lin += P.lam_extra[c * N + cell];
-    P.lamF[c * N + cell] = lin;
-    lamK[c] = P.is_E ? (P.cour * m) * u : -(P.cour * m) * u;
+    if (P.lam_extra) lin += extra[c];
+    lam_in[c] = lin;
+    lamK[c] = IS_E ? (P.cour * m) * u : -(P.cour * m) * u;
   }
-  if (P.g_mat && P.mat_tier == 1) P.g_mat[cell] += gacc;
   // ---- transpose of curl + CPML: cotangent of each derivative d_a G_c ----
+#pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int i = (a + 1) % 3, j = (a + 2) % 3;
     // d1 = d_a G_j enters K_i with sign -, d2 = d_a G_i enters K_j with sign +
@@ -152,9 +139,162 @@ __global__ void adj_local_kernel(const AdjParams P) {
       l1 = e1 * (1.0f + ck[a]) + ca[a] * t1;
       l2 = e2 * (1.0f + ck[a]) + ca[a] * t2;
     }
-    P.ld[(long long)(2 * a + 0) * N + cell] = l1;
-    P.ld[(long long)(2 * a + 1) * N + cell] = l2;
+    ldv6[2 * a + 0] = l1;
+    ldv6[2 * a + 1] = l2;
   }
+}
+
+__global__ void adj_local_kernel(const AdjParams P) {
+  const long long N = (long long)P.nx * P.ny * P.nz;
+  const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (cell >= N) return;
+  const int z = (int)(cell % P.nz);
+  const int y = (int)((cell / P.nz) % P.ny);
+  const int x = (int)(cell / ((long long)P.nz * P.ny));
+  const int pos[3] = {x, y, z};
+  // ---- primal derivatives at this cell (same arithmetic as the forward kernels) ----
+  float d[3][3];
+  const int s = P.is_E ? -1 : +1;
+  for (int a = 0; a < 3; ++a) {
+    const int ex = (a == 0) ? s : 0, ey = (a == 1) ? s : 0, ez = (a == 2) ? s : 0;
+    for (int c = 0; c < 3; ++c) {
+      if (c == a) continue;
+      const float here = a_at(P, P.G, c, x, y, z), there = a_at(P, P.G, c, x + ex, y + ey, z + ez);
+      float v = P.is_E ? (here - there) : (there - here);
+      if (P.sc[a]) v = v * P.sc[a][pos[a]];
+      d[a][c] = v;
+    }
+  }
+  float lam[3] = {P.lamF[cell], P.lamF[N + cell], P.lamF[2 * N + cell]};
+  float Fv[3], mv[3], sgv[3] = {0.f, 0.f, 0.f}, extra[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < 3; ++c) {
+    Fv[c] = P.F[c * N + cell];
+    mv[c] = P.mat_tier == 0 ? P.mat_scalar : P.mat[(long long)(P.mat_tier == 1 ? 0 : c) * P.mat_cs + cell];
+    if (P.sig) sgv[c] = P.sig[c * P.sig_cs + cell];
+    if (P.lam_extra) extra[c] = P.lam_extra[c * N + cell];
+  }
+  float lam_in[3], l6[6], gq[3];
+  if (P.is_E) adj_local_body<true>(P, x, y, z, cell, N, d, lam, Fv, mv, sgv, extra, lam_in, l6, gq);
+  else adj_local_body<false>(P, x, y, z, cell, N, d, lam, Fv, mv, sgv, extra, lam_in, l6, gq);
+  for (int c = 0; c < 3; ++c) P.lamF[c * N + cell] = lam_in[c];
+  if (P.g_mat) {
+    if (P.mat_tier == 3) { for (int c = 0; c < 3; ++c) P.g_mat[c * N + cell] += gq[c]; }
+    else P.g_mat[cell] += (gq[0] + gq[1]) + gq[2];
+  }
+  for (int q = 0; q < 6; ++q) P.ld[(long long)q * N + cell] = l6[q];
+}
+
+// 4 cells per thread, 128-bit accesses (Nz % 4 == 0, 16-byte aligned buffers): blockDim (32, 8),
+// grid (z tiles of 128, y tiles of 8, x planes).  Same per-cell arithmetic (adj_local_body).
+template <bool IS_E>
+__global__ void __launch_bounds__(256) adj_local4_kernel(const AdjParams P) {
+  constexpr int V = 4;
+  const int lane = threadIdx.x;
+  const int k0 = (blockIdx.x * 32 + lane) * V;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  const bool active = (k0 < P.nz) && (y < P.ny);
+  const long long plane = (long long)P.ny * P.nz, N = plane * P.nx;
+  const long long cell0 = (long long)x * plane + (long long)y * P.nz + k0;
+  const int s = IS_E ? -1 : +1;
+  // neighbour planes / rows (zero halo or wrap); *_ok false: zero
+  int xn = x + s, yn = y + s;
+  bool xok = true, yok = true;
+  if (xn < 0) { if (P.wrap[0]) xn = P.nx - 1; else xok = false; }
+  if (xn >= P.nx) { if (P.wrap[0]) xn = 0; else xok = false; }
+  if (yn < 0) { if (P.wrap[1]) yn = P.ny - 1; else yok = false; }
+  if (yn >= P.ny) { if (P.wrap[1]) yn = 0; else yok = false; }
+  Vec<V> g[3], gx[3], gy[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { g[c] = zerov<V>(); gx[c] = zerov<V>(); gy[c] = zerov<V>(); }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      g[c] = ldv<V>(P.G + c * N + cell0);
+      if (c != 0 && xok) gx[c] = ldv<V>(P.G + c * N + (long long)xn * plane + (long long)y * P.nz + k0);
+      if (c != 1 && yok) gy[c] = ldv<V>(P.G + c * N + (long long)x * plane + (long long)yn * P.nz + k0);
+    }
+  }
+  // z neighbour of the edge element: adjacent lane, or memory / halo at the tile edge
+  float gz_edge[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float v = IS_E ? __shfl_up_sync(0xffffffffu, g[c].v[V - 1], 1) : __shfl_down_sync(0xffffffffu, g[c].v[0], 1);
+    const bool edge = IS_E ? (lane == 0) : (lane == 31 || k0 + V >= P.nz);
+    if (edge) {
+      int kz = IS_E ? k0 - 1 : k0 + V;
+      bool ok = true;
+      if (kz < 0) { if (P.wrap[2]) kz = P.nz - 1; else ok = false; }
+      if (kz >= P.nz) { if (P.wrap[2]) kz = 0; else ok = false; }
+      v = (ok && active) ? P.G[c * N + (long long)x * plane + (long long)y * P.nz + kz] : 0.0f;
+    }
+    gz_edge[c] = v;
+  }
+  if (!active) return;
+  const float scx = P.sc[0] ? P.sc[0][x] : 1.0f, scy = P.sc[1] ? P.sc[1][y] : 1.0f;
+  Vec<V> scz;
+  if (P.sc[2]) scz = ldv<V>(P.sc[2] + k0);
+  Vec<V> lamv[3], Fq[3], mq[3], sq[3], xq[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    lamv[c] = ldv<V>(P.lamF + c * N + cell0);
+    Fq[c] = ldv<V>(P.F + c * N + cell0);
+    if (P.mat_tier != 0 && (c == 0 || P.mat_tier == 3)) mq[c] = ldv<V>(P.mat + (long long)c * P.mat_cs + cell0);
+    if (P.sig) sq[c] = ldv<V>(P.sig + c * P.sig_cs + cell0);
+    if (P.lam_extra) xq[c] = ldv<V>(P.lam_extra + c * N + cell0);
+  }
+  Vec<V> lin[3], l6[6], gq[3];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    float d[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c != 0) { float v = IS_E ? (g[c].v[e] - gx[c].v[e]) : (gx[c].v[e] - g[c].v[e]); if (P.sc[0]) v = v * scx; d[0][c] = v; }
+      if (c != 1) { float v = IS_E ? (g[c].v[e] - gy[c].v[e]) : (gy[c].v[e] - g[c].v[e]); if (P.sc[1]) v = v * scy; d[1][c] = v; }
+      if (c != 2) {
+        const float there = IS_E ? (e == 0 ? gz_edge[c] : g[c].v[e == 0 ? 0 : e - 1]) : (e == V - 1 ? gz_edge[c] : g[c].v[e == V - 1 ? e : e + 1]);
+        float v = IS_E ? (g[c].v[e] - there) : (there - g[c].v[e]);
+        if (P.sc[2]) v = v * scz.v[e];
+        d[2][c] = v;
+      }
+    }
+    d[0][0] = d[1][1] = d[2][2] = 0.0f;
+    float lam[3] = {lamv[0].v[e], lamv[1].v[e], lamv[2].v[e]};
+    const float Fv[3] = {Fq[0].v[e], Fq[1].v[e], Fq[2].v[e]};
+    float mv[3], sgv[3] = {0.f, 0.f, 0.f}, extra[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      mv[c] = P.mat_tier == 0 ? P.mat_scalar : (P.mat_tier == 1 ? mq[0].v[e] : mq[c].v[e]);
+      if (P.sig) sgv[c] = sq[c].v[e];
+      if (P.lam_extra) extra[c] = xq[c].v[e];
+    }
+    float lam_in[3], ll[6], gg[3];
+    adj_local_body<IS_E>(P, x, y, k0 + e, cell0 + e, N, d, lam, Fv, mv, sgv, extra, lam_in, ll, gg);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { lin[c].v[e] = lam_in[c]; gq[c].v[e] = gg[c]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) l6[q].v[e] = ll[q];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) stv<V>(P.lamF + c * N + cell0, lin[c]);
+  if (P.g_mat) {
+    if (P.mat_tier == 3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Vec<V> o = ldv<V>(P.g_mat + c * N + cell0);
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] += gq[c].v[e];
+        stv<V>(P.g_mat + c * N + cell0, o);
+      }
+    } else {
+      Vec<V> o = ldv<V>(P.g_mat + cell0);
+#pragma unroll
+      for (int e = 0; e < V; ++e) o.v[e] += (gq[0].v[e] + gq[1].v[e]) + gq[2].v[e];
+      stv<V>(P.g_mat + cell0, o);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) stv<V>(P.ld + (long long)q * N + cell0, l6[q]);
 }
 
 __global__ void adj_gather_kernel(const AdjParams P) {
@@ -191,6 +331,100 @@ __global__ void adj_gather_kernel(const AdjParams P) {
       }
     }
     P.lamG[c * N + cell] += acc;
+  }
+}
+
+// 4 cells per thread form of adj_gather_kernel (same accumulation order).
+template <bool IS_E>
+__global__ void __launch_bounds__(256) adj_gather4_kernel(const AdjParams P) {
+  constexpr int V = 4;
+  const int lane = threadIdx.x;
+  const int k0 = (blockIdx.x * 32 + lane) * V;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  const bool active = (k0 < P.nz) && (y < P.ny);
+  const long long plane = (long long)P.ny * P.nz, N = plane * P.nx;
+  const long long cell0 = (long long)x * plane + (long long)y * P.nz + k0;
+  const int s = IS_E ? +1 : -1;  // the transpose looks the other way
+  int xn = x + s, yn = y + s;
+  bool xok = true, yok = true;
+  if (xn < 0) { if (P.wrap[0]) xn = P.nx - 1; else xok = false; }
+  if (xn >= P.nx) { if (P.wrap[0]) xn = 0; else xok = false; }
+  if (yn < 0) { if (P.wrap[1]) yn = P.ny - 1; else yok = false; }
+  if (yn >= P.ny) { if (P.wrap[1]) yn = 0; else yok = false; }
+  // z-derivative cotangents (slots 4, 5) also need the k+-1 neighbour: adjacent lane or tile edge
+  Vec<V> Lz[2];
+  float Lz_edge[2];
+  int kz_edge = IS_E ? k0 + V : k0 - 1;
+  bool zok = true;
+  if (kz_edge < 0) { if (P.wrap[2]) kz_edge = P.nz - 1; else zok = false; }
+  if (kz_edge >= P.nz) { if (P.wrap[2]) kz_edge = 0; else zok = false; }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    Lz[q] = active ? ldv<V>(P.ld + (long long)(4 + q) * N + cell0) : zerov<V>();
+    float v = IS_E ? __shfl_down_sync(0xffffffffu, Lz[q].v[0], 1) : __shfl_up_sync(0xffffffffu, Lz[q].v[V - 1], 1);
+    const bool edge = IS_E ? (lane == 31 || k0 + V >= P.nz) : (lane == 0);
+    if (edge) v = (zok && active) ? P.ld[(long long)(4 + q) * N + (long long)x * plane + (long long)y * P.nz + kz_edge] : 0.0f;
+    Lz_edge[q] = v;
+  }
+  if (!active) return;
+  const float scx_h = P.sc[0] ? P.sc[0][x] : 1.0f, scy_h = P.sc[1] ? P.sc[1][y] : 1.0f;
+  const float scx_n = (P.sc[0] && xok) ? P.sc[0][xn] : 1.0f, scy_n = (P.sc[1] && yok) ? P.sc[1][yn] : 1.0f;
+  Vec<V> scz_h, scz_n;
+#pragma unroll
+  for (int e = 0; e < V; ++e) { scz_h.v[e] = 1.0f; scz_n.v[e] = 1.0f; }
+  if (P.sc[2]) {
+    scz_h = ldv<V>(P.sc[2] + k0);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      int kn = k0 + e + s;
+      if (kn < 0) kn = P.wrap[2] ? P.nz - 1 : 0;
+      if (kn >= P.nz) kn = P.wrap[2] ? 0 : P.nz - 1;
+      scz_n.v[e] = P.sc[2][kn];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    Vec<V> acc = zerov<V>();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (a == c) continue;
+      const int slot = (c == (a + 2) % 3) ? 2 * a : 2 * a + 1;
+      Vec<V> here, there = zerov<V>();
+      bool ok;
+      if (a == 2) {
+        here = Lz[slot - 4];
+        ok = true;  // per element below
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          there.v[e] = IS_E ? (e == V - 1 ? Lz_edge[slot - 4] : here.v[e == V - 1 ? e : e + 1]) : (e == 0 ? Lz_edge[slot - 4] : here.v[e == 0 ? 0 : e - 1]);
+      } else {
+        here = ldv<V>(P.ld + (long long)slot * N + cell0);
+        ok = (a == 0) ? xok : yok;
+        if (ok) there = ldv<V>(P.ld + (long long)slot * N + (a == 0 ? (long long)xn * plane + (long long)y * P.nz : (long long)x * plane + (long long)yn * P.nz) + k0);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float sh = (a == 0) ? scx_h : (a == 1) ? scy_h : scz_h.v[e];
+        const float sn = (a == 0) ? scx_n : (a == 1) ? scy_n : scz_n.v[e];
+        bool eok = ok;
+        if (a == 2) {
+          const int kn = k0 + e + s;
+          eok = P.wrap[2] || (kn >= 0 && kn < P.nz);
+        }
+        if (IS_E) {
+          acc.v[e] += sh * here.v[e];
+          if (eok) acc.v[e] -= sn * there.v[e];
+        } else {
+          acc.v[e] -= sh * here.v[e];
+          if (eok) acc.v[e] += sn * there.v[e];
+        }
+      }
+    }
+    Vec<V> o = ldv<V>(P.lamG + c * N + cell0);
+#pragma unroll
+    for (int e = 0; e < V; ++e) o.v[e] += acc.v[e];
+    stv<V>(P.lamG + c * N + cell0, o);
   }
 }
 
