@@ -31,6 +31,12 @@ from fdtdx_b200.sources import (
     gaussian_amplitude_profile,
     make_plane_source,
 )
+from fdtdx_b200.stop_conditions import (
+    DetectorConvergenceCondition,
+    EnergyThresholdCondition,
+    StoppingCondition,
+    TimeStepCondition,
+)
 from fdtdx_b200.switch import OnOffSwitch, WaveCharacter
 
 

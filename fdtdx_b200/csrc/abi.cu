@@ -98,6 +98,7 @@ struct FdtdxPlan {
   std::map<std::tuple<const void*, int, int>, CUtensorMap> tmaps;  // (base, components, box kind) -> map
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
+  double* d_energy_partial = nullptr;  // total_energy: per-block partial sums
 };
 
 extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
@@ -1108,6 +1109,23 @@ extern "C" int fdtdx_b200_run_half_range(FdtdxPlan* p, int t, int which, int x_b
     return rc;
   }
   return launch_H(p, P, t, false, st);
+}
+
+extern "C" int fdtdx_b200_total_energy(FdtdxPlan* p, float* d_out, void* stream) {
+  if (!p || !d_out) return fail(FDTDX_EINVAL, "total_energy: null argument");
+  if (p->eps_tier == 9 || p->mu_tier == 9) return fail(FDTDX_EUNSUPPORTED, "total_energy: full-tensor media are not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = finalize(p);
+  if (rc) return rc;
+  GridDev G;
+  make_grid(p, G);
+  if (!G.E || !G.H || !G.eps) return fail(FDTDX_EUNBOUND, "E, H and INV_EPS must be bound");
+  if (!p->d_energy_partial && (rc = to_device<double>(p, nullptr, FDTDX_ENERGY_BLOCKS, &p->d_energy_partial))) return rc;
+  energy_partial_kernel<<<FDTDX_ENERGY_BLOCKS, 256, 0, st>>>(G, p->d_energy_partial);
+  energy_final_kernel<<<1, 256, 0, st>>>(p->d_energy_partial, FDTDX_ENERGY_BLOCKS, d_out);
+  p->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
 }
 
 extern "C" int fdtdx_b200_get_xchunk(FdtdxPlan* p) {

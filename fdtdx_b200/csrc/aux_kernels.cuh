@@ -431,3 +431,49 @@ __global__ void halo_pack_kernel(const float* F, float* out, int nx, int ny, int
     out[idx] = F[c * N + (long long)plane_x * pn + (idx % pn)];
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Total field energy (core/physics/metrics.py:55-67, diagonal tiers), the per-step global reduction
+// of EnergyThresholdCondition (fdtd/stop_conditions.py:81-147).  Per cell, in float32 and in the
+// reference's op order: 0.5 * (1 / inv_eps_c) * E_c^2 summed over c as (x + y) + z, likewise for H,
+// then eE + eH.  The sum over cells is carried in float64 with a fixed launch geometry, so the result
+// is deterministic; stage 2 (one block) folds the per-block partials and writes one float.
+// ------------------------------------------------------------------------------------------------
+#define FDTDX_ENERGY_BLOCKS (148 * 4)
+__global__ void __launch_bounds__(256) energy_partial_kernel(const GridDev G, double* __restrict__ partial) {
+  const long long N = (long long)G.nx * G.ny * G.nz;
+  double acc = 0.0;
+  for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < N; cell += (long long)gridDim.x * blockDim.x) {
+    float eE[3], eH[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float e = G.E[c * N + cell], h = G.H[c * N + cell];
+      const float ie = G.eps[c * G.eps_cs + cell];
+      const float im = G.mu ? G.mu[c * G.mu_cs + cell] : G.inv_mu_scalar;
+      eE[c] = (0.5f * (1.0f / ie)) * (e * e);
+      eH[c] = (0.5f * (1.0f / im)) * (h * h);
+    }
+    const float cellE = ((eE[0] + eE[1]) + eE[2]) + ((eH[0] + eH[1]) + eH[2]);
+    acc += (double)cellE;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) energy_final_kernel(const double* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sh[0];
+}

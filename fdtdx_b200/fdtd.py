@@ -84,13 +84,27 @@ def checkpointed_fdtd(
 ) -> SimulationState:
     """``fdtd.py:421-496``: reset, then ``forward`` until ``time_steps_total``.
 
-    Only the default ``TimeStepCondition`` is on the hot path."""
-    if stopping_condition is not None:
-        raise NotImplementedError("custom stopping conditions need a per-step global reduction (SURVEY section 8 f4)")
+    With a ``stopping_condition`` (``fdtd/stop_conditions.py``) the loop is the reference's
+    ``while cond(state): state = forward(state)`` bounded by ``time_steps_total`` (``fdtd.py:482-493``):
+    steps are issued in bulk while the condition cannot fire (``earliest_stop``) and one at a time,
+    with one device reduction + 4-byte read-back each, afterwards."""
     arrays = arrays.reset()
     T = config.time_steps_total
-    arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
-    return T, arrays
+    if stopping_condition is None:
+        arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
+        return T, arrays
+    cond = stopping_condition.setup((0, arrays), config, objects)
+    t = min(max(int(cond.earliest_stop(config)), 0), T)
+    if t > 0:
+        if not cond((0, arrays), config, objects):  # a condition that refuses the initial state
+            return 0, arrays
+        arrays = _run_forward_loop(arrays, objects, config, 0, t, True, config.invertible_optimization, progress_callback)
+    while t < T and cond((t, arrays), config, objects):
+        arrays = _run_forward_loop(arrays, objects, config, t, t + 1, True, config.invertible_optimization, None)
+        t += 1
+        if progress_callback is not None:
+            progress_callback(t, T)
+    return t, arrays
 
 
 def custom_fdtd_forward(

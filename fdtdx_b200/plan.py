@@ -477,6 +477,16 @@ class Plan:
     def set_tuning(self, xchunk: int = 0, rows: int = 0):
         check(self.lib.fdtdx_b200_set_tuning(self.h, int(xchunk), int(rows)))
 
+    def total_energy(self, arrays):
+        """Sum over the grid of ``compute_energy`` (metrics.py:15-67) as a 1-element device tensor."""
+        import torch
+
+        self.bind(arrays)
+        if getattr(self, "_energy_out", None) is None:
+            self._energy_out = torch.zeros(1, dtype=torch.float32, device=arrays.fields.E.device)
+        check(self.lib.fdtdx_b200_total_energy(self.h, C.c_void_p(self._energy_out.data_ptr()), self._stream()))
+        return self._energy_out
+
     def set_tma(self, enable: int = -1, xchunk_tma: int = 0):
         """Select the TMA-staged (1) or register-marching (0) half-step kernels; -1 follows FDTDX_B200_TMA."""
         check(self.lib.fdtdx_b200_set_tma(self.h, int(enable), int(xchunk_tma)))

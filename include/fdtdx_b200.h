@@ -188,6 +188,12 @@ int fdtdx_b200_run_adjoint(FdtdxPlan* plan, int t_from, int n, void* stream);
 int fdtdx_b200_get_parity(FdtdxPlan* plan, int* p_parity, int* e_parity, int* h_parity);
 int fdtdx_b200_set_parity(FdtdxPlan* plan, int p_parity, int e_parity, int h_parity);
 
+/* Total electromagnetic energy of the bound fields, sum over all local cells of
+ * compute_energy (core/physics/metrics.py:15-67, diagonal tiers), written as one float to d_out (device).
+ * This is the per-step global reduction of EnergyThresholdCondition (fdtd/stop_conditions.py:81-147);
+ * on x-sharded plans the caller adds the ranks' values. */
+int fdtdx_b200_total_energy(FdtdxPlan* plan, float* d_out, void* stream);
+
 /* Kernel launches issued by this plan since creation (bench.py's gpu_launches claim). */
 long long fdtdx_b200_launch_count(FdtdxPlan* plan);
 /* Tuning knob: x-chunk length of the marching kernels (0 = auto). */

@@ -893,16 +893,50 @@ def custom_fdtd_forward(arrays, objects, config, key=None, reset_container=True,
     return state
 
 
-def checkpointed_fdtd(arrays, objects, config, key=None):
+def evaluate_condition(cond, state, config, objects) -> bool:
+    """CPU restatement of the reference's stopping conditions (fdtd/stop_conditions.py:65-78,
+    124-147, 269-332) on NumPy containers; ``cond`` is a set-up ``fdtdx_b200.stop_conditions`` object
+    (attributes only - none of its device code runs here)."""
+    name = type(cond).__name__
+    t, arrays = state
+    if name == "TimeStepCondition":
+        return bool(config.time_steps_total > t)
+    if name == "EnergyThresholdCondition":
+        time_condition = t < cond.max_steps
+        min_steps_condition = t < cond.min_steps
+        total_energy = np.sum(compute_energy(arrays.fields.E, arrays.fields.H, arrays.inv_permittivities, arrays.inv_permeabilities))
+        converged = total_energy < cond.threshold
+        return bool(time_condition & (min_steps_condition | (not converged)))
+    if name == "DetectorConvergenceCondition":
+        spp, pp, total = cond._spp, cond.prev_periods, config.time_steps_total
+        readings = next(iter(arrays.detector_states[cond.detector_name].values()))
+        time_condition = t < total
+        min_steps_condition = t >= cond.min_steps
+        converged = False
+        if min_steps_condition:
+            start_ref = int(np.clip(t - (pp + 1) * spp, 0, total - pp * spp))
+            start_last = int(np.clip(t - spp, 0, total - spp))
+            ref = readings[start_ref : start_ref + pp * spp, 0].astype(F)
+            last = readings[start_last : start_last + spp, 0].astype(F)
+            ref_mean = np.mean(ref.reshape(pp, spp), axis=0, dtype=F)
+            distance = np.linalg.norm(np.abs(np.fft.rfft(ref_mean, n=spp)) - np.abs(np.fft.rfft(last, n=spp)))
+            converged = bool(distance < cond.threshold)
+        return bool((not min_steps_condition) | (time_condition & (not converged)))
+    raise NotImplementedError(name)
+
+
+def checkpointed_fdtd(arrays, objects, config, key=None, stopping_condition=None):
+    """fdtd.py:421-496: ``while cond(state): state = forward(state)`` bounded by time_steps_total."""
     arrays = arrays.reset()
     state = (0, arrays)
-    while state[0] < config.time_steps_total:
+    cond = None if stopping_condition is None else stopping_condition.setup(state, config, objects)
+    while state[0] < config.time_steps_total and (cond is None or evaluate_condition(cond, state, config, objects)):
         state = forward(state, config, objects, key, True, config.invertible_optimization, True)
     return state
 
 
-def run_fdtd(arrays, objects, config, key=None):
-    return checkpointed_fdtd(arrays, objects, config, key)
+def run_fdtd(arrays, objects, config, key=None, stopping_condition=None):
+    return checkpointed_fdtd(arrays, objects, config, key, stopping_condition)
 
 
 def full_backward(state, objects, config, key=None, record_detectors=True, reset_fields=True, start_time_step=0):
