@@ -586,7 +586,7 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
 
 static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
   if (p->nz % 4 != 0) return false;
-  const void* ptrs[] = {P.E, P.H, P.eps, P.mu, P.haloH, P.haloE};
+  const void* ptrs[] = {P.E, P.H, P.eps, P.mu, P.haloH, P.haloE, P.sigE, P.sigH, P.P_cur, P.P_new, P.c1, P.c2, P.c3, P.c4};
   for (const void* q : ptrs)
     if (q && !aligned16(q)) return false;
   for (int a = 0; a < 2; ++a)

@@ -460,6 +460,133 @@ struct PmlLane {
   }                                                                                                                    \
   const bool psi_st = P.simulate && P.psi_store;
 
+// ------------------------------------------------------------------------------------------------
+// Material update of one plane for the V cells of a thread (update.py:298-354, 526-609 for E;
+// 736-750, 856-930 for H), shared by the marching and the TMA-staged kernels.  Conductivity, the ADE
+// polarisation arrays and their coefficients move as whole vectors (128-bit, or nv predicated 32-bit
+// accesses on ragged rows); `ok` is false for lanes that overhang the grid (staged kernels).
+// Arithmetic order is the reference's, element by element.
+// ------------------------------------------------------------------------------------------------
+template <int V, bool REV, bool SIG, bool ADE>
+__device__ __forceinline__ void material_update_E(const StepParams& P, const long long N, const long long cell0, const bool ok, const int nv,
+                                                  const Vec<V> (&Eo)[3], const Vec<V> (&K)[3], const Vec<V> (&ie)[3], Vec<V> (&out)[3]) {
+  Vec<V> sg[3];
+  if (SIG) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c == 0 || P.sigE_cs != 0) sg[c] = ok ? ldv<V>(P.sigE + c * P.sigE_cs + cell0, nv) : zerov<V>();
+      else sg[c] = sg[0];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    Vec<V> s, E1;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (REV) {
+        // update_E_reverse: ((1+s)E - c K inv_eps) / (1-s)
+        if (SIG) {
+          const float sv = (((P.cour * sg[c].v[e]) * P.eta0) * ie[c].v[e]) / 2.0f;
+          const float Ec = Eo[c].v[e] * (1.0f + sv);
+          E1.v[e] = (Ec - (P.cour * K[c].v[e]) * ie[c].v[e]) / (1.0f - sv);
+        } else {
+          E1.v[e] = Eo[c].v[e] - (P.cour * K[c].v[e]) * ie[c].v[e];
+        }
+      } else if (SIG) {
+        s.v[e] = (((P.cour * sg[c].v[e]) * P.eta0) * ie[c].v[e]) / 2.0f;
+        E1.v[e] = (1.0f - s.v[e]) * Eo[c].v[e] + (P.cour * K[c].v[e]) * ie[c].v[e];
+      } else {
+        s.v[e] = 0.0f;
+        E1.v[e] = Eo[c].v[e] + (P.cour * K[c].v[e]) * ie[c].v[e];
+      }
+    }
+    if (!REV && ADE) {
+      if (ok) {
+        // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
+        const long long pstride = 3 * N;
+        const long long cstride = P.c_cs ? 3 * N : N;
+        Vec<V> delta = zerov<V>(), c4sum = zerov<V>();
+        for (int p = 0; p < P.n_poles; ++p) {
+          const long long pi = p * pstride + c * N + cell0;
+          const long long ci = p * cstride + c * P.c_cs + cell0;
+          const Vec<V> Pc = ldv<V>(P.P_cur + pi, nv), Pp = ldv<V>(P.P_new + pi, nv);
+          const Vec<V> a1 = ldv<V>(P.c1 + ci, nv), a2 = ldv<V>(P.c2 + ci, nv), a3 = ldv<V>(P.c3 + ci, nv);
+          Vec<V> a4 = zerov<V>();
+          if (P.has_c4) a4 = ldv<V>(P.c4 + ci, nv);
+          Vec<V> Phat;
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            Phat.v[e] = (a1.v[e] * Pc.v[e] + a2.v[e] * Pp.v[e]) + a3.v[e] * Eo[c].v[e];
+            const float dd = Pc.v[e] - Phat.v[e];
+            delta.v[e] = (p == 0) ? dd : delta.v[e] + dd;
+            if (P.has_c4) c4sum.v[e] = (p == 0) ? a4.v[e] : c4sum.v[e] + a4.v[e];
+          }
+          stv<V>(P.P_new + pi, Phat, nv);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          E1.v[e] = E1.v[e] + ie[c].v[e] * delta.v[e];
+          if (P.has_c4) {
+            float divisor = 1.0f + ie[c].v[e] * c4sum.v[e];
+            if (SIG) divisor = divisor + s.v[e];
+            E1.v[e] = E1.v[e] / divisor;
+          } else if (SIG) {
+            E1.v[e] = E1.v[e] / (1.0f + s.v[e]);
+          }
+        }
+        if (P.has_c4) {
+          for (int p = 0; p < P.n_poles; ++p) {
+            const long long pi = p * pstride + c * N + cell0;
+            const long long ci = p * cstride + c * P.c_cs + cell0;
+            Vec<V> Pn = ldv<V>(P.P_new + pi, nv);
+            const Vec<V> a4 = ldv<V>(P.c4 + ci, nv);
+#pragma unroll
+            for (int e = 0; e < V; ++e) Pn.v[e] = Pn.v[e] + a4.v[e] * E1.v[e];
+            stv<V>(P.P_new + pi, Pn, nv);
+          }
+        }
+      }
+    } else if (!REV && SIG) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) E1.v[e] = E1.v[e] / (1.0f + s.v[e]);
+    }
+    out[c] = E1;
+  }
+}
+
+template <int V, bool REV, bool SIG>
+__device__ __forceinline__ void material_update_H(const StepParams& P, const long long cell0, const bool ok, const int nv,
+                                                  const Vec<V> (&Ho)[3], const Vec<V> (&K)[3], const Vec<V> (&im)[3], Vec<V> (&out)[3]) {
+  Vec<V> sg[3];
+  if (SIG) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c == 0 || P.sigH_cs != 0) sg[c] = ok ? ldv<V>(P.sigH + c * P.sigH_cs + cell0, nv) : zerov<V>();
+      else sg[c] = sg[0];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (SIG) {
+        const float sv = (((P.cour * sg[c].v[e]) / P.eta0) * im[c].v[e]) / 2.0f;
+        if (REV) {
+          const float Hc = Ho[c].v[e] * (1.0f + sv);
+          out[c].v[e] = (Hc + (P.cour * K[c].v[e]) * im[c].v[e]) / (1.0f - sv);
+        } else {
+          const float H1 = (1.0f - sv) * Ho[c].v[e] - (P.cour * K[c].v[e]) * im[c].v[e];
+          out[c].v[e] = H1 / (1.0f + sv);
+        }
+      } else if (REV) {
+        out[c].v[e] = Ho[c].v[e] + (P.cour * K[c].v[e]) * im[c].v[e];
+      } else {
+        out[c].v[e] = Ho[c].v[e] - (P.cour * K[c].v[e]) * im[c].v[e];
+      }
+    }
+  }
+}
+
 #if !defined(FDTDX_BUILD_H)
 // ------------------------------------------------------------------------------------------------
 // E half-step
@@ -601,71 +728,10 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     }
     FDTDX_CPML_BLOCK(psiE, aE, bE, kE)
     // material update
-    Vec<V> o0, o1, o2;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float Eo[3] = {ex.v[e], ey.v[e], ez.v[e]};
-      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-      const float ie[3] = {ie0.v[e], ie1.v[e], ie2.v[e]};
-      float En[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (REV) {
-          // update_E_reverse: ((1+s)E - c K inv_eps) / (1-s)
-          if (SIG) {
-            const float sg = (e < nv) ? P.sigE[c * P.sigE_cs + (pE - P.E) + e * FDTDX_ES] : 0.0f;
-            const float s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-            const float Ec = Eo[c] * (1.0f + s);
-            En[c] = (Ec - (P.cour * K[c]) * ie[c]) / (1.0f - s);
-          } else {
-            En[c] = Eo[c] - (P.cour * K[c]) * ie[c];
-          }
-        } else {
-          float s = 0.0f;
-          float E1;
-          if (SIG) {
-            const float sg = (e < nv) ? P.sigE[c * P.sigE_cs + (pE - P.E) + e * FDTDX_ES] : 0.0f;
-            s = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-            E1 = (1.0f - s) * Eo[c] + (P.cour * K[c]) * ie[c];
-          } else {
-            E1 = Eo[c] + (P.cour * K[c]) * ie[c];
-          }
-          if (ADE && e < nv) {
-            // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
-            const long long cell = (pE - P.E) + e * FDTDX_ES;
-            const long long pstride = 3 * N;
-            float delta = 0.0f, c4sum = 0.0f;
-            for (int p = 0; p < P.n_poles; ++p) {
-              const long long pi = p * pstride + c * N + cell;
-              const long long ci = (long long)p * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-              const float Pc = P.P_cur[pi], Pp = P.P_new[pi];
-              const float Phat = (P.c1[ci] * Pc + P.c2[ci] * Pp) + P.c3[ci] * Eo[c];
-              const float dd = Pc - Phat;
-              delta = (p == 0) ? dd : delta + dd;
-              if (P.has_c4) c4sum = (p == 0) ? P.c4[ci] : c4sum + P.c4[ci];
-              P.P_new[pi] = Phat;
-            }
-            E1 = E1 + ie[c] * delta;
-            if (P.has_c4) {
-              float divisor = 1.0f + ie[c] * c4sum;
-              if (SIG) divisor = divisor + s;
-              E1 = E1 / divisor;
-              for (int p = 0; p < P.n_poles; ++p) {
-                const long long pi = p * pstride + c * N + cell;
-                const long long ci = (long long)p * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-                P.P_new[pi] = P.P_new[pi] + P.c4[ci] * E1;
-              }
-            } else if (SIG) {
-              E1 = E1 / (1.0f + s);
-            }
-          } else if (SIG) {
-            E1 = E1 / (1.0f + s);
-          }
-          En[c] = E1;
-        }
-      }
-      o0.v[e] = En[0]; o1.v[e] = En[1]; o2.v[e] = En[2];
-    }
+    const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
+    Vec<V> o3[3];
+    material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, true, nv, Eo3, K3, ie3, o3);
+    Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
     if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
     stv<V>(pE, o0, nv);
@@ -828,35 +894,17 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
       dyFz.v[e] = dyEz; dzFy.v[e] = dzEy; dzFx.v[e] = dzEx;
     }
     FDTDX_CPML_BLOCK(psiH, aH, bH, kH)
-    Vec<V> o0, o1, o2;
+    Vec<V> im3[3];
+    if (MUT >= 1) { im3[0] = im0; im3[1] = im1; im3[2] = im2; }
+    else {
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float Ho[3] = {hx.v[e], hy.v[e], hz.v[e]};
-      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-      float im[3];
-      if (MUT >= 1) { im[0] = im0.v[e]; im[1] = im1.v[e]; im[2] = im2.v[e]; }
-      else { im[0] = im[1] = im[2] = P.inv_mu_scalar; }
-      float Hn[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (SIG) {
-          const float sg = (e < nv) ? P.sigH[c * P.sigH_cs + (pH - P.H) + e * FDTDX_ES] : 0.0f;
-          const float s = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
-          if (REV) {
-            const float Hc = Ho[c] * (1.0f + s);
-            Hn[c] = (Hc + (P.cour * K[c]) * im[c]) / (1.0f - s);
-          } else {
-            const float H1 = (1.0f - s) * Ho[c] - (P.cour * K[c]) * im[c];
-            Hn[c] = H1 / (1.0f + s);
-          }
-        } else if (REV) {
-          Hn[c] = Ho[c] + (P.cour * K[c]) * im[c];
-        } else {
-          Hn[c] = Ho[c] - (P.cour * K[c]) * im[c];
-        }
-      }
-      o0.v[e] = Hn[0]; o1.v[e] = Hn[1]; o2.v[e] = Hn[2];
+      for (int e = 0; e < V; ++e) im3[0].v[e] = P.inv_mu_scalar;
+      im3[1] = im3[0]; im3[2] = im3[0];
     }
+    const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
+    Vec<V> o3[3];
+    material_update_H<V, REV, SIG>(P, pH - P.H, true, nv, Ho3, K3, im3, o3);
+    Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     stv<V>(pH, o0, nv);
     stv<V>(pH + N, o1, nv);

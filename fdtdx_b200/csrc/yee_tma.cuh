@@ -406,72 +406,10 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     if (++s == S) { s = 0; ph ^= 1; }
 
-    Vec<V> o0, o1, o2;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float Eo[3] = {ex.v[e], ey.v[e], ez.v[e]};
-      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-      const float ie[3] = {ie0.v[e], ie1.v[e], ie2.v[e]};
-      float En[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (REV) {
-          if (SIG) {
-            const float sg = lane_ok ? P.sigE[c * P.sigE_cs + (pE - P.E) + e] : 0.0f;
-            const float sgm = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-            const float Ec = Eo[c] * (1.0f + sgm);
-            En[c] = (Ec - (P.cour * K[c]) * ie[c]) / (1.0f - sgm);
-          } else {
-            En[c] = Eo[c] - (P.cour * K[c]) * ie[c];
-          }
-        } else {
-          float sgm = 0.0f;
-          float E1;
-          if (SIG) {
-            const float sg = lane_ok ? P.sigE[c * P.sigE_cs + (pE - P.E) + e] : 0.0f;
-            sgm = (((P.cour * sg) * P.eta0) * ie[c]) / 2.0f;
-            E1 = (1.0f - sgm) * Eo[c] + (P.cour * K[c]) * ie[c];
-          } else {
-            E1 = Eo[c] + (P.cour * K[c]) * ie[c];
-          }
-          if (ADE) {
-            if (lane_ok) {
-              // P_hat = c1 P + c2 P_prev + c3 E ; E += inv_eps * sum_p (P - P_hat)   (update.py:330-332)
-              const long long cell = (pE - P.E) + e;
-              const long long pstride = 3 * N;
-              float delta = 0.0f, c4sum = 0.0f;
-              for (int q = 0; q < P.n_poles; ++q) {
-                const long long pi = q * pstride + c * N + cell;
-                const long long ci = (long long)q * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-                const float Pc = P.P_cur[pi], Pp = P.P_new[pi];
-                const float Phat = (P.c1[ci] * Pc + P.c2[ci] * Pp) + P.c3[ci] * Eo[c];
-                const float dd = Pc - Phat;
-                delta = (q == 0) ? dd : delta + dd;
-                if (P.has_c4) c4sum = (q == 0) ? P.c4[ci] : c4sum + P.c4[ci];
-                P.P_new[pi] = Phat;
-              }
-              E1 = E1 + ie[c] * delta;
-              if (P.has_c4) {
-                float divisor = 1.0f + ie[c] * c4sum;
-                if (SIG) divisor = divisor + sgm;
-                E1 = E1 / divisor;
-                for (int q = 0; q < P.n_poles; ++q) {
-                  const long long pi = q * pstride + c * N + cell;
-                  const long long ci = (long long)q * (P.c_cs ? 3 * N : N) + c * P.c_cs + cell;
-                  P.P_new[pi] = P.P_new[pi] + P.c4[ci] * E1;
-                }
-              } else if (SIG) {
-                E1 = E1 / (1.0f + sgm);
-              }
-            }
-          } else if (SIG) {
-            E1 = E1 / (1.0f + sgm);
-          }
-          En[c] = E1;
-        }
-      }
-      o0.v[e] = En[0]; o1.v[e] = En[1]; o2.v[e] = En[2];
-    }
+    const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
+    Vec<V> o3[3];
+    material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, lane_ok, V, Eo3, K3, ie3, o3);
+    Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
     if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
     if (lane_ok) {
@@ -660,35 +598,17 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     s = sn;
     ph = phn;
 
-    Vec<V> o0, o1, o2;
+    Vec<V> im3[3];
+    if (MUT >= 1) { im3[0] = im0; im3[1] = im1; im3[2] = im2; }
+    else {
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float Ho[3] = {hx.v[e], hy.v[e], hz.v[e]};
-      const float K[3] = {Kx.v[e], Ky.v[e], Kz.v[e]};
-      float im[3];
-      if (MUT >= 1) { im[0] = im0.v[e]; im[1] = im1.v[e]; im[2] = im2.v[e]; }
-      else { im[0] = im[1] = im[2] = P.inv_mu_scalar; }
-      float Hn[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (SIG) {
-          const float sg = lane_ok ? P.sigH[c * P.sigH_cs + (pH - P.H) + e] : 0.0f;
-          const float sgm = (((P.cour * sg) / P.eta0) * im[c]) / 2.0f;
-          if (REV) {
-            const float Hc = Ho[c] * (1.0f + sgm);
-            Hn[c] = (Hc + (P.cour * K[c]) * im[c]) / (1.0f - sgm);
-          } else {
-            const float H1 = (1.0f - sgm) * Ho[c] - (P.cour * K[c]) * im[c];
-            Hn[c] = H1 / (1.0f + sgm);
-          }
-        } else if (REV) {
-          Hn[c] = Ho[c] + (P.cour * K[c]) * im[c];
-        } else {
-          Hn[c] = Ho[c] - (P.cour * K[c]) * im[c];
-        }
-      }
-      o0.v[e] = Hn[0]; o1.v[e] = Hn[1]; o2.v[e] = Hn[2];
+      for (int e = 0; e < V; ++e) im3[0].v[e] = P.inv_mu_scalar;
+      im3[1] = im3[0]; im3[2] = im3[0];
     }
+    const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
+    Vec<V> o3[3];
+    material_update_H<V, REV, SIG>(P, pH - P.H, lane_ok, V, Ho3, K3, im3, o3);
+    Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     if (lane_ok) {
       stv<V>(pH, o0);
