@@ -603,6 +603,8 @@ void fdtdx_dispatch_E4(const StepParams& P, int t, int tier, int pm, bool rev, b
 void fdtdx_dispatch_E1(const StepParams& P, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g, dim3 b, cudaStream_t st);
 void fdtdx_dispatch_H4(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
 void fdtdx_dispatch_H1(const StepParams& P, int t, int mu_tier, int pm, bool rev, bool sig, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_E4_konly(const StepParams& P, int t, int pm, bool rev, bool met, dim3 g, dim3 b, cudaStream_t st);
+void fdtdx_dispatch_H4_konly(const StepParams& P, int t, int pm, bool rev, bool met, dim3 g, dim3 b, cudaStream_t st);
 struct alignas(64) TmaSet {
   CUtensorMap fld_halo, fld_plain, mat_plain, xhalo;
 };

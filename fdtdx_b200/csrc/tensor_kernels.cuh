@@ -241,7 +241,7 @@ static __device__ __noinline__ void t_inject(const TensorParams& P, int t, bool 
 
 // reverse pass: sources are removed from the field *before* the averages are taken
 // (update.py:558-584 / 877-903); in place on F_in's buffer (passed as F_out here).
-__global__ void tensor_inject_kernel(const TensorParams P, const int t, const int src_index) {
+__global__ void tensor_inject_kernel(const TensorParams P, const int t, const int src_index, const int inverse = 1) {
   const SrcDev& S = P.src[src_index];
   const int ex = S.hi[0] - S.lo[0], ey = S.hi[1] - S.lo[1], ez = S.hi[2] - S.lo[2];
   const long long n = (long long)ex * ey * ez;
@@ -255,7 +255,17 @@ __global__ void tensor_inject_kernel(const TensorParams P, const int t, const in
   TensorParams R = P;  // apply only source `src_index` (sources are independent additive terms)
   R.src = P.src + src_index;
   R.n_src = 1;
-  t_inject(R, t, true, x, y, z, cell, Fv);
+  t_inject(R, t, inverse != 0, x, y, z, cell, Fv);
+  if (!inverse) {  // forward order: update -> sources -> PEC / PMC mask
+    for (int w = 0; w < P.n_walls; ++w) {
+      const WallDev W = P.walls[w];
+      if (W.kind == (P.is_E ? 0 : 1) && in_box(W.lo, W.hi, x, y, z)) {
+        if (W.axis != 0) Fv[0] = 0.0f;
+        if (W.axis != 1) Fv[1] = 0.0f;
+        if (W.axis != 2) Fv[2] = 0.0f;
+      }
+    }
+  }
   P.F_out[cell] = Fv[0];
   P.F_out[N + cell] = Fv[1];
   P.F_out[2 * N + cell] = Fv[2];
@@ -296,4 +306,86 @@ __global__ void tensor_apply_kernel(const TensorParams P, const int t) {
   P.F_out[cell] = out[0];
   P.F_out[N + cell] = out[1];
   P.F_out[2 * N + cell] = out[2];
+}
+
+// phase 2, four cells per thread with 128-bit accesses (uniform grid, Nz % 4 == 0, aligned buffers):
+// same samples and the same summation order as tensor_apply_kernel / t_avg.  Sources are applied
+// afterwards by tensor_inject_kernel (O(surface)); blockDim (32, 8), grid (z tiles, y tiles, x planes).
+template <bool IS_E>
+__global__ void __launch_bounds__(256) tensor_apply4_kernel(const TensorParams P) {
+  constexpr int V = 4;
+  const int k0 = (blockIdx.x * 32 + threadIdx.x) * V;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (k0 >= P.nz || y >= P.ny) return;
+  const long long plane = (long long)P.ny * P.nz, N = plane * P.nx;
+  const long long cell0 = (long long)x * plane + (long long)y * P.nz + k0;
+  const bool plus = IS_E != (P.reverse != 0);
+  // component c of F at cells (x+dx, y+dy, k0+dz .. k0+dz+3), halo rule of pad_fields
+  auto ldsh = [&](const float* F, int c, int dx, int dy, int dz) -> Vec<V> {
+    int xx = x + dx, yy = y + dy;
+    if (xx < 0) { if (P.wrap[0]) xx += P.nx; else return zerov<V>(); }
+    if (xx >= P.nx) { if (P.wrap[0]) xx -= P.nx; else return zerov<V>(); }
+    if (yy < 0) { if (P.wrap[1]) yy += P.ny; else return zerov<V>(); }
+    if (yy >= P.ny) { if (P.wrap[1]) yy -= P.ny; else return zerov<V>(); }
+    const float* row = F + c * N + (long long)xx * plane + (long long)yy * P.nz;
+    const Vec<V> v = ldv<V>(row + k0);
+    if (dz == 0) return v;
+    int kz = (dz > 0) ? k0 + V : k0 - 1;
+    float edge = 0.0f;
+    bool ok = true;
+    if (kz < 0) { if (P.wrap[2]) kz = P.nz - 1; else ok = false; }
+    if (kz >= P.nz) { if (P.wrap[2]) kz = 0; else ok = false; }
+    if (ok) edge = row[kz];
+    Vec<V> r;
+    if (dz > 0) { r.v[0] = v.v[1]; r.v[1] = v.v[2]; r.v[2] = v.v[3]; r.v[3] = edge; }
+    else { r.v[0] = edge; r.v[1] = v.v[0]; r.v[2] = v.v[1]; r.v[3] = v.v[2]; }
+    return r;
+  };
+  Vec<V> F0[3], K0[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { F0[q] = ldv<V>(P.F_in + q * N + cell0); K0[q] = ldv<V>(P.K + q * N + cell0); }
+  Vec<V> out[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Vec<V> fa[3], ka[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q == r) { fa[q] = F0[q]; ka[q] = K0[q]; continue; }
+      // t_avg(F, c = q, l = r): E: p, p + e_l, p - e_c, p + e_l - e_c ; H: p, p - e_l, p + e_c, p - e_l + e_c
+      const int sl = IS_E ? +1 : -1, scn = IS_E ? -1 : +1;
+      const int lx = (r == 0) * sl, ly = (r == 1) * sl, lz = (r == 2) * sl;
+      const int cx = (q == 0) * scn, cy = (q == 1) * scn, cz = (q == 2) * scn;
+      const Vec<V> f10 = ldsh(P.F_in, q, lx, ly, lz), f01 = ldsh(P.F_in, q, cx, cy, cz), f11 = ldsh(P.F_in, q, lx + cx, ly + cy, lz + cz);
+      const Vec<V> k10 = ldsh(P.K, q, lx, ly, lz), k01 = ldsh(P.K, q, cx, cy, cz), k11 = ldsh(P.K, q, lx + cx, ly + cy, lz + cz);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        fa[q].v[e] = (((F0[q].v[e] + f10.v[e]) + f01.v[e]) + f11.v[e]) / 4.0f;
+        ka[q].v[e] = (((K0[q].v[e] + k10.v[e]) + k01.v[e]) + k11.v[e]) / 4.0f;
+      }
+    }
+    Vec<V> b0 = ldv<V>(P.B + (long long)(3 * r + 0) * N + cell0), b1 = ldv<V>(P.B + (long long)(3 * r + 1) * N + cell0), b2 = ldv<V>(P.B + (long long)(3 * r + 2) * N + cell0);
+    Vec<V> a0, a1, a2;
+    if (P.A) { a0 = ldv<V>(P.A + (long long)(3 * r + 0) * N + cell0); a1 = ldv<V>(P.A + (long long)(3 * r + 1) * N + cell0); a2 = ldv<V>(P.A + (long long)(3 * r + 2) * N + cell0); }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float t1 = P.A ? (a0.v[e] * fa[0].v[e] + a1.v[e] * fa[1].v[e]) + a2.v[e] * fa[2].v[e] : fa[r].v[e];
+      const float t2 = (b0.v[e] * ka[0].v[e] + b1.v[e] * ka[1].v[e]) + b2.v[e] * ka[2].v[e];
+      out[r].v[e] = plus ? (t1 + t2) : (t1 - t2);
+    }
+  }
+  for (int w = 0; w < P.n_walls; ++w) {
+    const WallDev W = P.walls[w];
+    if (W.kind != (IS_E ? 0 : 1) || x < W.lo[0] || x >= W.hi[0] || y < W.lo[1] || y >= W.hi[1]) continue;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (k0 + e >= W.lo[2] && k0 + e < W.hi[2]) {
+        if (W.axis != 0) out[0].v[e] = 0.0f;
+        if (W.axis != 1) out[1].v[e] = 0.0f;
+        if (W.axis != 2) out[2].v[e] = 0.0f;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) stv<V>(P.F_out + r * N + cell0, out[r]);
 }

@@ -57,8 +57,43 @@ static int tensor_step(FdtdxPlan* p, int t, int simulate, bool rev, bool is_E, c
       p->launches++;
     }
   }
-  tensor_curl_kernel<<<blocks, 256, 0, st>>>(T);
-  tensor_apply_kernel<<<blocks, 256, 0, st>>>(T, t);
+  // 128-bit fast path: phase 1 = the marching half-step kernel in curl-only mode (register queue,
+  // shuffles, L2 prefetch), phase 2 = tensor_apply4_kernel, sources by O(surface) launches afterwards
+  bool fast = (p->nz % 4 == 0) && can_vec4(p, S) && aligned16(T.K) && aligned16(T.A) && aligned16(T.B) && aligned16(T.F_in) &&
+              aligned16(T.F_out) && aligned16(T.F_other);
+  {
+    const char* e = getenv("FDTDX_B200_TENSOR_FAST");
+    if (e && e[0] == '0') fast = false;
+  }
+  if (fast && T.n_poles == 0) {
+    StepParams Q = S;
+    if (is_E) { Q.H = const_cast<float*>(T.F_other); Q.E = T.K; }
+    else { Q.E = const_cast<float*>(T.F_other); Q.H = T.K; }
+    dim3 b(32, p->rows);
+    dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    if (is_E) fdtdx_dispatch_E4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
+    else fdtdx_dispatch_H4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
+  } else {
+    tensor_curl_kernel<<<blocks, 256, 0, st>>>(T);
+  }
+  if (fast && T.w[0] == nullptr) {
+    TensorParams T2 = T;
+    T2.n_src = 0;
+    dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, p->nx);
+    if (is_E) tensor_apply4_kernel<true><<<g, b, 0, st>>>(T2);
+    else tensor_apply4_kernel<false><<<g, b, 0, st>>>(T2);
+    if (!rev) {
+      for (size_t si = 0; si < p->srcs.size(); ++si) {
+        const SrcDev& d = p->srcs[si].d;
+        const long long n = (long long)(d.hi[0] - d.lo[0]) * (d.hi[1] - d.lo[1]) * (d.hi[2] - d.lo[2]);
+        if (n <= 0) continue;
+        tensor_inject_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, t, (int)si, 0);
+        p->launches++;
+      }
+    }
+  } else {
+    tensor_apply_kernel<<<blocks, 256, 0, st>>>(T, t);
+  }
   p->launches += 2;
   CUDA_TRY(cudaGetLastError());
   if (is_E) {

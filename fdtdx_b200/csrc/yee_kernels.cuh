@@ -591,7 +591,9 @@ __device__ __forceinline__ void material_update_H(const StepParams& P, const lon
 // ------------------------------------------------------------------------------------------------
 // E half-step
 // ------------------------------------------------------------------------------------------------
-template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
+// KONLY: write the curl (with its CPML correction) to P.E instead of updating it - phase 1 of the
+// full-tensor tier (tensor_kernels.cuh); E, inv_eps, sources and walls are not touched.
+template <int V, int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, bool KONLY = false>
 static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
@@ -644,7 +646,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     hz_im = zerov<V>();
   }
 
-  if (REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
+  if (!KONLY && REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
     const Vec<V> hx = ldv<V>(pH, nv), hy = ldv<V>(pH + N, nv), hz = ldv<V>(pH + 2 * N, nv);
     Vec<V> hx_jm, hz_jm;
@@ -655,24 +657,28 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
       hx_jm = zerov<V>();
       hz_jm = zerov<V>();
     }
-    const Vec<V> ex = ldv<V>(pE, nv), ey = ldv<V>(pE + N, nv), ez = ldv<V>(pE + 2 * N, nv);
-    const Vec<V> ie0 = ldv<V>(pEps, nv);
-    Vec<V> ie1, ie2;
-    if (TIER == 3) {
-      ie1 = ldv<V>(pEps + P.eps_cs, nv);
-      ie2 = ldv<V>(pEps + 2 * P.eps_cs, nv);
-    } else {
-      ie1 = ie0;
-      ie2 = ie0;
+    Vec<V> ex, ey, ez, ie0, ie1, ie2;
+    if (!KONLY) {
+      ex = ldv<V>(pE, nv); ey = ldv<V>(pE + N, nv); ez = ldv<V>(pE + 2 * N, nv);
+      ie0 = ldv<V>(pEps, nv);
+      if (TIER == 3) {
+        ie1 = ldv<V>(pEps + P.eps_cs, nv);
+        ie2 = ldv<V>(pEps + 2 * P.eps_cs, nv);
+      } else {
+        ie1 = ie0;
+        ie2 = ie0;
+      }
     }
     FDTDX_CPML_LOADS(psiE)
     // L2 prefetch of this thread's lines FDTDX_PF_DIST planes ahead (holds no registers)
     if (i + FDTDX_PF_DIST < ic1) {
       const long long pb = FDTDX_PF_DIST * plane;
       prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb);
-      prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
-      prefetch_l2(pEps + pb);
-      if (TIER == 3) { prefetch_l2(pEps + P.eps_cs + pb); prefetch_l2(pEps + 2 * P.eps_cs + pb); }
+      if (!KONLY) {
+        prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
+        prefetch_l2(pEps + pb);
+        if (TIER == 3) { prefetch_l2(pEps + P.eps_cs + pb); prefetch_l2(pEps + 2 * P.eps_cs + pb); }
+      }
     }
     // z-neighbour (k-1) of the first element: last element of the previous lane
     Vec<V> hx_kmv, hy_kmv;
@@ -728,12 +734,16 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     }
     FDTDX_CPML_BLOCK(psiE, aE, bE, kE)
     // material update
-    const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
     Vec<V> o3[3];
-    material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, true, nv, Eo3, K3, ie3, o3);
+    if (KONLY) {
+      o3[0] = Kx; o3[1] = Ky; o3[2] = Kz;
+    } else {
+      const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
+      material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, true, nv, Eo3, K3, ie3, o3);
+    }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
-    if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
+    if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
     stv<V>(pE, o0, nv);
     stv<V>(pE + N, o1, nv);
     stv<V>(pE + 2 * N, o2, nv);
@@ -743,7 +753,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     pE += plane;
     pEps += plane;
   }
-  if (!REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (!KONLY && !REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
 }
 
 #endif  // !FDTDX_BUILD_H
@@ -752,7 +762,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
 // ------------------------------------------------------------------------------------------------
 // H half-step
 // ------------------------------------------------------------------------------------------------
-template <int V, int MUT, bool REV, bool SIG, bool MET, int PM>
+template <int V, int MUT, bool REV, bool SIG, bool MET, int PM, bool KONLY = false>
 static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const __grid_constant__ StepParams P, const int t) {
   const int lane = threadIdx.x;
   const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
@@ -792,7 +802,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
   // register queue: E of the current plane is the "next" plane loaded one step earlier
   Vec<V> ex = ldv<V>(pE, nv), ey = ldv<V>(pE + N, nv), ez = ldv<V>(pE + 2 * N, nv);
 
-  if (REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
+  if (!KONLY && REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
   for (int i = ic0; i < ic1; ++i) {
     Vec<V> ex_n, ey_n, ez_n;
     if (i + 1 < P.nx) {
@@ -817,9 +827,10 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
       ex_jp = zerov<V>();
       ez_jp = zerov<V>();
     }
-    const Vec<V> hx = ldv<V>(pH, nv), hy = ldv<V>(pH + N, nv), hz = ldv<V>(pH + 2 * N, nv);
+    Vec<V> hx, hy, hz;
+    if (!KONLY) { hx = ldv<V>(pH, nv); hy = ldv<V>(pH + N, nv); hz = ldv<V>(pH + 2 * N, nv); }
     Vec<V> im0, im1, im2;
-    if (MUT >= 1) {
+    if (!KONLY && MUT >= 1) {
       im0 = ldv<V>(pMu, nv);
       if (MUT == 3) {
         im1 = ldv<V>(pMu + P.mu_cs, nv);
@@ -832,9 +843,9 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     FDTDX_CPML_LOADS(psiH)
     if (i + FDTDX_PF_DIST < ic1) {
       const long long pb = FDTDX_PF_DIST * plane;
-      prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb);
+      if (!KONLY) { prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb); }
       prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
-      if (MUT >= 1) prefetch_l2(pMu + pb);
+      if (!KONLY && MUT >= 1) prefetch_l2(pMu + pb);
       if (MUT == 3) { prefetch_l2(pMu + P.mu_cs + pb); prefetch_l2(pMu + 2 * P.mu_cs + pb); }
     }
     Vec<V> ex_kpv, ey_kpv;
@@ -894,18 +905,22 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
       dyFz.v[e] = dyEz; dzFy.v[e] = dzEy; dzFx.v[e] = dzEx;
     }
     FDTDX_CPML_BLOCK(psiH, aH, bH, kH)
-    Vec<V> im3[3];
-    if (MUT >= 1) { im3[0] = im0; im3[1] = im1; im3[2] = im2; }
-    else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) im3[0].v[e] = P.inv_mu_scalar;
-      im3[1] = im3[0]; im3[2] = im3[0];
-    }
-    const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
     Vec<V> o3[3];
-    material_update_H<V, REV, SIG>(P, pH - P.H, true, nv, Ho3, K3, im3, o3);
+    if (KONLY) {
+      o3[0] = Kx; o3[1] = Ky; o3[2] = Kz;
+    } else {
+      Vec<V> im3[3];
+      if (MUT >= 1) { im3[0] = im0; im3[1] = im1; im3[2] = im2; }
+      else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) im3[0].v[e] = P.inv_mu_scalar;
+        im3[1] = im3[0]; im3[2] = im3[0];
+      }
+      const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
+      material_update_H<V, REV, SIG>(P, pH - P.H, true, nv, Ho3, K3, im3, o3);
+    }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
-    if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
+    if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     stv<V>(pH, o0, nv);
     stv<V>(pH + N, o1, nv);
     stv<V>(pH + 2 * N, o2, nv);
@@ -916,6 +931,6 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     pH += plane;
     if (MUT >= 1) pMu += plane;
   }
-  if (!REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (!KONLY && !REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
 }
 #endif  // !FDTDX_BUILD_E
