@@ -2,6 +2,12 @@
 #define FDTDX_BUILD_E 1
 #include "yee_tma.cuh"
 #include "tma_cfg.h"
+#include <cstdlib>
+
+static bool fdtdx_tma_pdl_enabled() {
+  const char* e = getenv("FDTDX_B200_PDL");
+  return !(e && e[0] == '0');
+}
 
 template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
 static cudaError_t go_E(const StepParams& P, const TmaSet& M, int t, dim3 g, cudaStream_t st) {
@@ -16,8 +22,18 @@ static cudaError_t go_E(const StepParams& P, const TmaSet& M, int t, dim3 g, cud
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k<<<g, dim3(32, R), smem, st>>>(P, M, t);
-  return cudaSuccess;
+  // programmatic dependent launch: this grid may begin while the previous kernel of the stream drains
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g;
+  cfg.blockDim = dim3(32, R);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = fdtdx_tma_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, P, M, t);
 }
 
 template <int TIER, bool REV, int PM>

@@ -276,12 +276,10 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   float* const ztab = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ZTAB;  // a, b, 1/kappa-1 of this tile's z cells
   float* const xs = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_XS;      // metric x scale of this chunk's planes
 
-  // reverse pass: update_E_reverse undoes the injection first; it must land in global memory before
-  // the first tile load reads it (generic -> async proxy)
-  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
-    src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
-    asm volatile("fence.proxy.async;" ::: "memory");
-  }
+  // Programmatic dependent launch: let the next kernel of the stream start scheduling its CTAs into
+  // this grid's tail as soon as every CTA of this grid is resident; everything up to the
+  // griddepcontrol.wait below touches only constant tables and shared memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
   for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
     const int tb = q / TZ, k = kt0 + (q - tb * TZ);
@@ -302,6 +300,14 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // the previous kernel of the stream (the other half-step) must have completed and flushed from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // reverse pass: update_E_reverse undoes the injection first; it must land in global memory before
+  // the first tile load reads it (generic -> async proxy)
+  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+    src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
+    asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1
@@ -479,10 +485,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   float* const ztab = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ZTAB;  // a, b, 1/kappa-1 of this tile's z cells
   float* const xs = fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_XS;      // metric x scale of this chunk's planes
 
-  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
-    src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
-    asm volatile("fence.proxy.async;" ::: "memory");
-  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
   for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
     const int tb = q / TZ, k = kt0 + (q - tb * TZ);
@@ -503,6 +506,11 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+    src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
+    asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1 (plane ic1 is the Ey,Ez-only stage)
