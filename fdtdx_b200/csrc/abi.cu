@@ -586,6 +586,11 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
 
 static bool can_vec4(const FdtdxPlan* p, const StepParams& P) {
   if (p->nz % 4 != 0) return false;
+  {
+    // the 4-cells-per-lane CPML paths assume a lane never touches both z slabs (tiny grids only)
+    const AxisPmlDev& Z = P.pml[2];
+    if (Z.lo_len > 0 && Z.hi_len > 0 && (Z.lo_len - 1) / 4 == Z.hi_start / 4) return false;
+  }
   const void* ptrs[] = {P.E, P.H, P.eps, P.mu, P.haloH, P.haloE, P.sigE, P.sigH, P.P_cur, P.P_new, P.c1, P.c2, P.c3, P.c4};
   for (const void* q : ptrs)
     if (q && !aligned16(q)) return false;

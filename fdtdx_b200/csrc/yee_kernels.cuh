@@ -309,6 +309,7 @@ __device__ __forceinline__ void cpml_axis_v(const Vec<V>& a, const Vec<V>& b, co
 template <int V>
 struct PmlLane {
   bool in_y, any_z, zvec, zh0, zh1;
+  int zm;  // aligned kernels, PM == 1: bit e set = cell k0+e lies in this lane's z slab
   long long ystride, yoff;  // psi index of plane i: i * ystride + yoff
   long long zstride, zoff;
   float ay, by, ky;
@@ -318,6 +319,14 @@ struct PmlLane {
 // The CPML block shared by both half-steps.  PSI selects the E-side (psiE, aE..) or H-side tables.
 // dX* are the six derivative vectors of this plane; K* the curl components to correct.
 // Object order of the reference: x slabs, y slabs, z slabs.
+// one cell of the masked z-slab path of the aligned kernels (PM == 1)
+#define FDTDX_CPML_ZCELL(E_)                                                                                           \
+      if (V == 4 && (L.zm & (1 << E_))) {                                                                              \
+        if (k1) cpml_axis_v<V, E_ % V, E_ % V + 1, !REV, true>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);      \
+        else cpml_axis_v<V, E_ % V, E_ % V + 1, !REV, false>(L.az, L.bz, L.kz, dzFy, dzFx, psz1, psz2, Kx, Ky);        \
+        if (!REV && psi_st) { qz1[E_ % V] = psz1.v[E_ % V]; qz2[E_ % V] = psz2.v[E_ % V]; }                            \
+      }
+
 #define FDTDX_CPML_BLOCK(PSI, AT, BT, KT)                                                                              \
   if (PM > 0) {                                                                                                        \
     if (in_x) {                                                                                                        \
@@ -352,7 +361,10 @@ struct PmlLane {
           }                                                                                                            \
         }                                                                                                              \
       }                                                                                                                \
-    } else if (L.any_z) {                                                                                              \
+    } else if (!FDTDX_RAGGED && L.zm) {                                                                                \
+      const bool k1 = pz.kappa_one;                                                                                    \
+      FDTDX_CPML_ZCELL(0) FDTDX_CPML_ZCELL(1) FDTDX_CPML_ZCELL(2) FDTDX_CPML_ZCELL(3)                                  \
+    } else if (FDTDX_RAGGED && L.any_z) {                                                                              \
       _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
         const int k = k0 + e * FDTDX_ES;                                                                               \
         if (k < nz && (k < pz.lo_len || k >= pz.hi_start)) {                                                           \
@@ -416,6 +428,13 @@ struct PmlLane {
         }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \
+    if (!FDTDX_RAGGED && PM == 1 && L.zm) {                                                                            \
+      const long long pidx = (long long)i * L.zstride + L.zoff;                                                        \
+      qz1 = pz1 + pidx;                                                                                                \
+      qz2 = pz2 + pidx;                                                                                                \
+      _Pragma("unroll") for (int e = 0; e < V; ++e)                                                                    \
+        if (L.zm & (1 << e)) { psz1.v[e] = qz1[e]; psz2.v[e] = qz2[e]; }                                               \
+    }                                                                                                                  \
   }
 
 // Loop-invariant slab membership of this thread (y: warp-uniform, z: per lane).
@@ -424,7 +443,7 @@ struct PmlLane {
   const AxisPmlDev& py = P.pml[1];                                                                                     \
   const AxisPmlDev& pz = P.pml[2];                                                                                     \
   PmlLane<V> L;                                                                                                        \
-  L.in_y = false; L.any_z = false; L.zvec = false; L.zh0 = false; L.zh1 = false;                                       \
+  L.in_y = false; L.any_z = false; L.zvec = false; L.zh0 = false; L.zh1 = false; L.zm = 0;                             \
   float *py1 = nullptr, *py2 = nullptr, *pz1 = nullptr, *pz2 = nullptr;                                                \
   if (PM > 0 && lane_ok) {                                                                                                        \
     L.in_y = (j < py.lo_len || j >= py.hi_start);                                                                      \
@@ -453,6 +472,23 @@ struct PmlLane {
       pz1 = pz.PSI[zside][0];                                                                                          \
       pz2 = pz.PSI[zside][1];                                                                                          \
       L.az = ldv<V>(pz.AT + k0, nv); L.bz = ldv<V>(pz.BT + k0, nv); L.kz = ldv<V>(pz.KT + k0, nv);                                 \
+      if (!P.simulate) {                                                                                               \
+        _Pragma("unroll") for (int e = 0; e < V; ++e) { L.az.v[e] = 0.0f; L.bz.v[e] = 1.0f; }                          \
+      }                                                                                                                \
+    }                                                                                                                  \
+    if (!FDTDX_RAGGED && PM == 1 && L.any_z) {                                                                         \
+      /* aligned rows, slabs of any thickness / position: per-cell mask, 32-bit psi accesses */                      \
+      const int zside = (k0 + V > pz.hi_start) ? 1 : 0;                                                                \
+      const int zL = zside ? pz.hi_len : pz.lo_len;                                                                    \
+      _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
+        const int k = k0 + e;                                                                                          \
+        if (zside ? (k >= pz.hi_start && k < nz) : (k < pz.lo_len)) L.zm |= 1 << e;                                    \
+      }                                                                                                                \
+      L.zstride = (long long)ny * zL;                                                                                  \
+      L.zoff = (long long)j * zL + (zside ? k0 - pz.hi_start : k0);                                                    \
+      pz1 = pz.PSI[zside][0];                                                                                          \
+      pz2 = pz.PSI[zside][1];                                                                                          \
+      L.az = ldv<V>(pz.AT + k0, nv); L.bz = ldv<V>(pz.BT + k0, nv); L.kz = ldv<V>(pz.KT + k0, nv);                     \
       if (!P.simulate) {                                                                                               \
         _Pragma("unroll") for (int e = 0; e < V; ++e) { L.az.v[e] = 0.0f; L.bz.v[e] = 1.0f; }                          \
       }                                                                                                                \

@@ -95,6 +95,7 @@ extern __shared__ __align__(128) float fdtdx_tma_smem[];
 // ------------------------------------------------------------------------------------------------
 struct PmlT {
   bool in_y, zh0, zh1;
+  int zm;  // PM == 1: bit e set = cell k0+e lies in this lane's z slab (slabs at any thickness / position)
   int yside, zside;
   int ystride, yoff, zstride, zoff;  // psi index of plane i: i * stride + off
   float ay, by, ky;
@@ -105,7 +106,7 @@ struct PmlT {
   const AxisPmlDev& py = P.pml[1];                                                                                     \
   const AxisPmlDev& pz = P.pml[2];                                                                                     \
   PmlT L;                                                                                                              \
-  L.in_y = false; L.zh0 = false; L.zh1 = false; L.yside = 0; L.zside = 0;                                              \
+  L.in_y = false; L.zh0 = false; L.zh1 = false; L.zm = 0; L.yside = 0; L.zside = 0;                                    \
   bool any_z = false;                                                                                                  \
   Vec<V> psy1, psy2, psz1, psz2;                                                                                       \
   if (PM > 0 && lane_ok) {                                                                                             \
@@ -140,6 +141,22 @@ struct PmlT {
         psz1.v[2] = t1.x; psz1.v[3] = t1.y; psz2.v[2] = t2.x; psz2.v[3] = t2.y;                                        \
       }                                                                                                                \
     }                                                                                                                  \
+    if (PM == 1 && any_z) {                                                                                            \
+      /* slabs of any thickness / position: per-cell membership mask, 32-bit psi accesses, same pipelining */       \
+      L.zside = (k0 + V > pz.hi_start) ? 1 : 0;                                                                        \
+      const int zL = L.zside ? pz.hi_len : pz.lo_len;                                                                  \
+      _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
+        const int k = k0 + e;                                                                                          \
+        if (L.zside ? (k >= pz.hi_start && k < nz) : (k < pz.lo_len)) L.zm |= 1 << e;                                  \
+      }                                                                                                                \
+      L.zstride = ny * zL;                                                                                             \
+      L.zoff = j * zL + (L.zside ? k0 - pz.hi_start : k0);                                                             \
+      const long long pidx = (long long)ic0 * L.zstride + L.zoff;                                                      \
+      const float* q1 = pz.PSI[L.zside][0] + pidx;                                                                     \
+      const float* q2 = pz.PSI[L.zside][1] + pidx;                                                                     \
+      _Pragma("unroll") for (int e = 0; e < V; ++e)                                                                    \
+        if (L.zm & (1 << e)) { psz1.v[e] = q1[e]; psz2.v[e] = q2[e]; }                                                 \
+    }                                                                                                                  \
   }                                                                                                                    \
   const bool psi_st = P.simulate && P.psi_store;
 
@@ -154,6 +171,15 @@ struct PmlT {
       prefetch_l2(px.PSI[side][1] + pidx);                                                                             \
     }                                                                                                                  \
   }
+
+// one cell of the masked z-slab path (PM == 1): update, store, fetch the next plane's psi
+#define FDTDX_TCPML_ZCELL(E_)                                                                                          \
+      if (L.zm & (1 << E_)) {                                                                                          \
+        if (k1) cpml_axis_v<V, E_, E_ + 1, !REV, true>(az, bz, kz, dzFy, dzFx, psz1, psz2, Kx, Ky);                    \
+        else cpml_axis_v<V, E_, E_ + 1, !REV, false>(az, bz, kz, dzFy, dzFx, psz1, psz2, Kx, Ky);                      \
+        if (!REV && psi_st) { q1[E_] = psz1.v[E_]; q2[E_] = psz2.v[E_]; }                                              \
+        if (i + 1 < ic1) { psz1.v[E_] = q1[E_ + L.zstride]; psz2.v[E_] = q2[E_ + L.zstride]; }                         \
+      }
 
 #define FDTDX_TCPML_BLOCK(PSI, AT, BT, KT)                                                                             \
   if (PM > 0) {                                                                                                        \
@@ -211,28 +237,13 @@ struct PmlT {
           }                                                                                                            \
         }                                                                                                              \
       }                                                                                                                \
-    } else if (any_z) {                                                                                                \
-      _Pragma("unroll") for (int e = 0; e < V; ++e) {                                                                  \
-        const int k = k0 + e;                                                                                          \
-        if (k < pz.lo_len || k >= pz.hi_start) {                                                                       \
-          const int side = (k >= pz.hi_start) ? 1 : 0;                                                                 \
-          const int kl = side ? k - pz.hi_start : k;                                                                   \
-          const int Lz = side ? pz.hi_len : pz.lo_len;                                                                 \
-          const long long pidx = ((long long)i * ny + j) * Lz + kl;                                                    \
-          float* s1 = pz.PSI[side][0] + pidx;                                                                          \
-          float* s2 = pz.PSI[side][1] + pidx;                                                                          \
-          float q1 = *s1, q2 = *s2;                                                                                    \
-          if (!REV && P.simulate) {                                                                                    \
-            q1 = pz.BT[k] * q1 + pz.AT[k] * dzFy.v[e];                                                                 \
-            q2 = pz.BT[k] * q2 + pz.AT[k] * dzFx.v[e];                                                                 \
-            if (psi_st) { *s1 = q1; *s2 = q2; }                                                                        \
-          }                                                                                                            \
-          float c1 = q1, c2 = q2;                                                                                      \
-          if (!pz.kappa_one) { c1 = pz.KT[k] * dzFy.v[e] + q1; c2 = pz.KT[k] * dzFx.v[e] + q2; }                       \
-          Kx.v[e] = Kx.v[e] - c1;                                                                                      \
-          Ky.v[e] = Ky.v[e] + c2;                                                                                      \
-        }                                                                                                              \
-      }                                                                                                                \
+    } else if (L.zm) {                                                                                                 \
+      const Vec<V> az = lds4(ztab + lane * V), bz = lds4(ztab + FDTDX_TMA_TZ + lane * V);                              \
+      const Vec<V> kz = lds4(ztab + 2 * FDTDX_TMA_TZ + lane * V);                                                      \
+      float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                            \
+      float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                            \
+      const bool k1 = pz.kappa_one;                                                                                    \
+      FDTDX_TCPML_ZCELL(0) FDTDX_TCPML_ZCELL(1) FDTDX_TCPML_ZCELL(2) FDTDX_TCPML_ZCELL(3)                              \
     }                                                                                                                  \
   }
 
