@@ -84,6 +84,15 @@ class Plan:
         self.local_shape = (nx, ny, nz)
         self.T = max(int(config.time_steps_total), 1)
         self._keep = []  # host arrays must stay alive until the C call returns; kept for safety
+        # Ragged rows (Nz % 4 != 0) cannot use 128-bit accesses or TMA tensor maps (16-byte strides).
+        # For forward-only runs the plan then works on z-padded shadow copies: Nz is rounded up to a
+        # multiple of 4, the extra cells are kept at zero by all-component PEC+PMC walls (so they are the
+        # zero halo the z-max face would see anyway), a z-max CPML slab is extended over them with zero
+        # coefficients, and the caller's arrays are copied in before / out after every run call.
+        self.pad = 0 if (x_range is not None or any(halo)) else self._z_padding(objects, config, arrays, nz)
+        self.nz_true = nz
+        nz = nz + self.pad
+        self._shadow = {}
 
         inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
         self.eps_tier = int(inv_eps.shape[0])
@@ -108,9 +117,12 @@ class Plan:
                 b_, f_ = metric_scales(config, a)
                 if a == 0:
                     b_, f_ = b_[x0:x1], f_[x0:x1]
+                w_ = np.ascontiguousarray(config.resolved_grid.cell_widths(a), dtype=_f32)
+                if a == 2 and self.pad:  # padded cells: any finite metric (they are masked to zero)
+                    b_, f_, w_ = (np.concatenate([v, np.repeat(v[-1:], self.pad)]) for v in (b_, f_, w_))
                 sB_l.append(np.ascontiguousarray(b_))
                 sF_l.append(np.ascontiguousarray(f_))
-                w_l.append(np.ascontiguousarray(config.resolved_grid.cell_widths(a), dtype=_f32))
+                w_l.append(np.ascontiguousarray(w_, dtype=_f32))
             self._keep += sB_l + sF_l + w_l
             mk = lambda lst: (C.POINTER(C.c_float) * 3)(*[_fptr(x) for x in lst])
             sB, sF, widths = mk(sB_l), mk(sF_l), mk(w_l)
@@ -141,6 +153,29 @@ class Plan:
         self.halo = halo
         self._bound = []
 
+    @staticmethod
+    def _z_padding(objects, config, arrays, nz: int) -> int:
+        import os
+
+        if nz % 4 == 0 or os.environ.get("FDTDX_B200_PAD_Z", "1") == "0":
+            return 0
+        if config.gradient_config is not None or arrays.recording_state is not None:
+            return 0  # reverse / adjoint passes bind further (., Nz) buffers; they keep the ragged kernels
+        if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
+            return 0
+        tiers = [int(arrays.inv_permittivities.shape[0])]
+        for a in (arrays.inv_permeabilities, arrays.electric_conductivity, arrays.magnetic_conductivity):
+            if a is not None and hasattr(a, "shape") and len(a.shape) > 0:
+                tiers.append(int(a.shape[0]))
+        if any(t == 9 for t in tiers):
+            return 0
+        if not getattr(arrays.fields.E, "is_cuda", False):
+            return 0
+        for b in objects.boundary_objects:
+            if b.uses_wrap_padding and b.axis == 2:
+                return 0  # a periodic z axis wraps at the true Nz
+        return (-nz) % 4
+
     # ------------------------------------------------------------------ tables
     def _add_boundaries(self):
         self.pml_index = {}
@@ -157,6 +192,10 @@ class Plan:
             for i in (2, 5):
                 if t[i].size == 1:
                     t[i] = np.full(hi - lo, t[i][0], _f32)
+            if self.pad and pml.axis == 2 and pml.direction == "+":
+                # the slab swallows the padded cells with a = b = 1/kappa - 1 = 0 (psi stays 0, no correction)
+                t = [np.ascontiguousarray(np.concatenate([x, np.zeros(self.pad, _f32)])) for x in t]
+                hi = hi + self.pad
             idx = check(
                 self.lib.fdtdx_b200_plan_add_pml(
                     self.h, pml.axis, 1 if pml.direction == "+" else 0, lo, hi, *[_fptr(x) for x in t], int(pml.kappa_is_one)
@@ -169,6 +208,10 @@ class Plan:
                 lo = [s[0] for s in b.grid_slice_tuple]
                 hi = [s[1] for s in b.grid_slice_tuple]
                 check(self.lib.fdtdx_b200_plan_add_wall(self.h, kind, b.axis, _iarr(lo), _iarr(hi)))
+        if self.pad:
+            gs = self.global_shape
+            for kind in (0, 1):  # axis 3: no component is normal to the wall, so all three are zeroed
+                check(self.lib.fdtdx_b200_plan_add_wall(self.h, kind, 3, _iarr([0, 0, self.nz_true]), _iarr([gs[0], gs[1], self.nz_true + self.pad])))
 
     def _switch_tables(self, src):
         if src.uses_default_switch:
@@ -330,28 +373,64 @@ class Plan:
         self._bound.append(t)
         check(self.lib.fdtdx_b200_bind(self.h, slot, index, C.c_void_p(t.data_ptr())))
 
+    def _bind_z(self, slot: int, index: int, t, dtype, shape, state: bool, fill: float = 0.0):
+        """Bind an array whose last axis runs along z.  Without padding: the array itself.  With padding:
+        a plan-owned shadow whose last axis is longer by the z padding; ``state`` arrays are copied back
+        after every run call, constants (materials) only copied in."""
+        import torch
+
+        if not self.pad:
+            return self._bind(slot, index, t, dtype, shape)
+        if dtype is not None and t.dtype != dtype:
+            raise ValueError(f"buffer dtype {t.dtype} != expected {dtype}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"buffer shape {tuple(t.shape)} != expected {tuple(shape)}")
+        n = t.shape[-1]
+        key = (slot, index)
+        sh = self._shadow.get(key)
+        want = (*t.shape[:-1], n + self.pad)
+        if sh is None or tuple(sh[1].shape) != want or sh[1].device != t.device:
+            sh = [t, torch.full(want, fill, dtype=t.dtype, device=t.device), n, state]
+            self._shadow[key] = sh
+        sh[0], sh[3] = t, state
+        self._bind(slot, index, sh[1], dtype)
+
+    def _sync_in(self):
+        for t, buf, n, _ in self._shadow.values():
+            buf[..., :n].copy_(t)
+
+    def _sync_out(self):
+        for t, buf, n, state in self._shadow.values():
+            if state:
+                t.copy_(buf[..., :n])
+
     def bind(self, arrays):
         import torch
 
         f32 = torch.float32
         self._bound = []
         L = self.local_shape
-        self._bind(_lib.SLOT_E, 0, arrays.fields.E, f32, (3, *L))
-        self._bind(_lib.SLOT_H, 0, arrays.fields.H, f32, (3, *L))
-        self._bind(_lib.SLOT_INV_EPS, 0, arrays.inv_permittivities, f32, (self.eps_tier, *L))
+        self._bind_z(_lib.SLOT_E, 0, arrays.fields.E, f32, (3, *L), True)
+        self._bind_z(_lib.SLOT_H, 0, arrays.fields.H, f32, (3, *L), True)
+        self._bind_z(_lib.SLOT_INV_EPS, 0, arrays.inv_permittivities, f32, (self.eps_tier, *L), False, fill=1.0)
         if self.mu_is_array:
-            self._bind(_lib.SLOT_INV_MU, 0, arrays.inv_permeabilities, f32, (self.mu_tier, *L))
+            self._bind_z(_lib.SLOT_INV_MU, 0, arrays.inv_permeabilities, f32, (self.mu_tier, *L), False, fill=1.0)
         if self.sigE_tier:
-            self._bind(_lib.SLOT_SIGMA_E, 0, arrays.electric_conductivity, f32, (self.sigE_tier, *L))
+            self._bind_z(_lib.SLOT_SIGMA_E, 0, arrays.electric_conductivity, f32, (self.sigE_tier, *L), False)
         if self.sigH_tier:
-            self._bind(_lib.SLOT_SIGMA_H, 0, arrays.magnetic_conductivity, f32, (self.sigH_tier, *L))
+            self._bind_z(_lib.SLOT_SIGMA_H, 0, arrays.magnetic_conductivity, f32, (self.sigH_tier, *L), False)
         for pml in self.objects.pml_objects:
             q = self.pml_index[pml.name]
             if pml.name not in arrays.fields.psi_E:
                 continue  # slab lives on another rank
             for w in range(2):
-                self._bind(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32)
-                self._bind(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32)
+                if self.pad and (pml.axis != 2 or pml.direction == "+"):
+                    # x / y slabs run along the padded z axis; the z-max slab is thicker by the padding
+                    self._bind_z(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32, None, True)
+                    self._bind_z(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32, None, True)
+                else:
+                    self._bind(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32)
+                    self._bind(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32)
         if self.n_poles:
             self._bind(_lib.SLOT_P_A, 0, arrays.fields.dispersive_P_curr, f32, (self.n_poles, 3, *L))
             self._bind(_lib.SLOT_P_B, 0, arrays.fields.dispersive_P_prev, f32, (self.n_poles, 3, *L))
@@ -422,14 +501,20 @@ class Plan:
 
     def run_forward(self, t0: int, n: int, record_detectors: bool, record_boundaries: bool, simulate_boundaries: bool = True):
         self.set_tensor_direction(False)
+        self._sync_in()
         check(self.lib.fdtdx_b200_run_forward(self.h, int(t0), int(n), int(record_detectors), int(record_boundaries), int(simulate_boundaries), self._stream()))
+        self._sync_out()
 
     def run_forward_phase(self, t: int, phase: int, record_detectors: bool, record_boundaries: bool, simulate_boundaries: bool = True):
+        self._sync_in()
         check(self.lib.fdtdx_b200_run_forward_phase(self.h, int(t), int(phase), int(record_detectors), int(record_boundaries), int(simulate_boundaries), self._stream()))
+        self._sync_out()
 
     def run_reverse(self, t_from: int, n: int, record_detectors: bool, reset_fields: bool):
         self.set_tensor_direction(True)
+        self._sync_in()
         check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
+        self._sync_out()
 
     def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False):
         """``fdtd_bwd`` loop (``fdtd/fdtd.py:262-333``): n iterations of reverse step + VJP of one forward
@@ -482,6 +567,7 @@ class Plan:
         import torch
 
         self.bind(arrays)
+        self._sync_in()
         if getattr(self, "_energy_out", None) is None:
             self._energy_out = torch.zeros(1, dtype=torch.float32, device=arrays.fields.E.device)
         check(self.lib.fdtdx_b200_total_energy(self.h, C.c_void_p(self._energy_out.data_ptr()), self._stream()))

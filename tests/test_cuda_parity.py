@@ -99,6 +99,43 @@ def test_seeded_step_parity(name):
     assert_fields_close(a_o, a_g)
 
 
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("ragged") or n == "scalar_path_odd_nz"])
+def test_ragged_kernels_without_z_padding(name, monkeypatch):
+    """Forward-only runs on ragged rows normally go through z-padded shadows (plan.py) and the staged
+    kernels; this forces the interleaved ragged marching kernels on the same scenes."""
+    monkeypatch.setenv("FDTDX_B200_PAD_Z", "0")
+    kw, steps = CASES[name]
+    objects, arrays, cfg = build_scene(**kw)
+    a_o, a_g = run_both(objects, arrays, cfg, steps)
+    assert_fields_close(a_o, a_g)
+
+
+def test_z_padding_leaves_no_trace():
+    """Padded shadows: results on a ragged grid are bit-identical with and without the padding path
+    (same arithmetic; the padded cells are the zero halo), detectors and sources included."""
+    import os
+
+    outs = []
+    for pad in ("1", "0"):
+        os.environ["FDTDX_B200_PAD_Z"] = pad
+        try:
+            objects, arrays, cfg = build_scene(shape=(14, 11, 21), thickness=3, source="plane_x", nonuniform=True, eps_tier=3,
+                                               detectors=("energy_slices", "phasor", "poynting"), time=6e-15)
+            steps = min(cfg.time_steps_total, 40)
+            _, a_g = run_both(objects, arrays, cfg, steps, seed=False)
+            outs.append(a_g)
+        finally:
+            os.environ.pop("FDTDX_B200_PAD_Z", None)
+    assert np.array_equal(_to_np(outs[0].fields.E), _to_np(outs[1].fields.E))
+    assert np.array_equal(_to_np(outs[0].fields.H), _to_np(outs[1].fields.H))
+    for name in outs[0].fields.psi_E:
+        for w in range(2):
+            assert np.array_equal(_to_np(outs[0].fields.psi_E[name][w]), _to_np(outs[1].fields.psi_E[name][w])), name
+    for name, st in outs[0].detector_states.items():
+        for key, v in st.items():
+            assert np.array_equal(_to_np(v), _to_np(outs[1].detector_states[name][key])), (name, key)
+
+
 TENSOR_CASES = {
     "eps9_pml": (dict(eps_tier=9), 8),
     "eps9_periodic": (dict(eps_tier=9, boundaries="periodic"), 8),
