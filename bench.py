@@ -192,9 +192,9 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N>1: read neighbour planes in place over NVLink (peer) or exchange packed planes with NCCL send/recv")
     ap.add_argument("--cpu-impl", default="torch", choices=["torch", "numpy"])
-    ap.add_argument("--cpu-cpl", type=int, default=5)
+    ap.add_argument("--cpu-cpl", type=int, default=8, help="coupler resolution of the bounded CPU sample (8 -> 759x116x52 = 4.6 Mcell)")
     ap.add_argument("--cpu-box-n", type=int, default=96)
-    ap.add_argument("--cpu-steps", type=int, default=30)
+    ap.add_argument("--cpu-steps", type=int, default=80)
     ap.add_argument("--xchunk", type=int, default=0)
     ap.add_argument("--rows", type=int, default=0)
     args = ap.parse_args()

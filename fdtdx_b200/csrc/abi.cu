@@ -1275,16 +1275,29 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     if ((rc = make_params(p, S, 1))) return rc;
     float* E = S.E;
     float* H = S.H;
-    // (2) recompute E_{t+1}, H_{t+1} from the reconstructed state without touching psi
-    CUDA_TRY(cudaMemcpyAsync(p->d_Etmp, E, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+    // (2) recompute E_{t+1}, H_{t+1} from the reconstructed state without touching psi.  The staged
+    // kernels write straight into the scratch buffers; the marching kernels update in place, so their
+    // input is copied first.
     StepParams F1 = S;
     F1.psi_store = 0;
-    F1.E = p->d_Etmp;
-    if ((rc = launch_E(p, F1, t, false, st))) return rc;
-    StepParams F2 = F1;
-    F2.H = p->d_Htmp;
-    if ((rc = launch_H(p, F2, t, false, st))) return rc;
+    StepParams F2;
+    if (can_tma(p, S, can_vec4(p, S))) {
+      F1.E_out = p->d_Etmp;
+      if ((rc = launch_E(p, F1, t, false, st))) return rc;
+      F2 = F1;
+      F2.E = p->d_Etmp;
+      F2.E_out = nullptr;
+      F2.H_out = p->d_Htmp;
+      if ((rc = launch_H(p, F2, t, false, st))) return rc;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(p->d_Etmp, E, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+      F1.E = p->d_Etmp;
+      if ((rc = launch_E(p, F1, t, false, st))) return rc;
+      F2 = F1;
+      F2.H = p->d_Htmp;
+      if ((rc = launch_H(p, F2, t, false, st))) return rc;
+    }
     // (3) detector cotangents at step t
     bool any_det = false;
     for (size_t di = 0; di < p->dets.size(); ++di) {

@@ -17,6 +17,10 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 
+#ifndef FDTDX_ADJ_MIN_CTAS
+#define FDTDX_ADJ_MIN_CTAS 2
+#endif
+
 struct AdjParams {
   int nx, ny, nz;
   int wrap[3];
@@ -56,7 +60,7 @@ __device__ __forceinline__ float a_at(const AdjParams& P, const float* F, int c,
 // primal derivatives d[a][c] = d_a G_c (c != a) are known.  Reads lam (cotangent of the updated field),
 // F, the material, psi / lambda_psi of the slabs the cell belongs to; writes lam_in[3], ld[6] and the
 // material-gradient contributions (gq[c] per component; the caller accumulates them).
-template <bool IS_E>
+template <bool IS_E, bool PML = true>
 __device__ __forceinline__ void adj_local_body(const AdjParams& P, const int x, const int y, const int z, const long long cell, const long long N,
                                                float d[3][3], float lam[3], const float Fv[3], const float mv[3], const float sgv[3],
                                                const float extra[3], float lam_in[3], float ldv6[6], float gq[3]) {
@@ -71,7 +75,7 @@ __device__ __forceinline__ void adj_local_body(const AdjParams& P, const int x, 
   for (int a = 0; a < 3; ++a) {
     const AxisPmlDev& A = P.pml[a];
     const int idx = pos[a];
-    inp[a] = (idx < A.lo_len || idx >= A.hi_start);
+    inp[a] = PML && (idx < A.lo_len || idx >= A.hi_start);
     side[a] = (idx >= A.hi_start) ? 1 : 0;
     ca[a] = cb[a] = ck[a] = 0.0f;
     pidx[a] = 0;
@@ -187,7 +191,7 @@ __global__ void adj_local_kernel(const AdjParams P) {
 // 4 cells per thread, 128-bit accesses (Nz % 4 == 0, 16-byte aligned buffers): blockDim (32, 8),
 // grid (z tiles of 128, y tiles of 8, x planes).  Same per-cell arithmetic (adj_local_body).
 template <bool IS_E>
-__global__ void __launch_bounds__(256) adj_local4_kernel(const AdjParams P) {
+__global__ void __launch_bounds__(256, FDTDX_ADJ_MIN_CTAS) adj_local4_kernel(const AdjParams P) {
   constexpr int V = 4;
   const int lane = threadIdx.x;
   const int k0 = (blockIdx.x * 32 + lane) * V;
@@ -243,6 +247,12 @@ __global__ void __launch_bounds__(256) adj_local4_kernel(const AdjParams P) {
     if (P.sig) sq[c] = ldv<V>(P.sig + c * P.sig_cs + cell0);
     if (P.lam_extra) xq[c] = ldv<V>(P.lam_extra + c * N + cell0);
   }
+  // CTA-uniform: does this tile (one x plane, 8 rows, 128 z cells) touch any CPML slab?  Interior tiles
+  // run the slab-free instantiation of the body.
+  const int y0 = blockIdx.y * blockDim.y, y1 = min(y0 + (int)blockDim.y, P.ny) - 1;
+  const int z0 = blockIdx.x * 32 * V, z1 = min(z0 + 32 * V, P.nz) - 1;
+  const bool cta_pml = (x < P.pml[0].lo_len || x >= P.pml[0].hi_start) || (y0 < P.pml[1].lo_len || y1 >= P.pml[1].hi_start) ||
+                       (z0 < P.pml[2].lo_len || z1 >= P.pml[2].hi_start);
   Vec<V> lin[3], l6[6], gq[3];
 #pragma unroll
   for (int e = 0; e < V; ++e) {
@@ -269,7 +279,8 @@ __global__ void __launch_bounds__(256) adj_local4_kernel(const AdjParams P) {
       if (P.lam_extra) extra[c] = xq[c].v[e];
     }
     float lam_in[3], ll[6], gg[3];
-    adj_local_body<IS_E>(P, x, y, k0 + e, cell0 + e, N, d, lam, Fv, mv, sgv, extra, lam_in, ll, gg);
+    if (cta_pml) adj_local_body<IS_E, true>(P, x, y, k0 + e, cell0 + e, N, d, lam, Fv, mv, sgv, extra, lam_in, ll, gg);
+    else adj_local_body<IS_E, false>(P, x, y, k0 + e, cell0 + e, N, d, lam, Fv, mv, sgv, extra, lam_in, ll, gg);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { lin[c].v[e] = lam_in[c]; gq[c].v[e] = gg[c]; }
 #pragma unroll

@@ -59,6 +59,10 @@ struct StepParams {
   float cour, eta0, inv_mu_scalar, dt;
   float* E;
   float* H;
+  // optional separate destinations of the E / H half-step (staged kernels only; nullptr = in place):
+  // the adjoint pass recomputes a step into scratch without copying the state first
+  float* E_out;
+  float* H_out;
   const float* eps;
   const float* mu;  // nullptr => scalar
   const float* sigE;

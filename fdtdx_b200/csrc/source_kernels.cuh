@@ -31,7 +31,7 @@ __global__ void src_apply_kernel(const StepParams P, const int t, const int is_E
       if (i >= P.src_lo[q][0] && i < P.src_hi[q][0] && j >= P.src_lo[q][1] && j < P.src_hi[q][1] && k >= P.src_lo[q][2] && k < P.src_hi[q][2]) first = false;
     if (!first) continue;
     const long long cell = (long long)i * plane + (long long)j * P.nz + k;
-    float* F = is_E ? P.E : P.H;
+    float* F = is_E ? (P.E_out ? P.E_out : P.E) : (P.H_out ? P.H_out : P.H);
     float f0 = F[cell], f1 = F[N + cell], f2 = F[2 * N + cell];
     float m0, m1, m2;
     if (is_E) {

@@ -190,7 +190,8 @@ static __device__ __noinline__ void src_pass_E(const StepParams& P, int t, bool 
     const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
     for (int e = 0; e < V && k0 + e * FDTDX_ES < P.nz; ++e) {
       const long long cell = cell0 + e * FDTDX_ES;
-      float e0 = P.E[cell], e1 = P.E[N + cell], e2 = P.E[2 * N + cell];
+      float* const Ed = P.E_out ? P.E_out : P.E;
+      float e0 = Ed[cell], e1 = Ed[N + cell], e2 = Ed[2 * N + cell];
       const float i0 = P.eps[cell];
       const float i1 = (TIER == 3) ? P.eps[P.eps_cs + cell] : i0;
       const float i2 = (TIER == 3) ? P.eps[2 * P.eps_cs + cell] : i0;
@@ -205,7 +206,7 @@ static __device__ __noinline__ void src_pass_E(const StepParams& P, int t, bool 
           }
         }
       }
-      P.E[cell] = e0; P.E[N + cell] = e1; P.E[2 * N + cell] = e2;
+      Ed[cell] = e0; Ed[N + cell] = e1; Ed[2 * N + cell] = e2;
     }
   }
 }
@@ -218,7 +219,8 @@ static __device__ __noinline__ void src_pass_H(const StepParams& P, int t, bool 
     const long long cell0 = (long long)i * plane + (long long)j * P.nz + k0;
     for (int e = 0; e < V && k0 + e * FDTDX_ES < P.nz; ++e) {
       const long long cell = cell0 + e * FDTDX_ES;
-      float h0 = P.H[cell], h1 = P.H[N + cell], h2 = P.H[2 * N + cell];
+      float* const Hd = P.H_out ? P.H_out : P.H;
+      float h0 = Hd[cell], h1 = Hd[N + cell], h2 = Hd[2 * N + cell];
       float m0 = P.inv_mu_scalar, m1 = m0, m2 = m0;
       if (MUT >= 1) {
         m0 = P.mu[cell];
@@ -236,7 +238,7 @@ static __device__ __noinline__ void src_pass_H(const StepParams& P, int t, bool 
           }
         }
       }
-      P.H[cell] = h0; P.H[N + cell] = h1; P.H[2 * N + cell] = h2;
+      Hd[cell] = h0; Hd[N + cell] = h1; Hd[2 * N + cell] = h2;
     }
   }
 }

@@ -338,7 +338,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     sBy = P.sB[1][j];
     sBz = lane_ok ? ldv<V>(P.sB[2] + k0) : zerov<V>();
   }
-  float* pE = P.E + (long long)ic0 * plane + row;
+  long long cell0 = (long long)ic0 * plane + row;  // this thread's first cell of the current plane
+  float* pE = (P.E_out ? P.E_out : P.E) + cell0;
 
   // register queue: Hy, Hz of the previous x plane
   Vec<V> hy_im = zerov<V>(), hz_im = zerov<V>();
@@ -425,7 +426,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 
     const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
     Vec<V> o3[3];
-    material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, lane_ok, V, Eo3, K3, ie3, o3);
+    material_update_E<V, REV, SIG, ADE>(P, N, cell0, lane_ok, V, Eo3, K3, ie3, o3);
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
     if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
@@ -435,6 +436,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       stv<V>(pE + 2 * N, o2);
     }
     pE += plane;
+    cell0 += plane;
   }
   if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
 }
@@ -542,7 +544,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     sFy = P.sF[1][j];
     sFz = lane_ok ? ldv<V>(P.sF[2] + k0) : zerov<V>();
   }
-  float* pH = P.H + (long long)ic0 * plane + row;
+  long long cell0 = (long long)ic0 * plane + row;
+  float* pH = (P.H_out ? P.H_out : P.H) + cell0;
   const int oh = warp * HZ + lane * V;
   const int op = warp * TZ + lane * V;
 
@@ -626,7 +629,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
     Vec<V> o3[3];
-    material_update_H<V, REV, SIG>(P, pH - P.H, lane_ok, V, Ho3, K3, im3, o3);
+    material_update_H<V, REV, SIG>(P, cell0, lane_ok, V, Ho3, K3, im3, o3);
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     if (lane_ok) {
@@ -635,6 +638,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       stv<V>(pH + 2 * N, o2);
     }
     pH += plane;
+    cell0 += plane;
   }
   // the extra Ey,Ez stage was consumed as the "next plane" of the last iteration; nothing to release
   if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
