@@ -99,6 +99,7 @@ struct FdtdxPlan {
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
   double* d_energy_partial = nullptr;  // total_energy: per-block partial sums
+  bool adjoint_exact = false;          // run_adjoint_exact: VJP at the bound state, no reverse step
 };
 
 extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
@@ -1269,8 +1270,9 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
   }
   for (int t = t_from - 1; t > t_from - 1 - n; --t) {
     if (t < 0) break;  // the reference's extra t = -1 iteration (fdtd.py:253-260) starts from the zero state; skipped
-    // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False)
-    if ((rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
+    // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False);
+    //     exact mode: the caller has bound the stored state of step t instead
+    if (!p->adjoint_exact && (rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
     StepParams S;
     if ((rc = make_params(p, S, 1))) return rc;
     float* E = S.E;
@@ -1332,6 +1334,14 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     if ((rc = adjoint_half(p, S, true, E, H, lamE, lamH, nullptr, st))) return rc;
   }
   return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_run_adjoint_exact(FdtdxPlan* p, int t, void* stream) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  p->adjoint_exact = true;
+  const int rc = fdtdx_b200_run_adjoint(p, t + 1, 1, stream);
+  p->adjoint_exact = false;
+  return rc;
 }
 
 extern "C" int fdtdx_b200_run_forward_host(FdtdxPlan* p, const float* h_E, const float* h_H, const float* h_inv_eps,

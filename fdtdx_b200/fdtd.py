@@ -88,8 +88,16 @@ def checkpointed_fdtd(
     ``while cond(state): state = forward(state)`` bounded by ``time_steps_total`` (``fdtd.py:482-493``):
     steps are issued in bulk while the condition cannot fire (``earliest_stop``) and one at a time,
     with one device reduction + 4-byte read-back each, afterwards."""
-    arrays = arrays.reset()
     T = config.time_steps_total
+    gc = config.gradient_config
+    if stopping_condition is None and gc is not None and gc.method == "checkpointed":
+        import torch
+
+        inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
+        needs_grad = torch.is_tensor(inv_eps) and (inv_eps.requires_grad or (isinstance(inv_mu, torch.Tensor) and inv_mu.requires_grad))
+        if needs_grad and torch.is_grad_enabled():
+            return _checkpointed_with_grad(arrays, objects, config, progress_callback)
+    arrays = arrays.reset()
     if stopping_condition is None:
         arrays = _run_forward_loop(arrays, objects, config, 0, T, True, config.invertible_optimization, progress_callback)
         return T, arrays
@@ -125,6 +133,122 @@ def custom_fdtd_forward(
     end = max(int(end_time), int(start_time))
     arrays = _run_forward_loop(arrays, objects, config, int(start_time), end, record_detectors, False, progress_callback)
     return end, arrays
+
+
+def _checkpointed_with_grad(arrays, objects, config, progress_callback):
+    """``GradientConfig(method="checkpointed")`` (``fdtd.py:482-493``, ``kind="checkpointed"``): the
+    forward run keeps ``num_checkpoints`` full states; the backward pass recomputes each segment from
+    its checkpoint, keeps that segment's per-step states, and applies the fused adjoint kernels at the
+    *stored* states (``fdtdx_b200_run_adjoint_exact``) - no time reversal, so the gradient is that of
+    the forward run itself, CPML included.  Differentiable w.r.t. the materials, like the reference's
+    ``reversible_fdtd``; dispersive media are not supported by the adjoint kernels yet."""
+    import torch
+
+    if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
+        raise NotImplementedError("checkpointed gradients for dispersive media need the ADE adjoint (SURVEY.md section 8 f3)")
+    _require_cuda(arrays)
+    inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
+    holder = {"arrays": arrays, "objects": objects, "config": config, "cb": progress_callback}
+    outs = _CheckpointedFunction.get().apply(inv_eps, inv_mu if isinstance(inv_mu, torch.Tensor) else None, holder)
+    out = holder["out"]
+    out = out.aset("fields->E", outs[0]).aset("fields->H", outs[1])
+    det = {d: dict(st) for d, st in out.detector_states.items()}
+    for (d, k), v in zip(holder["names"], outs[2:]):
+        det[d][k] = v
+    out = out.aset("detector_states", det)
+    out = out.aset("inv_permittivities", inv_eps)
+    if isinstance(inv_mu, torch.Tensor):
+        out = out.aset("inv_permeabilities", inv_mu)
+    return config.time_steps_total, out
+
+
+def _clone_state(a):
+    f = a.fields
+    return (f.E.clone(), f.H.clone(), {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_E.items()}, {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_H.items()})
+
+
+def _load_state(a, st):
+    E, H, pE, pH = st
+    a.fields.E.copy_(E)
+    a.fields.H.copy_(H)
+    for k in pE:
+        for w in range(2):
+            a.fields.psi_E[k][w].copy_(pE[k][w])
+            a.fields.psi_H[k][w].copy_(pH[k][w])
+
+
+class _CheckpointedFunction:
+    _cls = None
+
+    @classmethod
+    def get(cls):
+        if cls._cls is not None:
+            return cls._cls
+        import torch
+
+        class CheckpointedFDTD(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, inv_eps, inv_mu, holder):
+                arrays, objects, config = holder["arrays"], holder["objects"], holder["config"]
+                T = config.time_steps_total
+                nck = max(1, int(config.gradient_config.num_checkpoints))
+                seg_len = max(1, -(-T // nck))
+                with torch.no_grad():
+                    arrays = arrays.aset("inv_permittivities", inv_eps.detach())
+                    if inv_mu is not None:
+                        arrays = arrays.aset("inv_permeabilities", inv_mu.detach())
+                    arrays = arrays.reset()
+                    ckpts, t = [], 0
+                    while t < T:
+                        ckpts.append((t, _clone_state(arrays)))
+                        m = min(seg_len, T - t)
+                        arrays = _run_forward_loop(arrays, objects, config, t, t + m, True, False, holder["cb"])
+                        t += m
+                holder["ckpts"], holder["out"] = ckpts, arrays
+                ctx.holder = holder
+                ctx.set_materialize_grads(False)
+                names = [(d, k) for d, st in arrays.detector_states.items() for k in st]
+                holder["names"] = names
+                return (arrays.fields.E, arrays.fields.H, *[arrays.detector_states[d][k] for d, k in names])
+
+            @staticmethod
+            def backward(ctx, gE, gH, *gdet):
+                h = ctx.holder
+                arrays, objects, config = h["out"], h["objects"], h["config"]
+                T = config.time_steps_total
+                f = arrays.fields
+                work = arrays.aset("fields->E", f.E.detach().clone()).aset("fields->H", f.H.detach().clone())
+                work = work.aset("fields->psi_E", {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_E.items()})
+                work = work.aset("fields->psi_H", {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_H.items()})
+                cot_E = torch.zeros_like(f.E) if gE is None else gE.detach().clone().contiguous()
+                cot_H = torch.zeros_like(f.H) if gH is None else gH.detach().clone().contiguous()
+                cot_det = {}
+                for (d, k), g in zip(h["names"], gdet):
+                    if g is not None:
+                        cot_det.setdefault(d, {})[k] = g.detach().contiguous()
+                g_eps = torch.zeros_like(work.inv_permittivities)
+                mu = work.inv_permeabilities
+                g_mu = torch.zeros_like(mu) if isinstance(mu, torch.Tensor) else None
+                plan = get_plan(work, objects, config)
+                first = True
+                ends = [c[0] for c in h["ckpts"][1:]] + [T]
+                for (t0, st0), t1 in zip(reversed(h["ckpts"]), reversed(ends)):
+                    # recompute the segment from its checkpoint, keeping every step's input state
+                    _load_state(work, st0)
+                    states = []
+                    for t in range(t0, t1):
+                        states.append(_clone_state(work))
+                        plan.bind(work)
+                        plan.run_forward(t, 1, False, False, True)
+                    for t in range(t1 - 1, t0 - 1, -1):
+                        _load_state(work, states[t - t0])
+                        plan.run_adjoint(work, t + 1, 1, cot_E, cot_H, cot_det, g_eps, g_mu, keep_cot_psi=not first, exact=True)
+                        first = False
+                    del states
+                return g_eps, g_mu, None
+
+        cls._cls = CheckpointedFDTD
+        return CheckpointedFDTD
 
 
 class _ReversibleFunction:

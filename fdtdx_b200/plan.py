@@ -516,7 +516,7 @@ class Plan:
         check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
         self._sync_out()
 
-    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False):
+    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False, exact: bool = False):
         """``fdtd_bwd`` loop (``fdtd/fdtd.py:262-333``): n iterations of reverse step + VJP of one forward
         step.  ``arrays`` holds the state at ``t_from`` (fields are reconstructed in place); ``cot_E`` /
         ``cot_H`` carry the field cotangents in place; ``cot_det[name][key]`` are the detector-state
@@ -546,7 +546,11 @@ class Plan:
             for k in range(4):
                 g = cot_det.get(det.name, {}).get(keys[k]) if k < len(keys) else None
                 self._bind(_lib.SLOT_COT_DET, 4 * di + k, g)
-        check(self.lib.fdtdx_b200_run_adjoint(self.h, int(t_from), int(n), self._stream()))
+        if exact:
+            assert n == 1
+            check(self.lib.fdtdx_b200_run_adjoint_exact(self.h, int(t_from) - 1, self._stream()))
+        else:
+            check(self.lib.fdtdx_b200_run_adjoint(self.h, int(t_from), int(n), self._stream()))
 
     def parity(self) -> tuple[int, int, int]:
         a, b, c = C.c_int(), C.c_int(), C.c_int()

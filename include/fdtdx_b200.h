@@ -182,6 +182,11 @@ int fdtdx_b200_run_reverse(FdtdxPlan* plan, int t_from, int n, int record_detect
  * step, then the VJP of one forward step at the reconstructed state, accumulating
  * GRAD_INV_EPS / GRAD_INV_MU and carrying COT_E/COT_H/COT_PSI_*. */
 int fdtdx_b200_run_adjoint(FdtdxPlan* plan, int t_from, int n, void* stream);
+/* VJP of ONE forward step t at the state that is currently bound (E_t, H_t, psi_t), without the
+ * time-reversed reconstruction: the building block of the checkpointed gradient
+ * (fdtd/fdtd.py:482-493, kind="checkpointed": stored / recomputed states instead of reversed ones).
+ * Same cotangent and gradient slots as run_adjoint. */
+int fdtdx_b200_run_adjoint_exact(FdtdxPlan* plan, int t, void* stream);
 
 /* Current ping-pong parities after the last run (0: A is current). Callers that own P_A/P_B or
  * E/E_ALT need them to tell which buffer holds the current state. */
