@@ -808,6 +808,8 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
   G.mu = (const float*)p->slots[FDTDX_SLOT_INV_MU][0];
   G.eps_cs = (p->eps_tier == 1) ? 0 : N;
   G.mu_cs = (p->mu_tier <= 1) ? 0 : N;
+  G.eps_tier = p->eps_tier;
+  G.mu_tier = p->mu_tier;
   G.inv_mu_scalar = (float)p->inv_mu_scalar;
 }
 

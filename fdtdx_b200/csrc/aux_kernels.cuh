@@ -23,6 +23,7 @@ struct GridDev {
   const float* eps;
   const float* mu;
   long long eps_cs, mu_cs;
+  int eps_tier, mu_tier;  // 1 | 3 | 9 (mu: 0 = scalar)
   float inv_mu_scalar;
   const float* w[3];  // cell widths per axis (global indexing for x) or nullptr on a uniform grid
 };
@@ -184,13 +185,44 @@ __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& 
     const long long N = (long long)G.nx * G.ny * G.nz;
     const long long gidx = ((long long)x * G.ny + y) * G.nz + z;
     float eE = 0.0f, eH = 0.0f;
-    for (int c = 0; c < 3; ++c) {
-      const float ie = G.eps[c * G.eps_cs + gidx];
-      const float im = G.mu ? G.mu[c * G.mu_cs + gidx] : G.inv_mu_scalar;
-      const float a = (0.5f * (1.0f / ie)) * (fabsf(Es[c]) * fabsf(Es[c]));
-      const float b = (0.5f * (1.0f / im)) * (fabsf(Hs[c]) * fabsf(Hs[c]));
-      eE = (c == 0) ? a : eE + a;
-      eH = (c == 0) ? b : eH + b;
+    if (G.eps_tier == 9 || G.mu_tier == 9) {
+      // full-tensor media (metrics.py:37-53): eps = inv(inv_eps), energy = 0.5 E.eps.E + 0.5 H.mu.H
+      float A[2][3][3], Minv[2][3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          A[0][i][j] = (G.eps_tier == 9) ? G.eps[(long long)(3 * i + j) * G.eps_cs + gidx] : (i == j ? G.eps[(long long)(G.eps_tier == 1 ? 0 : i) * G.eps_cs + gidx] : 0.0f);
+          A[1][i][j] = (G.mu_tier == 9) ? G.mu[(long long)(3 * i + j) * G.mu_cs + gidx]
+                                        : (i == j ? (G.mu ? G.mu[(long long)(G.mu_tier == 1 ? 0 : i) * G.mu_cs + gidx] : G.inv_mu_scalar) : 0.0f);
+        }
+      for (int q = 0; q < 2; ++q) {
+        const float(*M)[3] = A[q];
+        const float c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1], c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2], c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+        const float det = (M[0][0] * c00 + M[0][1] * c01) + M[0][2] * c02;
+        const float id = 1.0f / det;
+        Minv[q][0][0] = c00 * id; Minv[q][1][0] = c01 * id; Minv[q][2][0] = c02 * id;
+        Minv[q][0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * id;
+        Minv[q][1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * id;
+        Minv[q][2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * id;
+        Minv[q][0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * id;
+        Minv[q][1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * id;
+        Minv[q][2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * id;
+      }
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          eE += (Es[i] * Minv[0][i][j]) * Es[j];
+          eH += (Hs[i] * Minv[1][i][j]) * Hs[j];
+        }
+      eE = 0.5f * eE;
+      eH = 0.5f * eH;
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        const float ie = G.eps[c * G.eps_cs + gidx];
+        const float im = G.mu ? G.mu[c * G.mu_cs + gidx] : G.inv_mu_scalar;
+        const float a = (0.5f * (1.0f / ie)) * (fabsf(Es[c]) * fabsf(Es[c]));
+        const float b = (0.5f * (1.0f / im)) * (fabsf(Hs[c]) * fabsf(Hs[c]));
+        eE = (c == 0) ? a : eE + a;
+        eH = (c == 0) ? b : eH + b;
+      }
     }
     (void)N;
     const float e = eE + eH;

@@ -301,8 +301,6 @@ class Plan:
                     weights = det._cached_cell_volume_weights
             elif isinstance(det, EnergyDetector):
                 kind = _lib.DET_ENERGY
-                if self.eps_tier == 9 or self.mu_tier == 9:
-                    raise NotImplementedError("EnergyDetector in full-tensor media is not on the hot path yet")
                 if det.as_slices:
                     flags |= _lib.DETF_SLICES
                     if det.use_mean:

@@ -163,7 +163,7 @@ def test_full_tensor_sources_and_detectors(src):
     """TFSF injection into all three rows under full anisotropy (tfsf.py:285-295, 384-391)."""
     shape = (16, 10, 12) if src == "plane_x" else (12, 10, 16)
     objects, arrays, cfg = build_scene(shape=shape, eps_tier=9, mu_tier=9 if src == "plane_z" else 0, source=src,
-                                       detectors=("field", "phasor", "poynting"), time=6e-15)
+                                       detectors=("field", "phasor", "poynting", "energy", "energy_reduce"), time=6e-15)
     steps = min(cfg.time_steps_total, 40)
     a_o, a_g = run_both(objects, arrays, cfg, steps, seed=False)
     assert np.abs(a_o.fields.E).max() > 0
