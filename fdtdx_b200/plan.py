@@ -160,7 +160,10 @@ class Plan:
         if nz % 4 == 0 or os.environ.get("FDTDX_B200_PAD_Z", "1") == "0":
             return 0
         if config.gradient_config is not None or arrays.recording_state is not None:
-            return 0  # reverse / adjoint passes bind further (., Nz) buffers; they keep the ragged kernels
+            # the interface recorder's buffers are shaped by the true Nz, and on the small grids where
+            # gradients are typically taken the padded pass measured slower (135x135x75: 0.70 vs 0.49
+            # ms per backward step); gradient runs keep the ragged kernels
+            return 0
         if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
             return 0
         tiers = [int(arrays.inv_permittivities.shape[0])]
@@ -522,10 +525,13 @@ class Plan:
         import torch
 
         self.bind(arrays)
-        self._bind(_lib.SLOT_COT_E, 0, cot_E, torch.float32)
-        self._bind(_lib.SLOT_COT_H, 0, cot_H, torch.float32)
-        self._bind(_lib.SLOT_GRAD_INV_EPS, 0, grad_inv_eps, torch.float32)
-        self._bind(_lib.SLOT_GRAD_INV_MU, 0, grad_inv_mu)
+        self._bind_z(_lib.SLOT_COT_E, 0, cot_E, torch.float32, None, True)
+        self._bind_z(_lib.SLOT_COT_H, 0, cot_H, torch.float32, None, True)
+        self._bind_z(_lib.SLOT_GRAD_INV_EPS, 0, grad_inv_eps, torch.float32, None, True)
+        if grad_inv_mu is None:
+            self._bind(_lib.SLOT_GRAD_INV_MU, 0, None)
+        else:
+            self._bind_z(_lib.SLOT_GRAD_INV_MU, 0, grad_inv_mu, None, None, True)
         if not keep_cot_psi or not getattr(self, "_cot_psi", None):
             self._cot_psi = {}
         for pml in self.objects.pml_objects:
@@ -534,7 +540,11 @@ class Plan:
                 for slot, src in ((_lib.SLOT_COT_PSI_E, arrays.fields.psi_E), (_lib.SLOT_COT_PSI_H, arrays.fields.psi_H)):
                     key = (slot, q, w)
                     if key not in self._cot_psi:
-                        self._cot_psi[key] = torch.zeros_like(src[pml.name][w])
+                        # plan-owned cotangent of psi, in the layout the kernels see (z-padded where psi is)
+                        shp = list(src[pml.name][w].shape)
+                        if self.pad and (pml.axis != 2 or pml.direction == "+"):
+                            shp[-1] += self.pad
+                        self._cot_psi[key] = torch.zeros(shp, dtype=torch.float32, device=src[pml.name][w].device)
                     self._bind(slot, 2 * q + w, self._cot_psi[key])
         for det in self.objects.detectors:
             if det.name not in self.det_index:
@@ -544,11 +554,13 @@ class Plan:
             for k in range(4):
                 g = cot_det.get(det.name, {}).get(keys[k]) if k < len(keys) else None
                 self._bind(_lib.SLOT_COT_DET, 4 * di + k, g)
+        self._sync_in()
         if exact:
             assert n == 1
             check(self.lib.fdtdx_b200_run_adjoint_exact(self.h, int(t_from) - 1, self._stream()))
         else:
             check(self.lib.fdtdx_b200_run_adjoint(self.h, int(t_from), int(n), self._stream()))
+        self._sync_out()
 
     def parity(self) -> tuple[int, int, int]:
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -40,6 +40,7 @@ def _loss(det, E=None):
 
 
 CASES = {
+    "ragged_nz21_pml_poynting": (dict(source="plane_z", detectors=("poynting", "phasor", "field_reduce"), time=4e-15, shape=(16, 14, 21), thickness=4), 5, False),
     "periodic_field_phasor": (dict(boundaries="periodic", source="plane_z", detectors=("field", "phasor"), time=3e-15), None, True),
     "pml_poynting_phasor": (dict(source="plane_z", detectors=("poynting", "phasor", "field_reduce"), time=4e-15, shape=(16, 14, 20), thickness=4), 5, False),
     "pml_energy_sigma_diag": (dict(source="plane_z", detectors=("energy_reduce", "poynting_full", "energy_slices"), eps_tier=3, sigma_E=True, sigma_H=True, time=3e-15, shape=(16, 14, 20), thickness=4), 5, False),
@@ -123,6 +124,8 @@ def test_reversible_needs_recorder_and_rejects_dispersion():
 
 
 CKPT_CASES = {
+    # ragged grid (Nz % 4 != 0): interleaved marching kernels + scalar adjoint kernels
+    "ragged_nz21_pml": dict(source="plane_z", detectors=("poynting", "phasor"), time=3e-15, shape=(16, 14, 21), thickness=4, eps_tier=3),
     "pml_poynting_phasor": dict(source="plane_z", detectors=("poynting", "phasor", "field_reduce"), time=4e-15, shape=(16, 14, 20), thickness=4),
     "pml_energy_sigma_diag_mu": dict(source="plane_z", detectors=("energy_reduce", "poynting_full"), eps_tier=3, sigma_E=True, mu_tier=3, time=3e-15, shape=(16, 14, 20), thickness=4),
     "nonuniform_kappa_dipole": dict(source="dipole", detectors=("poynting_all", "phasor_reduce"), nonuniform=True, kappa=True, time=3e-15, shape=(14, 12, 16), thickness=3),
@@ -163,3 +166,4 @@ def test_checkpointed_gradient_is_the_gradient_of_the_forward_run(name, nck):
     if has_mu:
         gm, gm_ref = dev.inv_permeabilities.grad.cpu().numpy(), im.grad.numpy()
         assert rel_l2(gm, gm_ref) <= 1e-4, f"d loss / d inv_mu rel-L2 {rel_l2(gm, gm_ref)}"
+
