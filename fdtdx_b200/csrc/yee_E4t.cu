@@ -11,7 +11,9 @@ static bool fdtdx_tma_pdl_enabled() {
 
 template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM>
 static cudaError_t go_E(const StepParams& P, const TmaSet& M, int t, dim3 g, cudaStream_t st) {
-  constexpr int R = FDTDX_TMA_R, S = FDTDX_TMA_S;
+  // three material components make a stage 39 KB: a 3-deep ring would leave one CTA per SM, so those
+  // variants run a 2-deep ring (78 KB, two CTAs per SM)
+  constexpr int R = FDTDX_TMA_R, S = (TIER == 3) ? 2 : FDTDX_TMA_S;
   constexpr int smem = tma_smem_bytes<R, TIER, S>();
   auto k = yee_E_tma<TIER, REV, SIG, ADE, MET, PM, R, S>;
   static bool attr_set = false;

@@ -505,17 +505,38 @@ struct PmlLane {
 // accesses on ragged rows); `ok` is false for lanes that overhang the grid (staged kernels).
 // Arithmetic order is the reference's, element by element.
 // ------------------------------------------------------------------------------------------------
-template <int V, bool REV, bool SIG, bool ADE>
-__device__ __forceinline__ void material_update_E(const StepParams& P, const long long N, const long long cell0, const bool ok, const int nv,
-                                                  const Vec<V> (&Eo)[3], const Vec<V> (&K)[3], const Vec<V> (&ie)[3], Vec<V> (&out)[3]) {
-  Vec<V> sg[3];
-  if (SIG) {
+// conductivity vectors of one plane (1 or 3 components): issued with the field loads so that their
+// latency overlaps the tile wait / curl instead of stalling the material update
+template <int V>
+__device__ __forceinline__ void load_sigma(const float* sig, const long long cs, const long long cell0, const bool ok, const int nv, Vec<V> (&sg)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c == 0 || cs != 0) sg[c] = ok ? ldv<V>(sig + c * cs + cell0, nv) : zerov<V>();
+    else sg[c] = sg[0];
+  }
+}
+// L2 prefetch of the ADE arrays of a later plane (polarisations and coefficients of every pole / component)
+__device__ __forceinline__ void prefetch_ade(const StepParams& P, const long long N, const long long cell) {
+  const long long cstride = P.c_cs ? 3 * N : N;
+  for (int p = 0; p < P.n_poles; ++p) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (c == 0 || P.sigE_cs != 0) sg[c] = ok ? ldv<V>(P.sigE + c * P.sigE_cs + cell0, nv) : zerov<V>();
-      else sg[c] = sg[0];
+      const long long pi = p * 3 * N + c * N + cell;
+      prefetch_l2(P.P_cur + pi);
+      prefetch_l2(P.P_new + pi);
+      if (c == 0 || P.c_cs != 0) {
+        const long long ci = p * cstride + c * P.c_cs + cell;
+        prefetch_l2(P.c1 + ci); prefetch_l2(P.c2 + ci); prefetch_l2(P.c3 + ci);
+        if (P.has_c4) prefetch_l2(P.c4 + ci);
+      }
     }
   }
+}
+
+template <int V, bool REV, bool SIG, bool ADE>
+__device__ __forceinline__ void material_update_E(const StepParams& P, const long long N, const long long cell0, const bool ok, const int nv,
+                                                  const Vec<V> (&Eo)[3], const Vec<V> (&K)[3], const Vec<V> (&ie)[3], const Vec<V> (&sg)[3],
+                                                  Vec<V> (&out)[3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     Vec<V> s, E1;
@@ -594,15 +615,8 @@ __device__ __forceinline__ void material_update_E(const StepParams& P, const lon
 
 template <int V, bool REV, bool SIG>
 __device__ __forceinline__ void material_update_H(const StepParams& P, const long long cell0, const bool ok, const int nv,
-                                                  const Vec<V> (&Ho)[3], const Vec<V> (&K)[3], const Vec<V> (&im)[3], Vec<V> (&out)[3]) {
-  Vec<V> sg[3];
-  if (SIG) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c == 0 || P.sigH_cs != 0) sg[c] = ok ? ldv<V>(P.sigH + c * P.sigH_cs + cell0, nv) : zerov<V>();
-      else sg[c] = sg[0];
-    }
-  }
+                                                  const Vec<V> (&Ho)[3], const Vec<V> (&K)[3], const Vec<V> (&im)[3], const Vec<V> (&sg)[3],
+                                                  Vec<V> (&out)[3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -695,7 +709,8 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
       hx_jm = zerov<V>();
       hz_jm = zerov<V>();
     }
-    Vec<V> ex, ey, ez, ie0, ie1, ie2;
+    Vec<V> ex, ey, ez, ie0, ie1, ie2, sg3[3];
+    if (SIG) load_sigma<V>(P.sigE, P.sigE_cs, pE - P.E, true, nv, sg3);
     if (!KONLY) {
       ex = ldv<V>(pE, nv); ey = ldv<V>(pE + N, nv); ez = ldv<V>(pE + 2 * N, nv);
       ie0 = ldv<V>(pEps, nv);
@@ -712,6 +727,8 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     if (i + FDTDX_PF_DIST < ic1) {
       const long long pb = FDTDX_PF_DIST * plane;
       prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb);
+      if (SIG) { prefetch_l2(P.sigE + (pE - P.E) + pb); if (P.sigE_cs) { prefetch_l2(P.sigE + P.sigE_cs + (pE - P.E) + pb); prefetch_l2(P.sigE + 2 * P.sigE_cs + (pE - P.E) + pb); } }
+      if (ADE) prefetch_ade(P, N, (pE - P.E) + pb);
       if (!KONLY) {
         prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
         prefetch_l2(pEps + pb);
@@ -777,7 +794,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
       o3[0] = Kx; o3[1] = Ky; o3[2] = Kz;
     } else {
       const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
-      material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, true, nv, Eo3, K3, ie3, o3);
+      material_update_E<V, REV, SIG, ADE>(P, N, pE - P.E, true, nv, Eo3, K3, ie3, sg3, o3);
     }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
@@ -865,7 +882,8 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
       ex_jp = zerov<V>();
       ez_jp = zerov<V>();
     }
-    Vec<V> hx, hy, hz;
+    Vec<V> hx, hy, hz, sg3[3];
+    if (SIG) load_sigma<V>(P.sigH, P.sigH_cs, pH - P.H, true, nv, sg3);
     if (!KONLY) { hx = ldv<V>(pH, nv); hy = ldv<V>(pH + N, nv); hz = ldv<V>(pH + 2 * N, nv); }
     Vec<V> im0, im1, im2;
     if (!KONLY && MUT >= 1) {
@@ -881,6 +899,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     FDTDX_CPML_LOADS(psiH)
     if (i + FDTDX_PF_DIST < ic1) {
       const long long pb = FDTDX_PF_DIST * plane;
+      if (SIG) { prefetch_l2(P.sigH + (pH - P.H) + pb); if (P.sigH_cs) { prefetch_l2(P.sigH + P.sigH_cs + (pH - P.H) + pb); prefetch_l2(P.sigH + 2 * P.sigH_cs + (pH - P.H) + pb); } }
       if (!KONLY) { prefetch_l2(pH + pb); prefetch_l2(pH + N + pb); prefetch_l2(pH + 2 * N + pb); }
       prefetch_l2(pE + pb); prefetch_l2(pE + N + pb); prefetch_l2(pE + 2 * N + pb);
       if (!KONLY && MUT >= 1) prefetch_l2(pMu + pb);
@@ -955,7 +974,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
         im3[1] = im3[0]; im3[2] = im3[0];
       }
       const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
-      material_update_H<V, REV, SIG>(P, pH - P.H, true, nv, Ho3, K3, im3, o3);
+      material_update_H<V, REV, SIG>(P, pH - P.H, true, nv, Ho3, K3, im3, sg3, o3);
     }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);

@@ -362,6 +362,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   uint32_t ph = 0;
   for (int i = ic0; i < ic1; ++i) {
     FDTDX_TCPML_PREFETCH(psiE)
+    Vec<V> sg3[3];
+    if (SIG) load_sigma<V>(P.sigE, P.sigE_cs, cell0, lane_ok, V, sg3);
+    if (ADE && lane_ok && i + 2 < ic1) prefetch_ade(P, N, cell0 + 2 * plane);
     mbar_wait(bar_full + s * 8, ph);
     const float* sb = fdtdx_tma_smem + s * STAGE_F;
     const float* sHx = sb + oh;
@@ -426,7 +429,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 
     const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
     Vec<V> o3[3];
-    material_update_E<V, REV, SIG, ADE>(P, N, cell0, lane_ok, V, Eo3, K3, ie3, o3);
+    material_update_E<V, REV, SIG, ADE>(P, N, cell0, lane_ok, V, Eo3, K3, ie3, sg3, o3);
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
     if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
@@ -553,6 +556,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   uint32_t ph = 0;
   for (int i = ic0; i < ic1; ++i) {
     FDTDX_TCPML_PREFETCH(psiH)
+    Vec<V> sg3[3];
+    if (SIG) load_sigma<V>(P.sigH, P.sigH_cs, cell0, lane_ok, V, sg3);
     int sn = s + 1;
     uint32_t phn = ph;
     if (sn == S) { sn = 0; phn ^= 1; }
@@ -629,7 +634,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
     Vec<V> o3[3];
-    material_update_H<V, REV, SIG>(P, cell0, lane_ok, V, Ho3, K3, im3, o3);
+    material_update_H<V, REV, SIG>(P, cell0, lane_ok, V, Ho3, K3, im3, sg3, o3);
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     if (lane_ok) {
