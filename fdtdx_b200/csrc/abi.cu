@@ -709,6 +709,19 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
     // coupler grid.  Short chunks keep the ~300 resident CTAs inside one narrow x window (same DRAM
     // pages, halo rows shared through L2); the 3-plane ring fill costs less than the drift of long chunks.
     xc = 8;
+    // Mid-size grids run only a few waves of the 148 x 2 resident CTAs: pick the chunk length in 5..10
+    // whose CTA count wastes the least of its last wave (large grids: no effect).
+    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R);
+    const long long nxr = P.x_end - P.x_begin;
+    if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
+      double best = -1.0;
+      for (int c = 10; c >= 5; --c) {
+        const long long ctas = tiles * ((nxr + c - 1) / c);
+        const long long waves = (ctas + 148 * 2 - 1) / (148 * 2);
+        const double eff = (double)ctas / (double)(waves * 148 * 2) - 0.004 * std::abs(c - 8);
+        if (eff > best) { best = eff; xc = c; }
+      }
+    }
   }
   return std::max(1, std::min(std::min(xc, 64), P.x_end - P.x_begin));  // 64 = FDTDX_TMA_XC_MAX
 }
