@@ -54,6 +54,10 @@ struct DetDev {
 #define DET_KEEP_ALL 32
 #define DET_NEGATIVE 64
 
+// CHK = false: the caller guarantees that (x, y, z) is inside the local grid (interior fast path of the
+// detector stencil: no halo rule, no wrap)
+template <bool CHK>
+__device__ __forceinline__ float grid_at_t(const GridDev& G, const float* F, int c, int x, int y, int z);
 __device__ __forceinline__ float grid_at(const GridDev& G, const float* F, int c, int x, int y, int z) {
   if (x < 0) { if (G.wrap[0]) x += G.nx; else return 0.0f; }
   if (x >= G.nx) { if (G.wrap[0]) x -= G.nx; else return 0.0f; }
@@ -88,48 +92,76 @@ __device__ __forceinline__ void det_gather_body(const GridDev& G, const DetDev& 
   const int sx = D.hi[0] - D.lo[0] + 1, sy = D.hi[1] - D.lo[1] + 1, sz = D.hi[2] - D.lo[2] + 1;
   const long long n = (long long)sx * sy * sz;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < 3 * n; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx / n);
-    long long r = idx - c * n;
-    const int g = (int)(r % sz); r /= sz;
-    const int b = (int)(r % sy);
-    const int a = (int)(r / sy);
+    // 32-bit index arithmetic whenever the region allows it (64-bit div/mod costs ~100 instructions each)
+    int c, a, b, g;
+    if (3 * n < 0x7fffffffLL) {
+      const unsigned u = (unsigned)idx, un = (unsigned)n;
+      c = (int)(u / un);
+      unsigned r = u - (unsigned)c * un;
+      g = (int)(r % (unsigned)sz); r /= (unsigned)sz;
+      b = (int)(r % (unsigned)sy);
+      a = (int)(r / (unsigned)sy);
+    } else {
+      c = (int)(idx / n);
+      long long r = idx - c * n;
+      g = (int)(r % sz); r /= sz;
+      b = (int)(r % sy);
+      a = (int)(r / sy);
+    }
+    // plane slices without averaging only sample three planes: copy just the H cells their stencils read
+    if ((D.flags & DET_SLICES) && !(D.flags & DET_SLICE_MEAN) && !(a == D.slice_idx[0] || a == D.slice_idx[0] + 1 || b == D.slice_idx[1] ||
+                                                                    b == D.slice_idx[1] + 1 || g == D.slice_idx[2] || g == D.slice_idx[2] + 1))
+      continue;
     D.hprev[idx] = grid_at(G, G.H, c, D.lo[0] - 1 + a, D.lo[1] - 1 + b, D.lo[2] + g);
   }
 }
 
+template <bool CHK>
+__device__ __forceinline__ float grid_at_t(const GridDev& G, const float* F, int c, int x, int y, int z) {
+  if (CHK) return grid_at(G, F, c, x, y, z);
+  const long long N = (long long)G.nx * G.ny * G.nz;
+  return F[c * N + ((long long)x * G.ny + y) * G.nz + z];
+}
+template <bool CHK = true>
 __device__ __forceinline__ float hbar(const GridDev& G, const DetDev& D, int c, int x, int y, int z) {
   const int sy = D.hi[1] - D.lo[1] + 1, sz = D.hi[2] - D.lo[2] + 1, sx = D.hi[0] - D.lo[0] + 1;
   const long long n = (long long)sx * sy * sz;
   const float hp = D.hprev[c * n + ((long long)(x - D.lo[0] + 1) * sy + (y - D.lo[1] + 1)) * sz + (z - D.lo[2])];
-  return (hp + grid_at(G, G.H, c, x, y, z)) / 2.0f;
+  return (hp + grid_at_t<CHK>(G, G.H, c, x, y, z)) / 2.0f;
 }
 
 // interpolate_fields at one cell (curl.py:86-224): everything co-located at the Ez point.
-__device__ __forceinline__ void colocate(const GridDev& G, const DetDev& D, int x, int y, int z, float* Es, float* Hs) {
+template <bool CHK>
+__device__ __forceinline__ void colocate_t(const GridDev& G, const DetDev& D, int x, int y, int z, float* Es, float* Hs) {
   if (!(D.flags & DET_EXACT)) {
     for (int c = 0; c < 3; ++c) {
-      Es[c] = grid_at(G, G.E, c, x, y, z);
-      Hs[c] = grid_at(G, G.H, c, x, y, z);
+      Es[c] = grid_at_t<CHK>(G, G.E, c, x, y, z);
+      Hs[c] = grid_at_t<CHK>(G, G.H, c, x, y, z);
     }
     return;
   }
   const float* E = G.E;
-  float lo = bea(G, grid_at(G, E, 0, x, y, z), grid_at(G, E, 0, x - 1, y, z), 0, x);
-  float hi = bea(G, grid_at(G, E, 0, x, y, z + 1), grid_at(G, E, 0, x - 1, y, z + 1), 0, x);
+  float lo = bea(G, grid_at_t<CHK>(G, E, 0, x, y, z), grid_at_t<CHK>(G, E, 0, x - 1, y, z), 0, x);
+  float hi = bea(G, grid_at_t<CHK>(G, E, 0, x, y, z + 1), grid_at_t<CHK>(G, E, 0, x - 1, y, z + 1), 0, x);
   Es[0] = (lo + hi) / 2.0f;
-  lo = bea(G, grid_at(G, E, 1, x, y, z), grid_at(G, E, 1, x, y - 1, z), 1, y);
-  hi = bea(G, grid_at(G, E, 1, x, y, z + 1), grid_at(G, E, 1, x, y - 1, z + 1), 1, y);
+  lo = bea(G, grid_at_t<CHK>(G, E, 1, x, y, z), grid_at_t<CHK>(G, E, 1, x, y - 1, z), 1, y);
+  hi = bea(G, grid_at_t<CHK>(G, E, 1, x, y, z + 1), grid_at_t<CHK>(G, E, 1, x, y - 1, z + 1), 1, y);
   Es[1] = (lo + hi) / 2.0f;
-  Es[2] = grid_at(G, E, 2, x, y, z);
-  Hs[0] = bea(G, hbar(G, D, 0, x, y, z), hbar(G, D, 0, x, y - 1, z), 1, y);
-  Hs[1] = bea(G, hbar(G, D, 1, x, y, z), hbar(G, D, 1, x - 1, y, z), 0, x);
-  float lx = bea(G, hbar(G, D, 2, x, y, z), hbar(G, D, 2, x - 1, y, z), 0, x);
-  float lxm = bea(G, hbar(G, D, 2, x, y - 1, z), hbar(G, D, 2, x - 1, y - 1, z), 0, x);
+  Es[2] = grid_at_t<CHK>(G, E, 2, x, y, z);
+  Hs[0] = bea(G, hbar<CHK>(G, D, 0, x, y, z), hbar<CHK>(G, D, 0, x, y - 1, z), 1, y);
+  Hs[1] = bea(G, hbar<CHK>(G, D, 1, x, y, z), hbar<CHK>(G, D, 1, x - 1, y, z), 0, x);
+  float lx = bea(G, hbar<CHK>(G, D, 2, x, y, z), hbar<CHK>(G, D, 2, x - 1, y, z), 0, x);
+  float lxm = bea(G, hbar<CHK>(G, D, 2, x, y - 1, z), hbar<CHK>(G, D, 2, x - 1, y - 1, z), 0, x);
   float lxy = bea(G, lx, lxm, 1, y);
-  float hx = bea(G, hbar(G, D, 2, x, y, z + 1), hbar(G, D, 2, x - 1, y, z + 1), 0, x);
-  float hxm = bea(G, hbar(G, D, 2, x, y - 1, z + 1), hbar(G, D, 2, x - 1, y - 1, z + 1), 0, x);
+  float hx = bea(G, hbar<CHK>(G, D, 2, x, y, z + 1), hbar<CHK>(G, D, 2, x - 1, y, z + 1), 0, x);
+  float hxm = bea(G, hbar<CHK>(G, D, 2, x, y - 1, z + 1), hbar<CHK>(G, D, 2, x - 1, y - 1, z + 1), 0, x);
   float hxy = bea(G, hx, hxm, 1, y);
   Hs[2] = (lxy + hxy) / 2.0f;
+}
+__device__ __forceinline__ void colocate(const GridDev& G, const DetDev& D, int x, int y, int z, float* Es, float* Hs) {
+  // the stencil reads x-1..x, y-1..y, z..z+1: away from the faces no halo rule applies
+  if (x >= 1 && x < G.nx && y >= 1 && y < G.ny && z >= 0 && z + 1 < G.nz) colocate_t<false>(G, D, x, y, z, Es, Hs);
+  else colocate_t<true>(G, D, x, y, z, Es, Hs);
 }
 
 // One thread per region cell: sample, then write the per-type result (or stage it for a reduction).
@@ -150,10 +182,20 @@ __global__ void det_sample_batch_kernel(const GridDev G, const DetDev* __restric
 __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& D, const int t, const long long cell) {
   const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
   const long long n = (long long)ex * ey * ez;
-  const int rz = (int)(cell % ez);
-  const int ry = (int)((cell / ez) % ey);
-  const int rx = (int)(cell / ((long long)ez * ey));
+  int rx, ry, rz;
+  if (n < 0x7fffffffLL) {
+    const unsigned u = (unsigned)cell;
+    rz = (int)(u % (unsigned)ez);
+    ry = (int)((u / (unsigned)ez) % (unsigned)ey);
+    rx = (int)(u / ((unsigned)ez * (unsigned)ey));
+  } else {
+    rz = (int)(cell % ez);
+    ry = (int)((cell / ez) % ey);
+    rx = (int)(cell / ((long long)ez * ey));
+  }
   const int x = D.lo[0] + rx, y = D.lo[1] + ry, z = D.lo[2] + rz;
+  // energy.py:118-143 with as_slices and no averaging keeps three planes of the region: O(surface) work
+  if ((D.flags & DET_SLICES) && !(D.flags & DET_SLICE_MEAN) && rx != D.slice_idx[0] && ry != D.slice_idx[1] && rz != D.slice_idx[2]) return;
   float Es[3], Hs[3];
   colocate(G, D, x, y, z, Es, Hs);
   const int slot = D.arr_idx[t];

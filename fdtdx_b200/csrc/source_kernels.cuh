@@ -17,6 +17,12 @@
 template <int TIER_E, int TIER_M>
 __global__ void src_apply_kernel(const StepParams P, const int t, const int is_E, const int reverse) {
   const int s = blockIdx.y;
+  // the source descriptors live in global memory; stage them once per block (they are read many times
+  // along a dependent chain: box, switch tables, profile parameters, array pointers)
+  __shared__ SrcDev s_src[FDTDX_MAX_SRC];
+  for (int q = threadIdx.x; q < P.n_src * (int)(sizeof(SrcDev) / 4); q += blockDim.x)
+    reinterpret_cast<int*>(s_src)[q] = reinterpret_cast<const int*>(P.src)[q];
+  __syncthreads();
   const int lo0 = max(P.src_lo[s][0], P.x_begin), hi0 = min(P.src_hi[s][0], P.x_end);
   const int d0 = hi0 - lo0, d1 = P.src_hi[s][1] - P.src_lo[s][1], d2 = P.src_hi[s][2] - P.src_lo[s][2];
   if (d0 <= 0 || d1 <= 0 || d2 <= 0) return;
@@ -38,7 +44,7 @@ __global__ void src_apply_kernel(const StepParams P, const int t, const int is_E
       m0 = P.eps[cell];
       m1 = (TIER_E == 3) ? P.eps[P.eps_cs + cell] : m0;
       m2 = (TIER_E == 3) ? P.eps[2 * P.eps_cs + cell] : m0;
-      inject_E(P.src, P.n_src, P.dt, t, reverse != 0, i, j, k, m0, m1, m2, &f0, &f1, &f2);
+      inject_E(s_src, P.n_src, P.dt, t, reverse != 0, i, j, k, m0, m1, m2, &f0, &f1, &f2);
     } else {
       m0 = m1 = m2 = P.inv_mu_scalar;
       if (TIER_M >= 1) {
@@ -46,7 +52,7 @@ __global__ void src_apply_kernel(const StepParams P, const int t, const int is_E
         m1 = (TIER_M == 3) ? P.mu[P.mu_cs + cell] : m0;
         m2 = (TIER_M == 3) ? P.mu[2 * P.mu_cs + cell] : m0;
       }
-      inject_H(P.src, P.n_src, P.dt, t, reverse != 0, i, j, k, m0, m1, m2, &f0, &f1, &f2);
+      inject_H(s_src, P.n_src, P.dt, t, reverse != 0, i, j, k, m0, m1, m2, &f0, &f1, &f2);
     }
     if (!reverse) {
       // the reference masks PEC / PMC cells after the injection (update.py order)

@@ -78,6 +78,7 @@ static __device__ __noinline__ void inject_E(const SrcDev* __restrict__ srcs, in
       long long f = ((long long)(i - S.lo[0]) * fy + (j - S.lo[1])) * fz + (k - S.lo[2]);
       int a = (S.normal_axis + 1) % 3, b = (S.normal_axis + 2) % 3;
       float sign = reverse ? -S.sign : S.sign;
+      const float inc_b = S.Hinc[b * fn + f], inc_a = S.Hinc[a * fn + f];  // loaded ahead of the profile calls
       float amp_a, amp_b;
       if (S.hfilter == nullptr) {
         amp_a = src_profile(S, (tf + S.toffH[a * fn + f]) * dt) * S.static_amp;
@@ -100,8 +101,8 @@ static __device__ __noinline__ void inject_E(const SrcDev* __restrict__ srcs, in
         amp_a = amps[0];
         amp_b = amps[1];
       }
-      float Hb = S.Hinc[b * fn + f] * amp_b;
-      float Ha = S.Hinc[a * fn + f] * amp_a;
+      float Hb = inc_b * amp_b;
+      float Ha = inc_a * amp_a;
       Hb = (Hb * S.cE) * ie[a];
       Ha = (Ha * S.cE) * ie[b];
       E[a] = E[a] + sign * Hb;
@@ -132,10 +133,12 @@ static __device__ __noinline__ void inject_H(const SrcDev* __restrict__ srcs, in
       long long f = ((long long)(i - S.lo[0]) * fy + (j - S.lo[1])) * fz + (k - S.lo[2]);
       int a = (S.normal_axis + 1) % 3, b = (S.normal_axis + 2) % 3;
       float sign = reverse ? -S.sign : S.sign;
-      float amp_a = src_profile(S, (tf + S.toffE[a * fn + f]) * dt) * S.static_amp;
-      float amp_b = src_profile(S, (tf + S.toffE[b * fn + f]) * dt) * S.static_amp;
-      float Ea = S.Einc[a * fn + f] * amp_a;
-      float Eb = S.Einc[b * fn + f] * amp_b;
+      const float inc_a = S.Einc[a * fn + f], inc_b = S.Einc[b * fn + f];
+      const float to_a = S.toffE[a * fn + f], to_b = S.toffE[b * fn + f];
+      float amp_a = src_profile(S, (tf + to_a) * dt) * S.static_amp;
+      float amp_b = src_profile(S, (tf + to_b) * dt) * S.static_amp;
+      float Ea = inc_a * amp_a;
+      float Eb = inc_b * amp_b;
       Ea = (Ea * S.cH) * im[b];
       Eb = (Eb * S.cH) * im[a];
       H[b] = H[b] + sign * Ea;
