@@ -617,6 +617,11 @@ struct alignas(64) TmaSet {
 cudaError_t fdtdx_dispatch_E4_tma(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
                                   cudaStream_t st);
 cudaError_t fdtdx_dispatch_H4_tma(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
+// 64-cell tile rows, two rows per warp: thin grids (Nz <= 64)
+cudaError_t fdtdx_dispatch_E4_tma64(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
+                                    cudaStream_t st);
+cudaError_t fdtdx_dispatch_H4_tma64(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
+static int tma_tz(const FdtdxPlan* p) { return p->nz <= 64 ? 64 : 128; }
 
 // 0: no CPML slab on this rank; 1: scalar z-slab accesses; 2: 128-bit z-slab accesses
 static int pml_mode(const FdtdxPlan* p, const StepParams& P) {
@@ -649,6 +654,7 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // kind 0: halo box (TZ+4, R+1), kind 1: plain box (TZ, R).  Arrays are (C, nx, ny, nz) float32.
 static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind, CUtensorMap* out) {
+  const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
   auto key = std::make_tuple(base, comps * 4 + (nx == p->nx ? 0 : 1), kind);
   auto it = p->tmaps.find(key);
   if (it != p->tmaps.end()) { *out = it->second; return FDTDX_OK; }
@@ -656,7 +662,7 @@ static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind,
   if (!enc) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)p->nz, (cuuint64_t)p->ny, (cuuint64_t)nx, (cuuint64_t)comps};
   const cuuint64_t strides[3] = {(cuuint64_t)p->nz * 4, (cuuint64_t)p->nz * p->ny * 4, (cuuint64_t)p->nz * p->ny * nx * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)(kind == 0 ? 128 + 4 : 128), (cuuint32_t)(kind == 0 ? FDTDX_TMA_R + 1 : FDTDX_TMA_R), 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)(kind == 0 ? tz + 4 : tz), (cuuint32_t)(kind == 0 ? rt + 1 : rt), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -676,7 +682,8 @@ static int get_xhalo_tmap(FdtdxPlan* p, const void* base, long long comp_stride,
   if (!enc) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)p->nz, (cuuint64_t)p->ny, 2, 1};
   const cuuint64_t strides[3] = {(cuuint64_t)p->nz * 4, (cuuint64_t)comp_stride * 4, (cuuint64_t)comp_stride * 8};
-  const cuuint32_t box[4] = {128 + 4, FDTDX_TMA_R + 1, 1, 1};
+  const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+  const cuuint32_t box[4] = {(cuuint32_t)(tz + 4), (cuuint32_t)(rt + 1), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -711,7 +718,8 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
     xc = 8;
     // Mid-size grids run only a few waves of the 148 x 2 resident CTAs: pick the chunk length in 5..10
     // whose CTA count wastes the least of its last wave (large grids: no effect).
-    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R);
+    const int tzc = tma_tz(p), rtc = FDTDX_TMA_R * (128 / tzc);
+    const long long tiles = (long long)((p->nz + tzc - 1) / tzc) * ((p->ny + rtc - 1) / rtc);
     const long long nxr = P.x_end - P.x_begin;
     if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
       double best = -1.0;
@@ -764,8 +772,10 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     M.xhalo = M.fld_halo;
     StepParams Q = P;
     Q.xchunk = tma_chunk(p, P);
-    dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
-    CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
+    const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+    dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    if (tz == 64) CUDA_TRY(fdtdx_dispatch_E4_tma64(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
+    else CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
   } else {
     // register-marching kernels, four cells per thread: 128-bit accesses (E4) or, on ragged rows, four
     // predicated 32-bit accesses (E1)
@@ -797,8 +807,10 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     if (P.x_hi_mode == 2 && (rc = get_xhalo_tmap(p, P.haloE, P.haloE_cs, &M.xhalo))) return rc;
     StepParams Q = P;
     Q.xchunk = tma_chunk(p, P);
-    dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
-    CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
+    const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+    dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    if (tz == 64) CUDA_TRY(fdtdx_dispatch_H4_tma64(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
+    else CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
   } else {
     dim3 b(32, p->rows);
     dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);

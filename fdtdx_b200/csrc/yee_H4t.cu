@@ -2,6 +2,9 @@
 #define FDTDX_BUILD_H 1
 #include "yee_tma.cuh"
 #include "tma_cfg.h"
+#ifndef FDTDX_TZ_SEL
+#define FDTDX_TZ_SEL 128  // tile width of this translation unit (yee_H4t64.cu re-includes this file with 64)
+#endif
 #include <cstdlib>
 
 static bool fdtdx_tma_pdl_enabled() {
@@ -14,8 +17,9 @@ static cudaError_t go_H(const StepParams& P, const TmaSet& M, int t, dim3 g, cud
   // three material components make a stage 39 KB: a 3-deep ring would leave one CTA per SM, so those
   // variants run a 2-deep ring (78 KB, two CTAs per SM)
   constexpr int R = FDTDX_TMA_R, S = (MUT == 3) ? 2 : FDTDX_TMA_S;
-  constexpr int smem = tma_smem_bytes<R, MUT, S>();
-  auto k = yee_H_tma<MUT, REV, SIG, MET, PM, R, S>;
+  constexpr int TZ = FDTDX_TZ_SEL;
+  constexpr int smem = tma_smem_bytes<R, TZ, MUT, S>();
+  auto k = yee_H_tma<MUT, REV, SIG, MET, PM, R, S, TZ>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -19,13 +19,15 @@
 #include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time in abi.cu)
 #include "yee_kernels.cuh"
 
-#define FDTDX_TMA_TZ 128                 // z cells per tile: one warp x float4
-#define FDTDX_TMA_HZ (FDTDX_TMA_TZ + 4)  // halo tile width: one 16-byte pad column group
+#define FDTDX_TMA_TZ 128                 // widest tile: z cells per tile row (one warp x float4)
+// Tile shapes: TZ = 128 (a warp owns one row of 128 z cells) or TZ = 64 for grids with Nz <= 64 (a warp
+// owns two rows of 64 cells: lanes 0-15 / 16-31), so thin grids fill their lanes.  A CTA is always 8
+// warps; it covers RT = 8 * (128 / TZ) rows.  Halo tiles are TZ + 4 wide (one 16-byte pad column group).
 #define FDTDX_TMA_XC_MAX 64              // longest x chunk (planes per CTA) the per-plane scalar table holds
 // tail of the dynamic shared memory, in floats: [full barriers 2*S <= 16][arrivals <= 8][pad][ztab 3*128][xs XC_MAX]
 #define FDTDX_TMA_TAIL_ARR 16
 #define FDTDX_TMA_TAIL_ZTAB 32
-#define FDTDX_TMA_TAIL_XS (FDTDX_TMA_TAIL_ZTAB + 3 * FDTDX_TMA_TZ)
+#define FDTDX_TMA_TAIL_XS (FDTDX_TMA_TAIL_ZTAB + 3 * FDTDX_TMA_TZ)  // sized for the widest tile
 #define FDTDX_TMA_TAIL_F (FDTDX_TMA_TAIL_XS + FDTDX_TMA_XC_MAX)
 #ifndef FDTDX_TMA_MAXREG
 #define FDTDX_TMA_MAXREG 128  // R * 32 = 256 threads x 128 registers: two CTAs per SM
@@ -38,17 +40,20 @@ struct alignas(64) TmaSet {
   CUtensorMap xhalo;      // H step, x_hi_mode 2: (2,ny,nz) Ey,Ez plane of the next rank, box (HZ, R+1, 1, 1)
 };
 
-template <int R>
+template <int R, int TZ>  // R warps per CTA
 struct TmaGeom {
-  static constexpr int HALO_RAW = FDTDX_TMA_HZ * (R + 1) * 4;   // bytes the TMA writes per halo tile
-  static constexpr int HALO_B = (HALO_RAW + 127) / 128 * 128;   // slot size (128-byte aligned)
-  static constexpr int PLAIN_B = FDTDX_TMA_TZ * R * 4;
+  static constexpr int WR = 128 / TZ;                            // rows per warp
+  static constexpr int RT = R * WR;                              // rows per CTA tile
+  static constexpr int HZ = TZ + 4;
+  static constexpr int HALO_RAW = HZ * (RT + 1) * 4;             // bytes the TMA writes per halo tile
+  static constexpr int HALO_B = (HALO_RAW + 127) / 128 * 128;    // slot size (128-byte aligned)
+  static constexpr int PLAIN_B = TZ * RT * 4;
   static constexpr int HALO_F = HALO_B / 4, PLAIN_F = PLAIN_B / 4;
 };
-template <int R, int NMAT, int S>
+template <int R, int TZ, int NMAT, int S>
 constexpr int tma_smem_bytes() {
   // stages, full barriers, arrival counters (padded to 16 B), z-slab coefficient tables, per-plane x scale
-  return S * (3 * TmaGeom<R>::HALO_B + (3 + NMAT) * TmaGeom<R>::PLAIN_B) + FDTDX_TMA_TAIL_F * 4;
+  return S * (3 * TmaGeom<R, TZ>::HALO_B + (3 + NMAT) * TmaGeom<R, TZ>::PLAIN_B) + FDTDX_TMA_TAIL_F * 4;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,8 +211,8 @@ struct PmlT {
     }                                                                                                                  \
     if (PM == 2) {                                                                                                     \
       if (L.zh0 || L.zh1) {                                                                                            \
-        const Vec<V> az = lds4(ztab + lane * V), bz = lds4(ztab + FDTDX_TMA_TZ + lane * V);                            \
-        const Vec<V> kz = lds4(ztab + 2 * FDTDX_TMA_TZ + lane * V);                                                    \
+        const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZ + zl * V);                                  \
+        const Vec<V> kz = lds4(ztab + 2 * TZ + zl * V);                                                                  \
         float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                          \
         float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                          \
         if (L.zh0) {                                                                                                   \
@@ -238,8 +243,8 @@ struct PmlT {
         }                                                                                                              \
       }                                                                                                                \
     } else if (L.zm) {                                                                                                 \
-      const Vec<V> az = lds4(ztab + lane * V), bz = lds4(ztab + FDTDX_TMA_TZ + lane * V);                              \
-      const Vec<V> kz = lds4(ztab + 2 * FDTDX_TMA_TZ + lane * V);                                                      \
+      const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZ + zl * V);                                    \
+      const Vec<V> kz = lds4(ztab + 2 * TZ + zl * V);                                                                    \
       float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                            \
       float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                            \
       const bool k1 = pz.kappa_one;                                                                                    \
@@ -253,9 +258,9 @@ struct PmlT {
 // E half-step, TMA-staged.  blockDim = (32, R).
 // Stage layout: [Hx halo][Hy halo][Hz halo][Ex][Ey][Ez][inv_eps x TIER]; halo tile origin (k0-4, j0-1).
 // ------------------------------------------------------------------------------------------------
-template <int TIER, int R>
+template <int TIER, int R, int TZ>
 __device__ __forceinline__ void tma_issue_E(const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i) {
-  using G = TmaGeom<R>;
+  using G = TmaGeom<R, TZ>;
   mbar_expect_tx(full, 3 * G::HALO_RAW + (3 + TIER) * G::PLAIN_B);
 #pragma unroll
   for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G::HALO_B, &M.fld_halo, kt0 - 4, j0 - 1, i, c, full);
@@ -265,22 +270,23 @@ __device__ __forceinline__ void tma_issue_E(const TmaSet& M, uint32_t dst, uint3
   for (int c = 0; c < TIER; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
 }
 
-template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, int R, int S>
+template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, int R, int S, int TZ>
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_E_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
-  using G = TmaGeom<R>;
-  constexpr int HZ = FDTDX_TMA_HZ, TZ = FDTDX_TMA_TZ;
+  using G = TmaGeom<R, TZ>;
+  constexpr int HZ = G::HZ, WR = G::WR, LZ = TZ / 4;  // lanes per row
   constexpr int STAGE_F = 3 * G::HALO_F + (3 + TIER) * G::PLAIN_F;
   const int lane = threadIdx.x, warp = threadIdx.y;
-  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * R;
+  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * G::RT;
+  const int zl = lane % LZ, trow = warp * WR + lane / LZ;  // z lane inside the row, row inside the tile
   const int nz = P.nz, ny = P.ny;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
-  const int j = j0 + warp;
-  const int k0 = kt0 + lane * V;
+  const int j = j0 + trow;
+  const int k0 = kt0 + zl * V;
   const bool lane_ok = (j < ny) && (k0 < nz);
-  const int n_act = min(R, ny - j0);  // warps that own a row (the others leave before the loop)
+  const int n_act = min(R, (ny - j0 + WR - 1) / WR);  // warps that own a row (the others leave before the loop)
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
   int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
@@ -322,9 +328,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1
-    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
+    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R, TZ>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
   }
-  if (j >= ny) return;
+  if (j0 + warp * WR >= ny) return;
 
   // ---------------- consumers ----------------
   const long long plane = (long long)ny * nz;
@@ -355,8 +361,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       hz_im = ldv<V>(P.haloH + P.haloH_cs + row);
     }
   }
-  const int oh = (warp + 1) * HZ + 4 + lane * V;  // own cells inside a halo tile
-  const int op = warp * TZ + lane * V;            // own cells inside a plain tile
+  const int oh = (trow + 1) * HZ + 4 + zl * V;  // own cells inside a halo tile
+  const int op = trow * TZ + zl * V;            // own cells inside a plain tile
 
   int s = 0;
   uint32_t ph = 0;
@@ -375,7 +381,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     // z-neighbour (k-1) of the first element: last element of the previous lane / the tile's pad column
     float hx_l = __shfl_up_sync(0xffffffffu, hx.v[V - 1], 1);
     float hy_l = __shfl_up_sync(0xffffffffu, hy.v[V - 1], 1);
-    if (lane == 0) {
+    if (zl == 0) {
       hx_l = sHx[-1];
       hy_l = sHy[-1];
     }
@@ -422,7 +428,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S < ic1) tma_issue_E<TIER, R>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
+        if (i + S < ic1) tma_issue_E<TIER, R, TZ>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
       }
     }
     if (++s == S) { s = 0; ph ^= 1; }
@@ -451,9 +457,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 // halo tile origin (k0, j0): row +1 is the j+1 neighbour, column +4.. the k+1 neighbour; the x+1
 // neighbour plane is the next ring stage (one extra Ey,Ez stage is loaded after the last plane).
 // ------------------------------------------------------------------------------------------------
-template <int MUT, int R>
+template <int MUT, int R, int TZ>
 __device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i, int ic1) {
-  using G = TmaGeom<R>;
+  using G = TmaGeom<R, TZ>;
   if (i < ic1) {
     mbar_expect_tx(full, 3 * G::HALO_RAW + (3 + MUT) * G::PLAIN_B);
 #pragma unroll
@@ -479,22 +485,23 @@ __device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M
   }
 }
 
-template <int MUT, bool REV, bool SIG, bool MET, int PM, int R, int S>
+template <int MUT, bool REV, bool SIG, bool MET, int PM, int R, int S, int TZ>
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_H_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
-  using G = TmaGeom<R>;
-  constexpr int HZ = FDTDX_TMA_HZ, TZ = FDTDX_TMA_TZ;
+  using G = TmaGeom<R, TZ>;
+  constexpr int HZ = G::HZ, WR = G::WR, LZ = TZ / 4;  // lanes per row
   constexpr int STAGE_F = 3 * G::HALO_F + (3 + MUT) * G::PLAIN_F;
   const int lane = threadIdx.x, warp = threadIdx.y;
-  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * R;
+  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * G::RT;
+  const int zl = lane % LZ, trow = warp * WR + lane / LZ;  // z lane inside the row, row inside the tile
   const int nz = P.nz, ny = P.ny;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
-  const int j = j0 + warp;
-  const int k0 = kt0 + lane * V;
+  const int j = j0 + trow;
+  const int k0 = kt0 + zl * V;
   const bool lane_ok = (j < ny) && (k0 < nz);
-  const int n_act = min(R, ny - j0);
+  const int n_act = min(R, (ny - j0 + WR - 1) / WR);
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
   int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
@@ -531,9 +538,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1 (plane ic1 is the Ey,Ez-only stage)
     for (int s = 0; s < S && ic0 + s <= ic1; ++s)
-      tma_issue_H<MUT, R>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
+      tma_issue_H<MUT, R, TZ>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
   }
-  if (j >= ny) return;
+  if (j0 + warp * WR >= ny) return;
 
   // ---------------- consumers ----------------
   const long long plane = (long long)ny * nz;
@@ -549,8 +556,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   }
   long long cell0 = (long long)ic0 * plane + row;
   float* pH = (P.H_out ? P.H_out : P.H) + cell0;
-  const int oh = warp * HZ + lane * V;
-  const int op = warp * TZ + lane * V;
+  const int oh = trow * HZ + zl * V;
+  const int op = trow * TZ + zl * V;
 
   int s = 0;
   uint32_t ph = 0;
@@ -570,7 +577,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     const Vec<V> ex_jp = lds4(sEx + HZ), ez_jp = lds4(sEz + HZ);
     float ex_r = __shfl_down_sync(0xffffffffu, ex.v[0], 1);
     float ey_r = __shfl_down_sync(0xffffffffu, ey.v[0], 1);
-    if (lane == 31) {
+    if (zl == LZ - 1) {
       ex_r = sEx[V];
       ey_r = sEy[V];
     }
@@ -619,7 +626,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S <= ic1) tma_issue_H<MUT, R>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
+        if (i + S <= ic1) tma_issue_H<MUT, R, TZ>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
       }
     }
     s = sn;
