@@ -621,7 +621,11 @@ cudaError_t fdtdx_dispatch_H4_tma(const StepParams& P, const TmaSet& M, int t, i
 cudaError_t fdtdx_dispatch_E4_tma64(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
                                     cudaStream_t st);
 cudaError_t fdtdx_dispatch_H4_tma64(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
-static int tma_tz(const FdtdxPlan* p) { return p->nz <= 64 ? 64 : 128; }
+static int tma_tz(const FdtdxPlan* p) {
+  const char* e = getenv("FDTDX_B200_TMA_TZ");
+  if (e && (atoi(e) == 64 || atoi(e) == 128)) return atoi(e);
+  return p->nz <= 64 ? 64 : 128;
+}
 
 // 0: no CPML slab on this rank; 1: scalar z-slab accesses; 2: 128-bit z-slab accesses
 static int pml_mode(const FdtdxPlan* p, const StepParams& P) {
