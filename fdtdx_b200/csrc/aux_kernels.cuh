@@ -83,8 +83,16 @@ __device__ __forceinline__ float bea(const GridDev& G, float cur, float prev, in
 __device__ __forceinline__ void det_gather_body(const GridDev& G, const DetDev& D);
 __global__ void det_gather_hprev_kernel(const GridDev G, const DetDev D) { det_gather_body(G, D); }
 // batched: one launch for all detectors (blockIdx.y = detector), gated on the device by on[t]
+// (the descriptor is staged in shared memory: read through a global reference it is re-loaded after
+// every store, because the stores may alias it)
+__device__ __forceinline__ void det_stage_descriptor(DetDev* dst, const DetDev* src) {
+  for (int q = threadIdx.x; q < (int)(sizeof(DetDev) / 4); q += blockDim.x) reinterpret_cast<int*>(dst)[q] = reinterpret_cast<const int*>(src)[q];
+  __syncthreads();
+}
 __global__ void det_gather_batch_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
-  const DetDev& D = dets[blockIdx.y];
+  __shared__ DetDev sD;
+  det_stage_descriptor(&sD, dets + blockIdx.y);
+  const DetDev& D = sD;
   if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_EXACT)) return;
   det_gather_body(G, D);
 }
@@ -158,10 +166,43 @@ __device__ __forceinline__ void colocate_t(const GridDev& G, const DetDev& D, in
   float hxy = bea(G, hx, hxm, 1, y);
   Hs[2] = (lxy + hxy) / 2.0f;
 }
+// Interior cells with exact interpolation: the same samples and the same arithmetic as colocate_t, but
+// every address is one base offset plus a constant stride (no halo rule, no per-sample index products).
+__device__ __forceinline__ void colocate_interior(const GridDev& G, const DetDev& D, int x, int y, int z, float* Es, float* Hs) {
+  const long long N = (long long)G.nx * G.ny * G.nz;
+  const long long sy_g = G.nz, sx_g = (long long)G.ny * G.nz;
+  const float* e = G.E + ((long long)x * G.ny + y) * G.nz + z;
+  const float* h = G.H + ((long long)x * G.ny + y) * G.nz + z;
+  const int hy_ = D.hi[1] - D.lo[1] + 1, hz_ = D.hi[2] - D.lo[2] + 1, hx_ = D.hi[0] - D.lo[0] + 1;
+  const long long hn = (long long)hx_ * hy_ * hz_, sy_h = hz_, sx_h = (long long)hy_ * hz_;
+  const float* p = D.hprev + ((long long)(x - D.lo[0] + 1) * hy_ + (y - D.lo[1] + 1)) * hz_ + (z - D.lo[2]);
+#define HB(c, off_h, off_g) ((p[(c) * hn + (off_h)] + h[(c) * N + (off_g)]) / 2.0f)
+  float lo = bea(G, e[0], e[-sx_g], 0, x);
+  float hi = bea(G, e[1], e[1 - sx_g], 0, x);
+  Es[0] = (lo + hi) / 2.0f;
+  lo = bea(G, e[N], e[N - sy_g], 1, y);
+  hi = bea(G, e[N + 1], e[N + 1 - sy_g], 1, y);
+  Es[1] = (lo + hi) / 2.0f;
+  Es[2] = e[2 * N];
+  Hs[0] = bea(G, HB(0, 0, 0), HB(0, -sy_h, -sy_g), 1, y);
+  Hs[1] = bea(G, HB(1, 0, 0), HB(1, -sx_h, -sx_g), 0, x);
+  const float lx = bea(G, HB(2, 0, 0), HB(2, -sx_h, -sx_g), 0, x);
+  const float lxm = bea(G, HB(2, -sy_h, -sy_g), HB(2, -sx_h - sy_h, -sx_g - sy_g), 0, x);
+  const float lxy = bea(G, lx, lxm, 1, y);
+  const float hx = bea(G, HB(2, 1, 1), HB(2, 1 - sx_h, 1 - sx_g), 0, x);
+  const float hxm = bea(G, HB(2, 1 - sy_h, 1 - sy_g), HB(2, 1 - sx_h - sy_h, 1 - sx_g - sy_g), 0, x);
+  const float hxy = bea(G, hx, hxm, 1, y);
+  Hs[2] = (lxy + hxy) / 2.0f;
+#undef HB
+}
 __device__ __forceinline__ void colocate(const GridDev& G, const DetDev& D, int x, int y, int z, float* Es, float* Hs) {
   // the stencil reads x-1..x, y-1..y, z..z+1: away from the faces no halo rule applies
-  if (x >= 1 && x < G.nx && y >= 1 && y < G.ny && z >= 0 && z + 1 < G.nz) colocate_t<false>(G, D, x, y, z, Es, Hs);
-  else colocate_t<true>(G, D, x, y, z, Es, Hs);
+  if (x >= 1 && x < G.nx && y >= 1 && y < G.ny && z >= 0 && z + 1 < G.nz) {
+    if (D.flags & DET_EXACT) colocate_interior(G, D, x, y, z, Es, Hs);
+    else colocate_t<false>(G, D, x, y, z, Es, Hs);
+  } else {
+    colocate_t<true>(G, D, x, y, z, Es, Hs);
+  }
 }
 
 // One thread per region cell: sample, then write the per-type result (or stage it for a reduction).
@@ -173,7 +214,9 @@ __global__ void det_sample_kernel(const GridDev G, const DetDev D, const int t) 
   det_sample_body(G, D, t, cell);
 }
 __global__ void det_sample_batch_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
-  const DetDev& D = dets[blockIdx.y];
+  __shared__ DetDev sD;
+  det_stage_descriptor(&sD, dets + blockIdx.y);
+  const DetDev& D = sD;
   if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t]) return;
   const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
   for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < n; cell += (long long)gridDim.x * blockDim.x)
