@@ -31,7 +31,7 @@ EXPORTS = [
     "fdtdx_b200_plan_add_dipole", "fdtdx_b200_plan_add_detector", "fdtdx_b200_plan_set_recorder",
     "fdtdx_b200_plan_set_dispersion", "fdtdx_b200_halo_bind", "fdtdx_b200_bind", "fdtdx_b200_run_forward",
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
-    "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
+    "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_peer_detach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
     "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
 ]
 
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_set_tma.argtypes = [_p, _i, _i]
     L.fdtdx_b200_total_energy.argtypes = [_p, _p, _p]
     L.fdtdx_b200_run_adjoint_exact.argtypes = [_p, _i, _p]
+    L.fdtdx_b200_peer_detach.argtypes = [_p]
     L.fdtdx_b200_peer_export.argtypes = [_p, _i, C.c_char_p, C.POINTER(C.c_longlong)]
     L.fdtdx_b200_peer_attach.argtypes = [_p, _i, C.c_char_p, C.c_longlong, C.c_char_p, C.c_longlong, _i]
     L.fdtdx_b200_run_forward_host.argtypes = [_p, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]

@@ -1067,6 +1067,15 @@ static int ipc_open(FdtdxPlan* p, const unsigned char* handle64, void** base) {
   return FDTDX_OK;
 }
 
+extern "C" int fdtdx_b200_peer_detach(FdtdxPlan* p) {
+  if (!p) return fail(FDTDX_EINVAL, "peer_detach: null plan");
+  p->peer_mode = false;
+  p->peer[0] = FdtdxPlan::PeerLink();
+  p->peer[1] = FdtdxPlan::PeerLink();
+  p->tmaps.clear();
+  return FDTDX_OK;
+}
+
 // side 0: low-x neighbour (its H array + flags), side 1: high-x neighbour (its E array + flags)
 extern "C" int fdtdx_b200_peer_attach(FdtdxPlan* p, int side, const unsigned char* field_handle64, long long field_offset,
                                       const unsigned char* flags_handle64, long long flags_offset, int nx_peer) {

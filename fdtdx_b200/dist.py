@@ -102,27 +102,52 @@ class SlabRunner:
         self.peer = bool(halo == "peer" and E.is_cuda and world > 1 and (has_lo or has_hi))
         if self.peer:
             self._attach_peers(group)
-        self.side = torch.cuda.Stream(device=E.device) if (self.overlap and E.is_cuda and not self.peer) else None
+        self.side = torch.cuda.Stream(device=E.device) if (self.overlap and E.is_cuda and not self.peer) else None  # after the attach: it may have fallen back
 
     def _attach_peers(self, group):
-        """Ship this rank's IPC handles (E, H, progress flags) to everybody, attach the two neighbours'."""
+        """Ship this rank's IPC handles (E, H, progress flags) to everybody, attach the two neighbours'.
+        If any rank cannot export or map (no CUDA IPC in the container, expandable-segment allocator, no
+        peer access), every rank falls back to the exchanged-plane transport together."""
+        import warnings
+
         import torch.distributed as dist
 
         lib, h = self.plan.lib, self.plan.h
-        mine = {"nx": int(self.nx)}
-        for what, name in ((0, "E"), (1, "H"), (2, "flags")):
-            buf = C.create_string_buffer(64)
-            off = C.c_longlong(0)
-            check(lib.fdtdx_b200_peer_export(h, what, buf, C.byref(off)))
-            mine[name] = (bytes(buf.raw), int(off.value))
+        import os
+
+        mine = {"nx": int(self.nx), "ok": True}
+        try:
+            if os.environ.get("FDTDX_B200_PEER_FAIL") == str(self.rank):  # test hook for the fallback path
+                raise RuntimeError("simulated CUDA IPC failure (FDTDX_B200_PEER_FAIL)")
+            for what, name in ((0, "E"), (1, "H"), (2, "flags")):
+                buf = C.create_string_buffer(64)
+                off = C.c_longlong(0)
+                check(lib.fdtdx_b200_peer_export(h, what, buf, C.byref(off)))
+                mine[name] = (bytes(buf.raw), int(off.value))
+        except RuntimeError as e:
+            mine = {"nx": int(self.nx), "ok": False, "why": str(e)}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
-        if self.hx.lo is not None:
-            q = everyone[self.hx.lo]
-            check(lib.fdtdx_b200_peer_attach(h, 0, q["H"][0], q["H"][1], q["flags"][0], q["flags"][1], q["nx"]))
-        if self.hx.hi is not None:
-            q = everyone[self.hx.hi]
-            check(lib.fdtdx_b200_peer_attach(h, 1, q["E"][0], q["E"][1], q["flags"][0], q["flags"][1], q["nx"]))
+        ok = all(q["ok"] for q in everyone)
+        why = next((q.get("why") for q in everyone if not q["ok"]), None)
+        if ok:
+            try:
+                if self.hx.lo is not None:
+                    q = everyone[self.hx.lo]
+                    check(lib.fdtdx_b200_peer_attach(h, 0, q["H"][0], q["H"][1], q["flags"][0], q["flags"][1], q["nx"]))
+                if self.hx.hi is not None:
+                    q = everyone[self.hx.hi]
+                    check(lib.fdtdx_b200_peer_attach(h, 1, q["E"][0], q["E"][1], q["flags"][0], q["flags"][1], q["nx"]))
+            except RuntimeError as e:
+                ok, why = False, str(e)
+        verdict = [None] * self.world
+        dist.all_gather_object(verdict, bool(ok), group=group)
+        if not all(verdict):
+            check(lib.fdtdx_b200_peer_detach(h))
+            self.peer = False
+            if self.rank == 0:
+                warnings.warn(f"fdtdx_b200: peer-memory halo unavailable ({why}); using the NCCL plane exchange")
+            return
         dist.barrier(group=group)  # nobody starts stepping before every mapping exists
 
     def _range(self, t, which, x_begin, x_end, simulate=True):

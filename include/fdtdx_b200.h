@@ -225,6 +225,8 @@ int fdtdx_b200_set_tma(FdtdxPlan* plan, int enable, int xchunk_tma);
 int fdtdx_b200_peer_export(FdtdxPlan* plan, int what, unsigned char* handle64, long long* offset);
 int fdtdx_b200_peer_attach(FdtdxPlan* plan, int side, const unsigned char* field_handle64, long long field_offset,
                            const unsigned char* flags_handle64, long long flags_offset, int nx_peer);
+/* Back to exchanged halo buffers (HALO_H_LO / HALO_E_HI): used when a neighbour could not map this rank. */
+int fdtdx_b200_peer_detach(FdtdxPlan* plan);
 
 /* Host-buffer convenience used for end-to-end timing: copies E,H,inv_eps from HOST memory into the
  * bound device buffers, runs n forward steps, copies E,H back.  Sizes in bytes are returned. */
