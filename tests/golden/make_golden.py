@@ -23,6 +23,11 @@ CASES = {
     "pml_source_detectors_nonuniform": (dict(source="plane_z", detectors=("energy_slices", "phasor", "poynting", "field_reduce"), nonuniform=True, eps_tier=3, time=6e-15), 40, False),
     "ade_c4_sigma_seeded": (dict(poles=2, c4=True, sigma_E=True, eps_tier=3, coeff_tier=3), 8, True),
     "periodic_sigma_mu_seeded": (dict(boundaries="periodic", sigma_E=True, sigma_H=True, mu_tier=3, eps_tier=3), 10, True),
+    # ragged rows (Nz % 4 != 0, z-padded shadows / interleaved kernels), x-normal plane source, odd CPML thickness
+    "ragged_nz21_plane_x": (dict(shape=(14, 11, 21), thickness=3, source="plane_x", nonuniform=True, eps_tier=3,
+                                 detectors=("energy_slices", "phasor", "poynting"), time=6e-15), 40, False),
+    # full-tensor tier with the energy detectors (3x3 inverse per cell)
+    "tensor_eps9_mu9_energy": (dict(shape=(12, 10, 16), eps_tier=9, mu_tier=9, source="plane_z", detectors=("energy", "energy_reduce", "poynting"), time=5e-15), 30, False),
 }
 
 
