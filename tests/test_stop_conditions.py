@@ -124,6 +124,26 @@ def test_detector_convergence_truth_table():
         assert (a, b) == (t - (pp + 1) * spp, t - spp)
 
 
+# ---- oracle runs (ref. tests/integration/fdtd/test_stop_conditions.py) --------------------------------
+def test_oracle_energy_threshold_stops_a_decaying_pulse_early():
+    objects, arrays, cfg = build_scene(shape=(10, 9, 12), thickness=3, source="pulse", detectors=("energy_reduce",), time=60e-15)
+    T = cfg.time_steps_total
+    full = yee.checkpointed_fdtd(arrays, objects, cfg)
+    assert full[0] == T  # default TimeStepCondition: runs to the end
+    trace = full[1].detector_states["energy_reduce"]["energy"][:, 0]
+    e_end = float(np.sum(yee.compute_energy(full[1].fields.E, full[1].fields.H, full[1].inv_permittivities, full[1].inv_permeabilities)))
+    thr = float(trace.max()) * 1e-2 * (e_end / float(trace[-1]))
+    peak = int(np.argmax(trace))
+    st = yee.checkpointed_fdtd(arrays, objects, cfg, stopping_condition=EnergyThresholdCondition(threshold=thr, min_steps=peak + 2))
+    assert peak + 2 <= st[0] < T
+    # stopped exactly when the energy first fell below the threshold: one more check would also stop
+    cond = EnergyThresholdCondition(threshold=thr, min_steps=peak + 2).setup((0, arrays), cfg, objects)
+    assert yee.evaluate_condition(cond, st, cfg, objects) is False
+    # max_steps is a hard cut-off
+    st2 = yee.checkpointed_fdtd(arrays, objects, cfg, stopping_condition=EnergyThresholdCondition(threshold=1e-300, min_steps=1, max_steps=17))
+    assert st2[0] == 17
+
+
 # ---- device side ------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", [dict(), dict(eps_tier=3, mu_tier=3, shape=(9, 7, 13))])
