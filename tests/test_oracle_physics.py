@@ -174,3 +174,55 @@ def test_one_step_time_reversal(kind):
     inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2)) if kind == "pml" else (slice(None),) * 4
     assert np.allclose(st[1].fields.E[inner], E0[inner], atol=1e-5)
     assert np.allclose(st[1].fields.H[inner], H0[inner], atol=1e-5)
+
+
+def _tensor_line_scene(nz, theta, eps_o, eps_e, pol, zstart=20, time=60e-15, detectors=()):
+    """Periodic-xy line of cells, +z plane wave launched in vacuum, then a uniaxial medium whose principal
+    axes are rotated by ``theta`` about z: eps = R diag(eps_o, eps_e, 1) R^T (all nine components stored)."""
+    shape = (3, 3, nz)
+    cfg = fx.SimulationConfig(time=time, grid=fx.UniformGrid(spacing=DX))
+    vol = fx.SimulationVolume(name="v", grid_slice_tuple=tuple((0, n) for n in shape))
+    types = {"min_x": "periodic", "max_x": "periodic", "min_y": "periodic", "max_y": "periodic", "min_z": "pml", "max_z": "pml"}
+    bl = fx.boundary_objects_from_config(shape, cfg, types, thickness=10)
+    c, s = math.cos(theta), math.sin(theta)
+    R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    inv_med = R @ np.diag([1.0 / eps_o, 1.0 / eps_e, 1.0]) @ R.T
+    inv_eps = np.zeros((9, *shape), F)
+    for i in range(3):
+        for j in range(3):
+            inv_eps[3 * i + j, :, :, :zstart] = 1.0 if i == j else 0.0
+            inv_eps[3 * i + j, :, :, zstart:] = inv_med[i, j]
+    src = fx.make_plane_source("s", ((0, 3), (0, 3), (14, 15)), cfg, inv_eps, direction="+", wave_character=fx.WaveCharacter(wavelength=WL),
+                               fixed_E_polarization_vector=pol, normalize_by_energy=False)
+    objs = [vol, *bl, src, *[d.place_on_grid(cfg) for d in detectors]]
+    objects, arrays, _, cfg, _ = fx.place_objects(objs, cfg, inv_permittivities=inv_eps)
+    return objects, arrays, cfg
+
+
+@pytest.mark.parametrize("axis", ["ordinary", "extraordinary"])
+def test_rotated_birefringence_full_tensor(axis):
+    """tests/simulation/physics/test_birefringence.py re-posed for the nine-component tier (update.py:356-492):
+    in a uniaxial medium whose axes are rotated by 30 degrees in the xy plane, a wave polarised along a
+    principal axis is an eigen-polarisation - it keeps its polarisation and travels with that axis' index."""
+    theta = math.radians(30.0)
+    eps_o, eps_e = 2.25, 4.0
+    e_o = (math.cos(theta), math.sin(theta), 0.0)
+    e_e = (-math.sin(theta), math.cos(theta), 0.0)
+    par, perp, n_med = (e_o, e_e, math.sqrt(eps_o)) if axis == "ordinary" else (e_e, e_o, math.sqrt(eps_e))
+    dets = [_point("a", 60, comps=("Ex", "Ey")), _point("b", 66, comps=("Ex", "Ey"))]
+    objects, arrays, cfg = _tensor_line_scene(140, theta, eps_o, eps_e, par, detectors=dets)
+    st = yee.checkpointed_fdtd(arrays, objects, cfg)
+    a = st[1].detector_states["a"]["fields"][:, :, 0, 0, 0]
+    b = st[1].detector_states["b"]["fields"][:, :, 0, 0, 0]
+    period_steps = WL / c0 / cfg.time_step_duration
+    n_last = int(4 * period_steps)
+    omega = 2 * np.pi * c0 / WL
+    proj = lambda f, e: f[-n_last:, 0] * e[0] + f[-n_last:, 1] * e[1]
+    pa = _fit_phase(proj(a, par), cfg.time_step_duration, omega)
+    pb = _fit_phase(proj(b, par), cfg.time_step_duration, omega)
+    k_meas = abs(np.angle(pb / pa)) / (6 * DX)
+    k_expected = 2 * np.pi * n_med / WL
+    assert abs(k_meas - k_expected) / k_expected < 0.05, (k_meas, k_expected)
+    # eigen-polarisation: the orthogonal in-plane component stays small
+    leak = np.abs(proj(a, perp)).max() / np.abs(proj(a, par)).max()
+    assert leak < 0.05, leak
