@@ -226,3 +226,40 @@ def test_rotated_birefringence_full_tensor(axis):
     # eigen-polarisation: the orthogonal in-plane component stays small
     leak = np.abs(proj(a, perp)).max() / np.abs(proj(a, par)).max()
     assert leak < 0.05, leak
+
+
+def test_stretched_grid_keeps_the_phase_velocity():
+    """tests/simulation/physics/test_nonuniform_grid.py: on a mildly stretched z grid (+-8 % cell widths,
+    metric scales of curl.py:10-39) the wave number measured over the PHYSICAL detector distance is
+    still n k0."""
+    nz, n_med = 140, 1.5
+    shape = (3, 3, nz)
+    cells = np.arange(nz, dtype=float)
+    widths = DX * (1.0 + 0.08 * np.sin(2.0 * np.pi * (cells + 0.5) / nz))
+    widths *= nz * DX / widths.sum()
+    z_edges = np.concatenate([[0.0], np.cumsum(widths)])
+    xy_edges = np.linspace(0.0, 3 * DX, 4)
+    cfg = fx.SimulationConfig(time=60e-15, grid=fx.RectilinearGrid(xy_edges, xy_edges, z_edges))
+    vol = fx.SimulationVolume(name="v", grid_slice_tuple=tuple((0, n) for n in shape))
+    types = {"min_x": "periodic", "max_x": "periodic", "min_y": "periodic", "max_y": "periodic", "min_z": "pml", "max_z": "pml"}
+    bl = fx.boundary_objects_from_config(shape, cfg, types, thickness=10)
+    inv_eps = np.full((1, *shape), 1.0 / n_med**2, F)
+    src = fx.make_plane_source("s", ((0, 3), (0, 3), (14, 15)), cfg, inv_eps, direction="+", wave_character=fx.WaveCharacter(wavelength=WL), normalize_by_energy=False)
+    za, zb = 60, 70
+    dets = [_point("a", za), _point("b", zb)]
+    objs = [vol, *bl, src, *[d.place_on_grid(cfg) for d in dets]]
+    objects, arrays, _, cfg, _ = fx.place_objects(objs, cfg, inv_permittivities=inv_eps)
+    st = yee.checkpointed_fdtd(arrays, objects, cfg)
+    a = st[1].detector_states["a"]["fields"][:, :, 0, 0, 0]
+    b = st[1].detector_states["b"]["fields"][:, :, 0, 0, 0]
+    period_steps = WL / c0 / cfg.time_step_duration
+    n_last = int(4 * period_steps)
+    omega = 2 * np.pi * c0 / WL
+    pa = _fit_phase(a[-n_last:, 0], cfg.time_step_duration, omega)
+    pb = _fit_phase(b[-n_last:, 0], cfg.time_step_duration, omega)
+    centers = 0.5 * (z_edges[:-1] + z_edges[1:])
+    dist = centers[zb] - centers[za]
+    k_meas = abs(np.angle(pb / pa)) / dist
+    k_expected = 2 * np.pi * n_med / WL
+    assert abs(dist - (zb - za) * DX) / ((zb - za) * DX) > 0.01  # the detectors really sit on stretched cells
+    assert abs(k_meas - k_expected) / k_expected < 0.05, (k_meas, k_expected)
