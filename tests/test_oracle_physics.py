@@ -263,3 +263,30 @@ def test_stretched_grid_keeps_the_phase_velocity():
     k_expected = 2 * np.pi * n_med / WL
     assert abs(dist - (zb - za) * DX) / ((zb - za) * DX) > 0.01  # the detectors really sit on stretched cells
     assert abs(k_meas - k_expected) / k_expected < 0.05, (k_meas, k_expected)
+
+
+def test_drude_medium_phase_velocity():
+    """ADE Drude pole (omega_0 = 0, coupling_sq = omega_p^2; coefficient formulas dispersion.py:852-856):
+    below-plasma-frequency dielectric response n(w) = sqrt(eps_inf - w_p^2 / (w^2 + i g w)), lossless here."""
+    nz = 150
+    eps_inf = 4.0
+    omega = 2 * np.pi * c0 / WL
+    wp, gamma = 1.2 * omega, 0.0
+    dt = fx.SimulationConfig(time=1e-15, grid=fx.UniformGrid(spacing=DX)).time_step_duration
+    denom = 1 + gamma * dt / 2
+    c1 = 2.0 / denom
+    c2 = -(1 - gamma * dt / 2) / denom
+    c3 = (wp * dt) ** 2 / denom
+    shape = (3, 3, nz)
+    full = lambda v: np.full((1, 1, *shape), v, F)
+    disp = {"c1": full(c1), "c2": full(c2), "c3": full(c3), "c4": None}
+    objects, arrays, cfg = _line_scene(nz, eps_fn=lambda z: np.full(z.shape, eps_inf), time=70e-15, dispersive=disp,
+                                       detectors=[_point("a", 60, ("Ex",)), _point("b", 66, ("Ex",))])
+    st = yee.checkpointed_fdtd(arrays, objects, cfg)
+    n_last = int(4 * WL / c0 / cfg.time_step_duration)
+    a = st[1].detector_states["a"]["fields"][-n_last:, 0, 0, 0, 0]
+    b = st[1].detector_states["b"]["fields"][-n_last:, 0, 0, 0, 0]
+    dphi = np.angle(_fit_phase(b, dt, omega) / _fit_phase(a, dt, omega))
+    n_meas = abs(dphi) / (6 * DX) / (omega / c0)
+    n_expected = math.sqrt(eps_inf - wp**2 / omega**2)
+    assert abs(n_meas - n_expected) / n_expected < 0.05, (n_meas, n_expected)
