@@ -33,6 +33,7 @@ EXPORTS = [
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
     "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_peer_detach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
     "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
+    "fdtdx_b200_plan_source_set_quadrature",
 ]
 
 _p = C.c_void_p
@@ -64,6 +65,7 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_plan_add_pml.argtypes = [_p, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i]
     L.fdtdx_b200_plan_add_wall.argtypes = [_p, _i, _i, _ip, _ip]
     L.fdtdx_b200_plan_add_plane_source.argtypes = [_p, _ip, _ip, _i, _i, _fp, _fp, _fp, _fp, _i, _dp, _fp, _i, _d, _d, _d, _u8p, _fp, _fp, _i]
+    L.fdtdx_b200_plan_source_set_quadrature.argtypes = [_p, _i, _fp, _fp, _d]
     L.fdtdx_b200_plan_add_dipole.argtypes = [_p, _ip, _i, _i, _d, _i, _dp, _fp, _i, _u8p, _fp]
     L.fdtdx_b200_plan_add_detector.argtypes = [_p, _i, _ip, _ip, _i, _i, _i, _u8p, _i32p, _fp, _i, _fp, _fp, _d, _ip]
     L.fdtdx_b200_plan_set_recorder.argtypes = [_p, _i, _i, _i32p, _i32p, _i32p, _fp]

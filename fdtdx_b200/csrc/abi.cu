@@ -267,6 +267,22 @@ extern "C" int fdtdx_b200_plan_add_plane_source(FdtdxPlan* p, const int lo[3], c
   return (int)p->srcs.size() - 1;
 }
 
+extern "C" int fdtdx_b200_plan_source_set_quadrature(FdtdxPlan* p, int source_index, const float* E_inc_imag,
+                                                      const float* H_inc_imag, double quadrature_phase) {
+  if (!p || source_index < 0 || source_index >= (int)p->srcs.size() || !E_inc_imag || !H_inc_imag)
+    return fail(FDTDX_EINVAL, "source_set_quadrature: bad arguments");
+  SrcDev& d = p->srcs[source_index].d;
+  if (d.kind != 0) return fail(FDTDX_EINVAL, "source_set_quadrature: not a plane source");
+  const size_t fn = (size_t)(d.hi[0] - d.lo[0]) * (d.hi[1] - d.lo[1]) * (d.hi[2] - d.lo[2]);
+  float *dE, *dH;
+  int rc;
+  if ((rc = to_device(p, E_inc_imag, 3 * fn, &dE))) return rc;
+  if ((rc = to_device(p, H_inc_imag, 3 * fn, &dH))) return rc;
+  d.EincI = dE; d.HincI = dH; d.pq = (float)quadrature_phase;
+  p->finalized = false;
+  return FDTDX_OK;
+}
+
 extern "C" int fdtdx_b200_plan_add_dipole(FdtdxPlan* p, const int cell[3], int polarization, int electric,
                                           double scale, int profile_kind, const double params[8],
                                           const float* signal, int signal_len, const uint8_t* on,
@@ -1345,7 +1361,11 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     for (size_t di = 0; di < p->dets.size(); ++di) {
       DetHost& h = p->dets[di];
       if ((h.d.flags & DET_INVERSE) || !h.on[t]) continue;
-      if (!p->slots[FDTDX_SLOT_COT_DET][4 * di]) continue;  // no cotangent for this detector
+      {  // a detector is skipped only when none of its state leaves carries a cotangent
+        bool any_cot = false;
+        for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
+        if (!any_cot) continue;
+      }
       if (!any_det) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
       any_det = true;
       GridDev G;
@@ -1363,6 +1383,8 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
       A.lamE = lamE; A.lamH = lamH; A.lamHprev = p->d_lamHx;
       A.g_eps = (float*)p->slots[FDTDX_SLOT_GRAD_INV_EPS][0];
       A.eps_tier = p->eps_tier;
+      A.g_mu = (p->mu_tier > 0) ? (float*)p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr;
+      A.mu_tier = p->mu_tier;
       const long long dn = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
       det_adjoint_kernel<<<(unsigned)((dn + 127) / 128), 128, 0, st>>>(G, h.d, A, t);
       p->launches++;

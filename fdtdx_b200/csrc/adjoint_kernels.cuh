@@ -448,8 +448,11 @@ struct DetAdj {
   float* lamH;          // (3,N) cotangent of H'
   float* lamHprev;      // (3,N) cotangent of the step's input H (through H_bar = (H + H')/2)
   float* g_eps;         // inv_eps gradient (energy detectors) or nullptr
-  int eps_tier;
+  float* g_mu;          // inv_mu gradient (energy detectors, array-valued inv_mu) or nullptr
+  int eps_tier, mu_tier;
 };
+// a missing cotangent (the loss does not depend on that state leaf) reads as zero
+__device__ __forceinline__ float cot_at(const float* c, long long i) { return c ? c[i] : 0.0f; }
 
 __device__ __forceinline__ void a_scatter(const GridDev& G, float* buf, int c, int x, int y, int z, float v) {
   if (x < 0) { if (G.wrap[0]) x += G.nx; else return; }
@@ -514,12 +517,12 @@ __global__ void det_adjoint_kernel(const GridDev G, const DetDev D, const DetAdj
     if (D.flags & DET_REDUCE) g = A.cot[0][slot] * D.weights[cell];
     else if (D.flags & DET_SLICES) {
       if (D.flags & DET_SLICE_MEAN)
-        g = A.cot[0][((long long)slot * ex + rx) * ey + ry] / (float)ez + A.cot[1][((long long)slot * ex + rx) * ez + rz] / (float)ey +
-            A.cot[2][((long long)slot * ey + ry) * ez + rz] / (float)ex;
+        g = cot_at(A.cot[0], ((long long)slot * ex + rx) * ey + ry) / (float)ez + cot_at(A.cot[1], ((long long)slot * ex + rx) * ez + rz) / (float)ey +
+            cot_at(A.cot[2], ((long long)slot * ey + ry) * ez + rz) / (float)ex;
       else
-        g = (rz == D.slice_idx[2] ? A.cot[0][((long long)slot * ex + rx) * ey + ry] : 0.0f) +
-            (ry == D.slice_idx[1] ? A.cot[1][((long long)slot * ex + rx) * ez + rz] : 0.0f) +
-            (rx == D.slice_idx[0] ? A.cot[2][((long long)slot * ey + ry) * ez + rz] : 0.0f);
+        g = (rz == D.slice_idx[2] ? cot_at(A.cot[0], ((long long)slot * ex + rx) * ey + ry) : 0.0f) +
+            (ry == D.slice_idx[1] ? cot_at(A.cot[1], ((long long)slot * ex + rx) * ez + rz) : 0.0f) +
+            (rx == D.slice_idx[0] ? cot_at(A.cot[2], ((long long)slot * ey + ry) * ez + rz) : 0.0f);
     } else g = A.cot[0][(long long)slot * n + cell];
     const long long N = (long long)G.nx * G.ny * G.nz;
     const long long gidx = ((long long)x * G.ny + y) * G.nz + z;
@@ -529,6 +532,8 @@ __global__ void det_adjoint_kernel(const GridDev G, const DetDev D, const DetAdj
       lE[c] = g * Es[c] / ie;
       lH[c] = g * Hs[c] / im;
       if (A.g_eps) atomicAdd(A.g_eps + (A.eps_tier == 1 ? 0 : c) * N + gidx, g * (-0.5f * Es[c] * Es[c] / (ie * ie)));
+      // d(energy)/d(inv_mu) (metrics.py:55-67 differentiated w.r.t. both materials)
+      if (A.g_mu && G.mu) atomicAdd(A.g_mu + (A.mu_tier == 1 ? 0 : c) * N + gidx, g * (-0.5f * Hs[c] * Hs[c] / (im * im)));
     }
   } else {
     float g[3] = {0.f, 0.f, 0.f};

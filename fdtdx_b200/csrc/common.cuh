@@ -41,6 +41,10 @@ struct SrcDev {
   float static_amp;
   float cE, cH;
   const float *Einc, *Hinc, *toffE, *toffH;  // (3, face)
+  // complex (lossy-mode) profiles: imaginary parts or nullptr, injected in quadrature with the carrier
+  // phase shifted by -pi/2 (tfsf.py:266-283, 366-383); pq = float32(phase_shift - pi/2)
+  const float *EincI, *HincI;
+  float pq;
   const float* signal;
   int signal_len;
   const float* hfilter;

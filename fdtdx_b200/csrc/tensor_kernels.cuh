@@ -207,7 +207,12 @@ static __device__ __noinline__ void t_inject(const TensorParams& P, int t, bool 
       const float c = P.is_E ? S.cE : S.cH;
       const float amp_a = src_profile(S, (tf + toff[a * fn + f]) * P.dt) * S.static_amp;
       const float amp_b = src_profile(S, (tf + toff[b * fn + f]) * P.dt) * S.static_amp;
-      const float Ia = inc[a * fn + f] * amp_a, Ib = inc[b * fn + f] * amp_b;
+      float Ia = inc[a * fn + f] * amp_a, Ib = inc[b * fn + f] * amp_b;
+      const float* incI = P.is_E ? S.HincI : S.EincI;
+      if (incI != nullptr) {
+        Ia = Ia + incI[a * fn + f] * (src_profile_ph(S, (tf + toff[a * fn + f]) * P.dt, S.pq) * S.static_amp);
+        Ib = Ib + incI[b * fn + f] * (src_profile_ph(S, (tf + toff[b * fn + f]) * P.dt, S.pq) * S.static_amp);
+      }
       if (P.mat_tier == 9) {
         const int rows[3] = {n, a, b};
         for (int q = 0; q < 3; ++q) {

@@ -21,9 +21,9 @@
 // temporal profiles (objects/sources/profile.py:263-273, 322-345, 412-439; core/window.py:16-30)
 // float32, same operation order as the reference; no FMA contraction (compiled with -fmad=false).
 // ------------------------------------------------------------------------------------------------
-static __device__ __noinline__ float src_profile(const SrcDev& S, float time) {
+static __device__ __noinline__ float src_profile_ph(const SrcDev& S, float time, const float ph1) {
   if (S.profile_kind == 0) {  // SingleFrequencyProfile
-    float phase = ((S.p[4] * time) / S.p[0] + S.p[1]) + S.p[2];  // 2*pi*time/period + phase_shift + self.phase_shift
+    float phase = ((S.p[4] * time) / S.p[0] + ph1) + S.p[2];  // 2*pi*time/period + phase_shift + self.phase_shift
     float raw = cosf(phase);                                     // Re(exp(-i*phase))
     float f = time / S.p[3];
     f = fminf(fmaxf(f, 0.0f), 1.0f);
@@ -31,7 +31,7 @@ static __device__ __noinline__ float src_profile(const SrcDev& S, float time) {
   } else if (S.profile_kind == 1) {  // GaussianPulseProfile
     float d = time - S.p[3];
     float env = expf(-(d * d) / S.p[5]);
-    float phase = (S.p[0] * time + S.p[1]) + S.p[2];
+    float phase = (S.p[0] * time + ph1) + S.p[2];
     return env * cosf(phase);
   } else {  // CustomTimeSignalProfile
     float idx = (time - S.p[0]) / S.p[1];
@@ -47,6 +47,8 @@ static __device__ __noinline__ float src_profile(const SrcDev& S, float time) {
     return valid ? y : S.p[2];
   }
 }
+
+__device__ __forceinline__ float src_profile(const SrcDev& S, float time) { return src_profile_ph(S, time, S.p[1]); }
 
 __device__ __forceinline__ bool src_time(const SrcDev& S, int t, float half, float* tf) {
   if (S.on != nullptr) {
@@ -103,6 +105,12 @@ static __device__ __noinline__ void inject_E(const SrcDev* __restrict__ srcs, in
       }
       float Hb = inc_b * amp_b;
       float Ha = inc_a * amp_a;
+      if (S.HincI != nullptr && S.hfilter == nullptr) {  // Re * amp + Im * amp_quadrature
+        const float aq_a = src_profile_ph(S, (tf + S.toffH[a * fn + f]) * dt, S.pq) * S.static_amp;
+        const float aq_b = src_profile_ph(S, (tf + S.toffH[b * fn + f]) * dt, S.pq) * S.static_amp;
+        Hb = Hb + S.HincI[b * fn + f] * aq_b;
+        Ha = Ha + S.HincI[a * fn + f] * aq_a;
+      }
       Hb = (Hb * S.cE) * ie[a];
       Ha = (Ha * S.cE) * ie[b];
       E[a] = E[a] + sign * Hb;
@@ -139,6 +147,12 @@ static __device__ __noinline__ void inject_H(const SrcDev* __restrict__ srcs, in
       float amp_b = src_profile(S, (tf + to_b) * dt) * S.static_amp;
       float Ea = inc_a * amp_a;
       float Eb = inc_b * amp_b;
+      if (S.EincI != nullptr) {
+        const float aq_a = src_profile_ph(S, (tf + to_a) * dt, S.pq) * S.static_amp;
+        const float aq_b = src_profile_ph(S, (tf + to_b) * dt, S.pq) * S.static_amp;
+        Ea = Ea + S.EincI[a * fn + f] * aq_a;
+        Eb = Eb + S.EincI[b * fn + f] * aq_b;
+      }
       Ea = (Ea * S.cH) * im[b];
       Eb = (Eb * S.cH) * im[a];
       H[b] = H[b] + sign * Ea;

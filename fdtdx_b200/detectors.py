@@ -248,6 +248,14 @@ class PhasorDetector(Detector):
         return {"phasor": ((nf, nc, *gs), np.complex64)}
 
 
+def phasor_table(det: "PhasorDetector", T: int, dt: float) -> np.ndarray:
+    """``exp(+i w t dt)`` for every time step and frequency as (T, nf, 2) float32 [cos, sin], rounded
+    like ``phasor.py:186-214``: ``time_passed = t * dt`` and ``w * time_passed`` in float32."""
+    tp = (np.arange(T, dtype=_f32) * _f32(dt)).astype(_f32)
+    ang = (det._angular_frequencies[None, :] * tp[:, None]).astype(_f32)
+    return np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], axis=-1), dtype=_f32)
+
+
 @dataclass
 class ModeOverlapDetector(PhasorDetector):
     """``mode.py:193-``: for the time step this *is* a ``PhasorDetector`` (all six components);

@@ -33,6 +33,8 @@ def get_plan(arrays: ArrayContainer, objects: ObjectContainer, config: Simulatio
     _require_cuda(arrays)
     cache = objects.__dict__.setdefault("_plan_cache", {})
     mu = arrays.inv_permeabilities
+    # the cache entry keeps the config alive (Plan.config), so its id cannot be recycled while the
+    # entry exists; entries whose config is a different object are never returned
     key = (
         id(config),
         arrays.fields.E.device.index,
@@ -44,6 +46,8 @@ def get_plan(arrays: ArrayContainer, objects: ObjectContainer, config: Simulatio
         arrays.dispersive_c4 is not None,
     )
     plan = cache.get(key)
+    if plan is not None and plan.config is not config:
+        plan = None
     if plan is None:
         plan = Plan(objects, config, arrays)
         cache[key] = plan
@@ -162,6 +166,22 @@ def _checkpointed_with_grad(arrays, objects, config, progress_callback):
     return config.time_steps_total, out
 
 
+def _detector_cotangents(names, gdet, arrays):
+    """Detector-state cotangents as plain contiguous buffers the kernels can read by pointer.  Autograd
+    may hand over a complex gradient with the lazy conj / neg bit set (e.g. a loss built from
+    ``phasor.conj()``); ``contiguous()`` alone keeps the bit, so it is materialised here."""
+    cot_det = {}
+    for (d, k), g in zip(names, gdet):
+        if g is None:
+            continue
+        st = arrays.detector_states[d][k]
+        g = g.detach().resolve_conj().resolve_neg().contiguous()
+        if g.dtype != st.dtype or tuple(g.shape) != tuple(st.shape):
+            raise ValueError(f"cotangent of detector state {d}/{k}: {g.dtype}{tuple(g.shape)} != state {st.dtype}{tuple(st.shape)}")
+        cot_det.setdefault(d, {})[k] = g
+    return cot_det
+
+
 def _clone_state(a):
     f = a.fields
     return (f.E.clone(), f.H.clone(), {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_E.items()}, {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_H.items()})
@@ -222,10 +242,7 @@ class _CheckpointedFunction:
                 work = work.aset("fields->psi_H", {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_H.items()})
                 cot_E = torch.zeros_like(f.E) if gE is None else gE.detach().clone().contiguous()
                 cot_H = torch.zeros_like(f.H) if gH is None else gH.detach().clone().contiguous()
-                cot_det = {}
-                for (d, k), g in zip(h["names"], gdet):
-                    if g is not None:
-                        cot_det.setdefault(d, {})[k] = g.detach().contiguous()
+                cot_det = _detector_cotangents(h["names"], gdet, arrays)
                 g_eps = torch.zeros_like(work.inv_permittivities)
                 mu = work.inv_permeabilities
                 g_mu = torch.zeros_like(mu) if isinstance(mu, torch.Tensor) else None
@@ -306,10 +323,7 @@ class _ReversibleFunction:
                 work = arrays.aset("fields->E", arrays.fields.E.detach().clone()).aset("fields->H", arrays.fields.H.detach().clone())
                 cot_E = torch.zeros_like(work.fields.E) if gE is None else gE.detach().clone().contiguous()
                 cot_H = torch.zeros_like(work.fields.H) if gH is None else gH.detach().clone().contiguous()
-                cot_det = {}
-                for (d, k), g in zip(h["names"], gdet):
-                    if g is not None:
-                        cot_det.setdefault(d, {})[k] = g.detach().contiguous()
+                cot_det = _detector_cotangents(h["names"], gdet, arrays)
                 g_eps = torch.zeros_like(work.inv_permittivities)
                 mu = work.inv_permeabilities
                 g_mu = torch.zeros_like(mu) if isinstance(mu, torch.Tensor) else None

@@ -23,6 +23,7 @@ from fdtdx_b200.detectors import (
     FieldDetector,
     PhasorDetector,
     PoyntingFluxDetector,
+    phasor_table,
 )
 from fdtdx_b200.profile import PROFILE_CW, PROFILE_PULSE, PROFILE_TABLE
 from fdtdx_b200.sources import PointDipoleSource, TFSFPlaneSource
@@ -242,13 +243,14 @@ class Plan:
                 xs = slice(max(sl[0][0], self.x0) - sl[0][0], min(sl[0][1], self.x1) - sl[0][0])
                 if xs.stop <= xs.start:
                     continue
-                arrs = [np.ascontiguousarray(a[:, xs], dtype=_f32) for a in (src._E, src._H, src._time_offset_E, src._time_offset_H)]
+                cplx = np.iscomplexobj(src._E) or np.iscomplexobj(src._H)
+                arrs = [np.ascontiguousarray(np.real(a)[:, xs], dtype=_f32) for a in (src._E, src._H, src._time_offset_E, src._time_offset_H)]
                 lo = [max(sl[0][0], self.x0), sl[1][0], sl[2][0]]
                 hi = [min(sl[0][1], self.x1), sl[1][1], sl[2][1]]
                 cE = float(_f32(cfg.courant_number) * _f32(src.metric_scale_at_plane(cfg, "backward")))
                 cH = float(_f32(cfg.courant_number) * _f32(src.metric_scale_at_plane(cfg, "forward")))
                 hf = None if src._temporal_H_filter is None else np.ascontiguousarray(src._temporal_H_filter, dtype=_f32)
-                check(
+                si = check(
                     self.lib.fdtdx_b200_plan_add_plane_source(
                         self.h, _iarr(lo), _iarr(hi), src.propagation_axis, 1 if src.direction == "+" else -1,
                         *[_fptr(a) for a in arrs], src.temporal_profile.kind, params, _fptr(signal),
@@ -256,6 +258,10 @@ class Plan:
                         _fptr(hf), 0 if hf is None else hf.shape[0],
                     )
                 )
+                if cplx:
+                    # lossy-mode profile: imaginary parts injected in quadrature (tfsf.py:266-283, 366-383)
+                    im = [np.ascontiguousarray(np.imag(a)[:, xs], dtype=_f32) for a in (src._E, src._H)]
+                    check(self.lib.fdtdx_b200_plan_source_set_quadrature(self.h, si, _fptr(im[0]), _fptr(im[1]), float(src.wave_character.phase_shift - 0.5 * np.pi)))
             elif isinstance(src, PointDipoleSource):
                 cell = [s[0] for s in sl]
                 if not (self.x0 <= cell[0] < self.x1):
@@ -291,9 +297,7 @@ class Plan:
                     weights = det._cached_cell_volume_weights
                 om = det._angular_frequencies
                 nf = om.shape[0]
-                tp = (np.arange(self.T, dtype=_f32) * _f32(cfg.time_step_duration)).astype(_f32)
-                ang = (om[None, :] * tp[:, None]).astype(_f32)
-                table = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], axis=-1), dtype=_f32)
+                table = phasor_table(det, self.T, cfg.time_step_duration)
                 window = self._pad_T(np.ascontiguousarray(det._window_at_time_step_arr, dtype=_f32))
                 scale = float(det._static_scale())
             elif isinstance(det, FieldDetector):
@@ -465,21 +469,34 @@ class Plan:
             return
         from fdtdx_b200.tensor_setup import update_matrices
 
-        dev = arrays.fields.E.device
+        def stamp(*ts):
+            # identity + in-place version of the material tensors: the 3x3 solves are redone only when
+            # the materials change (per-step drivers call bind() every step)
+            return tuple(None if t is None or not hasattr(t, "data_ptr") else (t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+        def alt_like(name, ref):
+            buf = getattr(self, name, None)
+            if buf is None or buf.shape != ref.shape or buf.device != ref.device:
+                buf = torch.zeros_like(ref)
+                setattr(self, name, buf)
+            return buf
+
         if self.tensor_E:
-            self.E_alt = torch.zeros_like(arrays.fields.E)
-            self._bind(_lib.SLOT_E_ALT, 0, self.E_alt)
-            A, B, Ar, Br = update_matrices(arrays.inv_permittivities, arrays.electric_conductivity, self.config.courant_number, "E")
-            if arrays.electric_conductivity is None:
-                A = Ar = None  # M1 = M2 = I: A is exactly the identity (fdtd/misc.py:88-96), not stored
-            self.tE = (A, B, Ar, Br)
+            self._bind(_lib.SLOT_E_ALT, 0, alt_like("E_alt", arrays.fields.E))
+            key = stamp(arrays.inv_permittivities, arrays.electric_conductivity)
+            if getattr(self, "_tE_key", None) != key:
+                A, B, Ar, Br = update_matrices(arrays.inv_permittivities, arrays.electric_conductivity, self.config.courant_number, "E")
+                if arrays.electric_conductivity is None:
+                    A = Ar = None  # M1 = M2 = I: A is exactly the identity (fdtd/misc.py:88-96), not stored
+                self.tE, self._tE_key = (A, B, Ar, Br), key
         if self.tensor_H:
-            self.H_alt = torch.zeros_like(arrays.fields.H)
-            self._bind(_lib.SLOT_H_ALT, 0, self.H_alt)
-            A, B, Ar, Br = update_matrices(arrays.inv_permeabilities, arrays.magnetic_conductivity, self.config.courant_number, "H")
-            if arrays.magnetic_conductivity is None:
-                A = Ar = None
-            self.tH = (A, B, Ar, Br)
+            self._bind(_lib.SLOT_H_ALT, 0, alt_like("H_alt", arrays.fields.H))
+            key = stamp(arrays.inv_permeabilities, arrays.magnetic_conductivity)
+            if getattr(self, "_tH_key", None) != key:
+                A, B, Ar, Br = update_matrices(arrays.inv_permeabilities, arrays.magnetic_conductivity, self.config.courant_number, "H")
+                if arrays.magnetic_conductivity is None:
+                    A = Ar = None
+                self.tH, self._tH_key = (A, B, Ar, Br), key
         self.set_tensor_direction(reverse=False)
         check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
 

@@ -170,6 +170,7 @@ def make_plane_source(
     static_amplitude_factor: float = 1.0,
     switch: OnOffSwitch | None = None,
     effective_index: float | None = None,
+    dispersive: dict | None = None,
 ) -> TFSFPlaneSource:
     """Uniform / Gaussian / mode-like plane source builder (setup helper, float32).
 
@@ -191,6 +192,17 @@ def make_plane_source(
     face = src.grid_shape
     gs = src.grid_slice
     inv_eps = np.asarray(inv_permittivities)[:, gs[0], gs[1], gs[2]].astype(_f32)
+    inv_eps_inf = inv_eps
+    disp = None
+    if dispersive is not None and dispersive.get("c1") is not None:
+        # linear_polarization.py:195-213: impedance / normalisation / time offsets use the real effective
+        # permittivity at the carrier frequency, not eps_infinity
+        from fdtdx_b200 import dispersion as _disp
+
+        disp = {k: (None if dispersive.get(k) is None else np.asarray(dispersive[k])[(slice(None), slice(None), *gs)]) for k in ("c1", "c2", "c3", "c4")}
+        inv_eps = _disp.effective_inv_permittivity(
+            inv_eps, disp["c1"], disp["c2"], disp["c3"], 2.0 * np.pi * wave_character.get_frequency(), config.time_step_duration, disp["c4"]
+        ).astype(_f32)
     if inv_eps.shape[0] == 9:
         inv_eps_iso = inv_eps[0]
     else:
@@ -231,6 +243,19 @@ def make_plane_source(
     tE, tH = calculate_time_offset_yee(center, k, n_idx, face, config, grid_slice_tuple)
     src._E, src._H = E.astype(_f32), H.astype(_f32)
     src._time_offset_E, src._time_offset_H = tE, tH
+    if disp is not None:
+        # broadband impedance correction (linear_polarization.py:330-351, tfsf.py:21-140): the H-side
+        # amplitude becomes a table sampled at integer time steps, interpolated at t + offset
+        from fdtdx_b200 import dispersion as _disp
+
+        T = config.time_steps_total
+        times = (np.arange(T, dtype=np.float64) * config.time_step_duration).astype(_f32)
+        raw = src.temporal_profile.get_amplitude(time=times, period=wave_character.get_period(), phase_shift=wave_character.phase_shift)
+        filt = _disp.dispersive_H_filter(
+            raw, config.time_step_duration, disp["c1"], disp["c2"], disp["c3"], inv_eps_inf,
+            2.0 * np.pi * wave_character.get_frequency(), disp["c4"],
+        )
+        src._temporal_H_filter = np.asarray(filt, _f32)
     return src
 
 

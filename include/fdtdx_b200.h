@@ -128,6 +128,12 @@ int fdtdx_b200_plan_add_plane_source(FdtdxPlan* plan, const int lo[3], const int
                                      double static_amplitude, double cE, double cH,
                                      const uint8_t* on, const float* t_adj,
                                      const float* h_filter, int h_filter_len);
+/* Complex (lossy-mode) plane source (objects/sources/mode.py:212-222, tfsf.py:266-283, 366-383): the
+ * imaginary parts of the incident profile, injected in quadrature - incident = Re * amp(phase) +
+ * Im * amp(phase - pi/2).  quadrature_phase = wave_character.phase_shift - pi/2 (rounded to float32
+ * like the reference's weak scalar).  Arrays are (3, *face) like E_inc / H_inc. */
+int fdtdx_b200_plan_source_set_quadrature(FdtdxPlan* plan, int source_index, const float* E_inc_imag,
+                                          const float* H_inc_imag, double quadrature_phase);
 /* Point dipole (dipole.py:195-277): scale = courant*amplitude*static. electric!=0 -> E update. */
 int fdtdx_b200_plan_add_dipole(FdtdxPlan* plan, const int cell[3], int polarization, int electric,
                                double scale, int profile_kind, const double params[8],

@@ -207,6 +207,23 @@ def expand_to_3x3(arr):
     return out
 
 
+_AB_CACHE: dict = {}
+
+
+def _update_matrices_cached(inv_raw, sigma_raw, c: float, eta_factor: float, reverse: bool = False):
+    """The reference re-solves A, B every step (update.py:363); they depend on the materials only, so
+    the result is memoised per (un-expanded) material array - value-identical, SURVEY App. C.5."""
+    key = (id(inv_raw), None if sigma_raw is None else id(sigma_raw), float(c), float(eta_factor), bool(reverse))
+    hit = _AB_CACHE.get(key)
+    if hit is not None and hit[0] is inv_raw and hit[1] is sigma_raw:
+        return hit[2], hit[3]
+    A, B = compute_anisotropic_update_matrices(expand_to_3x3(inv_raw), expand_to_3x3(sigma_raw), c, eta_factor, reverse)
+    if len(_AB_CACHE) > 8:
+        _AB_CACHE.clear()
+    _AB_CACHE[key] = (inv_raw, sigma_raw, A, B)
+    return A, B
+
+
 def compute_anisotropic_update_matrices(inv_prop, sigma, c: float, eta_factor: float, reverse: bool = False):
     sp = np.broadcast_shapes(inv_prop.shape[2:], (1, 1, 1) if sigma is None else sigma.shape[2:])
     eye = np.broadcast_to(np.eye(3, dtype=F)[:, :, None, None, None], (3, 3, *sp))
@@ -286,12 +303,12 @@ def _tensor_apply(field, curl, A, B, objects, config, kind: str, sign: float):
 # ----------------------------------------------------------------------------------------------
 # sources  (objects/sources/tfsf.py:193-409, 739-806; dipole.py:195-277)
 # ----------------------------------------------------------------------------------------------
-def _amplitude(src, time_step_f, offsets, config):
-    """amp = profile((t + off) * dt) * static   (tfsf.py:250-258 / 351-359), float32."""
+def _amplitude(src, time_step_f, offsets, config, quadrature: bool = False):
+    """amp = profile((t + off) * dt) * static   (tfsf.py:250-258 / 351-359), float32; ``quadrature``:
+    the carrier phase shifted by -pi/2 (tfsf.py:268-279)."""
     time = (F(time_step_f) + offsets).astype(F) * F(config.time_step_duration)
-    amp = src.temporal_profile.get_amplitude(
-        time=time, period=src.wave_character.get_period(), phase_shift=src.wave_character.phase_shift
-    )
+    ph = src.wave_character.phase_shift - (0.5 * np.pi if quadrature else 0.0)
+    amp = src.temporal_profile.get_amplitude(time=time, period=src.wave_character.get_period(), phase_shift=ph)
     return (amp * F(src.static_amplitude_factor)).astype(F)
 
 
@@ -314,8 +331,14 @@ def tfsf_update_E(src: TFSFPlaneSource, E, inv_eps, time_step_f, inverse: bool, 
             filt = src._temporal_H_filter.astype(F)
             xp = np.arange(filt.shape[0], dtype=F)
             amp[ax] = (np.interp(idx, xp, filt, left=0.0, right=0.0).astype(F) * F(src.static_amplitude_factor)).astype(F)
-    Hb = (src._H[b_ax] * amp[b_ax]).astype(F)
-    Ha = (src._H[a_ax] * amp[a_ax]).astype(F)
+    if np.iscomplexobj(src._H) and src._temporal_H_filter is None:
+        # complex (lossy-mode) profile: Re * amp + Im * amp(phase - pi/2)   (tfsf.py:266-283)
+        ampq = {ax: _amplitude(src, time_step_f, src._time_offset_H[ax], config, quadrature=True) for ax in (a_ax, b_ax)}
+        Hb = (np.real(src._H[b_ax]).astype(F) * amp[b_ax] + np.imag(src._H[b_ax]).astype(F) * ampq[b_ax]).astype(F)
+        Ha = (np.real(src._H[a_ax]).astype(F) * amp[a_ax] + np.imag(src._H[a_ax]).astype(F) * ampq[a_ax]).astype(F)
+    else:
+        Hb = (np.real(src._H[b_ax]).astype(F) * amp[b_ax]).astype(F)
+        Ha = (np.real(src._H[a_ax]).astype(F) * amp[a_ax]).astype(F)
     E = E.copy()
     if full:
         for row in (n, a_ax, b_ax):
@@ -343,8 +366,13 @@ def tfsf_update_H(src: TFSFPlaneSource, H, inv_mu, time_step_f, inverse: bool, c
     full = is_arr and inv_mu.shape[0] == 9
     mu_sl = inv_mu[(slice(None), *gs)] if is_arr else inv_mu
     amp = {ax: _amplitude(src, time_step_f, src._time_offset_E[ax], config) for ax in (a_ax, b_ax)}
-    Ea = (src._E[a_ax] * amp[a_ax]).astype(F)
-    Eb = (src._E[b_ax] * amp[b_ax]).astype(F)
+    if np.iscomplexobj(src._E):  # tfsf.py:366-383
+        ampq = {ax: _amplitude(src, time_step_f, src._time_offset_E[ax], config, quadrature=True) for ax in (a_ax, b_ax)}
+        Ea = (np.real(src._E[a_ax]).astype(F) * amp[a_ax] + np.imag(src._E[a_ax]).astype(F) * ampq[a_ax]).astype(F)
+        Eb = (np.real(src._E[b_ax]).astype(F) * amp[b_ax] + np.imag(src._E[b_ax]).astype(F) * ampq[b_ax]).astype(F)
+    else:
+        Ea = (src._E[a_ax] * amp[a_ax]).astype(F)
+        Eb = (src._E[b_ax] * amp[b_ax]).astype(F)
     H = H.copy()
     if full:
         for row in (n, a_ax, b_ax):
@@ -474,7 +502,7 @@ def update_E(time_step: int, arrays: ArrayContainer, objects, config, simulate_b
         elif sigma_E is not None:
             E = E / (F(1) + c * sigma_E * F(eta0) * inv_eps / F(2))
     else:
-        A, B = compute_anisotropic_update_matrices(expand_to_3x3(inv_eps), expand_to_3x3(sigma_E), config.courant_number, eta0)
+        A, B = _update_matrices_cached(inv_eps, sigma_E, config.courant_number, eta0)
         if arrays.fields.dispersive_P_curr is not None:
             P_curr, P_prev = arrays.fields.dispersive_P_curr, arrays.fields.dispersive_P_prev
             c1, c2, c3 = arrays.dispersive_c1, arrays.dispersive_c2, arrays.dispersive_c3
@@ -524,9 +552,7 @@ def update_E_reverse(time_step: int, arrays: ArrayContainer, objects, config) ->
             factor = F(1) - c * sigma_E * F(eta0) * inv_eps / F(2)
         E = (E - c * curl * inv_eps) / factor
     else:
-        A, B = compute_anisotropic_update_matrices(
-            expand_to_3x3(inv_eps), expand_to_3x3(sigma_E), config.courant_number, eta0, reverse=True
-        )
+        A, B = _update_matrices_cached(inv_eps, sigma_E, config.courant_number, eta0, reverse=True)
         E = _tensor_apply(E, curl, A, B, objects, config, "E", -1.0)
     E = apply_boundary_post_E_update(np.array(E, dtype=F), objects)
     return arrays.aset("fields->E", E)
@@ -551,7 +577,7 @@ def update_H(time_step: int, arrays: ArrayContainer, objects, config, simulate_b
         if sigma_H is not None:
             H = H / (F(1) + c * sigma_H / F(eta0) * mu / F(2))
     else:
-        A, B = compute_anisotropic_update_matrices(expand_to_3x3(inv_mu), expand_to_3x3(sigma_H), config.courant_number, 1 / eta0)
+        A, B = _update_matrices_cached(inv_mu, sigma_H, config.courant_number, 1 / eta0)
         H = _tensor_apply(arrays.fields.H, curl, A, B, objects, config, "H", -1.0)
     H = np.array(H, dtype=F)
     H = _apply_sources(H, arrays, objects, config, time_step, "H", inverse=False)
@@ -577,9 +603,7 @@ def update_H_reverse(time_step: int, arrays: ArrayContainer, objects, config) ->
             factor = F(1) - c * sigma_H / F(eta0) * mu / F(2)
         H = (H + c * curl * mu) / factor
     else:
-        A, B = compute_anisotropic_update_matrices(
-            expand_to_3x3(inv_mu), expand_to_3x3(sigma_H), config.courant_number, 1 / eta0, reverse=True
-        )
+        A, B = _update_matrices_cached(inv_mu, sigma_H, config.courant_number, 1 / eta0, reverse=True)
         H = _tensor_apply(H, curl, A, B, objects, config, "H", +1.0)
     H = apply_boundary_post_H_update(np.array(H, dtype=F), objects)
     return arrays.aset("fields->H", H)

@@ -257,7 +257,7 @@ def run_forward(arrays_np, objects, config, steps, inv_eps=None, inv_mu=None, dt
     return E, H, det
 
 
-def reversible_gradient(arrays_final_np, objects, config, loss_fn, dtype=torch.float64):
+def reversible_gradient(arrays_final_np, objects, config, loss_fn, dtype=torch.float64, progress=None):
     """The reference's ``fdtd_bwd`` (fdtd/fdtd.py:262-333) restated: starting from the final state,
     repeat { ``backward`` (NumPy oracle, reset_fields=False) -> VJP of one forward step at the
     reconstructed state with the frozen final psi }, accumulating d loss / d inv_eps (and inv_mu).
@@ -282,6 +282,8 @@ def reversible_gradient(arrays_final_np, objects, config, loss_fn, dtype=torch.f
     g_mu = torch.zeros(mu_np.shape, dtype=dtype) if isinstance(mu_np, np.ndarray) else None
     state = (T_total, arrays_final_np)
     for t in range(T_total - 1, -1, -1):
+        if progress is not None:
+            progress(t)
         state = yee.backward(state, config, objects, None, record_detectors=False, reset_fields=False)
         a = state[1]
         Et, Ht = S.T(a.fields.E).requires_grad_(True), S.T(a.fields.H).requires_grad_(True)

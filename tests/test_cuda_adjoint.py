@@ -167,3 +167,59 @@ def test_checkpointed_gradient_is_the_gradient_of_the_forward_run(name, nck):
         gm, gm_ref = dev.inv_permeabilities.grad.cpu().numpy(), im.grad.numpy()
         assert rel_l2(gm, gm_ref) <= 1e-4, f"d loss / d inv_mu rel-L2 {rel_l2(gm, gm_ref)}"
 
+
+
+def _ckpt_setup(**kw):
+    objects, arrays, cfg = build_scene(**kw)
+    cfg = cfg.aset("gradient_config", fx.GradientConfig(method="checkpointed", num_checkpoints=2))
+    mu_np = arrays.inv_permeabilities
+    has_mu = isinstance(mu_np, np.ndarray)
+    ie = torch.tensor(arrays.inv_permittivities.astype(np.float64), requires_grad=True)
+    im = torch.tensor(mu_np.astype(np.float64), requires_grad=True) if has_mu else None
+    E, H, det = yee_torch.run_forward(arrays.reset(), objects, cfg, cfg.time_steps_total, inv_eps=ie, inv_mu=im, dtype=torch.float64)
+    dev = arrays.to_torch("cuda")
+    dev.inv_permittivities.requires_grad_(True)
+    if has_mu:
+        dev.inv_permeabilities.requires_grad_(True)
+    _, out = fx.run_fdtd(dev, objects, cfg)
+    return det, out, ie, im, dev
+
+
+@pytest.mark.parametrize("key", ["XY Plane", "XZ Plane", "YZ Plane"])
+def test_loss_on_a_single_slice_plane(key):
+    """Partial detector cotangents: a loss that uses one leaf of a multi-leaf detector state leaves the
+    other leaves' cotangents unmaterialised (None).  The detector must still contribute, and the
+    missing leaves must read as zero (they used to be dereferenced / the detector used to be skipped)."""
+    det, out, ie, im, dev = _ckpt_setup(source="plane_z", detectors=("energy_slices", "poynting"), time=3e-15, shape=(16, 14, 20), thickness=4)
+    f = lambda d: (d["energy_slices"][key] ** 2).sum() * 1e3 + d["energy_slices"][key].sum()
+    f(det).backward()
+    f(out.detector_states).backward()
+    g, g_ref = dev.inv_permittivities.grad.cpu().numpy(), ie.grad.numpy()
+    assert np.abs(g_ref).max() > 0
+    assert rel_l2(g, g_ref) <= 1e-4
+
+
+def test_conjugated_phasor_cotangent():
+    """A loss built from ``phasor.conj()`` hands the backward pass a gradient with torch's lazy conj bit;
+    it must be materialised before the kernels read it by pointer."""
+    det, out, ie, im, dev = _ckpt_setup(source="plane_z", detectors=("phasor",), time=3e-15, shape=(16, 14, 20), thickness=4)
+    w = torch.tensor(np.random.default_rng(3).standard_normal(det["phasor"]["phasor"].shape) + 1j * np.random.default_rng(4).standard_normal(det["phasor"]["phasor"].shape))
+    f = lambda p, ww: (p.conj() * ww).imag.sum() + (p.conj() * p.conj()).real.sum() * 2.0
+    f(det["phasor"]["phasor"], w).backward()
+    f(out.detector_states["phasor"]["phasor"], w.to("cuda").to(torch.complex64)).backward()
+    g, g_ref = dev.inv_permittivities.grad.cpu().numpy(), ie.grad.numpy()
+    assert np.abs(g_ref).max() > 0
+    assert rel_l2(g, g_ref) <= 1e-4
+
+
+def test_energy_detector_gradient_wrt_inv_mu():
+    """d(energy)/d(inv_mu) = -0.5 H^2 / inv_mu^2 joins grad_inv_mu when inv_permeabilities is an array
+    (metrics.py:55-67 differentiated w.r.t. both materials)."""
+    det, out, ie, im, dev = _ckpt_setup(source="plane_z", detectors=("energy_reduce", "energy_slices"), mu_tier=3, time=3e-15, shape=(16, 14, 20), thickness=4)
+    f = lambda d: d["energy_reduce"]["energy"].sum() * 1e21 + (d["energy_slices"]["XZ Plane"] ** 2).sum() * 1e3
+    f(det).backward()
+    f(out.detector_states).backward()
+    assert rel_l2(dev.inv_permittivities.grad.cpu().numpy(), ie.grad.numpy()) <= 1e-4
+    gm, gm_ref = dev.inv_permeabilities.grad.cpu().numpy(), im.grad.numpy()
+    assert np.abs(gm_ref).max() > 0
+    assert rel_l2(gm, gm_ref) <= 1e-4
