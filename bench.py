@@ -40,6 +40,19 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _csrc_sha():
+    """sha256 (first 16 hex) over the kernel sources, in name order: ties profiles/traffic.json to the code."""
+    import hashlib
+
+    d = os.path.join(ROOT, "fdtdx_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".inl", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -176,6 +189,98 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def _timed(step_fn, barrier, Wm, K, world, device):
+    """W warm-up steps, then exactly K steps between CUDA events (barrier + synchronize on both sides),
+    max over ranks.  Returns milliseconds for the K steps."""
+    import torch
+    import torch.distributed as dist
+
+    step_fn(0, Wm)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    step_fn(Wm, K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_c5(args, device, rank, world, K, Wm, barrier):
+    """BASELINE.json configs[4] / SURVEY section 8d config 5: the 4.096e9-cell vacuum / dielectric box
+    (1600^3, 10-cell CPML, one dipole), STRONG-scaled over x-slabs of 1600/N planes.  At N = 1 the whole
+    grid (114.7 GB of E, H, 1/eps) lives on one B200."""
+    import torch
+
+    from fdtdx_b200 import workloads as W
+    from fdtdx_b200.dist import SlabRunner, slab_bounds
+    from fdtdx_b200.fdtd import get_plan
+
+    n = args.c5_n
+    shape = (n, n, n)
+    need = 28.0 * n**3 / world + 2.5e9
+    free, _ = torch.cuda.mem_get_info(device)
+    if need > free:
+        return {"skipped": f"needs {need / 1e9:.0f} GB per GPU, {free / 1e9:.0f} GB free"}
+    x_range = slab_bounds(n, world, rank)
+    objects, arrays, cfg = W.build_box(shape, device=device, x_range=x_range, time=1e-11)
+    local_shape = tuple(arrays.fields.E.shape[1:])
+    if world > 1:
+        runner = SlabRunner(objects, cfg, arrays, x_range, rank, world, overlap=not args.no_overlap, halo=args.halo)
+        plan, step_fn, halo = runner.plan, (lambda t0, m: runner.run(t0, m, False)), ("peer" if runner.peer else "nccl")
+    else:
+        plan = get_plan(arrays, objects, cfg)
+        step_fn, halo = (lambda t0, m: plan.run_forward(t0, m, False, False, True)), None
+    ms = _timed(step_fn, barrier, Wm, K, world, device)
+    cells = float(n) ** 3
+    gcs = cells * K / (ms * 1e-3) / 1e9
+    bpc = W.bytes_per_cell_step(objects, arrays, local_shape)
+    hbm_peak, _ = _peaks()
+    out = {
+        "workload": f"C5 vacuum/dielectric box {n}x{n}x{n} = {cells:.4g} cells, 10-cell CPML, x-slabs of {n // world} planes (strong scaling)",
+        "cells": cells, "gcell_s": gcs, "gcell_s_per_gpu": gcs / world, "ms_per_step": ms / K, "steps": K, "halo": halo,
+        "bytes_per_cell_step": bpc, "hbm_frac_per_gpu": bpc * gcs / world / hbm_peak,
+        "peer_wait_timeouts": int(plan.lib.fdtdx_b200_peer_status(plan.h)) if world > 1 else 0,
+    }
+    del arrays, plan
+    objects.__dict__.pop("_plan_cache", None)
+    torch.cuda.empty_cache()
+    return out
+
+
+def slab_selfcheck(args, device, rank, world):
+    """N > 1: a small box scene run x-sharded through the same transport as the bench must equal the
+    unsharded run of the same scene bit for bit (fields), on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from fdtdx_b200 import workloads as W
+    from fdtdx_b200.dist import SlabRunner, slab_bounds
+    from fdtdx_b200.fdtd import get_plan
+
+    shape, steps = (24 * world, 40, 64), 30
+    x0, x1 = slab_bounds(shape[0], world, rank)
+    objects, arrays, cfg = W.build_box(shape, device=device, x_range=(x0, x1), thickness=6)
+    runner = SlabRunner(objects, cfg, arrays, (x0, x1), rank, world, overlap=not args.no_overlap, halo=args.halo)
+    runner.run(0, steps, False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    objects_f, arrays_f, cfg_f = W.build_box(shape, device=device, thickness=6)
+    get_plan(arrays_f, objects_f, cfg_f).run_forward(0, steps, False, False, True)
+    torch.cuda.synchronize()
+    d = max(float((arrays.fields.E - arrays_f.fields.E[:, x0:x1]).abs().max()), float((arrays.fields.H - arrays_f.fields.H[:, x0:x1]).abs().max()))
+    live = float(arrays_f.fields.E.abs().max()) > 0
+    ok = torch.tensor([1 if (d == 0.0 and live) else 0], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    return "bit-exact vs 1 GPU" if int(ok.item()) == 1 else f"MISMATCH (max |delta| {d:.3e} on rank {rank})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +290,7 @@ def main():
     ap.add_argument("--workload", default="coupler", choices=["coupler", "box"])
     ap.add_argument("--cpl", type=int, default=20, help="cells per wavelength of the coupler scene (20 -> 70.7 Mcell)")
     ap.add_argument("--box-n", type=int, default=1024)
+    ap.add_argument("--c5-n", type=int, default=1600, help="cube side of the strong-scaled C5 box reported in config.c5 (0: skip)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-detectors", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -248,6 +354,8 @@ def main():
         plan = get_plan(arrays, objects, cfg)
         plan.set_tuning(args.xchunk, args.rows)
         step_fn = lambda t0, n: plan.run_forward(t0, n, record_det, False, True)
+
+    halo_desc = (("peer-memory reads over NVLink (CUDA IPC), in-kernel ordering, no exchange" if runner.peer else f"NCCL send/recv, overlap={not args.no_overlap}") if world > 1 else None)
 
     # ---- device-resident throughput ("value") -------------------------------------------------
     step_fn(0, Wm)
@@ -313,13 +421,33 @@ def main():
             "bytes_per_cell_step": bpc,
             "whole_step_frac": bpc * value / hbm_peak,
         }
+        n_mu = 0 if not hasattr(arrays.inv_permeabilities, "shape") else int(arrays.inv_permeabilities.shape[0])
+        bytes_H = (12 + 12 + 12 + 4 * n_mu + psi_b) * cells_local
+        roofline["yee_H"] = {
+            "kernel": "yee_H_tma (H half-step: TMA-staged curl_E + CPML + material update + PMC)",
+            "achieved": bytes_H / (ms_H * 1e-3) / 1e9, "frac": bytes_H / (ms_H * 1e-3) / 1e9 / hbm_peak,
+            "algorithmic_bytes_per_launch": bytes_H, "ms_per_launch": ms_H, "traffic": None,
+        }
+        # DRAM bytes per launch from the committed `ncu --set full` capture.  They are a property of the
+        # kernels as captured: reported only if the kernel sources still hash to what was profiled and the
+        # figure is consistent with this run's byte model; otherwise null with the reason.
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
                 with open(tr) as f:
-                    roofline["traffic"] = json.load(f).get(args.workload)
-            except Exception:
-                pass
+                    tj = json.load(f)
+                if tj.get("csrc_sha16") != _csrc_sha():
+                    roofline["traffic_note"] = f"stale capture ({tj.get('source')}): kernel sources changed since it was taken"
+                else:
+                    for key, dst, alg in ((args.workload, roofline, bytes_E), (args.workload + "_yee_H", roofline["yee_H"], bytes_H)):
+                        v = tj.get(key)
+                        if v is not None and not (0.7 * alg <= float(v) <= 1.3 * alg):
+                            roofline["traffic_note"] = f"capture {key}={v:.4g} B disagrees with the byte model ({alg:.4g} B): different workload?"
+                            v = None
+                        dst["traffic"] = v
+                    roofline["traffic_source"] = tj.get("source")
+            except Exception as e:  # noqa: BLE001
+                roofline["traffic_note"] = f"traffic.json unreadable: {e}"
 
     # ---- end-to-end through the public API with HOST buffers ------------------------------------
     # N = 1: custom_fdtd_forward (the reference's driver signature); N > 1: the slab runner each rank
@@ -376,6 +504,20 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
 
+    # ---- north-star multi-GPU target: the 4.096e9-cell C5 box, strong-scaled (same K / W) ----------
+    peer_timeouts = int(plan.lib.fdtdx_b200_peer_status(plan.h)) if world > 1 else 0
+    c5 = selfcheck = None
+    if args.workload == "coupler" and args.c5_n > 0:
+        del arrays, plan
+        if world > 1:
+            del runner
+        objects.__dict__.pop("_plan_cache", None)
+        step_fn = None
+        torch.cuda.empty_cache()
+        c5 = run_c5(args, device, rank, world, K, Wm, barrier)
+    if world > 1:
+        selfcheck = slab_selfcheck(args, device, rank, world)
+
     if rank == 0:
         line = {
             "metric": "Gcell-updates/s (E+H Yee step)",
@@ -395,7 +537,10 @@ def main():
                 "cells_total": cells_total,
                 "l2_policy": "inputs >> L2 (no flush needed)",
                 "detectors": record_det,
-                "halo": (("peer-memory reads over NVLink (CUDA IPC), no exchange" if runner.peer else f"NCCL send/recv, overlap={not args.no_overlap}") if world > 1 else None),
+                "halo": halo_desc,
+                "peer_wait_timeouts": peer_timeouts,
+                "slab_selfcheck": selfcheck,
+                "c5": c5,
             },
             "clocks": clocks,
             "e2e": e2e,

@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("FDTDX_B200_LIB") or os.path.join(os.path.dirname(os.p
 ) = range(32)
 
 DET_FIELD, DET_ENERGY, DET_POYNTING, DET_PHASOR = 0, 1, 2, 3
-DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE = 1, 2, 4, 8, 16, 32, 64
+DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE, DETF_VOLUME = 1, 2, 4, 8, 16, 32, 64, 128
 
 EXPORTS = [
     "fdtdx_b200_last_error", "fdtdx_b200_version", "fdtdx_b200_plan_create", "fdtdx_b200_plan_destroy",
@@ -33,7 +33,7 @@ EXPORTS = [
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
     "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_peer_detach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
     "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
-    "fdtdx_b200_plan_source_set_quadrature",
+    "fdtdx_b200_plan_source_set_quadrature", "fdtdx_b200_peer_status",
 ]
 
 _p = C.c_void_p
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_total_energy.argtypes = [_p, _p, _p]
     L.fdtdx_b200_run_adjoint_exact.argtypes = [_p, _i, _p]
     L.fdtdx_b200_peer_detach.argtypes = [_p]
+    L.fdtdx_b200_peer_status.argtypes = [_p]
     L.fdtdx_b200_peer_export.argtypes = [_p, _i, C.c_char_p, C.POINTER(C.c_longlong)]
     L.fdtdx_b200_peer_attach.argtypes = [_p, _i, C.c_char_p, C.c_longlong, C.c_char_p, C.c_longlong, _i]
     L.fdtdx_b200_run_forward_host.argtypes = [_p, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]

@@ -14,6 +14,7 @@
 #include "../../include/fdtdx_b200.h"
 #include "tma_cfg.h"
 #include "aux_kernels.cuh"
+#include "det_volume.cuh"
 #include "common.cuh"
 #include "tensor_kernels.cuh"
 #include "adjoint_kernels.cuh"
@@ -46,6 +47,7 @@ struct DetHost {
   DetDev d;
   std::vector<uint8_t> on;
   int nvals;
+  bool volume = false;  // DET_VOLUME requested and structurally possible (row-marching kernels, det_volume.cuh)
 };
 
 struct FdtdxPlan {
@@ -351,9 +353,24 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
     d.ph_table = reinterpret_cast<const float2*>(dt);
     d.window = dw;
   }
+  // large regions: aligned H_prev rows + row-marching kernels; needs 16-byte rows (Nz % 4 == 0)
+  h.volume = (flags & DET_VOLUME) && (p->nz % 4 == 0);
+  d.flags &= ~DET_VOLUME;  // set per launch by sync_dets once the bound buffers are known to be aligned
+  d.hz0 = lo[2] & ~3;
+  d.hrow = ((hi[2] + 1 - d.hz0) + 3) & ~3;
   if (flags & DET_EXACT) {
-    const size_t hn = (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+    size_t hn = (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+    if (h.volume) hn = std::max(hn, (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (size_t)d.hrow);
     if ((rc = to_device<float>(p, nullptr, hn, &d.hprev))) return rc;
+  }
+  if (h.volume && kind == FDTDX_DET_ENERGY && (flags & DET_SLICES) && (flags & DET_SLICE_MEAN)) {
+    const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    d.npart[0] = (hi[2] - d.hz0 + DETV_TZ - 1) / DETV_TZ;
+    d.npart[1] = (ey + DETV_ROWS - 1) / DETV_ROWS;
+    d.npart[2] = (ex + DETV_XC - 1) / DETV_XC;
+    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[0] * ex * ey, &d.part[0]))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[1] * ex * ez, &d.part[1]))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[2] * ey * ez, &d.part[2]))) return rc;
   }
   h.nvals = 0;
   const bool staged = (flags & DET_REDUCE) || ((flags & DET_SLICES) && (flags & DET_SLICE_MEAN));
@@ -794,6 +811,7 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     Q.xchunk = tma_chunk(p, P);
     const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
     dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    Q.peer_total = (int)g.x * ((p->ny + 128 / tz - 1) / (128 / tz));  // warps of one x chunk that own rows
     if (tz == 64) CUDA_TRY(fdtdx_dispatch_E4_tma64(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
     else CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
   } else {
@@ -801,8 +819,10 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     // predicated 32-bit accesses (E1)
     dim3 b(32, p->rows);
     dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
-    if (v4) fdtdx_dispatch_E4(P, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
-    else fdtdx_dispatch_E1(P, t, p->eps_tier, std::min(pml_mode(p, P), 1), rev, sig, ade, met, g, b, st);
+    StepParams Q = P;
+    Q.peer_total = (int)g.x * p->ny;  // one warp per row
+    if (v4) fdtdx_dispatch_E4(Q, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, b, st);
+    else fdtdx_dispatch_E1(Q, t, p->eps_tier, std::min(pml_mode(p, P), 1), rev, sig, ade, met, g, b, st);
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -829,13 +849,16 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     Q.xchunk = tma_chunk(p, P);
     const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
     dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+    Q.peer_total = (int)g.x * ((p->ny + 128 / tz - 1) / (128 / tz));
     if (tz == 64) CUDA_TRY(fdtdx_dispatch_H4_tma64(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
     else CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
   } else {
     dim3 b(32, p->rows);
     dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (P.x_end - P.x_begin + P.xchunk - 1) / P.xchunk);
-    if (v4) fdtdx_dispatch_H4(P, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
-    else fdtdx_dispatch_H1(P, t, p->mu_tier, std::min(pml_mode(p, P), 1), rev, p->sigH_tier > 0, p->metric, g, b, st);
+    StepParams Q = P;
+    Q.peer_total = (int)g.x * p->ny;
+    if (v4) fdtdx_dispatch_H4(Q, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, b, st);
+    else fdtdx_dispatch_H1(Q, t, p->mu_tier, std::min(pml_mode(p, P), 1), rev, p->sigH_tier > 0, p->metric, g, b, st);
   }
   p->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -869,6 +892,14 @@ static int sync_dets(FdtdxPlan* p, cudaStream_t st) {
     for (int k = 0; k < 4; ++k)
       if (st[k] != d.state[k]) { d.state[k] = st[k]; changed = true; }
     if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
+    {
+      const void* eh[3] = {p->slots[FDTDX_SLOT_E][0], p->slots[FDTDX_SLOT_H][0], d.hprev};
+      bool vol = p->dets[di].volume;
+      for (const void* q : eh) vol = vol && (q == nullptr || aligned16(q));
+      if (p->e_parity || p->h_parity) vol = vol && aligned16(p->slots[FDTDX_SLOT_E_ALT][0]) && aligned16(p->slots[FDTDX_SLOT_H_ALT][0]);
+      const int want = vol ? (d.flags | DET_VOLUME) : (d.flags & ~DET_VOLUME);
+      if (want != d.flags) { d.flags = want; changed = true; }
+    }
     if (d.kind == FDTDX_DET_ENERGY && (d.flags & DET_SLICES) && (!d.state[1] || !d.state[2]))
       return fail(FDTDX_EUNBOUND, "energy slice detector needs three state buffers");
   }
@@ -911,9 +942,25 @@ static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
   if (rc) return rc;
   GridDev G;
   make_grid(p, G);
-  dim3 g((unsigned)std::min<long long>((p->det_max_halo + 255) / 256, 148 * 8), (unsigned)p->dets.size());
-  det_gather_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
-  p->launches++;
+  bool any_generic = false, any_volume = false;
+  long long vol_rows = 0;
+  for (const DetHost& h : p->dets) {
+    if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t] || !(h.d.flags & DET_EXACT)) continue;
+    if (h.d.flags & DET_VOLUME) {
+      any_volume = true;
+      vol_rows = std::max(vol_rows, 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1));
+    } else any_generic = true;
+  }
+  if (any_generic) {
+    dim3 g((unsigned)std::min<long long>((p->det_max_halo + 255) / 256, 148 * 8), (unsigned)p->dets.size());
+    det_gather_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+    p->launches++;
+  }
+  if (any_volume) {
+    dim3 g((unsigned)std::min<long long>((vol_rows + 7) / 8, 148 * 16), (unsigned)p->dets.size());
+    det_gather_rows_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+    p->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
 }
@@ -925,14 +972,40 @@ static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
   if (rc) return rc;
   GridDev G;
   make_grid(p, G);
-  dim3 g((unsigned)std::min<long long>((p->det_max_cells + 255) / 256, 148 * 8), (unsigned)p->dets.size());
-  det_sample_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
-  p->launches++;
+  bool any_generic = false, vol_exact = false, vol_raw = false;
+  int gz = 1, gy = 1, nxc = 1;
+  for (const DetHost& h : p->dets) {
+    if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t]) continue;
+    if (h.d.flags & DET_VOLUME) {
+      ((h.d.flags & DET_EXACT) ? vol_exact : vol_raw) = true;
+      gz = std::max(gz, (h.d.hi[2] - h.d.hz0 + DETV_TZ - 1) / DETV_TZ);
+      gy = std::max(gy, (h.d.hi[1] - h.d.lo[1] + DETV_ROWS - 1) / DETV_ROWS);
+      nxc = std::max(nxc, (h.d.hi[0] - h.d.lo[0] + DETV_XC - 1) / DETV_XC);
+    } else any_generic = true;
+  }
+  if (any_generic) {
+    dim3 g((unsigned)std::min<long long>((p->det_max_cells + 255) / 256, 148 * 8), (unsigned)p->dets.size());
+    det_sample_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+    p->launches++;
+  }
+  if (vol_exact || vol_raw) {
+    dim3 g(gz, gy, nxc * (unsigned)p->dets.size()), b(32, DETV_ROWS);
+    if (vol_exact) { det_march_kernel<true><<<g, b, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0, nxc); p->launches++; }
+    if (vol_raw) { det_march_kernel<false><<<g, b, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0, nxc); p->launches++; }
+  }
   if (any_post) {
     for (size_t di = 0; di < p->dets.size(); ++di) {
       DetHost& h = p->dets[di];
       if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t]) continue;
       const long long n = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
+      if ((h.d.flags & DET_VOLUME) && h.d.kind == FDTDX_DET_ENERGY && (h.d.flags & DET_SLICES) && (h.d.flags & DET_SLICE_MEAN)) {
+        // the marching kernel reduced the three means into partial buffers: fold them
+        const long long ex = h.d.hi[0] - h.d.lo[0], ey = h.d.hi[1] - h.d.lo[1], ez = h.d.hi[2] - h.d.lo[2];
+        const long long nout = ex * ey + ex * ez + ey * ez;
+        det_mean_finish_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(p->d_dets, (int)di, t);
+        p->launches++;
+        continue;
+      }
       if (h.d.flags & DET_REDUCE) {
         const int wpv = (h.d.kind == FDTDX_DET_POYNTING && (h.d.flags & DET_KEEP_ALL)) ? 1 : 0;
         det_reduce_all_kernel<<<h.nvals, 1024, 0, st>>>(h.d, t, h.nvals, wpv);
@@ -977,36 +1050,33 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
 // has finished the half-step that produced it, and must finish before the neighbour overwrites it.
 // Both orders reduce to one rule per half-step: E waits for the low
 // neighbour's doneH == (H half-steps issued so far), H waits for the high neighbour's
-// doneE == (E half-steps issued so far).  The waits / signals are one-thread kernels on the caller's
-// stream, so the whole multi-step run stays a single asynchronous submission per rank.
-__global__ void peer_wait_kernel(const int* flag, int target) {
-  unsigned ns = 32;
-  for (;;) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if (v - target >= 0) break;
-    __nanosleep(ns);
-    if (ns < 1024) ns *= 2;
-  }
-}
-__global__ void peer_signal_kernel(int* flag, int value) {
-  __threadfence_system();
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
-}
-
+// doneE == (E half-steps issued so far).  The waits / signals live inside the half-step kernels
+// (yee_kernels.cuh: peer_wait_cta / peer_signal_warp): only the CTAs of the chunk that touches the
+// shared plane take part, so the interior chunks overlap the wait, the programmatic-dependent-launch
+// chain between the half-steps survives, and a whole multi-step run stays one asynchronous
+// submission per rank.
 static int step_E(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) {
   if (p->eps_tier == 9 || p->sigE_tier == 9) return tensor_step(p, t, simulate, rev, /*is_E=*/true, st);
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
-  if (p->peer_mode && p->halo_lo) peer_wait_kernel<<<1, 1, 0, st>>>(p->peer[0].flags + 1, (int)p->seqH);
+  if (p->peer_mode) {
+    // in-kernel ordering (common.cuh, StepParams::peer_*): the chunk holding plane 0 waits for the low
+    // neighbour's H counter and publishes this rank's E counter; it is scheduled last (z_reverse), a
+    // whole kernel after the neighbour's H half-step was issued, so the wait is normally already met
+    p->seqE++;
+    if (p->halo_lo) {
+      P.peer_wait = p->peer[0].flags + 1;
+      P.peer_wait_target = (int)p->seqH;
+      P.peer_signal = p->d_flags;
+      P.peer_signal_value = (int)p->seqE;
+      P.peer_ctr = p->d_flags + 8;
+      P.peer_err = p->d_flags + 2;
+      P.z_reverse = 1;
+    }
+  }
   rc = launch_E(p, P, t, rev, st);
   if (rc) return rc;
-  if (p->peer_mode) {
-    p->seqE++;
-    peer_signal_kernel<<<1, 1, 0, st>>>(p->d_flags, (int)p->seqE);
-    CUDA_TRY(cudaGetLastError());
-  }
   if (!rev && p->n_poles > 0) p->p_parity ^= 1;
   return FDTDX_OK;
 }
@@ -1016,14 +1086,21 @@ static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
-  if (p->peer_mode && p->halo_hi) peer_wait_kernel<<<1, 1, 0, st>>>(p->peer[1].flags, (int)p->seqE);
+  if (p->peer_mode) {
+    // the chunk holding plane nx-1 (scheduled last) waits for the high neighbour's E counter and
+    // publishes this rank's H counter
+    p->seqH++;
+    if (p->halo_hi) {
+      P.peer_wait = p->peer[1].flags;
+      P.peer_wait_target = (int)p->seqE;
+      P.peer_signal = p->d_flags + 1;
+      P.peer_signal_value = (int)p->seqH;
+      P.peer_ctr = p->d_flags + 9;
+      P.peer_err = p->d_flags + 2;
+    }
+  }
   rc = launch_H(p, P, t, rev, st);
   if (rc) return rc;
-  if (p->peer_mode) {
-    p->seqH++;
-    peer_signal_kernel<<<1, 1, 0, st>>>(p->d_flags + 1, (int)p->seqH);
-    CUDA_TRY(cudaGetLastError());
-  }
   return FDTDX_OK;
 }
 
@@ -1081,6 +1158,17 @@ static int ipc_open(FdtdxPlan* p, const unsigned char* handle64, void** base) {
   p->ipc_open.emplace_back(key, q);
   *base = q;
   return FDTDX_OK;
+}
+
+// 0: every neighbour wait of the runs issued so far was met; 1: a wait gave up (results invalid).
+// Synchronises the device.
+extern "C" int fdtdx_b200_peer_status(FdtdxPlan* p) {
+  if (!p) return fail(FDTDX_EINVAL, "peer_status: null plan");
+  if (!p->d_flags) return 0;
+  int err = 0;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(&err, p->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  return err ? 1 : 0;
 }
 
 extern "C" int fdtdx_b200_peer_detach(FdtdxPlan* p) {

@@ -42,7 +42,11 @@ struct DetDev {
   float scale;
   int slice_idx[3];
   float* hprev;    // (3, ex+1, ey+1, ez+1): H before this step's H update, halo rules applied
+                   // DET_VOLUME: (3, ex+1, ey+1, hrow) with 16-byte aligned rows, see det_volume.cuh
   float* scratch;  // (nvals, region) staging for reductions
+  int hrow, hz0;   // DET_VOLUME: row length of hprev and the global z of its element 0 (a multiple of 4)
+  float* part[3];  // DET_VOLUME slice means: partial sums over z tiles / y tiles / x chunks
+  int npart[3];
   float* state[4];
 };
 
@@ -53,6 +57,7 @@ struct DetDev {
 #define DET_SLICE_MEAN 16
 #define DET_KEEP_ALL 32
 #define DET_NEGATIVE 64
+#define DET_VOLUME 128  // large exact-interpolation region: row-marching gather / sample kernels (det_volume.cuh)
 
 // CHK = false: the caller guarantees that (x, y, z) is inside the local grid (interior fast path of the
 // detector stencil: no halo rule, no wrap)
@@ -93,7 +98,7 @@ __global__ void det_gather_batch_kernel(const GridDev G, const DetDev* __restric
   __shared__ DetDev sD;
   det_stage_descriptor(&sD, dets + blockIdx.y);
   const DetDev& D = sD;
-  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_EXACT)) return;
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_EXACT) || (D.flags & DET_VOLUME)) return;
   det_gather_body(G, D);
 }
 __device__ __forceinline__ void det_gather_body(const GridDev& G, const DetDev& D) {
@@ -207,6 +212,9 @@ __device__ __forceinline__ void colocate(const GridDev& G, const DetDev& D, int 
 
 // One thread per region cell: sample, then write the per-type result (or stage it for a reduction).
 __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& D, const int t, const long long cell);
+template <bool FUSED_MEAN>
+__device__ __forceinline__ void det_emit(const GridDev& G, const DetDev& D, const int t, const long long cell, const int rx, const int ry, const int rz,
+                                         const int x, const int y, const int z, const float* Es, const float* Hs, float* e_out);
 __global__ void det_sample_kernel(const GridDev G, const DetDev D, const int t) {
   const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
   const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -217,7 +225,7 @@ __global__ void det_sample_batch_kernel(const GridDev G, const DetDev* __restric
   __shared__ DetDev sD;
   det_stage_descriptor(&sD, dets + blockIdx.y);
   const DetDev& D = sD;
-  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t]) return;
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || (D.flags & DET_VOLUME)) return;
   const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
   for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < n; cell += (long long)gridDim.x * blockDim.x)
     det_sample_body(G, D, t, cell);
@@ -241,6 +249,16 @@ __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& 
   if ((D.flags & DET_SLICES) && !(D.flags & DET_SLICE_MEAN) && rx != D.slice_idx[0] && ry != D.slice_idx[1] && rz != D.slice_idx[2]) return;
   float Es[3], Hs[3];
   colocate(G, D, x, y, z, Es, Hs);
+  det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es, Hs, nullptr);
+}
+// Per-type Detector.update on the co-located sample of one cell (objects/detectors/*.py): writes the
+// state entry or stages the value for a reduction.  FUSED_MEAN: the caller reduces the slice means
+// itself (det_volume.cuh) and only wants the cell's energy back through e_out.
+template <bool FUSED_MEAN>
+__device__ __forceinline__ void det_emit(const GridDev& G, const DetDev& D, const int t, const long long cell, const int rx, const int ry, const int rz,
+                                         const int x, const int y, const int z, const float* Es, const float* Hs, float* e_out) {
+  const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
+  const long long n = (long long)ex * ey * ez;
   const int slot = D.arr_idx[t];
   const bool staged = (D.flags & DET_REDUCE) || ((D.flags & DET_SLICES) && (D.flags & DET_SLICE_MEAN));
   if (D.kind == 0 || D.kind == 3) {  // field / phasor: selected components
@@ -311,7 +329,9 @@ __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& 
     }
     (void)N;
     const float e = eE + eH;
-    if (staged) {
+    if (FUSED_MEAN) {
+      *e_out = e;
+    } else if (staged) {
       D.scratch[cell] = e;
     } else if (D.flags & DET_SLICES) {
       if (rz == D.slice_idx[2]) D.state[0][((long long)slot * ex + rx) * ey + ry] = e;

@@ -102,6 +102,19 @@ struct StepParams {
   long long haloH_cs, haloE_cs;
   int xchunk;
   int x_begin, x_end;  // plane range of this launch (sub-ranges let the halo exchange overlap)
+  // Peer-memory halo (x-slab sharding, neighbour arrays mapped over NVLink): producer / consumer order
+  // with the neighbour rank is kept INSIDE the half-step kernel.  Only the CTAs of the boundary chunk
+  // (E step: the chunk holding plane 0; H step: the chunk holding plane nx-1) poll the neighbour's
+  // progress counter before they touch the shared plane, and the last of their warps to finish
+  // publishes this rank's counter; every other CTA runs unordered, so the interior overlaps the wait.
+  const int* peer_wait;   // neighbour's counter (nullptr: nothing to wait for)
+  int peer_wait_target;
+  int* peer_signal;       // this rank's counter (nullptr: nobody listens)
+  int peer_signal_value;
+  int* peer_ctr;          // arrivals of the boundary chunk's warps (reset by the last one)
+  int peer_total;
+  int* peer_err;          // set to 1 when a wait gave up (neighbour stalled): results are invalid
+  int z_reverse;          // E step: blockIdx.z counts chunks from the high-x end, so the boundary chunk runs last
 };
 
 template <int V>

@@ -1,0 +1,263 @@
+// Detector accumulation for LARGE exact-interpolation regions (DET_VOLUME): full-volume energy videos,
+// field videos, volume reductions (update_detector_states, fdtd/update.py:1040-1137; interpolate_fields,
+// core/physics/curl.py:86-224; Detector.update of objects/detectors/*.py).
+//
+// The generic kernels of aux_kernels.cuh spend ~900 instructions per cell (one thread per cell, 64-bit
+// index arithmetic, 30 scalar loads, a scalar H_prev copy).  Here a warp owns one (x, y) row of the
+// region and a lane four consecutive z cells:
+//   det_gather_rows_kernel  copies the pre-update H rows (halo rules applied) into a 16-byte aligned box,
+//   det_march_kernel        reads every operand row of the co-location stencil with one 128-bit load
+//                           (k+1 by shuffle), evaluates the same expressions in the same order as
+//                           colocate_interior / colocate_t (bit-identical samples), and hands each cell to
+//                           det_emit - or, for averaged energy slices, reduces the three means itself
+//                           (row sum by warp shuffle, y sum over the CTA's rows, x sum along the march)
+//                           into small partial buffers,
+//   det_mean_finish_kernel  folds those partials in a fixed order and writes the three planes.
+// Sums are deterministic (fixed geometry, fixed order); they differ from the sequential order of
+// det_slice_mean_kernel by float32 rounding only (~1e-7 relative).
+#pragma once
+#include "aux_kernels.cuh"
+
+#define DETV_ROWS 8     // y rows (warps) per CTA
+#define DETV_TZ 128     // z cells per warp pass
+#define DETV_XC 8       // x planes per CTA
+
+// aligned H_prev box: element (c, a, b, g) holds H_c(lo_x - 1 + a, lo_y - 1 + b, hz0 + g)
+__device__ __forceinline__ long long detv_hidx(const DetDev& D, int c, int a, int b) {
+  const int sy = D.hi[1] - D.lo[1] + 1, sx = D.hi[0] - D.lo[0] + 1;
+  return (((long long)c * sx + a) * sy + b) * D.hrow;
+}
+
+// One warp per (c, a, b) row.  Source rows outside the grid follow the halo rule (zero / wrap).
+__global__ void __launch_bounds__(256) det_gather_rows_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
+  __shared__ DetDev sD;
+  det_stage_descriptor(&sD, dets + blockIdx.y);
+  const DetDev& D = sD;
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_VOLUME)) return;
+  const int sx = D.hi[0] - D.lo[0] + 1, sy = D.hi[1] - D.lo[1] + 1;
+  const long long rows = 3LL * sx * sy;
+  const int lane = threadIdx.x & 31;
+  const long long N = (long long)G.nx * G.ny * G.nz;
+  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int b = (int)(r % sy);
+    const int a = (int)((r / sy) % sx);
+    const int c = (int)(r / ((long long)sy * sx));
+    int x = D.lo[0] - 1 + a, y = D.lo[1] - 1 + b;
+    bool zero = false;
+    if (x < 0) { if (G.wrap[0]) x += G.nx; else zero = true; }
+    if (y < 0) { if (G.wrap[1]) y += G.ny; else zero = true; }
+    float4* dst = reinterpret_cast<float4*>(D.hprev + detv_hidx(D, c, a, b));
+    const float* src = G.H + c * N + ((long long)x * G.ny + y) * G.nz;
+    for (int q = lane; q < D.hrow / 4; q += 32) {
+      const int z = D.hz0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!zero) {
+        if (z + 3 < G.nz) {
+          v = *reinterpret_cast<const float4*>(src + z);
+        } else {  // the row's tail: z+1 of the last cell is the halo (zero / wrap to z = 0)
+          float e[4];
+          for (int k = 0; k < 4; ++k) e[k] = (z + k < G.nz) ? src[z + k] : ((G.wrap[2] && z + k < G.nz + 4) ? src[z + k - G.nz] : 0.0f);
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      dst[q] = v;
+    }
+  }
+}
+
+struct Row4 {
+  float v[4];
+  float nx;  // the element after v[3] (k+1 of the lane's last cell)
+};
+
+// Row (c, x, y) of a grid array at cells z0..z0+3 (+ the following element).  ok = false: halo row of zeros.
+__device__ __forceinline__ Row4 detv_ld_grid(const GridDev& G, const float* F, int c, int x, int y, int z0, const int lane) {
+  Row4 r;
+  bool zero = false;
+  if (x < 0) { if (G.wrap[0]) x += G.nx; else zero = true; }
+  if (y < 0) { if (G.wrap[1]) y += G.ny; else zero = true; }
+  const long long N = (long long)G.nx * G.ny * G.nz;
+  const float* row = F + c * N + ((long long)x * G.ny + y) * G.nz;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool in = !zero && z0 < G.nz;
+  if (in) t = *reinterpret_cast<const float4*>(row + z0);
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  float nxt = __shfl_down_sync(0xffffffffu, t.x, 1);
+  if (lane == 31 || z0 + 4 >= G.nz) {
+    nxt = 0.0f;
+    if (in) {
+      if (z0 + 4 < G.nz) nxt = row[z0 + 4];
+      else if (G.wrap[2]) nxt = row[0];
+    }
+  }
+  r.nx = nxt;
+  return r;
+}
+// The same row of the aligned H_prev box (halo rules were applied by the gather).
+__device__ __forceinline__ Row4 detv_ld_prev(const DetDev& D, int c, int x, int y, int z0, const int lane, const bool in) {
+  Row4 r;
+  const float* row = D.hprev + detv_hidx(D, c, x - D.lo[0] + 1, y - D.lo[1] + 1) + (z0 - D.hz0);
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in) t = *reinterpret_cast<const float4*>(row);
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  float nxt = __shfl_down_sync(0xffffffffu, t.x, 1);
+  if (lane == 31) nxt = (in && (z0 + 4 - D.hz0) < D.hrow) ? row[4] : 0.0f;
+  r.nx = nxt;
+  return r;
+}
+__device__ __forceinline__ float row_at(const Row4& r, int e) { return e < 4 ? r.v[e] : r.nx; }
+
+// H_bar = (H_prev + H) / 2 per element (update.py:1088, 1098)
+__device__ __forceinline__ Row4 detv_hbar(const Row4& p, const Row4& h) {
+  Row4 r;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) r.v[e] = (p.v[e] + h.v[e]) / 2.0f;
+  r.nx = (p.nx + h.nx) / 2.0f;
+  return r;
+}
+
+// grid: (z tiles of 128, y tiles of 8 rows, x chunks of 8 planes) of the detector box, blockIdx.z also
+// enumerates detectors: z = det * nxc + chunk.
+template <bool EXACT>
+__global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse, const int nxc_max) {
+  __shared__ DetDev sD;
+  __shared__ float s_rows[DETV_ROWS][DETV_TZ];
+  const int di = blockIdx.z / nxc_max, xc = blockIdx.z - di * nxc_max;
+  {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int q = tid; q < (int)(sizeof(DetDev) / 4); q += 256) reinterpret_cast<int*>(&sD)[q] = reinterpret_cast<const int*>(dets + di)[q];
+    __syncthreads();
+  }
+  const DetDev& D = sD;
+  if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_VOLUME)) return;
+  if (((D.flags & DET_EXACT) != 0) != EXACT) return;
+  const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
+  const int lane = threadIdx.x, wrow = threadIdx.y;
+  // lanes are aligned to global multiples of 4 in z; cells outside [lo_z, hi_z) are masked at emit
+  const int zt0 = (D.lo[2] & ~3) + blockIdx.x * DETV_TZ;
+  const int z0 = zt0 + 4 * lane;
+  const int ry = blockIdx.y * DETV_ROWS + wrow;
+  const int rx0 = xc * DETV_XC, rx1 = min(rx0 + DETV_XC, ex);
+  if (zt0 >= D.hi[2] || rx0 >= ex || blockIdx.y * DETV_ROWS >= ey) return;  // CTA-uniform
+  const bool row_ok = ry < ey;
+  const int y = D.lo[1] + ry;
+  const bool fused_mean = (D.flags & DET_SLICES) && (D.flags & DET_SLICE_MEAN) && D.kind == 1;
+  const bool lane_in = row_ok && z0 < G.nz && z0 < D.hi[2] && z0 + 4 > D.lo[2];
+  float accx[4] = {0.f, 0.f, 0.f, 0.f};  // sum over this chunk's x planes (YZ plane partial)
+  for (int rx = rx0; rx < rx1; ++rx) {
+    const int x = D.lo[0] + rx;
+    float Es[4][3], Hs[4][3];
+    if (row_ok) {  // warp-uniform: the shuffles inside the loaders need the whole warp
+      if (EXACT) {
+        const Row4 exc = detv_ld_grid(G, G.E, 0, x, y, z0, lane), exm = detv_ld_grid(G, G.E, 0, x - 1, y, z0, lane);
+        const Row4 eyc = detv_ld_grid(G, G.E, 1, x, y, z0, lane), eym = detv_ld_grid(G, G.E, 1, x, y - 1, z0, lane);
+        const Row4 ezc = detv_ld_grid(G, G.E, 2, x, y, z0, lane);
+        const bool in = row_ok && (z0 - D.hz0 + 4 <= D.hrow);  // inside the gathered row (covers hi_z: the k+1 halo)
+        const Row4 hx_c = detv_hbar(detv_ld_prev(D, 0, x, y, z0, lane, in), detv_ld_grid(G, G.H, 0, x, y, z0, lane));
+        const Row4 hx_m = detv_hbar(detv_ld_prev(D, 0, x, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 0, x, y - 1, z0, lane));
+        const Row4 hy_c = detv_hbar(detv_ld_prev(D, 1, x, y, z0, lane, in), detv_ld_grid(G, G.H, 1, x, y, z0, lane));
+        const Row4 hy_m = detv_hbar(detv_ld_prev(D, 1, x - 1, y, z0, lane, in), detv_ld_grid(G, G.H, 1, x - 1, y, z0, lane));
+        const Row4 hz_cc = detv_hbar(detv_ld_prev(D, 2, x, y, z0, lane, in), detv_ld_grid(G, G.H, 2, x, y, z0, lane));
+        const Row4 hz_mc = detv_hbar(detv_ld_prev(D, 2, x - 1, y, z0, lane, in), detv_ld_grid(G, G.H, 2, x - 1, y, z0, lane));
+        const Row4 hz_cm = detv_hbar(detv_ld_prev(D, 2, x, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 2, x, y - 1, z0, lane));
+        const Row4 hz_mm = detv_hbar(detv_ld_prev(D, 2, x - 1, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 2, x - 1, y - 1, z0, lane));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // same expressions, same order as colocate_interior / colocate_t (curl.py:120-222)
+          float lo = bea(G, exc.v[e], exm.v[e], 0, x);
+          float hi = bea(G, row_at(exc, e + 1), row_at(exm, e + 1), 0, x);
+          Es[e][0] = (lo + hi) / 2.0f;
+          lo = bea(G, eyc.v[e], eym.v[e], 1, y);
+          hi = bea(G, row_at(eyc, e + 1), row_at(eym, e + 1), 1, y);
+          Es[e][1] = (lo + hi) / 2.0f;
+          Es[e][2] = ezc.v[e];
+          Hs[e][0] = bea(G, hx_c.v[e], hx_m.v[e], 1, y);
+          Hs[e][1] = bea(G, hy_c.v[e], hy_m.v[e], 0, x);
+          const float lx = bea(G, hz_cc.v[e], hz_mc.v[e], 0, x);
+          const float lxm = bea(G, hz_cm.v[e], hz_mm.v[e], 0, x);
+          const float lxy = bea(G, lx, lxm, 1, y);
+          const float hx2 = bea(G, row_at(hz_cc, e + 1), row_at(hz_mc, e + 1), 0, x);
+          const float hxm = bea(G, row_at(hz_cm, e + 1), row_at(hz_mm, e + 1), 0, x);
+          const float hxy = bea(G, hx2, hxm, 1, y);
+          Hs[e][2] = (lxy + hxy) / 2.0f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const Row4 a = detv_ld_grid(G, G.E, c, x, y, z0, lane), b = detv_ld_grid(G, G.H, c, x, y, z0, lane);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { Es[e][c] = a.v[e]; Hs[e][c] = b.v[e]; }
+        }
+      }
+    }
+    float ev[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane_in) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int z = z0 + e;
+        if (z < D.lo[2] || z >= D.hi[2]) continue;
+        const int rz = z - D.lo[2];
+        const long long cell = ((long long)rx * ey + ry) * ez + rz;
+        if (fused_mean) det_emit<true>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], &ev[e]);
+        else det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], nullptr);
+      }
+    }
+    if (fused_mean) {  // CTA-uniform
+      // (1) sum over z of this row's 128-cell pass -> part[0][ztile][rx][ry]
+      float rs = (ev[0] + ev[1]) + (ev[2] + ev[3]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      if (lane == 0 && row_ok) D.part[0][((long long)blockIdx.x * ex + rx) * ey + ry] = rs;
+      // (2) sum over the CTA's rows -> part[1][ytile][rx][rz]
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s_rows[wrow][4 * lane + e] = ev[e];
+      __syncthreads();
+      if (wrow == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int z = z0 + e;
+          if (z < D.lo[2] || z >= D.hi[2] || z >= G.nz) continue;
+          float a = 0.0f;
+          for (int w = 0; w < DETV_ROWS; ++w) a += s_rows[w][4 * lane + e];
+          D.part[1][((long long)blockIdx.y * ex + rx) * ez + (z - D.lo[2])] = a;
+        }
+      }
+      // (3) running sum over x
+#pragma unroll
+      for (int e = 0; e < 4; ++e) accx[e] += ev[e];
+    }
+  }
+  if (fused_mean && lane_in) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int z = z0 + e;
+      if (z < D.lo[2] || z >= D.hi[2]) continue;
+      D.part[2][((long long)xc * ey + ry) * ez + (z - D.lo[2])] = accx[e];
+    }
+  }
+}
+
+// One thread per output element of the three mean planes: fold the partials in a fixed order.
+__global__ void det_mean_finish_kernel(const DetDev* __restrict__ dets, const int di, const int t) {
+  const DetDev D = dets[di];
+  const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
+  const long long nxy = (long long)ex * ey, nxz = (long long)ex * ez, nyz = (long long)ey * ez;
+  const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int slot = D.arr_idx[t];
+  if (o < nxy) {  // XY plane: mean over z
+    float a = 0.0f;
+    for (int q = 0; q < D.npart[0]; ++q) a += D.part[0][q * nxy + o];
+    D.state[0][slot * nxy + o] = a / (float)ez;
+  } else if (o < nxy + nxz) {  // XZ plane: mean over y
+    const long long i = o - nxy;
+    float a = 0.0f;
+    for (int q = 0; q < D.npart[1]; ++q) a += D.part[1][q * nxz + i];
+    D.state[1][slot * nxz + i] = a / (float)ey;
+  } else if (o < nxy + nxz + nyz) {  // YZ plane: mean over x
+    const long long i = o - nxy - nxz;
+    float a = 0.0f;
+    for (int q = 0; q < D.npart[2]; ++q) a += D.part[2][q * nyz + i];
+    D.state[2][slot * nyz + i] = a / (float)ex;
+  }
+}

@@ -168,6 +168,45 @@ static __device__ __noinline__ void inject_H(const SrcDev* __restrict__ srcs, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Peer-memory halo ordering (StepParams::peer_*).  One rule per half-step covers the read-after-write
+// and the write-after-read hazard on the plane shared with a neighbour.
+// ------------------------------------------------------------------------------------------------
+// Called by every thread of a boundary-chunk CTA before its first access to the shared plane: one
+// thread polls (acquire, system scope), the CTA barrier publishes the result.  Bounded: a neighbour
+// that never arrives (a rank that died or issued fewer half-steps) raises peer_err instead of hanging.
+__device__ __forceinline__ void peer_wait_cta(const StepParams& P) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned ns = 32;
+    const long long t0 = clock64();
+    for (;;) {
+      int v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(P.peer_wait) : "memory");
+      if (v - P.peer_wait_target >= 0) break;
+      if (clock64() - t0 > (1LL << 36)) {  // ~35 s at 1.9 GHz
+        atomicExch(P.peer_err, 1);
+        break;
+      }
+      __nanosleep(ns);
+      if (ns < 1024) ns *= 2;
+    }
+  }
+  __syncthreads();
+}
+// Called by the active lanes of a boundary-chunk warp after its last store.
+__device__ __forceinline__ void peer_signal_warp(const StepParams& P, const unsigned mask) {
+  __threadfence_system();  // this lane's stores are visible system-wide before the arrival
+  __syncwarp(mask);
+  if ((threadIdx.x & 31) == __ffs(mask) - 1) {
+    const int old = atomicAdd(P.peer_ctr, 1);
+    if (old == P.peer_total - 1) {
+      atomicExch(P.peer_ctr, 0);
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(P.peer_signal), "r"(P.peer_signal_value) : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Hot-loop helpers.  Everything the marching loop touches per plane lives in registers or in kernel
 // parameter (constant) space; source injection and wall masking are kept out of line so that the
 // common cell costs no local-memory traffic and no descriptor loads.
@@ -668,12 +707,14 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
   const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int nz = P.nz, ny = P.ny;
+  const int ic0 = P.x_begin + (P.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * P.xchunk;
+  const int ic1 = min(ic0 + P.xchunk, P.x_end);
+  const bool peer_cta = (ic0 == 0);  // the chunk that reads the low neighbour's H plane and owns E[0]
+  if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
   const bool active = (k0 < nz) && (j < ny);
   const unsigned wmask = __ballot_sync(0xffffffffu, active);
   if (!active) return;  // the shuffles below run under wmask
   const int nv = FDTDX_RAGGED ? min(V, (nz - k0 + FDTDX_ES - 1) / FDTDX_ES) : V;  // valid elements of this thread
-  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
-  const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const long long plane = (long long)ny * nz;
   const long long N = plane * P.nx;
   const long long row = (long long)j * nz + k0;
@@ -826,6 +867,7 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     pEps += plane;
   }
   if (!KONLY && !REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, wmask);
 }
 
 #endif  // !FDTDX_BUILD_H
@@ -840,12 +882,14 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
   const int k0 = FDTDX_RAGGED ? (int)blockIdx.x * 32 * V + lane : ((int)blockIdx.x * 32 + lane) * V;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int nz = P.nz, ny = P.ny;
+  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
+  const int ic1 = min(ic0 + P.xchunk, P.x_end);
+  const bool peer_cta = (ic1 == P.nx);  // the chunk that reads the high neighbour's E plane and owns H[nx-1]
+  if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
   const bool active = (k0 < nz) && (j < ny);
   const unsigned wmask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const int nv = FDTDX_RAGGED ? min(V, (nz - k0 + FDTDX_ES - 1) / FDTDX_ES) : V;
-  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
-  const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const long long plane = (long long)ny * nz;
   const long long N = plane * P.nx;
   const long long row = (long long)j * nz + k0;
@@ -1006,5 +1050,6 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     if (MUT >= 1) pMu += plane;
   }
   if (!KONLY && !REV && P.n_src > 0 && P.src_inline && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, wmask);
 }
 #endif  // !FDTDX_BUILD_E

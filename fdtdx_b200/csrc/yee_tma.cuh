@@ -281,8 +281,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * G::RT;
   const int zl = lane % LZ, trow = warp * WR + lane / LZ;  // z lane inside the row, row inside the tile
   const int nz = P.nz, ny = P.ny;
-  const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
+  const int ic0 = P.x_begin + (P.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
+  const bool peer_cta = (ic0 == 0);  // the chunk that reads the low neighbour's H plane and owns E[0]
   const int j = j0 + trow;
   const int k0 = kt0 + zl * V;
   const bool lane_ok = (j < ny) && (k0 < nz);
@@ -322,6 +323,10 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // reverse pass: update_E_reverse undoes the injection first; it must land in global memory before
   // the first tile load reads it (generic -> async proxy)
+  // x-slab neighbour over NVLink: its H[-1] plane of the previous half-step must be final before the
+  // register queue below reads it, and its H half-step must have finished reading E[0] before this CTA
+  // overwrites it
+  if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
   if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -448,6 +453,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     cell0 += plane;
   }
   if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, 0xffffffffu);
 }
 #endif  // !FDTDX_BUILD_H
 
@@ -479,6 +485,9 @@ __device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M
       tma_load_4d(dst + G::HALO_B, &M.fld_halo, kt0, j0, 0, 1, full);
       tma_load_4d(dst + 2 * G::HALO_B, &M.fld_halo, kt0, j0, 0, 2, full);
     } else {
+      // the neighbour's stores were observed through an acquire load in the generic proxy (peer_wait_cta
+      // + CTA barrier); order them before this async-proxy read
+      asm volatile("fence.proxy.async;" ::: "memory");
       tma_load_4d(dst + G::HALO_B, &M.xhalo, kt0, j0, 0, 0, full);
       tma_load_4d(dst + 2 * G::HALO_B, &M.xhalo, kt0, j0, 1, 0, full);
     }
@@ -498,6 +507,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   const int nz = P.nz, ny = P.ny;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
+  const bool peer_cta = (ic1 == P.nx);  // the chunk that reads the high neighbour's E plane and owns H[nx-1]
   const int j = j0 + trow;
   const int k0 = kt0 + zl * V;
   const bool lane_ok = (j < ny) && (k0 < nz);
@@ -531,6 +541,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // x-slab neighbour over NVLink: its E[0] plane of this step must be final before the extra ring stage
+  // loads it, and its E half-step must have finished reading H[nx-1] before this CTA overwrites it
+  if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
   if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -654,5 +667,6 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   }
   // the extra Ey,Ez stage was consumed as the "next plane" of the last iteration; nothing to release
   if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, 0xffffffffu);
 }
 #endif  // !FDTDX_BUILD_E

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -331,6 +332,12 @@ class Plan:
                 raise NotImplementedError(f"detector type {type(det).__name__} is not on the hot path")
             lo = [s[0] for s in det.grid_slice_tuple]
             hi = [s[1] for s in det.grid_slice_tuple]
+            # large exact regions (videos, volume reductions, whole cross-sections): row-marching kernels
+            # with 128-bit accesses instead of one thread per cell (csrc/det_volume.cuh)
+            ext = [h_ - l_ for l_, h_ in zip(lo, hi)]
+            if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0":
+                if not (isinstance(det, EnergyDetector) and det.as_slices and not det.use_mean):  # three planes only: O(surface) already
+                    flags |= _lib.DETF_VOLUME
             on = self._pad_T(np.ascontiguousarray(det._is_on_at_time_step_arr, dtype=np.uint8))
             idx = self._pad_T(np.ascontiguousarray(det._time_step_to_arr_idx, dtype=np.int32))
             if isinstance(det, PhasorDetector):

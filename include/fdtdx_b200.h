@@ -141,7 +141,9 @@ int fdtdx_b200_plan_add_dipole(FdtdxPlan* plan, const int cell[3], int polarizat
 
 /* Detector (detector.py:195-244 + per-type update).  on[t], arr_idx[t] tables of length T.
  * flags: bit0 exact_interpolation, bit1 inverse, bit2 reduce_volume, bit3 as_slices,
- *        bit4 slices-use-mean, bit5 keep_all_components, bit6 negative direction.
+ *        bit4 slices-use-mean, bit5 keep_all_components, bit6 negative direction,
+ *        bit7 large region (hint): accumulate with the row-marching 128-bit kernels; same results
+ *        (slice means: same sums in a different, fixed order).  Ignored when rows are not 16-byte aligned.
  * comp_mask: bit c set = component c of (Ex,Ey,Ez,Hx,Hy,Hz) recorded (field / phasor).
  * weights: cell-volume (field/energy/phasor reduce) or face-area (Poynting reduce) weights of the
  * region, or NULL.  phasor_table: (T, nf) complex64 = exp(i*omega_f*t*dt) (phasor.py:221-224),
@@ -231,6 +233,9 @@ int fdtdx_b200_set_tma(FdtdxPlan* plan, int enable, int xchunk_tma);
 int fdtdx_b200_peer_export(FdtdxPlan* plan, int what, unsigned char* handle64, long long* offset);
 int fdtdx_b200_peer_attach(FdtdxPlan* plan, int side, const unsigned char* field_handle64, long long field_offset,
                            const unsigned char* flags_handle64, long long flags_offset, int nx_peer);
+/* 1 if an in-kernel neighbour wait gave up (a rank stalled or issued fewer half-steps; the results of
+ * this rank are then invalid), else 0.  Synchronises the device. */
+int fdtdx_b200_peer_status(FdtdxPlan* plan);
 /* Back to exchanged halo buffers (HALO_H_LO / HALO_E_HI): used when a neighbour could not map this rank. */
 int fdtdx_b200_peer_detach(FdtdxPlan* plan);
 

@@ -78,12 +78,20 @@ def make_c1():
     return out
 
 
+C3A_MID = 4500  # the pulse is in the middle of the domain (between the two detectors)
+
+
 def make_c3a():
     objects, arrays, cfg = configs.build_c3a()
     out = {}
-    st = run_forward("c3a", objects, arrays, cfg, False)
+    st = (0, arrays.reset())
+    while st[0] < C3A_MID:
+        st = yee.forward(st, cfg, objects, None, True, False, True)
+    out["mid_E"], out["mid_H"], out["mid_P"] = st[1].fields.E.copy(), st[1].fields.H.copy(), st[1].fields.dispersive_P_curr.copy()
+    while st[0] < cfg.time_steps_total:
+        st = yee.forward(st, cfg, objects, None, True, False, True)
+    # after 350 fs the pulse has left through the CPML: the final field is a ~1e-6 residue of the peak
     out["fwd_E"], out["fwd_H"] = st[1].fields.E, st[1].fields.H
-    out["P_curr"] = st[1].fields.dispersive_P_curr
     for n in ("pulse_trace_A", "pulse_trace_B"):
         out[n] = st[1].detector_states[n]["fields"]
     return out
