@@ -16,10 +16,13 @@ from fdtdx_b200.boundaries import (
 from fdtdx_b200.config import GradientConfig, RectilinearGrid, SimulationConfig, UniformGrid
 from fdtdx_b200.container import ArrayContainer, FieldState, ObjectContainer, RecordingState
 from fdtdx_b200.detectors import (
+    ClosedSurfacePhasorPoyntingFluxDetector,
+    ClosedSurfacePoyntingFluxDetector,
     EnergyDetector,
     FieldDetector,
     ModeOverlapDetector,
     PhasorDetector,
+    PhasorPoyntingFluxDetector,
     PoyntingFluxDetector,
 )
 from fdtdx_b200.initialization import Material, UniformMaterialObject, init_arrays, place_objects

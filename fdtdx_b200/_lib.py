@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("FDTDX_B200_LIB") or os.path.join(os.path.dirname(os.p
 ) = range(32)
 
 DET_FIELD, DET_ENERGY, DET_POYNTING, DET_PHASOR = 0, 1, 2, 3
-DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE, DETF_VOLUME = 1, 2, 4, 8, 16, 32, 64, 128
+DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE, DETF_VOLUME, DETF_CLOSED = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 EXPORTS = [
     "fdtdx_b200_last_error", "fdtdx_b200_version", "fdtdx_b200_plan_create", "fdtdx_b200_plan_destroy",

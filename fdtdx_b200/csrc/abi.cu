@@ -375,7 +375,7 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
   h.nvals = 0;
   const bool staged = (flags & DET_REDUCE) || ((flags & DET_SLICES) && (flags & DET_SLICE_MEAN));
   if (staged) {
-    h.nvals = (kind == FDTDX_DET_FIELD || kind == FDTDX_DET_PHASOR) ? d.ncomp : (keep_all ? 3 : 1);
+    h.nvals = (kind == FDTDX_DET_FIELD || kind == FDTDX_DET_PHASOR) ? d.ncomp : ((keep_all && !(flags & DET_CLOSED)) ? 3 : 1);
     if ((rc = to_device<float>(p, nullptr, (size_t)h.nvals * n, &d.scratch))) return rc;
   }
   p->dets.push_back(h);
@@ -1454,6 +1454,7 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
         for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
         if (!any_cot) continue;
       }
+      if (h.d.flags & DET_CLOSED) return fail(FDTDX_EUNSUPPORTED, "run_adjoint: closed-surface Poynting detectors have no adjoint kernel yet");
       if (!any_det) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
       any_det = true;
       GridDev G;

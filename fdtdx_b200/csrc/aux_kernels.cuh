@@ -57,6 +57,7 @@ struct DetDev {
 #define DET_SLICE_MEAN 16
 #define DET_KEEP_ALL 32
 #define DET_NEGATIVE 64
+#define DET_CLOSED 256  // Poynting: net flux through the box faces (aux = bit mask of the active axes)
 #define DET_VOLUME 128  // large exact-interpolation region: row-marching gather / sample kernels (det_volume.cuh)
 
 // CHK = false: the caller guarantees that (x, y, z) is inside the local grid (interior fast path of the
@@ -247,6 +248,11 @@ __device__ __forceinline__ void det_sample_body(const GridDev& G, const DetDev& 
   const int x = D.lo[0] + rx, y = D.lo[1] + ry, z = D.lo[2] + rz;
   // energy.py:118-143 with as_slices and no averaging keeps three planes of the region: O(surface) work
   if ((D.flags & DET_SLICES) && !(D.flags & DET_SLICE_MEAN) && rx != D.slice_idx[0] && ry != D.slice_idx[1] && rz != D.slice_idx[2]) return;
+  if (D.flags & DET_CLOSED) {  // only the shell contributes (interior scratch cells stay at their initial zero)
+    const bool fx = ((D.aux >> 0) & 1) && (rx == 0 || rx == ex - 1), fy = ((D.aux >> 1) & 1) && (ry == 0 || ry == ey - 1);
+    const bool fz = ((D.aux >> 2) & 1) && (rz == 0 || rz == ez - 1);
+    if (!fx && !fy && !fz) return;
+  }
   float Es[3], Hs[3];
   colocate(G, D, x, y, z, Es, Hs);
   det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es, Hs, nullptr);
@@ -343,7 +349,19 @@ __device__ __forceinline__ void det_emit(const GridDev& G, const DetDev& D, cons
   } else {  // Poynting (metrics.py:99-117, poynting_flux.py:171-195)
     float S[3] = {Es[1] * Hs[2] - Es[2] * Hs[1], Es[2] * Hs[0] - Es[0] * Hs[2], Es[0] * Hs[1] - Es[1] * Hs[0]};
     if (D.flags & DET_NEGATIVE) { S[0] = -S[0]; S[1] = -S[1]; S[2] = -S[2]; }
-    if (D.flags & DET_KEEP_ALL) {
+    if (D.flags & DET_CLOSED) {
+      // net_poynting_flux_through_box (metrics.py:120-160): +S_a * area on the max face, -S_a * area on
+      // the min face of every active axis; the per-cell terms are summed by det_reduce_all_kernel
+      const int r[3] = {rx, ry, rz}, e3[3] = {ex, ey, ez};
+      float c = 0.0f;
+      for (int a = 0; a < 3; ++a) {
+        if (!((D.aux >> a) & 1)) continue;
+        const float sw = S[a] * D.weights[a * n + cell];
+        if (r[a] == e3[a] - 1) c = c + sw;
+        if (r[a] == 0) c = c - sw;
+      }
+      D.scratch[cell] = c;
+    } else if (D.flags & DET_KEEP_ALL) {
       for (int c = 0; c < 3; ++c) {
         if (staged) D.scratch[c * n + cell] = S[c];
         else D.state[0][((long long)slot * 3 + c) * n + cell] = S[c];
@@ -361,7 +379,7 @@ __global__ void det_reduce_all_kernel(const DetDev D, const int t, const int nva
   const long long n = (long long)(D.hi[0] - D.lo[0]) * (D.hi[1] - D.lo[1]) * (D.hi[2] - D.lo[2]);
   __shared__ float sm[1024];
   float acc = 0.0f;
-  const float* w = D.weights ? D.weights + (w_per_val ? (long long)v * n : 0) : nullptr;
+  const float* w = (D.weights && !(D.flags & DET_CLOSED)) ? D.weights + (w_per_val ? (long long)v * n : 0) : nullptr;
   for (long long c = threadIdx.x; c < n; c += blockDim.x) {
     const float val = D.scratch[v * n + c];
     acc += w ? val * w[c] : val;

@@ -20,7 +20,7 @@
 
 #define DETV_ROWS 8     // y rows (warps) per CTA
 #define DETV_TZ 128     // z cells per warp pass
-#define DETV_XC 8       // x planes per CTA
+#define DETV_XC 4       // x planes per CTA
 
 // aligned H_prev box: element (c, a, b, g) holds H_c(lo_x - 1 + a, lo_y - 1 + b, hz0 + g)
 __device__ __forceinline__ long long detv_hidx(const DetDev& D, int c, int a, int b) {
@@ -69,40 +69,53 @@ struct Row4 {
   float v[4];
   float nx;  // the element after v[3] (k+1 of the lane's last cell)
 };
+// A row operand is fetched in two phases so that the ~20 row loads of a plane are all in flight before
+// the first warp shuffle (a shuffle right after each load serialises the round trips: ncu showed 12 us
+// per plane).  Phase 1 (RowLd): the 128-bit load plus, for the lane that cannot get k+1 from its
+// neighbour, the scalar behind it.  Phase 2 (row_finish): k+1 from the next lane.
+struct RowLd {
+  float4 t;
+  float tail;  // element z0+4 where the next lane cannot supply it (lane 31 / end of the row); else unused
+  bool own_tail;
+};
 
-// Row (c, x, y) of a grid array at cells z0..z0+3 (+ the following element).  ok = false: halo row of zeros.
-__device__ __forceinline__ Row4 detv_ld_grid(const GridDev& G, const float* F, int c, int x, int y, int z0, const int lane) {
-  Row4 r;
+// Row (c, x, y) of a grid array at cells z0..z0+3; out-of-grid rows follow the halo rule (zero / wrap).
+__device__ __forceinline__ RowLd detv_ld_grid(const GridDev& G, const float* F, int c, int x, int y, int z0, const int lane, const bool want_next) {
+  RowLd r;
   bool zero = false;
   if (x < 0) { if (G.wrap[0]) x += G.nx; else zero = true; }
   if (y < 0) { if (G.wrap[1]) y += G.ny; else zero = true; }
   const long long N = (long long)G.nx * G.ny * G.nz;
   const float* row = F + c * N + ((long long)x * G.ny + y) * G.nz;
-  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.t = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool in = !zero && z0 < G.nz;
-  if (in) t = *reinterpret_cast<const float4*>(row + z0);
-  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-  float nxt = __shfl_down_sync(0xffffffffu, t.x, 1);
-  if (lane == 31 || z0 + 4 >= G.nz) {
-    nxt = 0.0f;
-    if (in) {
-      if (z0 + 4 < G.nz) nxt = row[z0 + 4];
-      else if (G.wrap[2]) nxt = row[0];
-    }
+  if (in) r.t = *reinterpret_cast<const float4*>(row + z0);
+  r.own_tail = want_next && (lane == 31 || z0 + 4 >= G.nz);
+  r.tail = 0.0f;
+  if (r.own_tail && in) {
+    if (z0 + 4 < G.nz) r.tail = row[z0 + 4];
+    else if (G.wrap[2]) r.tail = row[0];
   }
-  r.nx = nxt;
   return r;
 }
 // The same row of the aligned H_prev box (halo rules were applied by the gather).
-__device__ __forceinline__ Row4 detv_ld_prev(const DetDev& D, int c, int x, int y, int z0, const int lane, const bool in) {
-  Row4 r;
+__device__ __forceinline__ RowLd detv_ld_prev(const DetDev& D, int c, int x, int y, int z0, const int lane, const bool in, const bool want_next) {
+  RowLd r;
   const float* row = D.hprev + detv_hidx(D, c, x - D.lo[0] + 1, y - D.lo[1] + 1) + (z0 - D.hz0);
-  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in) t = *reinterpret_cast<const float4*>(row);
-  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-  float nxt = __shfl_down_sync(0xffffffffu, t.x, 1);
-  if (lane == 31) nxt = (in && (z0 + 4 - D.hz0) < D.hrow) ? row[4] : 0.0f;
-  r.nx = nxt;
+  r.t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in) r.t = *reinterpret_cast<const float4*>(row);
+  r.own_tail = want_next && lane == 31;
+  r.tail = (r.own_tail && in && (z0 + 4 - D.hz0) < D.hrow) ? row[4] : 0.0f;
+  return r;
+}
+__device__ __forceinline__ Row4 row_finish(const RowLd& l, const bool want_next) {
+  Row4 r;
+  r.v[0] = l.t.x; r.v[1] = l.t.y; r.v[2] = l.t.z; r.v[3] = l.t.w;
+  r.nx = 0.0f;
+  if (want_next) {
+    const float nxt = __shfl_down_sync(0xffffffffu, l.t.x, 1);
+    r.nx = l.own_tail ? l.tail : nxt;
+  }
   return r;
 }
 __device__ __forceinline__ float row_at(const Row4& r, int e) { return e < 4 ? r.v[e] : r.nx; }
@@ -116,7 +129,7 @@ __device__ __forceinline__ Row4 detv_hbar(const Row4& p, const Row4& h) {
   return r;
 }
 
-// grid: (z tiles of 128, y tiles of 8 rows, x chunks of 8 planes) of the detector box, blockIdx.z also
+// grid: (z tiles of 128, y tiles of 8 rows, x chunks of DETV_XC planes) of the detector box, blockIdx.z also
 // enumerates detectors: z = det * nxc + chunk.
 template <bool EXACT>
 __global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse, const int nxc_max) {
@@ -149,18 +162,26 @@ __global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const D
     float Es[4][3], Hs[4][3];
     if (row_ok) {  // warp-uniform: the shuffles inside the loaders need the whole warp
       if (EXACT) {
-        const Row4 exc = detv_ld_grid(G, G.E, 0, x, y, z0, lane), exm = detv_ld_grid(G, G.E, 0, x - 1, y, z0, lane);
-        const Row4 eyc = detv_ld_grid(G, G.E, 1, x, y, z0, lane), eym = detv_ld_grid(G, G.E, 1, x, y - 1, z0, lane);
-        const Row4 ezc = detv_ld_grid(G, G.E, 2, x, y, z0, lane);
         const bool in = row_ok && (z0 - D.hz0 + 4 <= D.hrow);  // inside the gathered row (covers hi_z: the k+1 halo)
-        const Row4 hx_c = detv_hbar(detv_ld_prev(D, 0, x, y, z0, lane, in), detv_ld_grid(G, G.H, 0, x, y, z0, lane));
-        const Row4 hx_m = detv_hbar(detv_ld_prev(D, 0, x, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 0, x, y - 1, z0, lane));
-        const Row4 hy_c = detv_hbar(detv_ld_prev(D, 1, x, y, z0, lane, in), detv_ld_grid(G, G.H, 1, x, y, z0, lane));
-        const Row4 hy_m = detv_hbar(detv_ld_prev(D, 1, x - 1, y, z0, lane, in), detv_ld_grid(G, G.H, 1, x - 1, y, z0, lane));
-        const Row4 hz_cc = detv_hbar(detv_ld_prev(D, 2, x, y, z0, lane, in), detv_ld_grid(G, G.H, 2, x, y, z0, lane));
-        const Row4 hz_mc = detv_hbar(detv_ld_prev(D, 2, x - 1, y, z0, lane, in), detv_ld_grid(G, G.H, 2, x - 1, y, z0, lane));
-        const Row4 hz_cm = detv_hbar(detv_ld_prev(D, 2, x, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 2, x, y - 1, z0, lane));
-        const Row4 hz_mm = detv_hbar(detv_ld_prev(D, 2, x - 1, y - 1, z0, lane, in), detv_ld_grid(G, G.H, 2, x - 1, y - 1, z0, lane));
+        // phase 1: every load of this plane
+        const RowLd l_exc = detv_ld_grid(G, G.E, 0, x, y, z0, lane, true), l_exm = detv_ld_grid(G, G.E, 0, x - 1, y, z0, lane, true);
+        const RowLd l_eyc = detv_ld_grid(G, G.E, 1, x, y, z0, lane, true), l_eym = detv_ld_grid(G, G.E, 1, x, y - 1, z0, lane, true);
+        const RowLd l_ezc = detv_ld_grid(G, G.E, 2, x, y, z0, lane, false);
+        const RowLd p_hxc = detv_ld_prev(D, 0, x, y, z0, lane, in, false), n_hxc = detv_ld_grid(G, G.H, 0, x, y, z0, lane, false);
+        const RowLd p_hxm = detv_ld_prev(D, 0, x, y - 1, z0, lane, in, false), n_hxm = detv_ld_grid(G, G.H, 0, x, y - 1, z0, lane, false);
+        const RowLd p_hyc = detv_ld_prev(D, 1, x, y, z0, lane, in, false), n_hyc = detv_ld_grid(G, G.H, 1, x, y, z0, lane, false);
+        const RowLd p_hym = detv_ld_prev(D, 1, x - 1, y, z0, lane, in, false), n_hym = detv_ld_grid(G, G.H, 1, x - 1, y, z0, lane, false);
+        const RowLd p_zcc = detv_ld_prev(D, 2, x, y, z0, lane, in, true), n_zcc = detv_ld_grid(G, G.H, 2, x, y, z0, lane, true);
+        const RowLd p_zmc = detv_ld_prev(D, 2, x - 1, y, z0, lane, in, true), n_zmc = detv_ld_grid(G, G.H, 2, x - 1, y, z0, lane, true);
+        const RowLd p_zcm = detv_ld_prev(D, 2, x, y - 1, z0, lane, in, true), n_zcm = detv_ld_grid(G, G.H, 2, x, y - 1, z0, lane, true);
+        const RowLd p_zmm = detv_ld_prev(D, 2, x - 1, y - 1, z0, lane, in, true), n_zmm = detv_ld_grid(G, G.H, 2, x - 1, y - 1, z0, lane, true);
+        // phase 2: k+1 neighbours by shuffle, time-centred H
+        const Row4 exc = row_finish(l_exc, true), exm = row_finish(l_exm, true), eyc = row_finish(l_eyc, true), eym = row_finish(l_eym, true);
+        const Row4 ezc = row_finish(l_ezc, false);
+        const Row4 hx_c = detv_hbar(row_finish(p_hxc, false), row_finish(n_hxc, false)), hx_m = detv_hbar(row_finish(p_hxm, false), row_finish(n_hxm, false));
+        const Row4 hy_c = detv_hbar(row_finish(p_hyc, false), row_finish(n_hyc, false)), hy_m = detv_hbar(row_finish(p_hym, false), row_finish(n_hym, false));
+        const Row4 hz_cc = detv_hbar(row_finish(p_zcc, true), row_finish(n_zcc, true)), hz_mc = detv_hbar(row_finish(p_zmc, true), row_finish(n_zmc, true));
+        const Row4 hz_cm = detv_hbar(row_finish(p_zcm, true), row_finish(n_zcm, true)), hz_mm = detv_hbar(row_finish(p_zmm, true), row_finish(n_zmm, true));
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           // same expressions, same order as colocate_interior / colocate_t (curl.py:120-222)
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const D
       } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const Row4 a = detv_ld_grid(G, G.E, c, x, y, z0, lane), b = detv_ld_grid(G, G.H, c, x, y, z0, lane);
+          const Row4 a = row_finish(detv_ld_grid(G, G.E, c, x, y, z0, lane, false), false), b = row_finish(detv_ld_grid(G, G.H, c, x, y, z0, lane, false), false);
 #pragma unroll
           for (int e = 0; e < 4; ++e) { Es[e][c] = a.v[e]; Hs[e][c] = b.v[e]; }
         }

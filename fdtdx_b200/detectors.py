@@ -248,6 +248,50 @@ class PhasorDetector(Detector):
         return {"phasor": ((nf, nc, *gs), np.complex64)}
 
 
+def _face_area_weights(config, slice_tuple, axis: int) -> np.ndarray:
+    """``_resolve_face_area_weights`` (``poynting_flux.py:14-43``)."""
+    grid = config.resolved_grid
+    if grid is not None:
+        return grid.face_area(slice_tuple, axis)
+    sp = config.uniform_spacing()
+    shape = tuple(hi - lo for lo, hi in slice_tuple)
+    return (np.ones(shape, _f32) * _f32(sp) * _f32(sp)).astype(_f32)
+
+
+def _phasor_poynting_vector(phasors: np.ndarray) -> np.ndarray:
+    """``Re(E x conj(H))`` of a (nf, 6, *spatial) phasor stack (``poynting_flux.py:58-70``)."""
+    E, H = phasors[:, :3], np.conj(phasors[:, 3:])
+    return np.stack([E[:, 1] * H[:, 2] - E[:, 2] * H[:, 1], E[:, 2] * H[:, 0] - E[:, 0] * H[:, 2], E[:, 0] * H[:, 1] - E[:, 1] * H[:, 0]], axis=1).real
+
+
+@dataclass
+class ClosedSurfacePoyntingFluxDetector(Detector):
+    """Net Poynting flux through the faces of the detector box, one scalar per recorded step
+    (``poynting_flux.py:199-284``, ``metrics.py:120-160``): for every active axis a,
+    ``+sum(S_a * area)`` on the max face and ``-sum(S_a * area)`` on the min face."""
+
+    orientation: Literal["outward", "inward"] = "outward"
+    axes: tuple[int, ...] | None = None
+    _face_area_weights_per_axis: np.ndarray | None = None
+
+    def _resolve_active_axes(self) -> tuple[int, ...]:
+        if self.axes is not None:
+            return tuple(self.axes)
+        return tuple(a for a in range(3) if self.grid_shape[a] > 1)
+
+    def place_on_grid(self, config):
+        if self.orientation not in ("outward", "inward"):
+            raise ValueError(f"orientation must be 'outward' or 'inward', got {self.orientation!r}")
+        if self.axes is not None and any(a not in (0, 1, 2) for a in self.axes):
+            raise ValueError(f"axes entries must be in (0, 1, 2), got {self.axes}")
+        super().place_on_grid(config)
+        self._face_area_weights_per_axis = np.stack([_face_area_weights(config, self.grid_slice_tuple, a) for a in range(3)])
+        return self
+
+    def _shape_dtype_single_time_step(self):
+        return {"poynting_flux": ((1,), self.dtype)}
+
+
 def phasor_table(det: "PhasorDetector", T: int, dt: float) -> np.ndarray:
     """``exp(+i w t dt)`` for every time step and frequency as (T, nf, 2) float32 [cos, sin], rounded
     like ``phasor.py:186-214``: ``time_passed = t * dt`` and ``w * time_passed`` in float32."""
@@ -260,3 +304,111 @@ def phasor_table(det: "PhasorDetector", T: int, dt: float) -> np.ndarray:
 class ModeOverlapDetector(PhasorDetector):
     """``mode.py:193-``: for the time step this *is* a ``PhasorDetector`` (all six components);
     the overlap integral is post-processing and out of scope."""
+
+
+@dataclass
+class PhasorPoyntingFluxDetector(PhasorDetector):
+    """Frequency-domain plane flux (``poynting_flux.py:287-388``): for the time step a six-component
+    ``PhasorDetector``; ``compute_poynting_flux`` is the post-run surface integral."""
+
+    direction: Literal["+", "-"] = "+"
+    fixed_propagation_axis: int | None = None
+    keep_all_components: bool = False
+    _cached_face_area_weights: np.ndarray | None = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.components, self.reduce_volume = COMPONENT_NAMES, False
+
+    @property
+    def propagation_axis(self) -> int:
+        if self.fixed_propagation_axis is not None:
+            if self.fixed_propagation_axis not in (0, 1, 2):
+                raise Exception(f"Invalid: {self.fixed_propagation_axis=}")
+            return self.fixed_propagation_axis
+        if sum(a == 1 for a in self.grid_shape) != 1:
+            raise Exception(f"Invalid poynting flux detector shape: {self.grid_shape}")
+        return self.grid_shape.index(1)
+
+    def place_on_grid(self, config):
+        super().place_on_grid(config)
+        if self.keep_all_components:
+            self._cached_face_area_weights = np.stack([_face_area_weights(config, self.grid_slice_tuple, a) for a in range(3)])
+        else:
+            self._cached_face_area_weights = _face_area_weights(config, self.grid_slice_tuple, self.propagation_axis)
+        return self
+
+    def compute_poynting_flux(self, state) -> np.ndarray:
+        ph = np.asarray(state["phasor"].cpu() if hasattr(state["phasor"], "cpu") else state["phasor"])[0]
+        pv = _phasor_poynting_vector(ph)
+        if self.direction == "-":
+            pv = -pv
+        w = self._cached_face_area_weights
+        flux = (pv * w[None]).sum(axis=(2, 3, 4)) if self.keep_all_components else (pv[:, self.propagation_axis] * w).sum(axis=(1, 2, 3))
+        return 0.5 * flux if self.scaling_mode == "continuous" else flux
+
+
+@dataclass
+class ClosedSurfacePhasorPoyntingFluxDetector(PhasorDetector):
+    """Frequency-domain closed-surface flux (``poynting_flux.py:391-540``): only the hollow shell is
+    recorded - one six-component phasor plane per face of every active axis (state keys
+    ``phasor_axis{a}_min`` / ``_max``); ``compute_net_flux`` integrates after the run.  The plan lowers
+    it to one plane phasor accumulation per face."""
+
+    orientation: Literal["outward", "inward"] = "outward"
+    axes: tuple[int, ...] | None = None
+    _face_area_weights_per_axis: tuple | None = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.components, self.reduce_volume = COMPONENT_NAMES, False
+
+    def _resolve_active_axes(self) -> tuple[int, ...]:
+        if self.axes is not None:
+            return tuple(self.axes)
+        return tuple(a for a in range(3) if self.grid_shape[a] > 1)
+
+    def face_slices(self):
+        """[(state key, grid_slice_tuple of the one-cell-thick face)] in state order."""
+        out = []
+        for a in self._resolve_active_axes():
+            lo, hi = self.grid_slice_tuple[a]
+            for side, (l_, h_) in (("min", (lo, lo + 1)), ("max", (hi - 1, hi))):
+                sl = list(self.grid_slice_tuple)
+                sl[a] = (l_, h_)
+                out.append((f"phasor_axis{a}_{side}", tuple(sl)))
+        return out
+
+    def place_on_grid(self, config):
+        if self.orientation not in ("outward", "inward"):
+            raise ValueError(f"orientation must be 'outward' or 'inward', got {self.orientation!r}")
+        if self.axes is not None and any(a not in (0, 1, 2) for a in self.axes):
+            raise ValueError(f"axes entries must be in (0, 1, 2), got {self.axes}")
+        super().place_on_grid(config)
+        ws = []
+        for a in range(3):
+            w = _face_area_weights(config, self.grid_slice_tuple, a)
+            idx = [slice(None)] * 3
+            idx[a] = slice(0, 1)
+            ws.append(w[tuple(idx)])
+        self._face_area_weights_per_axis = tuple(ws)
+        return self
+
+    def _shape_dtype_single_time_step(self):
+        nf = len(self.wave_characters)
+        out = {}
+        for key, sl in self.face_slices():
+            out[key] = ((nf, 6, *[h_ - l_ for l_, h_ in sl]), np.complex64)
+        return out
+
+    def compute_net_flux(self, state) -> np.ndarray:
+        net = np.zeros(len(self.wave_characters), np.float64)
+        get = lambda k: np.asarray(state[k].cpu() if hasattr(state[k], "cpu") else state[k])[0]
+        for a in self._resolve_active_axes():
+            area = self._face_area_weights_per_axis[a]
+            for side, sign in (("max", 1.0), ("min", -1.0)):
+                s_a = _phasor_poynting_vector(get(f"phasor_axis{a}_{side}"))[:, a]
+                net = net + sign * (s_a * area).sum(axis=(1, 2, 3))
+        if self.orientation == "inward":
+            net = -net
+        return 0.5 * net if self.scaling_mode == "continuous" else net

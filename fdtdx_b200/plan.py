@@ -20,6 +20,8 @@ from fdtdx_b200.boundaries import PerfectElectricConductor, PerfectMagneticCondu
 from fdtdx_b200.constants import c as c0
 from fdtdx_b200.detectors import (
     COMPONENT_NAMES,
+    ClosedSurfacePhasorPoyntingFluxDetector,
+    ClosedSurfacePoyntingFluxDetector,
     EnergyDetector,
     FieldDetector,
     PhasorDetector,
@@ -279,11 +281,29 @@ class Plan:
 
     def _add_detectors(self):
         cfg = self.config
-        self.det_index = {}
+        self.det_index, self.det_faces = {}, {}
         for det in self.objects.detectors:
             dlo, dhi = det.grid_slice_tuple[0]
             if dhi <= self.x0 or dlo >= self.x1:
                 continue  # lives on another rank's slab
+            if isinstance(det, ClosedSurfacePhasorPoyntingFluxDetector):
+                # hollow shell (poynting_flux.py:391-503): one six-component phasor plane per face
+                if self.x0 != 0 or self.x1 != self.global_shape[0]:
+                    raise NotImplementedError("closed-surface phasor detectors on x-sharded plans")
+                faces = []
+                for key, sl in det.face_slices():
+                    face = PhasorDetector(name=f"{det.name}/{key}", grid_slice_tuple=sl, wave_characters=det.wave_characters, components=COMPONENT_NAMES,
+                                          scaling_mode=det.scaling_mode, dft_subsample=det.dft_subsample, switch=det.switch,
+                                          exact_interpolation=det.exact_interpolation, inverse=det.inverse)
+                    face.place_on_grid(cfg)
+                    faces.append((key, self._add_detector(face)))
+                self.det_faces[det.name] = faces
+                continue
+            self.det_index[det.name] = self._add_detector(det)
+
+    def _add_detector(self, det) -> int:
+        cfg = self.config
+        if True:
             flags = 0
             if det.exact_interpolation:
                 flags |= _lib.DETF_EXACT
@@ -317,6 +337,15 @@ class Plan:
                 elif det.reduce_volume:
                     flags |= _lib.DETF_REDUCE
                     weights = det._cached_cell_volume_weights
+            elif isinstance(det, ClosedSurfacePoyntingFluxDetector):
+                # net flux through the box faces (poynting_flux.py:199-284): a staged per-cell sum of
+                # (+/-) S_a * area over the face cells of every active axis, reduced like reduce_volume
+                kind = _lib.DET_POYNTING
+                flags |= _lib.DETF_CLOSED | _lib.DETF_REDUCE | _lib.DETF_KEEP_ALL
+                aux = sum(1 << a for a in det._resolve_active_axes())
+                if det.orientation == "inward":
+                    flags |= _lib.DETF_NEGATIVE
+                weights = det._face_area_weights_per_axis
             elif isinstance(det, PoyntingFluxDetector):
                 kind = _lib.DET_POYNTING
                 if det.keep_all_components:
@@ -336,7 +365,8 @@ class Plan:
             # with 128-bit accesses instead of one thread per cell (csrc/det_volume.cuh)
             ext = [h_ - l_ for l_, h_ in zip(lo, hi)]
             if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0":
-                if not (isinstance(det, EnergyDetector) and det.as_slices and not det.use_mean):  # three planes only: O(surface) already
+                surface_only = (isinstance(det, EnergyDetector) and det.as_slices and not det.use_mean) or isinstance(det, ClosedSurfacePoyntingFluxDetector)
+                if not surface_only:  # three planes / the box shell only: O(surface) work already
                     flags |= _lib.DETF_VOLUME
             on = self._pad_T(np.ascontiguousarray(det._is_on_at_time_step_arr, dtype=np.uint8))
             idx = self._pad_T(np.ascontiguousarray(det._time_step_to_arr_idx, dtype=np.int32))
@@ -350,7 +380,7 @@ class Plan:
                     _fptr(w), nf, _fptr(None if table is None else table.reshape(-1)), _fptr(window), scale, _iarr(slice_idx),
                 )
             )
-            self.det_index[det.name] = di
+            return di
 
     def _set_recorder(self):
         gc = self.config.gradient_config
@@ -453,6 +483,10 @@ class Plan:
                 self._bind(_lib.SLOT_C4, 0, arrays.dispersive_c4, f32)
             check(self.lib.fdtdx_b200_set_parity(self.h, 0, 0, 0))
         for det in self.objects.detectors:
+            if det.name in self.det_faces:
+                for key, di in self.det_faces[det.name]:
+                    self._bind(_lib.SLOT_DET_STATE, 4 * di, arrays.detector_states[det.name][key])
+                continue
             if det.name not in self.det_index:
                 continue
             di = self.det_index[det.name]
@@ -571,6 +605,10 @@ class Plan:
                         self._cot_psi[key] = torch.zeros(shp, dtype=torch.float32, device=src[pml.name][w].device)
                     self._bind(slot, 2 * q + w, self._cot_psi[key])
         for det in self.objects.detectors:
+            if det.name in self.det_faces:
+                for key, di in self.det_faces[det.name]:
+                    self._bind(_lib.SLOT_COT_DET, 4 * di, cot_det.get(det.name, {}).get(key))
+                continue
             if det.name not in self.det_index:
                 continue
             di = self.det_index[det.name]

@@ -33,6 +33,8 @@ from fdtdx_b200.constants import eta0
 from fdtdx_b200.container import ArrayContainer, RecordingState, _TorchLeaf
 from fdtdx_b200.detectors import (
     COMPONENT_NAMES,
+    ClosedSurfacePhasorPoyntingFluxDetector,
+    ClosedSurfacePoyntingFluxDetector,
     EnergyDetector,
     FieldDetector,
     PhasorDetector,
@@ -697,6 +699,32 @@ def _select_components(det, E, H):
 
 def detector_update(det, time_step: int, E, H, state: dict, inv_eps, inv_mu) -> dict:
     state = {k: v.copy() for k, v in state.items()}
+    if isinstance(det, ClosedSurfacePhasorPoyntingFluxDetector):
+        # poynting_flux.py:476-503: the two boundary planes of every active axis, no window factor
+        time_passed = F(time_step) * F(det._dt)
+        EH = np.stack([E[0], E[1], E[2], H[0], H[1], H[2]], axis=0)
+        ang = (det._angular_frequencies * time_passed).astype(F)
+        ph = (np.cos(ang) + 1j * np.sin(ang)).astype(np.complex64).reshape((len(ang),) + (1,) * EH.ndim)
+        new = ((EH[None].astype(np.complex64) * ph).astype(np.complex64) * np.complex64(det._static_scale())).astype(np.complex64)
+        for a in det._resolve_active_axes():
+            for side, sl in (("min", slice(0, 1)), ("max", slice(-1, None))):
+                idx = [slice(None)] * new.ndim
+                idx[a + 2] = sl
+                key = f"phasor_axis{a}_{side}"
+                face = new[tuple(idx)][None]
+                state[key] = (state[key] - face if det.inverse else state[key] + face).astype(np.complex64)
+        return state
+    if isinstance(det, ClosedSurfacePoyntingFluxDetector):
+        # poynting_flux.py:263-284 + metrics.py:120-160
+        pf = compute_poynting_flux(E, H)
+        net = F(0.0)
+        for a in det._resolve_active_axes():
+            weighted = (pf[a] * det._face_area_weights_per_axis[a]).astype(F)
+            net = net + np.take(weighted, -1, axis=a).sum(dtype=F) - np.take(weighted, 0, axis=a).sum(dtype=F)
+        if det.orientation == "inward":
+            net = -net
+        state["poynting_flux"][int(det._time_step_to_arr_idx[time_step])] = F(net)
+        return state
     if isinstance(det, PhasorDetector):
         time_passed = F(time_step) * F(det._dt)
         scale = det._static_scale()

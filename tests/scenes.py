@@ -141,6 +141,10 @@ def build_scene(
         "poynting_all": lambda: fx.PoyntingFluxDetector(name="poynting_all", grid_slice_tuple=inner, direction="+", keep_all_components=True, fixed_propagation_axis=2),
         "phasor": lambda: fx.PhasorDetector(name="phasor", grid_slice_tuple=xplane, wave_characters=(wc, fx.WaveCharacter(wavelength=1.0e-6))),
         "phasor_pulse": lambda: fx.ModeOverlapDetector(name="phasor_pulse", grid_slice_tuple=plane, wave_characters=(wc,), scaling_mode="pulse", dft_subsample=2),
+        "closed_flux": lambda: fx.ClosedSurfacePoyntingFluxDetector(name="closed_flux", grid_slice_tuple=((off, nx - off), (off, ny - off), (off, nz - off))),
+        "closed_flux_in": lambda: fx.ClosedSurfacePoyntingFluxDetector(name="closed_flux_in", grid_slice_tuple=inner, orientation="inward", axes=(0, 2), switch=fx.OnOffSwitch(interval=2)),
+        "closed_phasor": lambda: fx.ClosedSurfacePhasorPoyntingFluxDetector(name="closed_phasor", grid_slice_tuple=((off, nx - off), (off, ny - off), (off, nz - off)), wave_characters=(wc,)),
+        "phasor_flux": lambda: fx.PhasorPoyntingFluxDetector(name="phasor_flux", grid_slice_tuple=plane, wave_characters=(wc, fx.WaveCharacter(wavelength=1.0e-6)), direction="+"),
         "phasor_reduce": lambda: fx.PhasorDetector(name="phasor_reduce", grid_slice_tuple=inner, wave_characters=(wc,), reduce_volume=True, components=("Ex", "Hy", "Hz")),
     }
     for d in detectors:
