@@ -25,6 +25,7 @@ from fdtdx_b200.detectors import (
     PhasorPoyntingFluxDetector,
     PoyntingFluxDetector,
 )
+from fdtdx_b200.device import ClosestIndex, Device, GaussianSmoothing2D, TanhProjection
 from fdtdx_b200.initialization import Material, UniformMaterialObject, init_arrays, place_objects
 from fdtdx_b200.profile import CustomTimeSignalProfile, GaussianPulseProfile, SingleFrequencyProfile
 from fdtdx_b200.recorder import DtypeConversion, LinearReconstructEveryK, Recorder

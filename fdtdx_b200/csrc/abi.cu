@@ -366,11 +366,9 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
   if (h.volume && kind == FDTDX_DET_ENERGY && (flags & DET_SLICES) && (flags & DET_SLICE_MEAN)) {
     const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
     d.npart[0] = (hi[2] - d.hz0 + DETV_TZ - 1) / DETV_TZ;
-    d.npart[1] = (ey + DETV_ROWS - 1) / DETV_ROWS;
-    d.npart[2] = (ex + DETV_XC - 1) / DETV_XC;
+    d.npart[1] = d.npart[2] = 0;
+    (void)ez;
     if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[0] * ex * ey, &d.part[0]))) return rc;
-    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[1] * ex * ez, &d.part[1]))) return rc;
-    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[2] * ey * ez, &d.part[2]))) return rc;
   }
   h.nvals = 0;
   const bool staged = (flags & DET_REDUCE) || ((flags & DET_SLICES) && (flags & DET_SLICE_MEAN));

@@ -75,51 +75,19 @@ struct Row4 {
 // neighbour, the scalar behind it.  Phase 2 (row_finish): k+1 from the next lane.
 struct RowLd {
   float4 t;
-  float tail;  // element z0+4 where the next lane cannot supply it (lane 31 / end of the row); else unused
-  bool own_tail;
+  float tail;
 };
-
-// Row (c, x, y) of a grid array at cells z0..z0+3; out-of-grid rows follow the halo rule (zero / wrap).
-__device__ __forceinline__ RowLd detv_ld_grid(const GridDev& G, const float* F, int c, int x, int y, int z0, const int lane, const bool want_next) {
-  RowLd r;
-  bool zero = false;
-  if (x < 0) { if (G.wrap[0]) x += G.nx; else zero = true; }
-  if (y < 0) { if (G.wrap[1]) y += G.ny; else zero = true; }
-  const long long N = (long long)G.nx * G.ny * G.nz;
-  const float* row = F + c * N + ((long long)x * G.ny + y) * G.nz;
-  r.t = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool in = !zero && z0 < G.nz;
-  if (in) r.t = *reinterpret_cast<const float4*>(row + z0);
-  r.own_tail = want_next && (lane == 31 || z0 + 4 >= G.nz);
-  r.tail = 0.0f;
-  if (r.own_tail && in) {
-    if (z0 + 4 < G.nz) r.tail = row[z0 + 4];
-    else if (G.wrap[2]) r.tail = row[0];
-  }
-  return r;
-}
-// The same row of the aligned H_prev box (halo rules were applied by the gather).
-__device__ __forceinline__ RowLd detv_ld_prev(const DetDev& D, int c, int x, int y, int z0, const int lane, const bool in, const bool want_next) {
-  RowLd r;
-  const float* row = D.hprev + detv_hidx(D, c, x - D.lo[0] + 1, y - D.lo[1] + 1) + (z0 - D.hz0);
-  r.t = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in) r.t = *reinterpret_cast<const float4*>(row);
-  r.own_tail = want_next && lane == 31;
-  r.tail = (r.own_tail && in && (z0 + 4 - D.hz0) < D.hrow) ? row[4] : 0.0f;
-  return r;
-}
-__device__ __forceinline__ Row4 row_finish(const RowLd& l, const bool want_next) {
+__device__ __forceinline__ Row4 row_finish(const RowLd& l, const bool want_next, const bool own_tail) {
   Row4 r;
   r.v[0] = l.t.x; r.v[1] = l.t.y; r.v[2] = l.t.z; r.v[3] = l.t.w;
   r.nx = 0.0f;
   if (want_next) {
     const float nxt = __shfl_down_sync(0xffffffffu, l.t.x, 1);
-    r.nx = l.own_tail ? l.tail : nxt;
+    r.nx = own_tail ? l.tail : nxt;
   }
   return r;
 }
 __device__ __forceinline__ float row_at(const Row4& r, int e) { return e < 4 ? r.v[e] : r.nx; }
-
 // H_bar = (H_prev + H) / 2 per element (update.py:1088, 1098)
 __device__ __forceinline__ Row4 detv_hbar(const Row4& p, const Row4& h) {
   Row4 r;
@@ -129,12 +97,20 @@ __device__ __forceinline__ Row4 detv_hbar(const Row4& p, const Row4& h) {
   return r;
 }
 
-// grid: (z tiles of 128, y tiles of 8 rows, x chunks of DETV_XC planes) of the detector box, blockIdx.z also
-// enumerates detectors: z = det * nxc + chunk.
+// Addresses of the four stencil rows (x, y), (x-1, y), (x, y-1), (x-1, y-1) of one thread: element
+// offsets into a (Nx, Ny, Nz) component, or "zero row" where the halo rule says so.
+struct RowSet {
+  long long o[4];
+  bool zero[4];
+};
+
+// grid: (z tiles of 128, y tiles of 8 rows, x chunks of DETV_XC planes) of the detector box; blockIdx.z
+// also enumerates detectors: z = det * nxc + chunk.  No CTA-wide barrier in the plane loop: warps are
+// independent (slice means: the z sum is a warp reduction, the y / x sums are folded from the per-cell
+// energies by det_mean_finish_kernel).
 template <bool EXACT>
-__global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse, const int nxc_max) {
+__global__ void __launch_bounds__(256, 2) det_march_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse, const int nxc_max) {
   __shared__ DetDev sD;
-  __shared__ float s_rows[DETV_ROWS][DETV_TZ];
   const int di = blockIdx.z / nxc_max, xc = blockIdx.z - di * nxc_max;
   {
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -151,64 +127,107 @@ __global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const D
   const int z0 = zt0 + 4 * lane;
   const int ry = blockIdx.y * DETV_ROWS + wrow;
   const int rx0 = xc * DETV_XC, rx1 = min(rx0 + DETV_XC, ex);
-  if (zt0 >= D.hi[2] || rx0 >= ex || blockIdx.y * DETV_ROWS >= ey) return;  // CTA-uniform
-  const bool row_ok = ry < ey;
+  if (zt0 >= D.hi[2] || rx0 >= ex || ry >= ey) return;  // warp-uniform
   const int y = D.lo[1] + ry;
   const bool fused_mean = (D.flags & DET_SLICES) && (D.flags & DET_SLICE_MEAN) && D.kind == 1;
-  const bool lane_in = row_ok && z0 < G.nz && z0 < D.hi[2] && z0 + 4 > D.lo[2];
-  float accx[4] = {0.f, 0.f, 0.f, 0.f};  // sum over this chunk's x planes (YZ plane partial)
+  const bool z_in = z0 < G.nz;                                        // this lane holds grid cells
+  const bool lane_in = z_in && z0 < D.hi[2] && z0 + 4 > D.lo[2];      // ... and cells of the region
+  const bool hp_in = (z0 - D.hz0 + 4 <= D.hrow);                      // inside the gathered row (covers hi_z)
+  const bool own_tail = (lane == 31) || (z0 + 4 >= G.nz);             // k+1 of the last cell is not in the next lane
+  const long long plane = (long long)G.ny * G.nz, N = plane * G.nx;
+  // y-neighbour row (halo rule on the min-y face)
+  long long dy = -(long long)G.nz;
+  bool y_zero = false;
+  if (y == 0) { if (G.wrap[1]) dy = (long long)(G.ny - 1) * G.nz; else y_zero = true; }
+  // H_prev box strides
+  const int hsy = ey + 1;
+  const long long h_row = D.hrow, h_pl = (long long)hsy * D.hrow, h_c = (long long)(ex + 1) * h_pl;
+  const float* const hp0 = D.hprev + ((long long)(ry + 1)) * h_row + (z0 - D.hz0);  // (c=0, a=0, b=ry+1)
+
+  auto ld = [&](const float* F, const long long off, const bool zero, const bool want_next) {
+    RowLd r;
+    r.t = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.tail = 0.0f;
+    if (!zero && z_in) {
+      r.t = *reinterpret_cast<const float4*>(F + off);
+      if (want_next && own_tail) {
+        if (z0 + 4 < G.nz) r.tail = F[off + 4];
+        else if (G.wrap[2]) r.tail = F[off - z0];
+      }
+    }
+    return r;
+  };
+  auto ldp = [&](const float* q, const bool want_next) {
+    RowLd r;
+    r.t = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.tail = 0.0f;
+    if (hp_in) {
+      r.t = *reinterpret_cast<const float4*>(q);
+      if (want_next && lane == 31 && (z0 + 4 - D.hz0) < D.hrow) r.tail = q[4];
+    }
+    return r;
+  };
+
   for (int rx = rx0; rx < rx1; ++rx) {
     const int x = D.lo[0] + rx;
+    const long long o_c = ((long long)x * G.ny + y) * G.nz + z0;
+    long long dx = -plane;
+    bool x_zero = false;
+    if (x == 0) { if (G.wrap[0]) dx = (long long)(G.nx - 1) * plane; else x_zero = true; }
     float Es[4][3], Hs[4][3];
-    if (row_ok) {  // warp-uniform: the shuffles inside the loaders need the whole warp
-      if (EXACT) {
-        const bool in = row_ok && (z0 - D.hz0 + 4 <= D.hrow);  // inside the gathered row (covers hi_z: the k+1 halo)
-        // phase 1: every load of this plane
-        const RowLd l_exc = detv_ld_grid(G, G.E, 0, x, y, z0, lane, true), l_exm = detv_ld_grid(G, G.E, 0, x - 1, y, z0, lane, true);
-        const RowLd l_eyc = detv_ld_grid(G, G.E, 1, x, y, z0, lane, true), l_eym = detv_ld_grid(G, G.E, 1, x, y - 1, z0, lane, true);
-        const RowLd l_ezc = detv_ld_grid(G, G.E, 2, x, y, z0, lane, false);
-        const RowLd p_hxc = detv_ld_prev(D, 0, x, y, z0, lane, in, false), n_hxc = detv_ld_grid(G, G.H, 0, x, y, z0, lane, false);
-        const RowLd p_hxm = detv_ld_prev(D, 0, x, y - 1, z0, lane, in, false), n_hxm = detv_ld_grid(G, G.H, 0, x, y - 1, z0, lane, false);
-        const RowLd p_hyc = detv_ld_prev(D, 1, x, y, z0, lane, in, false), n_hyc = detv_ld_grid(G, G.H, 1, x, y, z0, lane, false);
-        const RowLd p_hym = detv_ld_prev(D, 1, x - 1, y, z0, lane, in, false), n_hym = detv_ld_grid(G, G.H, 1, x - 1, y, z0, lane, false);
-        const RowLd p_zcc = detv_ld_prev(D, 2, x, y, z0, lane, in, true), n_zcc = detv_ld_grid(G, G.H, 2, x, y, z0, lane, true);
-        const RowLd p_zmc = detv_ld_prev(D, 2, x - 1, y, z0, lane, in, true), n_zmc = detv_ld_grid(G, G.H, 2, x - 1, y, z0, lane, true);
-        const RowLd p_zcm = detv_ld_prev(D, 2, x, y - 1, z0, lane, in, true), n_zcm = detv_ld_grid(G, G.H, 2, x, y - 1, z0, lane, true);
-        const RowLd p_zmm = detv_ld_prev(D, 2, x - 1, y - 1, z0, lane, in, true), n_zmm = detv_ld_grid(G, G.H, 2, x - 1, y - 1, z0, lane, true);
-        // phase 2: k+1 neighbours by shuffle, time-centred H
-        const Row4 exc = row_finish(l_exc, true), exm = row_finish(l_exm, true), eyc = row_finish(l_eyc, true), eym = row_finish(l_eym, true);
-        const Row4 ezc = row_finish(l_ezc, false);
-        const Row4 hx_c = detv_hbar(row_finish(p_hxc, false), row_finish(n_hxc, false)), hx_m = detv_hbar(row_finish(p_hxm, false), row_finish(n_hxm, false));
-        const Row4 hy_c = detv_hbar(row_finish(p_hyc, false), row_finish(n_hyc, false)), hy_m = detv_hbar(row_finish(p_hym, false), row_finish(n_hym, false));
-        const Row4 hz_cc = detv_hbar(row_finish(p_zcc, true), row_finish(n_zcc, true)), hz_mc = detv_hbar(row_finish(p_zmc, true), row_finish(n_zmc, true));
-        const Row4 hz_cm = detv_hbar(row_finish(p_zcm, true), row_finish(n_zcm, true)), hz_mm = detv_hbar(row_finish(p_zmm, true), row_finish(n_zmm, true));
+    if (EXACT) {
+      const float *E0 = G.E, *E1 = G.E + N, *E2 = G.E + 2 * N, *H0 = G.H, *H1 = G.H + N, *H2 = G.H + 2 * N;
+      const float* hp = hp0 + (long long)(rx + 1) * h_pl;  // (c=0, a=rx+1, b=ry+1)
+      // phase 1: every load of this plane
+      const RowLd l_exc = ld(E0, o_c, false, true), l_exm = ld(E0, o_c + dx, x_zero, true);
+      const RowLd l_eyc = ld(E1, o_c, false, true), l_eym = ld(E1, o_c + dy, y_zero, true);
+      const RowLd l_ezc = ld(E2, o_c, false, false);
+      const RowLd n_hxc = ld(H0, o_c, false, false), n_hxm = ld(H0, o_c + dy, y_zero, false);
+      const RowLd n_hyc = ld(H1, o_c, false, false), n_hym = ld(H1, o_c + dx, x_zero, false);
+      const RowLd n_zcc = ld(H2, o_c, false, true), n_zmc = ld(H2, o_c + dx, x_zero, true);
+      const RowLd n_zcm = ld(H2, o_c + dy, y_zero, true), n_zmm = ld(H2, o_c + dx + dy, x_zero || y_zero, true);
+      const RowLd p_hxc = ldp(hp, false), p_hxm = ldp(hp - h_row, false);
+      const RowLd p_hyc = ldp(hp + h_c, false), p_hym = ldp(hp + h_c - h_pl, false);
+      const RowLd p_zcc = ldp(hp + 2 * h_c, true), p_zmc = ldp(hp + 2 * h_c - h_pl, true);
+      const RowLd p_zcm = ldp(hp + 2 * h_c - h_row, true), p_zmm = ldp(hp + 2 * h_c - h_pl - h_row, true);
+      // phase 2: k+1 neighbours by shuffle, time-centred H
+      const Row4 exc = row_finish(l_exc, true, own_tail), exm = row_finish(l_exm, true, own_tail);
+      const Row4 eyc = row_finish(l_eyc, true, own_tail), eym = row_finish(l_eym, true, own_tail);
+      const Row4 ezc = row_finish(l_ezc, false, false);
+      const Row4 hx_c = detv_hbar(row_finish(p_hxc, false, false), row_finish(n_hxc, false, false));
+      const Row4 hx_m = detv_hbar(row_finish(p_hxm, false, false), row_finish(n_hxm, false, false));
+      const Row4 hy_c = detv_hbar(row_finish(p_hyc, false, false), row_finish(n_hyc, false, false));
+      const Row4 hy_m = detv_hbar(row_finish(p_hym, false, false), row_finish(n_hym, false, false));
+      const Row4 hz_cc = detv_hbar(row_finish(p_zcc, true, lane == 31), row_finish(n_zcc, true, own_tail));
+      const Row4 hz_mc = detv_hbar(row_finish(p_zmc, true, lane == 31), row_finish(n_zmc, true, own_tail));
+      const Row4 hz_cm = detv_hbar(row_finish(p_zcm, true, lane == 31), row_finish(n_zcm, true, own_tail));
+      const Row4 hz_mm = detv_hbar(row_finish(p_zmm, true, lane == 31), row_finish(n_zmm, true, own_tail));
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // same expressions, same order as colocate_interior / colocate_t (curl.py:120-222)
-          float lo = bea(G, exc.v[e], exm.v[e], 0, x);
-          float hi = bea(G, row_at(exc, e + 1), row_at(exm, e + 1), 0, x);
-          Es[e][0] = (lo + hi) / 2.0f;
-          lo = bea(G, eyc.v[e], eym.v[e], 1, y);
-          hi = bea(G, row_at(eyc, e + 1), row_at(eym, e + 1), 1, y);
-          Es[e][1] = (lo + hi) / 2.0f;
-          Es[e][2] = ezc.v[e];
-          Hs[e][0] = bea(G, hx_c.v[e], hx_m.v[e], 1, y);
-          Hs[e][1] = bea(G, hy_c.v[e], hy_m.v[e], 0, x);
-          const float lx = bea(G, hz_cc.v[e], hz_mc.v[e], 0, x);
-          const float lxm = bea(G, hz_cm.v[e], hz_mm.v[e], 0, x);
-          const float lxy = bea(G, lx, lxm, 1, y);
-          const float hx2 = bea(G, row_at(hz_cc, e + 1), row_at(hz_mc, e + 1), 0, x);
-          const float hxm = bea(G, row_at(hz_cm, e + 1), row_at(hz_mm, e + 1), 0, x);
-          const float hxy = bea(G, hx2, hxm, 1, y);
-          Hs[e][2] = (lxy + hxy) / 2.0f;
-        }
-      } else {
+      for (int e = 0; e < 4; ++e) {
+        // same expressions, same order as colocate_interior / colocate_t (curl.py:120-222)
+        float lo = bea(G, exc.v[e], exm.v[e], 0, x);
+        float hi = bea(G, row_at(exc, e + 1), row_at(exm, e + 1), 0, x);
+        Es[e][0] = (lo + hi) / 2.0f;
+        lo = bea(G, eyc.v[e], eym.v[e], 1, y);
+        hi = bea(G, row_at(eyc, e + 1), row_at(eym, e + 1), 1, y);
+        Es[e][1] = (lo + hi) / 2.0f;
+        Es[e][2] = ezc.v[e];
+        Hs[e][0] = bea(G, hx_c.v[e], hx_m.v[e], 1, y);
+        Hs[e][1] = bea(G, hy_c.v[e], hy_m.v[e], 0, x);
+        const float lx = bea(G, hz_cc.v[e], hz_mc.v[e], 0, x);
+        const float lxm = bea(G, hz_cm.v[e], hz_mm.v[e], 0, x);
+        const float lxy = bea(G, lx, lxm, 1, y);
+        const float hx2 = bea(G, row_at(hz_cc, e + 1), row_at(hz_mc, e + 1), 0, x);
+        const float hxm = bea(G, row_at(hz_cm, e + 1), row_at(hz_mm, e + 1), 0, x);
+        const float hxy = bea(G, hx2, hxm, 1, y);
+        Hs[e][2] = (lxy + hxy) / 2.0f;
+      }
+    } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const Row4 a = row_finish(detv_ld_grid(G, G.E, c, x, y, z0, lane, false), false), b = row_finish(detv_ld_grid(G, G.H, c, x, y, z0, lane, false), false);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { Es[e][c] = a.v[e]; Hs[e][c] = b.v[e]; }
-        }
+      for (int c = 0; c < 3; ++c) {
+        const RowLd a = ld(G.E + c * N, o_c, false, false), b = ld(G.H + c * N, o_c, false, false);
+        Es[0][c] = a.t.x; Es[1][c] = a.t.y; Es[2][c] = a.t.z; Es[3][c] = a.t.w;
+        Hs[0][c] = b.t.x; Hs[1][c] = b.t.y; Hs[2][c] = b.t.z; Hs[3][c] = b.t.w;
       }
     }
     float ev[4] = {0.f, 0.f, 0.f, 0.f};
@@ -219,66 +238,47 @@ __global__ void __launch_bounds__(256) det_march_kernel(const GridDev G, const D
         if (z < D.lo[2] || z >= D.hi[2]) continue;
         const int rz = z - D.lo[2];
         const long long cell = ((long long)rx * ey + ry) * ez + rz;
-        if (fused_mean) det_emit<true>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], &ev[e]);
-        else det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], nullptr);
+        if (fused_mean) {
+          det_emit<true>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], &ev[e]);
+          D.scratch[cell] = ev[e];
+        } else {
+          det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], nullptr);
+        }
       }
     }
-    if (fused_mean) {  // CTA-uniform
-      // (1) sum over z of this row's 128-cell pass -> part[0][ztile][rx][ry]
+    if (fused_mean) {  // warp-uniform: sum over z of this row's 128-cell pass -> part[0][ztile][rx][ry]
       float rs = (ev[0] + ev[1]) + (ev[2] + ev[3]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-      if (lane == 0 && row_ok) D.part[0][((long long)blockIdx.x * ex + rx) * ey + ry] = rs;
-      // (2) sum over the CTA's rows -> part[1][ytile][rx][rz]
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s_rows[wrow][4 * lane + e] = ev[e];
-      __syncthreads();
-      if (wrow == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int z = z0 + e;
-          if (z < D.lo[2] || z >= D.hi[2] || z >= G.nz) continue;
-          float a = 0.0f;
-          for (int w = 0; w < DETV_ROWS; ++w) a += s_rows[w][4 * lane + e];
-          D.part[1][((long long)blockIdx.y * ex + rx) * ez + (z - D.lo[2])] = a;
-        }
-      }
-      // (3) running sum over x
-#pragma unroll
-      for (int e = 0; e < 4; ++e) accx[e] += ev[e];
-    }
-  }
-  if (fused_mean && lane_in) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int z = z0 + e;
-      if (z < D.lo[2] || z >= D.hi[2]) continue;
-      D.part[2][((long long)xc * ey + ry) * ez + (z - D.lo[2])] = accx[e];
+      if (lane == 0) D.part[0][((long long)blockIdx.x * ex + rx) * ey + ry] = rs;
     }
   }
 }
 
-// One thread per output element of the three mean planes: fold the partials in a fixed order.
+// Averaged energy slices: the XY plane folds the per-row z sums, the XZ / YZ planes sum the staged
+// per-cell energies over y / x (consecutive threads read consecutive z: coalesced), each in a fixed order.
 __global__ void det_mean_finish_kernel(const DetDev* __restrict__ dets, const int di, const int t) {
   const DetDev D = dets[di];
   const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
   const long long nxy = (long long)ex * ey, nxz = (long long)ex * ez, nyz = (long long)ey * ez;
   const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int slot = D.arr_idx[t];
-  if (o < nxy) {  // XY plane: mean over z
+  if (o < nxz) {  // XZ plane: mean over y
+    const int rx = (int)(o / ez), rz = (int)(o - (long long)rx * ez);
+    const float* p = D.scratch + (long long)rx * ey * ez + rz;
     float a = 0.0f;
-    for (int q = 0; q < D.npart[0]; ++q) a += D.part[0][q * nxy + o];
-    D.state[0][slot * nxy + o] = a / (float)ez;
-  } else if (o < nxy + nxz) {  // XZ plane: mean over y
-    const long long i = o - nxy;
+    for (int q = 0; q < ey; ++q) a += p[(long long)q * ez];
+    D.state[1][slot * nxz + o] = a / (float)ey;
+  } else if (o < nxz + nyz) {  // YZ plane: mean over x
+    const long long i = o - nxz;
+    const float* p = D.scratch + i;
     float a = 0.0f;
-    for (int q = 0; q < D.npart[1]; ++q) a += D.part[1][q * nxz + i];
-    D.state[1][slot * nxz + i] = a / (float)ey;
-  } else if (o < nxy + nxz + nyz) {  // YZ plane: mean over x
-    const long long i = o - nxy - nxz;
-    float a = 0.0f;
-    for (int q = 0; q < D.npart[2]; ++q) a += D.part[2][q * nyz + i];
+    for (int q = 0; q < ex; ++q) a += p[(long long)q * nyz];
     D.state[2][slot * nyz + i] = a / (float)ex;
+  } else if (o < nxz + nyz + nxy) {  // XY plane: mean over z
+    const long long i = o - nxz - nyz;
+    float a = 0.0f;
+    for (int q = 0; q < D.npart[0]; ++q) a += D.part[0][q * nxy + i];
+    D.state[0][slot * nxy + i] = a / (float)ez;
   }
 }

@@ -302,8 +302,65 @@ def phasor_table(det: "PhasorDetector", T: int, dt: float) -> np.ndarray:
 
 @dataclass
 class ModeOverlapDetector(PhasorDetector):
-    """``mode.py:193-``: for the time step this *is* a ``PhasorDetector`` (all six components);
-    the overlap integral is post-processing and out of scope."""
+    """``objects/detectors/mode.py:193-470``: for the time step this *is* a six-component
+    ``PhasorDetector``; ``apply`` solves the reference waveguide mode on the detector plane
+    (``fdtdx_b200.modes``) and ``compute_overlap`` is the post-run overlap integral."""
+
+    direction: Literal["+", "-"] = "+"
+    mode_index: int = 0
+    filter_pol: Literal["te", "tm"] | None = None
+    _mode_E: np.ndarray | None = None
+    _mode_H: np.ndarray | None = None
+    _mode_neff: np.ndarray | None = None
+    _cached_face_area_weights: np.ndarray | None = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.components = COMPONENT_NAMES
+
+    @property
+    def propagation_axis(self) -> int:
+        if sum(a == 1 for a in self.grid_shape) != 1:
+            raise Exception(f"Invalid ModeOverlapDetector shape: {self.grid_shape}")
+        return self.grid_shape.index(1)
+
+    def place_on_grid(self, config):
+        super().place_on_grid(config)
+        self._config = config
+        if sum(a == 1 for a in self.grid_shape) == 1:
+            w = _face_area_weights(config, self.grid_slice_tuple, self.propagation_axis)
+            self._cached_face_area_weights = (w / w.mean()).astype(_f32)  # mode.py:246 (consistent with compute_mode)
+        return self
+
+    def apply(self, inv_permittivities, inv_permeabilities=1.0, inv_eps_slice=None):
+        """Solve the reference mode per recorded frequency (``mode.py:302-377``).  ``inv_eps_slice``: the
+        (C, *plane) cross-section itself, for callers that never materialise the volume on the host."""
+        from fdtdx_b200 import modes
+
+        gs = self.grid_slice
+        inv_eps = np.asarray(inv_eps_slice) if inv_eps_slice is not None else np.asarray(inv_permittivities)[(slice(None), *gs)]
+        mu = inv_permeabilities
+        if hasattr(mu, "shape") and np.ndim(mu) > 0:
+            mu = np.asarray(mu)[(slice(None), *gs)]
+        cfg = self._config
+        spacing = None if cfg.has_nonuniform_grid else cfg.uniform_spacing()
+        Es, Hs, ns = [], [], []
+        for wc in self.wave_characters:
+            E, H, n = modes.compute_mode(wc.get_frequency(), inv_eps, mu, resolution=spacing, direction=self.direction, mode_index=self.mode_index,
+                                         filter_pol=self.filter_pol, transverse_coords=modes._transverse_edges(cfg, self.grid_slice_tuple, self.propagation_axis))
+            Es.append(E), Hs.append(H), ns.append(n)
+        self._mode_E, self._mode_H, self._mode_neff = np.stack(Es), np.stack(Hs), np.asarray(ns)
+        return self
+
+    def compute_overlap(self, state) -> np.ndarray:
+        """Complex overlap coefficient per frequency (``mode.py:379-470``)."""
+        from fdtdx_b200 import modes
+
+        ph = state["phasor"]
+        ph = np.asarray(ph.cpu() if hasattr(ph, "cpu") else ph)[0]
+        out = [modes.mode_overlap(ph[f], self._mode_E[f], self._mode_H[f], self.propagation_axis, self._cached_face_area_weights, pulse=self.scaling_mode == "pulse")
+               for f in range(ph.shape[0])]
+        return np.asarray(out)
 
 
 @dataclass

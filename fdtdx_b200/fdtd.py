@@ -445,9 +445,9 @@ def full_backward(state: SimulationState, objects, config, key=None, record_dete
     return int(start_time_step), plan.finish(arrays)
 
 
-def apply_params(arrays, objects, params, key=None, **kwargs):
-    """``initialization.py:317-323`` stand-in: device parameter mapping is out of scope (SURVEY
-    section 8 f2); with no devices the arrays pass through unchanged."""
-    if params:
-        raise NotImplementedError("apply_params with device parameters is outside the hot-path scope")
-    return arrays, objects, {}
+def apply_params(arrays, objects, params, key=None, **transform_kwargs):
+    """``initialization.py:317-521``: latent device parameters -> ``inv_permittivities`` on the GPU,
+    differentiably (``fdtdx_b200/device.py``).  With no devices the arrays pass through unchanged."""
+    from fdtdx_b200.device import apply_params as _apply
+
+    return _apply(arrays, objects, params or {}, key, **transform_kwargs)

@@ -190,7 +190,7 @@ def _transverse_edges(config, slice_tuple, p):
 
 def make_mode_source(name: str, grid_slice_tuple, config, inv_permittivities, inv_permeabilities=1.0, *, direction: str = "+",
                      wave_character, temporal_profile=None, mode_index: int = 0, filter_pol: str | None = None,
-                     static_amplitude_factor: float = 1.0, switch: OnOffSwitch | None = None, electric_conductivity=None):
+                     static_amplitude_factor: float = 1.0, switch: OnOffSwitch | None = None, electric_conductivity=None, inv_eps_slice=None):
     """``ModePlaneSource.apply`` (``objects/sources/mode.py:95-276``): solve the cross-section's mode,
     keep the real part of a lossless mode (the complex profile of a lossy one: quadrature injection,
     ``tfsf.py:266-283``), per-component Yee time offsets from ``Re(n_eff)``."""
@@ -202,7 +202,8 @@ def make_mode_source(name: str, grid_slice_tuple, config, inv_permittivities, in
     src.place_on_grid(config)
     p = src.propagation_axis
     gs = src.grid_slice
-    inv_eps = np.asarray(inv_permittivities)[(slice(None), *gs)]
+    # ``inv_eps_slice``: the (C, *face) cross-section itself, for callers that never materialise the volume
+    inv_eps = np.asarray(inv_eps_slice) if inv_eps_slice is not None else np.asarray(inv_permittivities)[(slice(None), *gs)]
     mode_inv_eps = inv_eps
     sigma = None if electric_conductivity is None else np.asarray(electric_conductivity)[(slice(None), *gs)]
     if sigma is not None:

@@ -53,40 +53,50 @@ def coupler_grid(cells_per_lambda: int, n_copies: int = 1, domain=(42e-6, 7e-6, 
     return fx.RectilinearGrid(x_edges, y_edges, z_edges), nx1, dx_f
 
 
-def _coupler_centerlines(x_um: np.ndarray):
-    """Centre y (um, GDS frame) of the two arms at GDS x (um): straight for x in [0, 20], cosine
-    S-bends over [-10, 0] and [20, 30] to the port heights, straight stubs outside."""
-    def arm(y_mid, y_port):
-        y = np.full_like(x_um, y_mid)
-        left = x_um < 0
-        right = x_um > 20
-        s_l = np.clip((-x_um) / 10.0, 0, 1)
-        s_r = np.clip((x_um - 20) / 10.0, 0, 1)
-        y = np.where(left, y_mid + (y_port - y_mid) * 0.5 * (1 - np.cos(np.pi * s_l)), y)
-        y = np.where(right, y_mid + (y_port - y_mid) * 0.5 * (1 - np.cos(np.pi * s_r)), y)
-        return y
-    return arm(0.0, -1.632), arm(0.736, 2.368)
+def coupler_core_mask(grid, nx1: int, x0: int, x1: int):
+    """Boolean (x1-x0, Ny) core mask + (Nz,) z mask of the SOI coupler for the global x range [x0, x1).
 
+    Geometry: the layer-1 polygons of the reference's ``performance/coupler.gds`` (extracted once by
+    ``scripts/extract_coupler_gds.py`` into ``fdtdx_b200/data/coupler_gds.npz``) plus the four port stubs
+    that ``extend_gds_with_port_stubs`` adds (``directional_coupler.py:117-140``): 0.5 um wide
+    rectangles from each port to the domain edge; Si where a cell CENTRE lies inside; 220 nm thick
+    around the mid-plane (``CouplerConfig.si_z_base``)."""
+    import os
 
-def coupler_inv_eps_slab(grid, nx1: int, x0: int, x1: int, xp):
-    """inv_eps (1, x1-x0, Ny, Nz) float32 for the global x range [x0, x1) using array module xp
-    (numpy or torch-like via callbacks)."""
+    from fdtdx_b200.gds import rasterize_polygons
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "coupler_gds.npz"))
+    polys = [d[f"p{i}"] for i in range(int(d["n"]))]
+    dom_x = float(grid.x_edges[nx1])
+    gds_center = (10e-6, 0.368e-6)
+    left, right = gds_center[0] - dom_x / 2, gds_center[0] + dom_x / 2
+    for px, py, orient in ((-10e-6, -1.632e-6, 180.0), (-10e-6, 2.368e-6, 180.0), (30e-6, 2.368e-6, 0.0), (30e-6, -1.632e-6, 0.0)):
+        xa, xb = (left, px) if orient == 180.0 else (px, right)
+        polys.append(np.array([[xa, py - 0.25e-6], [xb, py - 0.25e-6], [xb, py + 0.25e-6], [xa, py + 0.25e-6]]))
     xc = grid.centers(0)[x0:x1].astype(np.float64)
     yc = grid.centers(1).astype(np.float64)
     zc = grid.centers(2).astype(np.float64)
-    dom_x = float(grid.x_edges[nx1])
-    x_local = np.mod(xc, dom_x)
-    gx_um = (x_local - 21e-6 + 10e-6) * 1e6  # sim -> GDS frame (gds_center = (10, 0.368) um)
-    gy_um = (yc - 3.5e-6 + 0.368e-6) * 1e6
-    c1, c2 = _coupler_centerlines(gx_um)
-    in_xy = (np.abs(gy_um[None, :] - c1[:, None]) <= 0.25) | (np.abs(gy_um[None, :] - c2[:, None]) <= 0.25)
+    gx = np.mod(xc, dom_x) - dom_x / 2 + gds_center[0]  # sim -> GDS frame (chained copies repeat)
+    gy = yc - 3.5e-6 + gds_center[1]
+    in_xy = rasterize_polygons(polys, gx, gy) if np.all(np.diff(gx) > 0) else np.concatenate(
+        [rasterize_polygons(polys, gx[a:b], gy) for a, b in _monotone_runs(gx)], axis=0)
     in_z = (zc >= 2e-6 - 110e-9) & (zc <= 2e-6 + 110e-9)
     return in_xy, in_z
 
 
+def _monotone_runs(v):
+    cuts = [0] + [i + 1 for i in range(len(v) - 1) if v[i + 1] <= v[i]] + [len(v)]
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
 def build_coupler(cells_per_lambda: int = 20, device=None, n_copies: int = 1, x_range=None, with_detectors=True, time_steps_cap=None):
-    """Returns (objects, arrays, config).  With ``x_range=(x0, x1)`` only that x-slab of every
-    array is allocated (objects keep global coordinates; the plan clips them)."""
+    """C2 (``performance/directional_coupler.py:183-260``): returns (objects, arrays, config).  With
+    ``x_range=(x0, x1)`` only that x-slab of every array is allocated (objects keep global
+    coordinates; the plan clips them).  The TE0 mode of the o1 port cross-section (2 um x full z) drives
+    an x-normal mode plane with a Gaussian pulse; three ``ModeOverlapDetector`` planes (pulse scaling) sit
+    one fine cell after the source and at the thru / cross ports, each with its solved reference mode."""
+    from fdtdx_b200.modes import make_mode_source
+
     grid, nx1, dx_f = coupler_grid(cells_per_lambda, n_copies)
     shape = grid.shape
     sim_time = 2.0 * math.sqrt(EPS_SI) * 42e-6 / 3e8
@@ -95,11 +105,10 @@ def build_coupler(cells_per_lambda: int = 20, device=None, n_copies: int = 1, x_
     vol = fx.SimulationVolume(name="volume", grid_slice_tuple=((0, nx), (0, ny), (0, nz)))
     bl = fx.boundary_objects_from_config(shape, cfg, "pml", thickness=12)
     x0, x1 = x_range if x_range is not None else (0, nx)
-    in_xy, in_z = coupler_inv_eps_slab(grid, nx1, x0, x1, np)
+    in_xy, in_z = coupler_core_mask(grid, nx1, x0, x1)
     wc = fx.WaveCharacter(wavelength=1550e-9)
     prof = fx.GaussianPulseProfile(center_wave=wc, spectral_width=fx.WaveCharacter(wavelength=1550e-9 * 10))
     objs = [vol, *bl]
-    yc, zc = grid.centers(1).astype(np.float64), grid.centers(2).astype(np.float64)
     xe = grid.x_edges.astype(np.float64)
 
     def y_window(center_y):
@@ -107,46 +116,45 @@ def build_coupler(cells_per_lambda: int = 20, device=None, n_copies: int = 1, x_
         hi = int(np.searchsorted(grid.y_edges, center_y + 1e-6))
         return lo, max(hi, lo + 1)
 
+    def plane_inv_eps(ix, ylo, yhi):
+        """(1, 1, ny_window, Nz) inverse permittivity of the cross-section at global plane ix: every
+        rank solves the same mode, so the plane is rasterised from the geometry, not read from a slab."""
+        m_xy, m_z = coupler_core_mask(grid, nx1, ix, ix + 1)
+        core = m_xy[0, ylo:yhi, None] & m_z[None, :]
+        return np.where(core, _f32(1.0 / EPS_SI), _f32(1.0 / EPS_SIO2)).astype(_f32)[None, None]
+
     ports = {"o1": (-10e-6, -1.632e-6), "o2": (-10e-6, 2.368e-6), "o3": (30e-6, 2.368e-6), "o4": (30e-6, -1.632e-6)}
     to_sim = lambda p: (p[0] + 21e-6 - 10e-6, p[1] + 3.5e-6 - 0.368e-6)
+    mode_cache = {}
     for c in range(n_copies):
         off = c * nx1
         sx, sy = to_sim(ports["o1"])
         ix = off + int(np.searchsorted(xe[: nx1 + 1], sx))
         ylo, yhi = y_window(sy)
         sl = ((ix, ix + 1), (ylo, yhi), (0, nz))
-        # synthetic TE0-like profile: Gaussian in y and z around the core, E along y, H along z
-        wy = np.exp(-0.5 * ((yc[ylo:yhi] - sy) / 0.22e-6) ** 2)
-        wz = np.exp(-0.5 * ((zc - 2e-6) / 0.14e-6) ** 2)
-        amp = (wy[:, None] * wz[None, :]).astype(_f32)[None]
-        eps_face = np.where(in_xy[ix - x0 : ix - x0 + 1, ylo:yhi, None] & in_z[None, None, :], 1.0 / EPS_SI, 1.0 / EPS_SIO2).astype(_f32) if x0 <= ix < x1 else np.full((1, yhi - ylo, nz), 1.0 / EPS_SIO2, _f32)
-        src = fx.sources.TFSFPlaneSource(
-            name=f"source{c}" if n_copies > 1 else "source", grid_slice_tuple=sl, wave_character=wc, temporal_profile=prof, direction="+"
-        )
+        key = ("src", ix - off, ylo, yhi)
+        if key not in mode_cache:
+            mode_cache[key] = make_mode_source("tmp", sl, cfg, None, direction="+", wave_character=wc, temporal_profile=prof, mode_index=0, filter_pol="te",
+                                               inv_eps_slice=plane_inv_eps(ix, ylo, yhi))
+        m = mode_cache[key]
+        src = fx.sources.TFSFPlaneSource(name=f"source{c}" if n_copies > 1 else "source", grid_slice_tuple=sl, wave_character=wc, temporal_profile=prof, direction="+")
         src.place_on_grid(cfg)
-        n_eff = 2.4
-        E = np.zeros((3, *amp.shape), _f32)
-        H = np.zeros((3, *amp.shape), _f32)
-        E[1] = amp
-        H[2] = amp * _f32(n_eff)  # H = k x E / Z with Z = 1/n_eff in the solver's normalised units
-        norm = np.sqrt(float((0.5 * (E[1] ** 2 / eps_face + H[2] ** 2)).sum()))
-        E, H = (E / _f32(norm)).astype(_f32), (H / _f32(norm)).astype(_f32)
-        center = [0.0, float(grid.y_edges[yhi] - grid.y_edges[ylo]) * 0.5, float(grid.z_edges[nz] - grid.z_edges[0]) * 0.5]
-        tE, tH = fx.sources.calculate_time_offset_yee(center, np.array([1.0, 0.0, 0.0], _f32), np.full(amp.shape, n_eff, _f32), amp.shape, cfg, sl)
-        src._E, src._H, src._time_offset_E, src._time_offset_H = E, H, tE, tH
+        src._E, src._H, src._time_offset_E, src._time_offset_H, src._neff = m._E, m._H, m._time_offset_E, m._time_offset_H, m._neff
         objs.append(src)
         if with_detectors:
             for name, port, shift in (("det_source", "o1", 1), ("det_thru", "o4", 0), ("det_cross", "o3", 0)):
                 px_, py_ = to_sim(ports[port])
                 dix = off + int(np.searchsorted(xe[: nx1 + 1], px_)) + shift
                 dlo, dhi = y_window(py_)
-                det = fx.ModeOverlapDetector(
-                    name=f"{name}{c}" if n_copies > 1 else name,
-                    grid_slice_tuple=((dix, dix + 1), (dlo, dhi), (0, nz)),
-                    wave_characters=(wc,),
-                    scaling_mode="pulse",
-                )
+                dsl = ((dix, dix + 1), (dlo, dhi), (0, nz))
+                det = fx.ModeOverlapDetector(name=f"{name}{c}" if n_copies > 1 else name, grid_slice_tuple=dsl, wave_characters=(wc,), scaling_mode="pulse",
+                                             direction="+", mode_index=0, filter_pol="te")
                 det.place_on_grid(cfg)
+                key = ("det", dix - off, dlo, dhi)
+                if key not in mode_cache:
+                    det.apply(None, inv_eps_slice=plane_inv_eps(dix, dlo, dhi))
+                    mode_cache[key] = (det._mode_E, det._mode_H, det._mode_neff)
+                det._mode_E, det._mode_H, det._mode_neff = mode_cache[key]
                 objs.append(det)
     objects = fx.ObjectContainer(objs)
     arrays = _alloc(objects, cfg, (x0, x1), device, lambda: _coupler_eps(in_xy, in_z, device))

@@ -138,7 +138,14 @@ def make_c4():
     return out
 
 
-C2_STEPS = 2500
+C2_MID = 2500  # the pulse is inside the coupling section
+
+
+def c2_transmissions(objects, detector_states):
+    """|a|^2 / |a_source|^2 of the thru and cross ports (performance/directional_coupler.py:433-444)."""
+    dets = {d.name: d for d in objects.detectors}
+    norm = abs(complex(dets["det_source"].compute_overlap(detector_states["det_source"])[0])) ** 2
+    return {n: abs(complex(dets[n].compute_overlap(detector_states[n])[0])) ** 2 / norm for n in ("det_thru", "det_cross")}
 
 
 def make_c2():
@@ -146,12 +153,20 @@ def make_c2():
     out = {}
     st = (0, arrays.reset())
     t0 = time.time()
-    while st[0] < C2_STEPS:
+    T = cfg.time_steps_total
+    while st[0] < C2_MID:
         st = yee.forward(st, cfg, objects, None, True, False, True)
-        _log("c2", t0, st[0], C2_STEPS)
+        _log("c2", t0, st[0], T)
+    _fields("mid", st[1], out)
+    while st[0] < T:
+        st = yee.forward(st, cfg, objects, None, True, False, True)
+        _log("c2", t0, st[0], T)
     _fields("fwd", st[1], out)
     for n in ("det_source", "det_thru", "det_cross"):
         out[n] = st[1].detector_states[n]["phasor"]
+    tr = c2_transmissions(objects, st[1].detector_states)
+    out["T_thru"], out["T_cross"] = tr["det_thru"], tr["det_cross"]
+    print("transmissions", tr, flush=True)
     return out
 
 
