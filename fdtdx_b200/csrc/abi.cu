@@ -955,7 +955,7 @@ static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
     p->launches++;
   }
   if (any_volume) {
-    dim3 g((unsigned)std::min<long long>((vol_rows + 7) / 8, 148 * 16), (unsigned)p->dets.size());
+    dim3 g((unsigned)std::min<long long>((vol_rows + 7) / 8, 148 * 64), (unsigned)p->dets.size());
     det_gather_rows_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
     p->launches++;
   }
@@ -970,12 +970,12 @@ static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
   if (rc) return rc;
   GridDev G;
   make_grid(p, G);
-  bool any_generic = false, vol_exact = false, vol_raw = false;
+  bool any_generic = false, vol[2][2] = {{false, false}, {false, false}};  // [exact][mode]
   int gz = 1, gy = 1, nxc = 1;
   for (const DetHost& h : p->dets) {
     if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t]) continue;
     if (h.d.flags & DET_VOLUME) {
-      ((h.d.flags & DET_EXACT) ? vol_exact : vol_raw) = true;
+      vol[(h.d.flags & DET_EXACT) ? 1 : 0][(h.d.kind == FDTDX_DET_ENERGY && G.eps_tier != 9 && G.mu_tier != 9) ? 1 : 0] = true;
       gz = std::max(gz, (h.d.hi[2] - h.d.hz0 + DETV_TZ - 1) / DETV_TZ);
       gy = std::max(gy, (h.d.hi[1] - h.d.lo[1] + DETV_ROWS - 1) / DETV_ROWS);
       nxc = std::max(nxc, (h.d.hi[0] - h.d.lo[0] + DETV_XC - 1) / DETV_XC);
@@ -986,10 +986,13 @@ static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
     det_sample_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
     p->launches++;
   }
-  if (vol_exact || vol_raw) {
+  {
     dim3 g(gz, gy, nxc * (unsigned)p->dets.size()), b(32, DETV_ROWS);
-    if (vol_exact) { det_march_kernel<true><<<g, b, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0, nxc); p->launches++; }
-    if (vol_raw) { det_march_kernel<false><<<g, b, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0, nxc); p->launches++; }
+    const int inv = inverse ? 1 : 0;
+    if (vol[1][1]) { det_march_kernel<true, 1><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
+    if (vol[1][0]) { det_march_kernel<true, 0><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
+    if (vol[0][1]) { det_march_kernel<false, 1><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
+    if (vol[0][0]) { det_march_kernel<false, 0><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
   }
   if (any_post) {
     for (size_t di = 0; di < p->dets.size(); ++di) {

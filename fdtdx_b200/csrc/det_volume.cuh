@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) det_gather_rows_kernel(const GridDev G, c
   const long long rows = 3LL * sx * sy;
   const int lane = threadIdx.x & 31;
   const long long N = (long long)G.nx * G.ny * G.nz;
-  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {  // grid covers all rows: one row per warp
     const int b = (int)(r % sy);
     const int a = (int)((r / sy) % sx);
     const int c = (int)(r / ((long long)sy * sx));
@@ -108,7 +108,13 @@ struct RowSet {
 // also enumerates detectors: z = det * nxc + chunk.  No CTA-wide barrier in the plane loop: warps are
 // independent (slice means: the z sum is a warp reduction, the y / x sums are folded from the per-cell
 // energies by det_mean_finish_kernel).
-template <bool EXACT>
+// MODE 1: energy detectors on isotropic / diagonal media - the energy density is evaluated inline
+// (metrics.py:55-67, same expressions as det_emit) with 128-bit material loads and one division per
+// distinct material component; MODE 0: every other kind goes through det_emit.
+__device__ __forceinline__ int detv_mode(const GridDev& G, const DetDev& D) {
+  return (D.kind == 1 && G.eps_tier != 9 && G.mu_tier != 9) ? 1 : 0;
+}
+template <bool EXACT, int MODE>
 __global__ void __launch_bounds__(256, 2) det_march_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse, const int nxc_max) {
   __shared__ DetDev sD;
   const int di = blockIdx.z / nxc_max, xc = blockIdx.z - di * nxc_max;
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(256, 2) det_march_kernel(const GridDev G, cons
   }
   const DetDev& D = sD;
   if (((D.flags & DET_INVERSE) != 0) != (inverse != 0) || !D.on[t] || !(D.flags & DET_VOLUME)) return;
-  if (((D.flags & DET_EXACT) != 0) != EXACT) return;
+  if (((D.flags & DET_EXACT) != 0) != EXACT || detv_mode(G, D) != MODE) return;
   const int ex = D.hi[0] - D.lo[0], ey = D.hi[1] - D.lo[1], ez = D.hi[2] - D.lo[2];
   const int lane = threadIdx.x, wrow = threadIdx.y;
   // lanes are aligned to global multiples of 4 in z; cells outside [lo_z, hi_z) are masked at emit
@@ -231,19 +237,58 @@ __global__ void __launch_bounds__(256, 2) det_march_kernel(const GridDev G, cons
       }
     }
     float ev[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane_in) {
+    if (MODE == 1) {
+      if (lane_in) {
+        // 0.5 * (1 / inv_eps_c) and 0.5 * (1 / inv_mu_c) per component (one division per distinct array)
+        float he[3][4], hm[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c == 0 || G.eps_tier == 3) {
+            const float4 q = *reinterpret_cast<const float4*>(G.eps + c * G.eps_cs + o_c);
+            he[c][0] = 0.5f * (1.0f / q.x); he[c][1] = 0.5f * (1.0f / q.y); he[c][2] = 0.5f * (1.0f / q.z); he[c][3] = 0.5f * (1.0f / q.w);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) he[c][e] = he[0][e];
+          }
+          if (G.mu == nullptr) {
+            const float h = 0.5f * (1.0f / G.inv_mu_scalar);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hm[c][e] = h;
+          } else if (c == 0 || G.mu_tier == 3) {
+            const float4 q = *reinterpret_cast<const float4*>(G.mu + c * G.mu_cs + o_c);
+            hm[c][0] = 0.5f * (1.0f / q.x); hm[c][1] = 0.5f * (1.0f / q.y); hm[c][2] = 0.5f * (1.0f / q.z); hm[c][3] = 0.5f * (1.0f / q.w);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hm[c][e] = hm[0][e];
+          }
+        }
+        const bool staged = (D.flags & DET_REDUCE) != 0;
+        const int slot = D.arr_idx[t];
+        const long long n_cells = (long long)ex * ey * ez;
+        const long long cell0 = ((long long)rx * ey + ry) * ez + (z0 - D.lo[2]);
+        float* const dst = (fused_mean || staged) ? D.scratch : D.state[0] + (long long)slot * n_cells;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int z = z0 + e;
+          if (z < D.lo[2] || z >= D.hi[2]) continue;
+          // eE = sum_c 0.5/inv_eps_c * |E_c|^2 accumulated as (x + y) + z, likewise eH (metrics.py:58-66)
+          const float a0 = he[0][e] * (fabsf(Es[e][0]) * fabsf(Es[e][0])), a1 = he[1][e] * (fabsf(Es[e][1]) * fabsf(Es[e][1]));
+          const float a2 = he[2][e] * (fabsf(Es[e][2]) * fabsf(Es[e][2]));
+          const float b0 = hm[0][e] * (fabsf(Hs[e][0]) * fabsf(Hs[e][0])), b1 = hm[1][e] * (fabsf(Hs[e][1]) * fabsf(Hs[e][1]));
+          const float b2 = hm[2][e] * (fabsf(Hs[e][2]) * fabsf(Hs[e][2]));
+          const float en = ((a0 + a1) + a2) + ((b0 + b1) + b2);
+          ev[e] = en;
+          dst[cell0 + e] = en;
+        }
+      }
+    } else if (lane_in) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int z = z0 + e;
         if (z < D.lo[2] || z >= D.hi[2]) continue;
         const int rz = z - D.lo[2];
         const long long cell = ((long long)rx * ey + ry) * ez + rz;
-        if (fused_mean) {
-          det_emit<true>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], &ev[e]);
-          D.scratch[cell] = ev[e];
-        } else {
-          det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], nullptr);
-        }
+        det_emit<false>(G, D, t, cell, rx, ry, rz, x, y, z, Es[e], Hs[e], nullptr);
       }
     }
     if (fused_mean) {  // warp-uniform: sum over z of this row's 128-cell pass -> part[0][ztile][rx][ry]
@@ -267,12 +312,14 @@ __global__ void det_mean_finish_kernel(const DetDev* __restrict__ dets, const in
     const int rx = (int)(o / ez), rz = (int)(o - (long long)rx * ez);
     const float* p = D.scratch + (long long)rx * ey * ez + rz;
     float a = 0.0f;
+#pragma unroll 8
     for (int q = 0; q < ey; ++q) a += p[(long long)q * ez];
     D.state[1][slot * nxz + o] = a / (float)ey;
   } else if (o < nxz + nyz) {  // YZ plane: mean over x
     const long long i = o - nxz;
     const float* p = D.scratch + i;
     float a = 0.0f;
+#pragma unroll 8
     for (int q = 0; q < ex; ++q) a += p[(long long)q * nyz];
     D.state[2][slot * nyz + i] = a / (float)ex;
   } else if (o < nxz + nyz + nxy) {  // XY plane: mean over z

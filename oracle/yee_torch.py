@@ -205,13 +205,25 @@ class Stepper:
         det = {k: {k2: torch.as_tensor(v2, dtype=cdt if np.iscomplexobj(v2) else self.dtype) for k2, v2 in v.items()} for k, v in a.detector_states.items()}
         return self.T(a.fields.E), self.T(a.fields.H), psiE, psiH, det
 
-    def step(self, t, E, H, psiE, psiH, det, inv_eps, inv_mu):
+    def step(self, t, E, H, psiE, psiH, det, inv_eps, inv_mu, ade=None):
+        """``ade``: None or a dict with P, Pprev (n_poles, 3, *shape) and c1, c2, c3, c4 (n_poles, 1|3, *shape;
+        c4 may be None); the updated P / Pprev are written back into the dict (update.py:316-350)."""
         config, objects, dtype, shape = self.config, self.objects, self.dtype, self.shape
         c = config.courant_number
         H_prev = H
         K, psiE = _curl(config, _pad(H, self.wrap), psiE, objects, False, dtype)
-        if self.sE is not None:
-            s = c * self.sE * eta0 * inv_eps / 2
+        s = c * self.sE * eta0 * inv_eps / 2 if self.sE is not None else None
+        if ade is not None:
+            P, Q = ade["P"], ade["Pprev"]
+            P_hat = ade["c1"] * P + ade["c2"] * Q + ade["c3"] * E
+            E = (E if s is None else (1 - s) * E) + c * K * inv_eps + inv_eps * (P - P_hat).sum(0)
+            den = 1.0 if s is None else 1 + s
+            if ade.get("c4") is not None:
+                den = den + inv_eps * ade["c4"].sum(0)
+            E = E / den
+            ade["Pprev"] = P
+            ade["P"] = P_hat + ade["c4"] * E if ade.get("c4") is not None else P_hat
+        elif s is not None:
             E = ((1 - s) * E + c * K * inv_eps) / (1 + s)
         else:
             E = E + c * K * inv_eps
@@ -238,9 +250,10 @@ class Stepper:
         return E, H, psiE, psiH, det
 
 
-def run_forward(arrays_np, objects, config, steps, inv_eps=None, inv_mu=None, dtype=torch.float64, E0=None, H0=None):
+def run_forward(arrays_np, objects, config, steps, inv_eps=None, inv_mu=None, dtype=torch.float64, E0=None, H0=None, coeffs=None):
     """Runs ``steps`` forward steps from the container's state (diagonal tier); ``inv_eps`` /
-    ``inv_mu`` may be leaf tensors requiring grad.  Returns (E, H, detector_states)."""
+    ``inv_mu`` (and, for dispersive media, ``coeffs = {"c1": ..., "c2": ..., "c3": ..., "c4": ...}``) may be
+    leaf tensors requiring grad.  Returns (E, H, detector_states)."""
     S = Stepper(arrays_np, objects, config, dtype)
     E, H, psiE, psiH, det = S.initial()
     if E0 is not None:
@@ -252,8 +265,12 @@ def run_forward(arrays_np, objects, config, steps, inv_eps=None, inv_mu=None, dt
     mu_np = arrays_np.inv_permeabilities
     if inv_mu is None:
         inv_mu = S.T(mu_np) if isinstance(mu_np, np.ndarray) else float(mu_np)
+    ade = None
+    if arrays_np.dispersive_c1 is not None:
+        get = lambda k: (coeffs[k] if coeffs is not None and coeffs.get(k) is not None else (None if getattr(arrays_np, "dispersive_" + k) is None else S.T(getattr(arrays_np, "dispersive_" + k))))
+        ade = {"P": S.T(arrays_np.fields.dispersive_P_curr), "Pprev": S.T(arrays_np.fields.dispersive_P_prev), "c1": get("c1"), "c2": get("c2"), "c3": get("c3"), "c4": get("c4")}
     for t in range(steps):
-        E, H, psiE, psiH, det = S.step(t, E, H, psiE, psiH, det, inv_eps, inv_mu)
+        E, H, psiE, psiH, det = S.step(t, E, H, psiE, psiH, det, inv_eps, inv_mu, ade)
     return E, H, det
 
 
