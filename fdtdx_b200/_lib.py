@@ -19,8 +19,9 @@ LIB_PATH = os.environ.get("FDTDX_B200_LIB") or os.path.join(os.path.dirname(os.p
     SLOT_P_A, SLOT_P_B, SLOT_C1, SLOT_C2, SLOT_C3, SLOT_C4, SLOT_DET_STATE, SLOT_REC_DATA,
     SLOT_E_ALT, SLOT_H_ALT, SLOT_TENSOR_A_E, SLOT_TENSOR_B_E, SLOT_TENSOR_A_H, SLOT_TENSOR_B_H,
     SLOT_HALO_H_LO, SLOT_HALO_E_HI, SLOT_GRAD_INV_EPS, SLOT_GRAD_INV_MU, SLOT_COT_E, SLOT_COT_H,
-    SLOT_COT_PSI_E, SLOT_COT_PSI_H, SLOT_COT_DET, SLOT_COUNT,
-) = range(32)
+    SLOT_COT_PSI_E, SLOT_COT_PSI_H, SLOT_COT_DET, SLOT_COT_P, SLOT_COT_P_PREV, SLOT_GRAD_C1, SLOT_GRAD_C2, SLOT_GRAD_C3,
+    SLOT_GRAD_C4, SLOT_COUNT,
+) = range(38)
 
 DET_FIELD, DET_ENERGY, DET_POYNTING, DET_PHASOR = 0, 1, 2, 3
 DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE, DETF_VOLUME, DETF_CLOSED = 1, 2, 4, 8, 16, 32, 64, 128, 256

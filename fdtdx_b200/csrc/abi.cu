@@ -544,6 +544,7 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   }
   P.simulate = simulate;
   P.psi_store = 1;
+  P.p_store = 1;
   P.n_walls = (int)p->walls.size();
   P.walls = p->d_walls;
   P.n_src = (int)p->srcs.size();
@@ -1375,6 +1376,15 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
       A.lam_psi[h.axis][h.dir][w] = (float*)p->slots[is_E ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H][2 * q + w];
   }
   A.n_walls = S.n_walls; A.walls = S.walls;
+  if (is_E && p->n_poles > 0) {
+    A.n_poles = p->n_poles; A.has_c4 = p->has_c4; A.c_cs = S.c_cs;
+    A.Pc = S.P_cur; A.Pq = S.P_new;  // the input state's P_curr / P_prev (parity as bound)
+    A.cf[0] = S.c1; A.cf[1] = S.c2; A.cf[2] = S.c3; A.cf[3] = S.c4;
+    A.lamP = (float*)p->slots[FDTDX_SLOT_COT_P][0];
+    A.lamQ = (float*)p->slots[FDTDX_SLOT_COT_P_PREV][0];
+    if (!A.lamP || !A.lamQ) return fail(FDTDX_EUNBOUND, "COT_P / COT_P_PREV must be bound for the adjoint of a dispersive step");
+    for (int k = 0; k < 4; ++k) A.g_c[k] = (float*)p->slots[FDTDX_SLOT_GRAD_C1 + k][0];
+  }
   // 128-bit form when every (., N)-shaped operand is 16-byte aligned and rows are multiples of 4 cells
   bool v4 = (p->nz % 4 == 0);
   const void* ptrs[] = {F, G, lamF, lamG, lam_extra, A.ld, A.mat, A.sig, A.g_mat, A.sc[2]};
@@ -1402,7 +1412,8 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
   if (p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "run_adjoint on x-sharded plans is not supported yet");
   if (p->eps_tier == 9 || p->mu_tier == 9 || p->sigE_tier == 9 || p->sigH_tier == 9)
     return fail(FDTDX_EUNSUPPORTED, "run_adjoint: full-tensor media are not supported yet");
-  if (p->n_poles > 0) return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
+  if (p->n_poles > 0 && !p->adjoint_exact)
+    return fail(FDTDX_EUNSUPPORTED, "Dispersive time-reversible gradient computation under active development. Use GradientConfig(method='checkpointed') instead.");
   const long long N = (long long)p->nx * p->ny * p->nz;
   float* lamE = (float*)p->slots[FDTDX_SLOT_COT_E][0];
   float* lamH = (float*)p->slots[FDTDX_SLOT_COT_H][0];
@@ -1427,6 +1438,7 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     // input is copied first.
     StepParams F1 = S;
     F1.psi_store = 0;
+    F1.p_store = 0;
     StepParams F2;
     if (can_tma(p, S, can_vec4(p, S))) {
       F1.E_out = p->d_Etmp;

@@ -43,6 +43,14 @@ struct AdjParams {
   float* g_mat;        // gradient accumulator (tier comps, N) or nullptr
   int n_walls;
   const WallDev* walls;
+  // ADE (E half-step only; update.py:316-350): primal polarisations of the step's input state, the
+  // recurrence coefficients, the cotangents of P / P_prev (updated in place) and the coefficient gradients
+  int n_poles, has_c4;
+  long long c_cs;            // coefficient component stride (0: isotropic coefficients)
+  const float *Pc, *Pq;      // (n_poles, 3, N): P_curr, P_prev
+  const float* cf[4];        // c1..c4 (n_poles, 1|3, N); cf[3] nullptr without CCPR poles
+  float *lamP, *lamQ;        // (n_poles, 3, N)
+  float* g_c[4];             // gradient accumulators shaped like the coefficients, or nullptr
 };
 
 __device__ __forceinline__ float a_at(const AdjParams& P, const float* F, int c, int x, int y, int z) {
@@ -122,6 +130,45 @@ __device__ __forceinline__ void adj_local_body(const AdjParams& P, const int x, 
     }
     gq[c] = IS_E ? u * (cK - alpha * Fc - alpha * Fpre) : u * (-cK - alpha * Fc - alpha * Fpre);
     float lin = (1.0f - sv) * u;
+    if (IS_E && P.n_poles > 0) {
+      // Transpose of the ADE branch (update.py:316-350), with D = sum_p (P_p - Phat_p), den = 1 + s + m sum c4:
+      //   Phat_p = c1 P + c2 Q + c3 E;  E1 = (1-s) E + cK m + m D;  E' = E1 / den;  P' = Phat + c4 E';  Q' = P
+      const long long pst = 3 * N, cst = P.c_cs ? 3 * N : N;
+      float D = 0.0f, c4sum = 0.0f, gEp = lam[c];
+      for (int p = 0; p < P.n_poles; ++p) {
+        const long long pi = p * pst + c * N + cell, ci = p * cst + c * P.c_cs + cell;
+        const float Pp = P.Pc[pi], Qp = P.Pq[pi];
+        const float Phat = (P.cf[0][ci] * Pp + P.cf[1][ci] * Qp) + P.cf[2][ci] * Fc;
+        D += Pp - Phat;
+        if (P.has_c4) { c4sum += P.cf[3][ci]; gEp += P.cf[3][ci] * P.lamP[pi]; }
+      }
+      const float den = (1.0f + sv) + m * c4sum;
+      const float E1 = ((1.0f - sv) * Fc + cK * m) + m * D;
+      const float Epre = E1 / den;
+      u = gEp / den;                       // cotangent of E1
+      const float g_den = -u * Epre;       // cotangent of den
+      const float g_s = g_den - Fc * u;    // cotangent of s = alpha m
+      gq[c] = u * (cK + D) + g_den * c4sum + alpha * g_s;
+      lin = (1.0f - sv) * u;
+      const float gD = m * u;
+      for (int p = 0; p < P.n_poles; ++p) {
+        const long long pi = p * pst + c * N + cell, ci = p * cst + c * P.c_cs + cell;
+        const float Pp = P.Pc[pi], Qp = P.Pq[pi];
+        const float lP = P.lamP[pi], lQ = P.lamQ[pi];
+        const float gPhat = lP - gD;
+        lin += P.cf[2][ci] * gPhat;
+        P.lamP[pi] = (gD + P.cf[0][ci] * gPhat) + lQ;
+        P.lamQ[pi] = P.cf[1][ci] * gPhat;
+        // isotropic coefficients are shared by the three components: accumulate atomically
+        if (P.g_c[0]) { if (P.c_cs) P.g_c[0][ci] += Pp * gPhat; else atomicAdd(P.g_c[0] + ci, Pp * gPhat); }
+        if (P.g_c[1]) { if (P.c_cs) P.g_c[1][ci] += Qp * gPhat; else atomicAdd(P.g_c[1] + ci, Qp * gPhat); }
+        if (P.g_c[2]) { if (P.c_cs) P.g_c[2][ci] += Fc * gPhat; else atomicAdd(P.g_c[2] + ci, Fc * gPhat); }
+        if (P.has_c4 && P.g_c[3]) {
+          const float v = lP * Epre + g_den * m;
+          if (P.c_cs) P.g_c[3][ci] += v; else atomicAdd(P.g_c[3] + ci, v);
+        }
+      }
+    }
     if (P.lam_extra) lin += extra[c];
     lam_in[c] = lin;
     lamK[c] = IS_E ? (P.cour * m) * u : -(P.cour * m) * u;

@@ -77,6 +77,7 @@ struct StepParams {
   AxisPmlDev pml[3];
   int simulate;
   int psi_store;  // 0: compute psi' for the correction but leave the stored psi untouched (adjoint recompute)
+  int p_store;    // 0: likewise leave the ADE polarisation buffers untouched
   int n_walls;
   const WallDev* walls;  // device array
   int n_src;

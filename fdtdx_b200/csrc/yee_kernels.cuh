@@ -636,7 +636,7 @@ __device__ __forceinline__ void material_update_E(const StepParams& P, const lon
             delta.v[e] = (p == 0) ? dd : delta.v[e] + dd;
             if (P.has_c4) c4sum.v[e] = (p == 0) ? a4.v[e] : c4sum.v[e] + a4.v[e];
           }
-          stv<V>(P.P_new + pi, Phat, nv);
+          if (P.p_store) stv<V>(P.P_new + pi, Phat, nv);
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -649,7 +649,7 @@ __device__ __forceinline__ void material_update_E(const StepParams& P, const lon
             E1.v[e] = E1.v[e] / (1.0f + s.v[e]);
           }
         }
-        if (P.has_c4) {
+        if (P.has_c4 && P.p_store) {
           for (int p = 0; p < P.n_poles; ++p) {
             const long long pi = p * pstride + c * N + cell0;
             const long long ci = p * cstride + c * P.c_cs + cell0;

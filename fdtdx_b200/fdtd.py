@@ -98,7 +98,8 @@ def checkpointed_fdtd(
         import torch
 
         inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
-        needs_grad = torch.is_tensor(inv_eps) and (inv_eps.requires_grad or (isinstance(inv_mu, torch.Tensor) and inv_mu.requires_grad))
+        coef_grad = any(torch.is_tensor(c) and c.requires_grad for c in (arrays.dispersive_c1, arrays.dispersive_c2, arrays.dispersive_c3, arrays.dispersive_c4))
+        needs_grad = torch.is_tensor(inv_eps) and (inv_eps.requires_grad or (isinstance(inv_mu, torch.Tensor) and inv_mu.requires_grad) or coef_grad)
         if needs_grad and torch.is_grad_enabled():
             return _checkpointed_with_grad(arrays, objects, config, progress_callback)
     arrays = arrays.reset()
@@ -148,12 +149,11 @@ def _checkpointed_with_grad(arrays, objects, config, progress_callback):
     ``reversible_fdtd``; dispersive media are not supported by the adjoint kernels yet."""
     import torch
 
-    if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
-        raise NotImplementedError("checkpointed gradients for dispersive media need the ADE adjoint (SURVEY.md section 8 f3)")
     _require_cuda(arrays)
     inv_eps, inv_mu = arrays.inv_permittivities, arrays.inv_permeabilities
     holder = {"arrays": arrays, "objects": objects, "config": config, "cb": progress_callback}
-    outs = _CheckpointedFunction.get().apply(inv_eps, inv_mu if isinstance(inv_mu, torch.Tensor) else None, holder)
+    coeffs = [arrays.dispersive_c1, arrays.dispersive_c2, arrays.dispersive_c3, arrays.dispersive_c4]
+    outs = _CheckpointedFunction.get().apply(inv_eps, inv_mu if isinstance(inv_mu, torch.Tensor) else None, holder, *coeffs)
     out = holder["out"]
     out = out.aset("fields->E", outs[0]).aset("fields->H", outs[1])
     det = {d: dict(st) for d, st in out.detector_states.items()}
@@ -163,6 +163,9 @@ def _checkpointed_with_grad(arrays, objects, config, progress_callback):
     out = out.aset("inv_permittivities", inv_eps)
     if isinstance(inv_mu, torch.Tensor):
         out = out.aset("inv_permeabilities", inv_mu)
+    for name, c in zip(("dispersive_c1", "dispersive_c2", "dispersive_c3", "dispersive_c4"), coeffs):
+        if c is not None:
+            out = out.aset(name, c)
     return config.time_steps_total, out
 
 
@@ -184,17 +187,21 @@ def _detector_cotangents(names, gdet, arrays):
 
 def _clone_state(a):
     f = a.fields
-    return (f.E.clone(), f.H.clone(), {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_E.items()}, {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_H.items()})
+    P = None if f.dispersive_P_curr is None else (f.dispersive_P_curr.clone(), f.dispersive_P_prev.clone())
+    return (f.E.clone(), f.H.clone(), {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_E.items()}, {k: (x.clone(), y.clone()) for k, (x, y) in f.psi_H.items()}, P)
 
 
 def _load_state(a, st):
-    E, H, pE, pH = st
+    E, H, pE, pH, P = st
     a.fields.E.copy_(E)
     a.fields.H.copy_(H)
     for k in pE:
         for w in range(2):
             a.fields.psi_E[k][w].copy_(pE[k][w])
             a.fields.psi_H[k][w].copy_(pH[k][w])
+    if P is not None:
+        a.fields.dispersive_P_curr.copy_(P[0])
+        a.fields.dispersive_P_prev.copy_(P[1])
 
 
 class _CheckpointedFunction:
@@ -208,15 +215,19 @@ class _CheckpointedFunction:
 
         class CheckpointedFDTD(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, inv_eps, inv_mu, holder):
+            def forward(ctx, inv_eps, inv_mu, holder, c1=None, c2=None, c3=None, c4=None):
                 arrays, objects, config = holder["arrays"], holder["objects"], holder["config"]
                 T = config.time_steps_total
                 nck = max(1, int(config.gradient_config.num_checkpoints))
                 seg_len = max(1, -(-T // nck))
+                holder["coeff_needs_grad"] = [c is not None and c.requires_grad for c in (c1, c2, c3, c4)]
                 with torch.no_grad():
                     arrays = arrays.aset("inv_permittivities", inv_eps.detach())
                     if inv_mu is not None:
                         arrays = arrays.aset("inv_permeabilities", inv_mu.detach())
+                    for name, c in zip(("dispersive_c1", "dispersive_c2", "dispersive_c3", "dispersive_c4"), (c1, c2, c3, c4)):
+                        if c is not None:
+                            arrays = arrays.aset(name, c.detach())
                     arrays = arrays.reset()
                     ckpts, t = [], 0
                     while t < T:
@@ -240,6 +251,13 @@ class _CheckpointedFunction:
                 work = arrays.aset("fields->E", f.E.detach().clone()).aset("fields->H", f.H.detach().clone())
                 work = work.aset("fields->psi_E", {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_E.items()})
                 work = work.aset("fields->psi_H", {k: (a.clone(), b.clone()) for k, (a, b) in f.psi_H.items()})
+                cot_P = cot_Q = g_coef = None
+                if f.dispersive_P_curr is not None:
+                    # the final P / P_prev are not outputs of the autograd node: their cotangents start at zero
+                    work = work.aset("fields->dispersive_P_curr", f.dispersive_P_curr.clone()).aset("fields->dispersive_P_prev", f.dispersive_P_prev.clone())
+                    cot_P, cot_Q = torch.zeros_like(f.dispersive_P_curr), torch.zeros_like(f.dispersive_P_prev)
+                    cs = (work.dispersive_c1, work.dispersive_c2, work.dispersive_c3, work.dispersive_c4)
+                    g_coef = [torch.zeros_like(c) if (c is not None and need) else None for c, need in zip(cs, h["coeff_needs_grad"])]
                 cot_E = torch.zeros_like(f.E) if gE is None else gE.detach().clone().contiguous()
                 cot_H = torch.zeros_like(f.H) if gH is None else gH.detach().clone().contiguous()
                 cot_det = _detector_cotangents(h["names"], gdet, arrays)
@@ -257,12 +275,15 @@ class _CheckpointedFunction:
                         states.append(_clone_state(work))
                         plan.bind(work)
                         plan.run_forward(t, 1, False, False, True)
+                        work = plan.finish(work)  # ADE: P_curr / P_prev swap roles every step
                     for t in range(t1 - 1, t0 - 1, -1):
                         _load_state(work, states[t - t0])
-                        plan.run_adjoint(work, t + 1, 1, cot_E, cot_H, cot_det, g_eps, g_mu, keep_cot_psi=not first, exact=True)
+                        plan.run_adjoint(work, t + 1, 1, cot_E, cot_H, cot_det, g_eps, g_mu, keep_cot_psi=not first, exact=True,
+                                         cot_P=cot_P, cot_P_prev=cot_Q, grad_coeffs=g_coef)
                         first = False
                     del states
-                return g_eps, g_mu, None
+                gc = [None] * 4 if g_coef is None else g_coef
+                return (g_eps, g_mu, None, *gc)
 
         cls._cls = CheckpointedFDTD
         return CheckpointedFDTD

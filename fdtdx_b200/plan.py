@@ -575,7 +575,8 @@ class Plan:
         check(self.lib.fdtdx_b200_run_reverse(self.h, int(t_from), int(n), int(record_detectors), int(reset_fields), self._stream()))
         self._sync_out()
 
-    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False, exact: bool = False):
+    def run_adjoint(self, arrays, t_from: int, n: int, cot_E, cot_H, cot_det: dict, grad_inv_eps, grad_inv_mu=None, keep_cot_psi: bool = False, exact: bool = False,
+                    cot_P=None, cot_P_prev=None, grad_coeffs=None):
         """``fdtd_bwd`` loop (``fdtd/fdtd.py:262-333``): n iterations of reverse step + VJP of one forward
         step.  ``arrays`` holds the state at ``t_from`` (fields are reconstructed in place); ``cot_E`` /
         ``cot_H`` carry the field cotangents in place; ``cot_det[name][key]`` are the detector-state
@@ -590,6 +591,12 @@ class Plan:
             self._bind(_lib.SLOT_GRAD_INV_MU, 0, None)
         else:
             self._bind_z(_lib.SLOT_GRAD_INV_MU, 0, grad_inv_mu, None, None, True)
+        if self.n_poles:
+            # ADE adjoint: cotangents of P / P_prev carried in place, optional coefficient gradients
+            self._bind(_lib.SLOT_COT_P, 0, cot_P, torch.float32)
+            self._bind(_lib.SLOT_COT_P_PREV, 0, cot_P_prev, torch.float32)
+            for k, slot in enumerate((_lib.SLOT_GRAD_C1, _lib.SLOT_GRAD_C2, _lib.SLOT_GRAD_C3, _lib.SLOT_GRAD_C4)):
+                self._bind(slot, 0, None if grad_coeffs is None else grad_coeffs[k])
         if not keep_cot_psi or not getattr(self, "_cot_psi", None):
             self._cot_psi = {}
         for pml in self.objects.pml_objects:

@@ -71,7 +71,15 @@ enum FdtdxSlot {
   FDTDX_SLOT_COT_PSI_E = 28,  /* index as PSI_E */
   FDTDX_SLOT_COT_PSI_H = 29,
   FDTDX_SLOT_COT_DET = 30,    /* index as DET_STATE: cotangent of the detector state */
-  FDTDX_SLOT_COUNT = 31
+  /* ADE adjoint (run_adjoint_exact on dispersive plans): cotangents of dispersive_P_curr / _prev, carried
+   * in place like COT_E / COT_H, and optional gradient accumulators shaped like c1..c4 */
+  FDTDX_SLOT_COT_P = 31,
+  FDTDX_SLOT_COT_P_PREV = 32,
+  FDTDX_SLOT_GRAD_C1 = 33,
+  FDTDX_SLOT_GRAD_C2 = 34,
+  FDTDX_SLOT_GRAD_C3 = 35,
+  FDTDX_SLOT_GRAD_C4 = 36,
+  FDTDX_SLOT_COUNT = 37
 };
 
 enum FdtdxBoundaryKind { FDTDX_WALL_PEC = 0, FDTDX_WALL_PMC = 1 };

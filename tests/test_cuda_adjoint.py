@@ -223,3 +223,44 @@ def test_energy_detector_gradient_wrt_inv_mu():
     gm, gm_ref = dev.inv_permeabilities.grad.cpu().numpy(), im.grad.numpy()
     assert np.abs(gm_ref).max() > 0
     assert rel_l2(gm, gm_ref) <= 1e-4
+
+
+ADE_CASES = {
+    "lorentz_1pole_iso": dict(poles=1, source="plane_z", detectors=("poynting", "phasor"), time=3e-15, shape=(16, 14, 20), thickness=4),
+    "2poles_c4_sigma_diag": dict(poles=2, c4=True, coeff_tier=3, eps_tier=3, sigma_E=True, source="plane_z", detectors=("poynting", "field_reduce", "energy_reduce"), time=3e-15, shape=(16, 14, 20), thickness=4),
+    "ragged_periodic_1pole_c4": dict(poles=1, c4=True, boundaries="periodic", source="plane_z", detectors=("field", "phasor"), time=3e-15, shape=(12, 10, 18)),
+}
+
+
+@pytest.mark.parametrize("name", list(ADE_CASES))
+def test_checkpointed_gradient_through_dispersive_media(name):
+    """ADE adjoint (the reference pins it in
+    tests/simulation/fdtd/test_time_reversal.py:955-1044 with finite differences on c1, c2, c3): the
+    checkpointed gradient w.r.t. inv_eps AND the recurrence coefficients c1..c4 equals float64 autograd
+    through the restated dispersive forward run."""
+    kw = ADE_CASES[name]
+    objects, arrays, cfg = build_scene(**kw)
+    cfg = cfg.aset("gradient_config", fx.GradientConfig(method="checkpointed", num_checkpoints=3))
+    T = cfg.time_steps_total
+    names = ["c1", "c2", "c3"] + (["c4"] if arrays.dispersive_c4 is not None else [])
+    ie = torch.tensor(arrays.inv_permittivities.astype(np.float64), requires_grad=True)
+    co = {k: torch.tensor(getattr(arrays, "dispersive_" + k).astype(np.float64), requires_grad=True) for k in names}
+    E, H, det = yee_torch.run_forward(arrays.reset(), objects, cfg, T, inv_eps=ie, dtype=torch.float64, coeffs=co)
+    loss_ref = _loss(det, E)
+    loss_ref.backward()
+    dev = arrays.to_torch("cuda")
+    dev.inv_permittivities.requires_grad_(True)
+    for k in names:
+        getattr(dev, "dispersive_" + k).requires_grad_(True)
+    t_end, out = fx.run_fdtd(dev, objects, cfg)
+    assert t_end == T
+    loss = _loss(out.detector_states, out.fields.E)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    loss.backward()
+    g, g_ref = dev.inv_permittivities.grad.cpu().numpy(), ie.grad.numpy()
+    assert np.abs(g_ref).max() > 0
+    assert rel_l2(g, g_ref) <= 1e-4, f"d loss / d inv_eps rel-L2 {rel_l2(g, g_ref)}"
+    for k in names:
+        gk, gk_ref = getattr(dev, "dispersive_" + k).grad.cpu().numpy(), co[k].grad.numpy()
+        assert np.abs(gk_ref).max() > 0
+        assert rel_l2(gk, gk_ref) <= 1e-4, f"d loss / d {k} rel-L2 {rel_l2(gk, gk_ref)}"
