@@ -1032,12 +1032,17 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
   R.n_planes = 0;
   for (size_t q = 0; q < p->pmls.size(); ++q) {
     const PmlHost& h = p->pmls[q];
-    if (p->xoff != 0 || p->nx != p->nxg) return fail(FDTDX_EUNSUPPORTED, "recorder on x-sharded plans is not supported yet");
+    // x-sharded plans (interfaces/state.py:72-78 shards every recorder array on x): a y / z interface
+    // plane is this rank's x-slice of it, an x interface plane lives on the rank that owns that plane
+    int cell = (h.dir == 1) ? h.lo : h.hi - 1;  // boundary.py:134-144
+    if (h.axis == 0) {
+      cell -= p->xoff;
+      if (cell < 0 || cell >= p->nx) continue;
+    }
     RecPlane& pl = R.planes[R.n_planes++];
     const int n[3] = {p->nx, p->ny, p->nz};
     for (int a = 0; a < 3; ++a) { pl.lo[a] = 0; pl.hi[a] = n[a]; }
-    if (h.dir == 1) { pl.lo[h.axis] = h.lo; pl.hi[h.axis] = h.lo + 1; }
-    else { pl.lo[h.axis] = h.hi - 1; pl.hi[h.axis] = h.hi; }
+    pl.lo[h.axis] = cell; pl.hi[h.axis] = cell + 1;
     pl.data[0] = p->slots[FDTDX_SLOT_REC_DATA][2 * q + 0];
     pl.data[1] = p->slots[FDTDX_SLOT_REC_DATA][2 * q + 1];
     if (!pl.data[0] || !pl.data[1]) return fail(FDTDX_EUNBOUND, "REC_DATA must be bound for every PML slab");
@@ -1057,17 +1062,66 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
 // shared plane take part, so the interior chunks overlap the wait, the programmatic-dependent-launch
 // chain between the half-steps survives, and a whole multi-step run stays one asynchronous
 // submission per rank.
+// Kernels other than the half-steps that WRITE field planes a neighbour reads in place (interface replay,
+// PML field reset of the reverse pass) are bracketed by a stream-ordered fence: wait until both
+// neighbours have finished the half-steps issued so far, run the kernel, then advance BOTH progress
+// counters (every rank does the same, so the half-step targets stay aligned).
+__global__ void peer_fence_wait_kernel(const int* lo_doneH, int targetH, const int* hi_doneE, int targetE, int* err) {
+  const int* flag[2] = {lo_doneH, hi_doneE};
+  const int target[2] = {targetH, targetE};
+  for (int q = 0; q < 2; ++q) {
+    if (!flag[q]) continue;
+    unsigned ns = 32;
+    const long long t0 = clock64();
+    for (;;) {
+      int v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag[q]) : "memory");
+      if (v - target[q] >= 0) break;
+      if (clock64() - t0 > (1LL << 36)) { atomicExch(err, 1); break; }
+      __nanosleep(ns);
+      if (ns < 1024) ns *= 2;
+    }
+  }
+}
+__global__ void peer_fence_signal_kernel(int* flags, int valueE, int valueH) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flags), "r"(valueE) : "memory");
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flags + 1), "r"(valueH) : "memory");
+}
+__global__ void peer_flag_set_kernel(int* flag, int value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+static int peer_fence_begin(FdtdxPlan* p, cudaStream_t st) {
+  if (!p->peer_mode) return FDTDX_OK;
+  peer_fence_wait_kernel<<<1, 1, 0, st>>>(p->halo_lo ? p->peer[0].flags + 1 : nullptr, (int)p->seqH, p->halo_hi ? p->peer[1].flags : nullptr, (int)p->seqE,
+                                          p->d_flags + 2);
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+static int peer_fence_end(FdtdxPlan* p, cudaStream_t st) {
+  if (!p->peer_mode) return FDTDX_OK;
+  p->seqE++; p->seqH++;
+  peer_fence_signal_kernel<<<1, 1, 0, st>>>(p->d_flags, (int)p->seqE, (int)p->seqH);
+  CUDA_TRY(cudaGetLastError());
+  return FDTDX_OK;
+}
+
 static int step_E(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) {
   if (p->eps_tier == 9 || p->sigE_tier == 9) return tensor_step(p, t, simulate, rev, /*is_E=*/true, st);
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
+  // Sources injected by their own O(surface) launch (y / z-normal planes) may touch the plane a neighbour
+  // reads; they run outside the half-step kernel, so the in-kernel signal would publish too early (and
+  // the reversed pass would un-inject before the wait).  Such plans order whole launches instead.
+  const bool whole = p->peer_mode && P.n_src > 0 && !P.src_inline;
   if (p->peer_mode) {
     // in-kernel ordering (common.cuh, StepParams::peer_*): the chunk holding plane 0 waits for the low
     // neighbour's H counter and publishes this rank's E counter; it is scheduled last (z_reverse), a
     // whole kernel after the neighbour's H half-step was issued, so the wait is normally already met
     p->seqE++;
-    if (p->halo_lo) {
+    if (p->halo_lo && !whole) {
       P.peer_wait = p->peer[0].flags + 1;
       P.peer_wait_target = (int)p->seqH;
       P.peer_signal = p->d_flags;
@@ -1076,9 +1130,14 @@ static int step_E(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
       P.peer_err = p->d_flags + 2;
       P.z_reverse = 1;
     }
+    if (whole && p->halo_lo) peer_fence_wait_kernel<<<1, 1, 0, st>>>(p->peer[0].flags + 1, (int)p->seqH, nullptr, 0, p->d_flags + 2);
   }
   rc = launch_E(p, P, t, rev, st);
   if (rc) return rc;
+  if (whole) {
+    peer_flag_set_kernel<<<1, 1, 0, st>>>(p->d_flags, (int)p->seqE);
+    CUDA_TRY(cudaGetLastError());
+  }
   if (!rev && p->n_poles > 0) p->p_parity ^= 1;
   return FDTDX_OK;
 }
@@ -1088,11 +1147,12 @@ static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
   StepParams P;
   int rc = make_params(p, P, simulate);
   if (rc) return rc;
+  const bool whole = p->peer_mode && P.n_src > 0 && !P.src_inline;
   if (p->peer_mode) {
     // the chunk holding plane nx-1 (scheduled last) waits for the high neighbour's E counter and
     // publishes this rank's H counter
     p->seqH++;
-    if (p->halo_hi) {
+    if (p->halo_hi && !whole) {
       P.peer_wait = p->peer[1].flags;
       P.peer_wait_target = (int)p->seqE;
       P.peer_signal = p->d_flags + 1;
@@ -1100,9 +1160,14 @@ static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
       P.peer_ctr = p->d_flags + 9;
       P.peer_err = p->d_flags + 2;
     }
+    if (whole && p->halo_hi) peer_fence_wait_kernel<<<1, 1, 0, st>>>(nullptr, 0, p->peer[1].flags, (int)p->seqE, p->d_flags + 2);
   }
   rc = launch_H(p, P, t, rev, st);
   if (rc) return rc;
+  if (whole) {
+    peer_flag_set_kernel<<<1, 1, 0, st>>>(p->d_flags + 1, (int)p->seqH);
+    CUDA_TRY(cudaGetLastError());
+  }
   return FDTDX_OK;
 }
 
@@ -1215,10 +1280,12 @@ static int step_record(FdtdxPlan* p, int t, int record_detectors, int record_bou
         const RecPlane& pl = R.planes[q];
         fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
       }
-      dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
-      rec_record_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, slot);
-      p->launches++;
-      CUDA_TRY(cudaGetLastError());
+      if (R.n_planes > 0) {
+        dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
+        rec_record_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, slot);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
     }
   }
   if (record_detectors) return detectors_sample(p, t, false, st);
@@ -1310,6 +1377,8 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
   for (int t = t_from - 1; t > t_from - 1 - n; --t) {
     if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "reverse time step outside [0, T)");
     if (!p->has_rec) return fail(FDTDX_EINVAL, "Need recorder to record boundaries");
+    if ((p->halo_lo || p->halo_hi) && !p->peer_mode)
+      return fail(FDTDX_EUNSUPPORTED, "run_reverse on an x-sharded plan needs the peer-memory halo (peer_attach)");
     if (!p->pmls.empty()) {
       RecDev R;
       if ((rc = make_rec(p, R))) return rc;
@@ -1320,11 +1389,15 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
         const RecPlane& pl = R.planes[q];
         fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
       }
-      dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
-      rec_replay_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, p->replay_a[t],
-                                           p->replay_b[t], p->replay_w[t]);
-      p->launches++;
-      CUDA_TRY(cudaGetLastError());
+      if ((rc = peer_fence_begin(p, st))) return rc;
+      if (R.n_planes > 0) {
+        dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
+        rec_replay_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, p->replay_a[t],
+                                             p->replay_b[t], p->replay_w[t]);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
+      if ((rc = peer_fence_end(p, st))) return rc;
     }
     if (record_detectors && (rc = detectors_gather(p, t, true, st))) return rc;
     if ((rc = step_H(p, t, 0, true, st))) return rc;
@@ -1336,16 +1409,25 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
       const int nn[3] = {p->nx, p->ny, p->nz};
       for (const PmlHost& h : p->pmls) {
         for (int a = 0; a < 3; ++a) { B.lo[B.n][a] = 0; B.hi[B.n][a] = nn[a]; }
-        B.lo[B.n][h.axis] = h.lo; B.hi[B.n][h.axis] = h.hi;
-        nmax = std::max(nmax, (long long)(h.hi - h.lo) * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
+        int lo = h.lo, hi = h.hi;
+        if (h.axis == 0) {  // this rank's part of an x slab
+          lo = std::max(lo - p->xoff, 0); hi = std::min(hi - p->xoff, p->nx);
+          if (hi <= lo) continue;
+        }
+        B.lo[B.n][h.axis] = lo; B.hi[B.n][h.axis] = hi;
+        nmax = std::max(nmax, (long long)(hi - lo) * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
         B.n++;
       }
       GridDev G;
       make_grid(p, G);
-      dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
-      reset_pml_kernel<<<g, 256, 0, st>>>(B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
-      p->launches++;
-      CUDA_TRY(cudaGetLastError());
+      if ((rc = peer_fence_begin(p, st))) return rc;
+      if (B.n > 0) {
+        dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
+        reset_pml_kernel<<<g, 256, 0, st>>>(B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
+      if ((rc = peer_fence_end(p, st))) return rc;
     }
     if (record_detectors && (rc = detectors_sample(p, t, true, st))) return rc;
   }

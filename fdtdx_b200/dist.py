@@ -44,6 +44,67 @@ def neighbours(rank: int, world: int, periodic_x: bool) -> tuple[int | None, int
     return lo, hi
 
 
+def shard_arrays(arrays, objects, x_range, device=None):
+    """This rank's x-slab of a whole-grid (NumPy) ``ArrayContainer`` - what the reference's
+    ``NamedSharding`` on the x axis gives every device (``fdtd/initialization.py:598-611``,
+    ``interfaces/state.py:72-78``): fields, materials, ADE arrays and y / z CPML psi are sliced on x; an x
+    CPML slab, an x interface plane of the recorder and a detector state stay with the rank that owns
+    their planes (detectors must not straddle a slab edge).  ``device``: move to that torch device."""
+    import numpy as np
+
+    from fdtdx_b200.container import ArrayContainer, FieldState, RecordingState, _TorchLeaf
+
+    x0, x1 = x_range
+
+    def cut(a, axis):
+        if a is None or not hasattr(a, "shape") or len(a.shape) == 0:
+            return a
+        idx = [slice(None)] * len(a.shape)
+        idx[axis] = slice(x0, x1)
+        if isinstance(a, _TorchLeaf):
+            return _TorchLeaf(a.t[tuple(idx)].contiguous())
+        return np.ascontiguousarray(a[tuple(idx)])
+
+    f = arrays.fields
+    psi_E, psi_H = {}, {}
+    for pml in objects.pml_objects:
+        lo, hi = pml.grid_slice_tuple[0]
+        a, b = max(lo, x0), min(hi, x1)
+        if b <= a:
+            continue
+        sl = (slice(a - lo, b - lo),)
+        psi_E[pml.name] = tuple(np.ascontiguousarray(q[sl]) for q in f.psi_E[pml.name])
+        psi_H[pml.name] = tuple(np.ascontiguousarray(q[sl]) for q in f.psi_H[pml.name])
+    det = {}
+    for d in objects.detectors:
+        lo, hi = d.grid_slice_tuple[0]
+        if hi <= x0 or lo >= x1:
+            continue
+        if lo < x0 or hi > x1:
+            raise NotImplementedError(f"detector {d.name!r} straddles the slab edge at x = {x0 if lo < x0 else x1}")
+        det[d.name] = arrays.detector_states[d.name]
+    rec = None
+    if arrays.recording_state is not None:
+        data = {}
+        for pml in objects.pml_objects:
+            for fs in ("E", "H"):
+                buf = arrays.recording_state.data[f"{pml.name}_{fs}"]
+                if pml.axis == 0:
+                    plane = pml.interface_slice()[0].start
+                    if x0 <= plane < x1:
+                        data[f"{pml.name}_{fs}"] = buf
+                else:
+                    data[f"{pml.name}_{fs}"] = cut(buf, 2)  # (slots, 3, Nx, ...)
+        rec = RecordingState(data=data, state={})
+    out = ArrayContainer(
+        fields=FieldState(E=cut(f.E, 1), H=cut(f.H, 1), psi_E=psi_E, psi_H=psi_H, dispersive_P_curr=cut(f.dispersive_P_curr, 2), dispersive_P_prev=cut(f.dispersive_P_prev, 2)),
+        inv_permittivities=cut(arrays.inv_permittivities, 1), inv_permeabilities=cut(arrays.inv_permeabilities, 1), detector_states=det, recording_state=rec,
+        electric_conductivity=cut(arrays.electric_conductivity, 1), magnetic_conductivity=cut(arrays.magnetic_conductivity, 1),
+        dispersive_c1=cut(arrays.dispersive_c1, 2), dispersive_c2=cut(arrays.dispersive_c2, 2), dispersive_c3=cut(arrays.dispersive_c3, 2), dispersive_c4=cut(arrays.dispersive_c4, 2),
+    )
+    return out if device is None else out.to_torch(device)
+
+
 class HaloExchange:
     """Point-to-point exchange of one packed plane with the two x-neighbours over
     ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests)."""
@@ -195,9 +256,19 @@ class SlabRunner:
             self._range(t, 1, last, self.nx)
         self.plan.run_forward_phase(t, 2, record_detectors, False, True)
 
-    def run(self, t0: int, n: int, record_detectors: bool = False):
+    def run(self, t0: int, n: int, record_detectors: bool = False, record_boundaries: bool = False):
         if self.peer:  # one asynchronous submission for the whole run
-            self.plan.run_forward(t0, n, record_detectors, False, True)
+            self.plan.run_forward(t0, n, record_detectors, record_boundaries, True)
             return
+        if record_boundaries:
+            raise NotImplementedError("interface recording on slabs runs on the peer-memory halo")
         for t in range(t0, t0 + n):
             self.step(t, record_detectors)
+
+    def run_reverse(self, t_from: int, n: int, record_detectors: bool = False, reset_fields: bool = True):
+        """``full_backward`` on this rank's slab (``backward.py:18-135``): interface replay, reverse H and
+        E half-steps reading the neighbours' planes in place, PML field reset, inverse detectors.  One
+        asynchronous submission; needs the peer-memory halo."""
+        if not self.peer:
+            raise NotImplementedError("the time-reversed pass on slabs runs on the peer-memory halo")
+        self.plan.run_reverse(t_from, n, record_detectors, reset_fields)

@@ -497,7 +497,10 @@ class Plan:
             for pml in self.objects.pml_objects:
                 q = self.pml_index[pml.name]
                 for f, fs in enumerate(("E", "H")):
-                    self._bind(_lib.SLOT_REC_DATA, 2 * q + f, arrays.recording_state.data[f"{pml.name}_{fs}"], self.recorder.torch_dtype())
+                    buf = arrays.recording_state.data.get(f"{pml.name}_{fs}")
+                    if buf is None:
+                        continue  # x-sharded: this x interface plane lives on another rank
+                    self._bind(_lib.SLOT_REC_DATA, 2 * q + f, buf, self.recorder.torch_dtype())
         self._bind_tensor_path(arrays)
 
     def _bind_tensor_path(self, arrays):

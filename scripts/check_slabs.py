@@ -42,6 +42,60 @@ for name, build, steps in (
         ok = ok and good
         print(f"[rank {rank}] {name} halo={halo} overlap={overlap}: max|dE|={dE:.3e} max|dH|={dH:.3e} det={ddet:.3e} (|E|max={mx:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
         objects_f.__dict__.pop("_plan_cache", None)
+# ---- recorder + time-reversed pass on slabs (peer-memory halo): forward with PML-interface recording,
+# full_backward with interface replay, PML reset and an inverse detector, vs the single-GPU run
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from scenes import build_scene
+from fdtdx_b200.dist import shard_arrays
+
+for rec_name, modules in (("f32", []), ("every3+bf16", [fx.LinearReconstructEveryK(k=3), fx.DtypeConversion(dtype="bfloat16")])):
+    nxs = 16 * world
+    objects, arrays_np, cfg = build_scene(shape=(nxs, 14, 20), thickness=4, source="plane_z", time=5e-15, recorder=fx.Recorder(modules=modules), eps_tier=3, sigma_E=True)
+    dets = [fx.EnergyDetector(name=f"inv{r}", grid_slice_tuple=((16 * r + 2, 16 * r + 13), (1, 13), (2, 18)), as_slices=True, inverse=True) for r in range(world)]
+    dets += [fx.FieldDetector(name=f"fld{r}", grid_slice_tuple=((16 * r + 1, 16 * r + 15), (2, 12), (3, 17)), switch=fx.OnOffSwitch(interval=2)) for r in range(world)]
+    objects, arrays_np, _, cfg, _ = fx.place_objects(list(objects.object_list) + dets, cfg, inv_permittivities=arrays_np.inv_permittivities,
+                                                     electric_conductivity=arrays_np.electric_conductivity)
+    T = cfg.time_steps_total
+    x0, x1 = slab_bounds(nxs, world, rank)
+    arrays = shard_arrays(arrays_np, objects, (x0, x1), dev)
+    runner = SlabRunner(objects, cfg, arrays, (x0, x1), rank, world, halo="peer")
+    good = runner.peer
+    if good:
+        # forward and time-reversed pass are enqueued back to back, with no host synchronisation in between
+        runner.run(0, T, record_detectors=True, record_boundaries=True)
+        fwd = {"E": arrays.fields.E.clone(), "H": arrays.fields.H.clone(), "rec": {k: v.clone() for k, v in arrays.recording_state.data.items()}}
+        runner.run_reverse(T, T, record_detectors=True, reset_fields=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        full = arrays_np.to_torch(dev)
+        st = fx.run_fdtd(full, objects, cfg)
+        torch.cuda.synchronize()
+        fE = float((fwd["E"] - st[1].fields.E[:, x0:x1]).abs().max())
+        fH = float((fwd["H"] - st[1].fields.H[:, x0:x1]).abs().max())
+        frec = 0.0
+        for k, v in fwd["rec"].items():
+            r = st[1].recording_state.data[k]
+            r = r if k.split("_")[2] == "x" else r[:, :, x0:x1]
+            frec = max(frec, float((v.float() - r.float()).abs().max()))
+        print(f"[rank {rank}] recorder({rec_name}) forward on slabs: max|dE|={fE:.3e} max|dH|={fH:.3e} recorder buffers {frec:.3e}", flush=True)
+        good = good and fE == 0.0 and fH == 0.0 and frec == 0.0
+        st = fx.full_backward(st, objects, cfg, record_detectors=True, reset_fields=True)
+        torch.cuda.synchronize()
+        ref = st[1]
+        dE = float((arrays.fields.E - ref.fields.E[:, x0:x1]).abs().max())
+        dH = float((arrays.fields.H - ref.fields.H[:, x0:x1]).abs().max())
+        ddet, live = 0.0, 0.0
+        for k, v in arrays.detector_states.items():
+            for k2, v2 in v.items():
+                ddet = max(ddet, float((v2 - ref.detector_states[k][k2]).abs().max()))
+                live = max(live, float(ref.detector_states[k][k2].abs().max()))
+        good = good and dE == 0.0 and dH == 0.0 and ddet == 0.0 and live > 0 and int(runner.plan.lib.fdtdx_b200_peer_status(runner.plan.h)) == 0
+        print(f"[rank {rank}] recorder({rec_name}) + full_backward on slabs: max|dE|={dE:.3e} max|dH|={dH:.3e} det={ddet:.3e} (|det|max={live:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
+        objects.__dict__.pop("_plan_cache", None)
+    else:
+        print(f"[rank {rank}] recorder + full_backward on slabs: peer-memory halo unavailable, skipped", flush=True)
+        good = os.environ.get("FDTDX_B200_PEER_FAIL") is not None
+    ok = ok and good
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
