@@ -267,7 +267,35 @@ __device__ __forceinline__ void det_emit(const GridDev& G, const DetDev& D, cons
   const long long n = (long long)ex * ey * ez;
   const int slot = D.arr_idx[t];
   const bool staged = (D.flags & DET_REDUCE) || ((D.flags & DET_SLICES) && (D.flags & DET_SLICE_MEAN));
-  if (D.kind == 0 || D.kind == 3) {  // field / phasor: selected components
+  if (D.kind == 3 && !staged) {
+    // phasor accumulation (phasor.py:186-235): state += v * exp(i w t) * scale * window.  All read-modify-
+    // write operands of the cell are loaded before the first store (the state may alias nothing the
+    // compiler can prove, so interleaved loads / stores would serialise into one DRAM round trip each)
+    float vals[6];
+    int nci = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      if (D.comp_mask & (1 << c)) vals[nci++] = (c < 3) ? Es[c] : Hs[c - 3];
+    float2* __restrict__ st = reinterpret_cast<float2*>(D.state[0]);
+    const float w = D.window[t];
+    for (int f = 0; f < D.nf; ++f) {
+      const float2 ph = D.ph_table[(long long)t * D.nf + f];
+      float2 acc[6];
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci)
+        if (ci < nci) acc[ci] = st[((long long)f * D.ncomp + ci) * n + cell];
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci) {
+        if (ci >= nci) continue;
+        const float re = ((vals[ci] * ph.x) * D.scale) * w;
+        const float im = ((vals[ci] * ph.y) * D.scale) * w;
+        if (D.flags & DET_INVERSE) { acc[ci].x -= re; acc[ci].y -= im; } else { acc[ci].x += re; acc[ci].y += im; }
+      }
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci)
+        if (ci < nci) st[((long long)f * D.ncomp + ci) * n + cell] = acc[ci];
+    }
+  } else if (D.kind == 0 || D.kind == 3) {  // field / phasor: selected components
     int ci = 0;
     for (int c = 0; c < 6; ++c) {
       if (!(D.comp_mask & (1 << c))) continue;

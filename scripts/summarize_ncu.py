@@ -17,7 +17,7 @@ for r in rows:
     a[1] += us
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(pr, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write(f"# {tag} launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e\n")
+    f.write(f"# {tag} launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --c5-n 0\n")
     f.write("# (cold-cache, serialised per-launch times: compare SHARES, not absolutes). First 400 launches of the process.\n")
     f.write(f"{'kernel':90s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
     for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -38,7 +38,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 traffic = {}
 with open(os.path.join(pr, f"{tag}_coupler_yee_kernels.txt"), "w") as f:
-    f.write(f"# {tag}: ncu --set full --clock-control none --import-source on -k regex:yee_ -s 10 -c 2 python bench.py --steps 10 --warmup 3 (C2 coupler cpl=20, 70.7 Mcell)\n\n")
+    f.write(f"# {tag}: ncu --set full --clock-control none --import-source on -k regex:yee_ -s 10 -c 2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --c5-n 0 (C2 coupler cpl=20, 70.7 Mcell)\n\n")
     for r in rr[2:]:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
@@ -60,6 +60,10 @@ cur = json.load(open(tj)) if os.path.exists(tj) else {}
 cur["coupler"] = traffic.get("yee_E", cur.get("coupler"))
 cur["coupler_yee_H"] = traffic.get("yee_H")
 cur["source"] = f"profiles/{tag}_coupler_yee_kernels.txt"
+sys.path.insert(0, root)
+import bench  # noqa: E402
+
+cur["csrc_sha16"] = bench._csrc_sha()  # bench.py reports these figures only while the kernel sources are unchanged
 json.dump(cur, open(tj, "w"))
 print(open(os.path.join(pr, f"{tag}_launches_summary.txt")).read())
 print(open(os.path.join(pr, f"{tag}_coupler_yee_kernels.txt")).read())
