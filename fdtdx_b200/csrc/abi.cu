@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <array>
 #include <map>
 #include <tuple>
 
@@ -102,6 +103,13 @@ struct FdtdxPlan {
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
   double* d_energy_partial = nullptr;  // total_energy: per-block partial sums
   bool adjoint_exact = false;          // run_adjoint_exact: VJP at the bound state, no reverse step
+  // row-marching detector kernels (det_volume.cuh): plan-wide H_prev scratch in the layout of H, the
+  // step whose forward H half-step fills it itself (StepParams::hprev_out), x planes per CTA
+  float* d_hprev_full = nullptr;
+  int hprev_fused_t = -1;
+  int hprev_nbox = 0;
+  int hprev_box[FDTDX_MAX_HPBOX][4];  // {x0, x1, y0, y1}: rows the detectors active at that step read
+  int detv_xcl = 4;
 };
 
 extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
@@ -354,21 +362,28 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
     d.window = dw;
   }
   // large regions: aligned H_prev rows + row-marching kernels; needs 16-byte rows (Nz % 4 == 0)
-  h.volume = (flags & DET_VOLUME) && (p->nz % 4 == 0);
+  const size_t Ngrid = (size_t)p->nx * p->ny * p->nz;
+  h.volume = (flags & DET_VOLUME) && (p->nz % 4 == 0) && (3 * Ngrid * sizeof(float) <= ((size_t)16 << 30));
   d.flags &= ~DET_VOLUME;  // set per launch by sync_dets once the bound buffers are known to be aligned
   d.hz0 = lo[2] & ~3;
   d.hrow = ((hi[2] + 1 - d.hz0) + 3) & ~3;
   if (flags & DET_EXACT) {
-    size_t hn = (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
-    if (h.volume) hn = std::max(hn, (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (size_t)d.hrow);
+    const size_t hn = (size_t)3 * (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
     if ((rc = to_device<float>(p, nullptr, hn, &d.hprev))) return rc;
+    if (h.volume) {  // one (3,Nx,Ny,Nz) H_prev scratch for all row-marching detectors
+      if (!p->d_hprev_full && (rc = to_device<float>(p, nullptr, 3 * Ngrid, &p->d_hprev_full))) return rc;
+      d.hprev_full = p->d_hprev_full;
+    }
   }
   if (h.volume && kind == FDTDX_DET_ENERGY && (flags & DET_SLICES) && (flags & DET_SLICE_MEAN)) {
+    // partial sums of the three slice means: over z tiles, over y tiles, over x chunks (>= 4 planes each)
     const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
     d.npart[0] = (hi[2] - d.hz0 + DETV_TZ - 1) / DETV_TZ;
-    d.npart[1] = d.npart[2] = 0;
-    (void)ez;
+    d.npart[1] = (ey + DETV_ROWS - 1) / DETV_ROWS;
+    d.npart[2] = (ex + 3) / 4;
     if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[0] * ex * ey, &d.part[0]))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[1] * ex * ez, &d.part[1]))) return rc;
+    if ((rc = to_device<float>(p, nullptr, (size_t)d.npart[2] * ey * ez, &d.part[2]))) return rc;
   }
   h.nvals = 0;
   const bool staged = (flags & DET_REDUCE) || ((flags & DET_SLICES) && (flags & DET_SLICE_MEAN));
@@ -770,6 +785,41 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
   return std::max(1, std::min(std::min(xc, 64), P.x_end - P.x_begin));  // 64 = FDTDX_TMA_XC_MAX
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may start (up to its
+// pdl_wait()) while the previous kernel of the stream drains.  Only for kernels that call pdl_wait()
+// before touching anything a previous kernel wrote.  FDTDX_B200_PDL=0 turns the attribute off.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FDTDX_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// the small per-step kernels (sources, recorder, detectors): opt-in, FDTDX_B200_PDL_AUX=1
+static bool pdl_aux_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FDTDX_B200_PDL_AUX");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1 && pdl_enabled();
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*k)(KArgs...), dim3 g, dim3 b, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g;
+  cfg.blockDim = b;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_aux_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError()
+}
+
 static int launch_sources(FdtdxPlan* p, const StepParams& P, int t, bool is_E, bool rev, cudaStream_t st) {
   if (P.n_src == 0 || P.src_inline) return FDTDX_OK;
   long long mx = 0;
@@ -781,7 +831,7 @@ static int launch_sources(FdtdxPlan* p, const StepParams& P, int t, bool is_E, b
   if (mx <= 0) return FDTDX_OK;
   dim3 g((unsigned)std::min<long long>((mx + 255) / 256, 148 * 8), (unsigned)P.n_src);
   const int te = p->eps_tier == 1 ? 1 : 3, tm = p->mu_tier;
-#define GO(A, B) src_apply_kernel<A, B><<<g, 256, 0, st>>>(P, t, is_E ? 1 : 0, rev ? 1 : 0)
+#define GO(A, B) launch_pdl(src_apply_kernel<A, B>, g, dim3(256), st, P, t, is_E ? 1 : 0, rev ? 1 : 0)
   if (te == 1) { if (tm == 0) GO(1, 0); else if (tm == 1) GO(1, 1); else GO(1, 3); }
   else { if (tm == 0) GO(3, 0); else if (tm == 1) GO(3, 1); else GO(3, 3); }
 #undef GO
@@ -884,6 +934,26 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
 static int sync_dets(FdtdxPlan* p, cudaStream_t st) {
   if (p->dets.empty()) return FDTDX_OK;
   bool changed = p->dets_dirty;
+  {
+    // x planes per CTA of det_march_kernel: about one wave of CTAs (148 SMs x 2) over the largest region,
+    // 4..DETV_XC_MAX planes each (longer chunks amortise the x-1 rows carried in registers)
+    long long tiles = 1, max_ex = 1;
+    for (const DetHost& h : p->dets) {
+      if (!h.volume) continue;
+      tiles = std::max(tiles, (long long)((h.d.hi[2] - h.d.hz0 + DETV_TZ - 1) / DETV_TZ) * ((h.d.hi[1] - h.d.lo[1] + DETV_ROWS - 1) / DETV_ROWS));
+      max_ex = std::max<long long>(max_ex, h.d.hi[0] - h.d.lo[0]);
+    }
+    const long long chunks = std::max(1LL, 296 / tiles);
+    int xcl = (int)std::min<long long>(DETV_XC_MAX, std::max(4LL, (max_ex + chunks - 1) / chunks));
+    const char* e = getenv("FDTDX_B200_DETV_XC");
+    if (e && atoi(e) >= 4 && atoi(e) <= DETV_XC_MAX) xcl = atoi(e);
+    p->detv_xcl = xcl;
+    for (DetHost& h : p->dets) {
+      if (!h.volume || !h.d.part[2]) continue;
+      const int want = (h.d.hi[0] - h.d.lo[0] + xcl - 1) / xcl;
+      if (h.d.npart[2] != want) { h.d.npart[2] = want; changed = true; }
+    }
+  }
   for (size_t di = 0; di < p->dets.size(); ++di) {
     DetDev& d = p->dets[di].d;
     float* st[4];
@@ -892,7 +962,7 @@ static int sync_dets(FdtdxPlan* p, cudaStream_t st) {
       if (st[k] != d.state[k]) { d.state[k] = st[k]; changed = true; }
     if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
     {
-      const void* eh[3] = {p->slots[FDTDX_SLOT_E][0], p->slots[FDTDX_SLOT_H][0], d.hprev};
+      const void* eh[3] = {p->slots[FDTDX_SLOT_E][0], p->slots[FDTDX_SLOT_H][0], d.hprev_full};
       bool vol = p->dets[di].volume;
       for (const void* q : eh) vol = vol && (q == nullptr || aligned16(q));
       if (p->e_parity || p->h_parity) vol = vol && aligned16(p->slots[FDTDX_SLOT_E_ALT][0]) && aligned16(p->slots[FDTDX_SLOT_H_ALT][0]);
@@ -943,22 +1013,44 @@ static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
   make_grid(p, G);
   bool any_generic = false, any_volume = false;
   long long vol_rows = 0;
+  std::vector<std::array<int, 4>> boxes;
   for (const DetHost& h : p->dets) {
     if (((h.d.flags & DET_INVERSE) != 0) != inverse || !h.on[t] || !(h.d.flags & DET_EXACT)) continue;
     if (h.d.flags & DET_VOLUME) {
       any_volume = true;
+      // rows this detector reads: x in [lo-1, hi), y in [lo-1, hi); a wrapped halo row lies on the far face
+      std::array<int, 4> box = {std::max(h.d.lo[0] - 1, 0), h.d.hi[0], std::max(h.d.lo[1] - 1, 0), h.d.hi[1]};
+      if (h.d.lo[0] == 0 && p->wrap[0]) { box[0] = 0; box[1] = p->nx; }
+      if (h.d.lo[1] == 0 && p->wrap[1]) { box[2] = 0; box[3] = p->ny; }
+      boxes.push_back(box);
       vol_rows = std::max(vol_rows, 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1));
     } else any_generic = true;
   }
   if (any_generic) {
     dim3 g((unsigned)std::min<long long>((p->det_max_halo + 255) / 256, 148 * 8), (unsigned)p->dets.size());
-    det_gather_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+    launch_pdl(det_gather_batch_kernel, g, dim3(256), st, G, (const DetDev*)p->d_dets, t, inverse ? 1 : 0);
     p->launches++;
   }
+  p->hprev_fused_t = -1;
   if (any_volume) {
-    dim3 g((unsigned)std::min<long long>((vol_rows + 7) / 8, 148 * 64), (unsigned)p->dets.size());
-    det_gather_rows_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
-    p->launches++;
+    // forward direction, H half-step on the staged / marching kernels: that kernel stores the H it loads
+    // into the plan-wide H_prev scratch (StepParams::hprev_out) - no copy pass.  The time-reversed H
+    // kernel un-injects the sources before it loads H, and the full-tensor tier ping-pongs: copy here.
+    if (!inverse && !(p->mu_tier == 9 || p->sigH_tier == 9)) {
+      p->hprev_fused_t = t;
+      if ((int)boxes.size() > FDTDX_MAX_HPBOX) {  // more detectors than box slots: one bounding box
+        std::array<int, 4> u = boxes[0];
+        for (const auto& b : boxes) { u[0] = std::min(u[0], b[0]); u[1] = std::max(u[1], b[1]); u[2] = std::min(u[2], b[2]); u[3] = std::max(u[3], b[3]); }
+        boxes.assign(1, u);
+      }
+      p->hprev_nbox = (int)boxes.size();
+      for (int b = 0; b < p->hprev_nbox; ++b)
+        for (int q = 0; q < 4; ++q) p->hprev_box[b][q] = boxes[b][q];
+    } else {
+      dim3 g((unsigned)std::min<long long>((vol_rows + 7) / 8, 148 * 64), (unsigned)p->dets.size());
+      launch_pdl(det_gather_rows_kernel, g, dim3(256), st, G, (const DetDev*)p->d_dets, t, inverse ? 1 : 0);
+      p->launches++;
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return FDTDX_OK;
@@ -979,21 +1071,37 @@ static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
       vol[(h.d.flags & DET_EXACT) ? 1 : 0][(h.d.kind == FDTDX_DET_ENERGY && G.eps_tier != 9 && G.mu_tier != 9) ? 1 : 0] = true;
       gz = std::max(gz, (h.d.hi[2] - h.d.hz0 + DETV_TZ - 1) / DETV_TZ);
       gy = std::max(gy, (h.d.hi[1] - h.d.lo[1] + DETV_ROWS - 1) / DETV_ROWS);
-      nxc = std::max(nxc, (h.d.hi[0] - h.d.lo[0] + DETV_XC - 1) / DETV_XC);
+      nxc = std::max(nxc, (h.d.hi[0] - h.d.lo[0] + p->detv_xcl - 1) / p->detv_xcl);
     } else any_generic = true;
   }
   if (any_generic) {
     dim3 g((unsigned)std::min<long long>((p->det_max_cells + 255) / 256, 148 * 8), (unsigned)p->dets.size());
-    det_sample_batch_kernel<<<g, 256, 0, st>>>(G, p->d_dets, t, inverse ? 1 : 0);
+    launch_pdl(det_sample_batch_kernel, g, dim3(256), st, G, (const DetDev*)p->d_dets, t, inverse ? 1 : 0);
     p->launches++;
   }
   {
     dim3 g(gz, gy, nxc * (unsigned)p->dets.size()), b(32, DETV_ROWS);
     const int inv = inverse ? 1 : 0;
-    if (vol[1][1]) { det_march_kernel<true, 1><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
-    if (vol[1][0]) { det_march_kernel<true, 0><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
-    if (vol[0][1]) { det_march_kernel<false, 1><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
-    if (vol[0][0]) { det_march_kernel<false, 0><<<g, b, 0, st>>>(G, p->d_dets, t, inv, nxc); p->launches++; }
+    if (vol[1][1]) {
+      if (G.w[0] || G.w[1] || G.w[2]) launch_pdl(det_march_kernel<true, 1, true>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      else launch_pdl(det_march_kernel<true, 1, false>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      p->launches++;
+    }
+    if (vol[1][0]) {
+      if (G.w[0] || G.w[1] || G.w[2]) launch_pdl(det_march_kernel<true, 0, true>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      else launch_pdl(det_march_kernel<true, 0, false>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      p->launches++;
+    }
+    if (vol[0][1]) {
+      if (G.w[0] || G.w[1] || G.w[2]) launch_pdl(det_march_kernel<false, 1, true>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      else launch_pdl(det_march_kernel<false, 1, false>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      p->launches++;
+    }
+    if (vol[0][0]) {
+      if (G.w[0] || G.w[1] || G.w[2]) launch_pdl(det_march_kernel<false, 0, true>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      else launch_pdl(det_march_kernel<false, 0, false>, g, b, st, G, (const DetDev*)p->d_dets, t, inv, nxc, p->detv_xcl);
+      p->launches++;
+    }
   }
   if (any_post) {
     for (size_t di = 0; di < p->dets.size(); ++di) {
@@ -1004,7 +1112,7 @@ static int detectors_sample(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
         // the marching kernel reduced the three means into partial buffers: fold them
         const long long ex = h.d.hi[0] - h.d.lo[0], ey = h.d.hi[1] - h.d.lo[1], ez = h.d.hi[2] - h.d.lo[2];
         const long long nout = ex * ey + ex * ez + ey * ez;
-        det_mean_finish_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(p->d_dets, (int)di, t);
+        launch_pdl(det_mean_finish_kernel, dim3((unsigned)((nout + 255) / 256)), dim3(256), st, (const DetDev*)p->d_dets, (int)di, t);
         p->launches++;
         continue;
       }
@@ -1162,6 +1270,11 @@ static int step_H(FdtdxPlan* p, int t, int simulate, bool rev, cudaStream_t st) 
     }
     if (whole && p->halo_hi) peer_fence_wait_kernel<<<1, 1, 0, st>>>(nullptr, 0, p->peer[1].flags, (int)p->seqE, p->d_flags + 2);
   }
+  if (!rev && p->hprev_fused_t == t) {
+    P.hprev_out = p->d_hprev_full;
+    P.hprev_nbox = p->hprev_nbox;
+    memcpy(P.hprev_box, p->hprev_box, sizeof(P.hprev_box));
+  }
   rc = launch_H(p, P, t, rev, st);
   if (rc) return rc;
   if (whole) {
@@ -1282,7 +1395,7 @@ static int step_record(FdtdxPlan* p, int t, int record_detectors, int record_bou
       }
       if (R.n_planes > 0) {
         dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
-        rec_record_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, slot);
+        launch_pdl(rec_record_kernel, g, dim3(256), st, R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, slot);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
       }
@@ -1328,6 +1441,11 @@ extern "C" int fdtdx_b200_run_half_range(FdtdxPlan* p, int t, int which, int x_b
     // ADE ping-pong flips once per step: callers issue the range starting at plane 0 last
     if (!rc && p->n_poles > 0 && x_begin == 0) p->p_parity ^= 1;
     return rc;
+  }
+  if (p->hprev_fused_t == t) {
+    P.hprev_out = p->d_hprev_full;
+    P.hprev_nbox = p->hprev_nbox;
+    memcpy(P.hprev_box, p->hprev_box, sizeof(P.hprev_box));
   }
   return launch_H(p, P, t, false, st);
 }
@@ -1392,8 +1510,8 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
       if ((rc = peer_fence_begin(p, st))) return rc;
       if (R.n_planes > 0) {
         dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
-        rec_replay_kernel<<<g, 256, 0, st>>>(R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, p->replay_a[t],
-                                             p->replay_b[t], p->replay_w[t]);
+        launch_pdl(rec_replay_kernel, g, dim3(256), st, R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, (int)p->replay_a[t],
+                   (int)p->replay_b[t], p->replay_w[t]);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
       }
@@ -1423,7 +1541,7 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
       if ((rc = peer_fence_begin(p, st))) return rc;
       if (B.n > 0) {
         dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
-        reset_pml_kernel<<<g, 256, 0, st>>>(B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
+        launch_pdl(reset_pml_kernel, g, dim3(256), st, B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
       }

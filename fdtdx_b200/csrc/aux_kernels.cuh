@@ -47,6 +47,7 @@ struct DetDev {
   int hrow, hz0;   // DET_VOLUME: row length of hprev and the global z of its element 0 (a multiple of 4)
   float* part[3];  // DET_VOLUME slice means: partial sums over z tiles / y tiles / x chunks
   int npart[3];
+  float* hprev_full;  // DET_VOLUME: plan-wide (3,Nx,Ny,Nz) copy of H before this step's H update (det_volume.cuh)
   float* state[4];
 };
 
@@ -92,8 +93,10 @@ __global__ void det_gather_hprev_kernel(const GridDev G, const DetDev D) { det_g
 // (the descriptor is staged in shared memory: read through a global reference it is re-loaded after
 // every store, because the stores may alias it)
 __device__ __forceinline__ void det_stage_descriptor(DetDev* dst, const DetDev* src) {
+  pdl_trigger();
   for (int q = threadIdx.x; q < (int)(sizeof(DetDev) / 4); q += blockDim.x) reinterpret_cast<int*>(dst)[q] = reinterpret_cast<const int*>(src)[q];
   __syncthreads();
+  pdl_wait();
 }
 __global__ void det_gather_batch_kernel(const GridDev G, const DetDev* __restrict__ dets, const int t, const int inverse) {
   __shared__ DetDev sD;
@@ -542,37 +545,42 @@ struct RecDev {
 };
 
 // blockIdx.y = plane * 2 + field
+// a face holds < 2^31 / 3 cells: 32-bit index arithmetic (64-bit div / mod is ~100 instructions each)
 __global__ void rec_record_kernel(const RecDev R, float* E, float* H, int nx, int ny, int nz, int slot) {
+  pdl_trigger();
   const RecPlane& pl = R.planes[blockIdx.y >> 1];
   const int fld = blockIdx.y & 1;
   const float* F = fld ? H : E;
   const int ex = pl.hi[0] - pl.lo[0], ey = pl.hi[1] - pl.lo[1], ez = pl.hi[2] - pl.lo[2];
-  const long long fn = (long long)ex * ey * ez;
+  const unsigned fn = (unsigned)ex * ey * ez;
   const long long N = (long long)nx * ny * nz;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < 3 * fn; idx += (long long)gridDim.x * blockDim.x) {
+  pdl_wait();
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 3 * fn; idx += gridDim.x * blockDim.x) {
     const int c = (int)(idx / fn);
-    long long r = idx - c * fn;
-    const int z = pl.lo[2] + (int)(r % ez); r /= ez;
-    const int y = pl.lo[1] + (int)(r % ey);
-    const int x = pl.lo[0] + (int)(r / ey);
+    unsigned r = idx - c * fn;
+    const int z = pl.lo[2] + (int)(r % (unsigned)ez); r /= (unsigned)ez;
+    const int y = pl.lo[1] + (int)(r % (unsigned)ey);
+    const int x = pl.lo[0] + (int)(r / (unsigned)ey);
     const float v = F[c * N + ((long long)x * ny + y) * nz + z];
     rec_store(pl.data[fld], R.dtype, (long long)slot * 3 * fn + idx, v);
   }
 }
 
 __global__ void rec_replay_kernel(const RecDev R, float* E, float* H, int nx, int ny, int nz, int sa, int sb, float w) {
+  pdl_trigger();
   const RecPlane& pl = R.planes[blockIdx.y >> 1];
   const int fld = blockIdx.y & 1;
   float* F = fld ? H : E;
   const int ex = pl.hi[0] - pl.lo[0], ey = pl.hi[1] - pl.lo[1], ez = pl.hi[2] - pl.lo[2];
-  const long long fn = (long long)ex * ey * ez;
+  const unsigned fn = (unsigned)ex * ey * ez;
   const long long N = (long long)nx * ny * nz;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < 3 * fn; idx += (long long)gridDim.x * blockDim.x) {
+  pdl_wait();
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 3 * fn; idx += gridDim.x * blockDim.x) {
     const int c = (int)(idx / fn);
-    long long r = idx - c * fn;
-    const int z = pl.lo[2] + (int)(r % ez); r /= ez;
-    const int y = pl.lo[1] + (int)(r % ey);
-    const int x = pl.lo[0] + (int)(r / ey);
+    unsigned r = idx - c * fn;
+    const int z = pl.lo[2] + (int)(r % (unsigned)ez); r /= (unsigned)ez;
+    const int y = pl.lo[1] + (int)(r % (unsigned)ey);
+    const int x = pl.lo[0] + (int)(r / (unsigned)ey);
     float v = rec_load(pl.data[fld], R.dtype, (long long)sa * 3 * fn + idx);
     if (sb != sa) {
       const float nxt = rec_load(pl.data[fld], R.dtype, (long long)sb * 3 * fn + idx);
@@ -588,6 +596,8 @@ struct BoxList {
 };
 // zero E and H inside every PML slab (backward.py:117-122)
 __global__ void reset_pml_kernel(const BoxList B, float* E, float* H, int nx, int ny, int nz) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int ex = B.hi[b][0] - B.lo[b][0], ey = B.hi[b][1] - B.lo[b][1], ez = B.hi[b][2] - B.lo[b][2];
   const long long n = (long long)ex * ey * ez;

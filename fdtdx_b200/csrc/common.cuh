@@ -11,6 +11,7 @@
 
 #define FDTDX_MAX_SRC 8
 #define FDTDX_MAX_WALL 12
+#define FDTDX_MAX_HPBOX 4
 
 struct AxisPmlDev {
   int lo_len;    // local cells [0, lo_len) belong to the '-' slab (0: none)
@@ -116,7 +117,28 @@ struct StepParams {
   int peer_total;
   int* peer_err;          // set to 1 when a wait gave up (neighbour stalled): results are invalid
   int z_reverse;          // E step: blockIdx.z counts chunks from the high-x end, so the boundary chunk runs last
+  // Forward H half-step on a step where a large exact-interpolation detector is on: the kernel also
+  // stores the H it loaded (H before this update = H_prev of update.py:1088) into this (3,Nx,Ny,Nz)
+  // scratch, so the detector pass needs no separate H_prev copy (det_volume.cuh).  nullptr: off.
+  float* hprev_out;
+  // planes / rows the active detectors read (incl. their x-1 / y-1 halo): {x0, x1, y0, y1} per box
+  int hprev_nbox;
+  int hprev_box[FDTDX_MAX_HPBOX][4];
 };
+__device__ __forceinline__ bool hprev_wanted(const StepParams& P, const int i, const int j) {
+  bool w = false;
+#pragma unroll
+  for (int q = 0; q < FDTDX_MAX_HPBOX; ++q)
+    if (q < P.hprev_nbox && i >= P.hprev_box[q][0] && i < P.hprev_box[q][1] && j >= P.hprev_box[q][2] && j < P.hprev_box[q][3]) w = true;
+  return w;
+}
+
+// Programmatic dependent launch (every per-step kernel is launched with the programmatic-stream-
+// serialization attribute): pdl_trigger() lets the next kernel of the stream begin its prologue as soon as
+// all CTAs of this grid have started; pdl_wait() returns once the previous kernel of the stream has
+// completed and its writes are visible.  Everything before pdl_wait() may touch only constant tables.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <int V>
 struct Vec {

@@ -20,9 +20,11 @@ __global__ void src_apply_kernel(const StepParams P, const int t, const int is_E
   // the source descriptors live in global memory; stage them once per block (they are read many times
   // along a dependent chain: box, switch tables, profile parameters, array pointers)
   __shared__ SrcDev s_src[FDTDX_MAX_SRC];
+  pdl_trigger();
   for (int q = threadIdx.x; q < P.n_src * (int)(sizeof(SrcDev) / 4); q += blockDim.x)
     reinterpret_cast<int*>(s_src)[q] = reinterpret_cast<const int*>(P.src)[q];
   __syncthreads();
+  pdl_wait();
   const int lo0 = max(P.src_lo[s][0], P.x_begin), hi0 = min(P.src_hi[s][0], P.x_end);
   const int d0 = hi0 - lo0, d1 = P.src_hi[s][1] - P.src_lo[s][1], d2 = P.src_hi[s][2] - P.src_lo[s][2];
   if (d0 <= 0 || d1 <= 0 || d2 <= 0) return;

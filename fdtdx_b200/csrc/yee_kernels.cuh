@@ -1039,6 +1039,12 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
+    if (!KONLY && !REV && P.hprev_out != nullptr && hprev_wanted(P, i, j)) {  // H_prev for the detector pass
+      float* hp = P.hprev_out + (pH - P.H);
+      stv<V>(hp, hx, nv);
+      stv<V>(hp + N, hy, nv);
+      stv<V>(hp + 2 * N, hz, nv);
+    }
     stv<V>(pH, o0, nv);
     stv<V>(pH + N, o1, nv);
     stv<V>(pH + 2 * N, o2, nv);

@@ -623,6 +623,12 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     FDTDX_TCPML_BLOCK(psiH, aH, bH, kH)
     const float* sH = sb + 3 * G::HALO_F + op;
     const Vec<V> hx = lds4(sH), hy = lds4(sH + G::PLAIN_F), hz = lds4(sH + 2 * G::PLAIN_F);
+    if (!REV && P.hprev_out != nullptr && lane_ok && hprev_wanted(P, i, j)) {  // H_prev for the detector pass
+      float* hp = P.hprev_out + cell0;
+      stv<V>(hp, hx);
+      stv<V>(hp + N, hy);
+      stv<V>(hp + 2 * N, hz);
+    }
     Vec<V> im0, im1, im2;
     if (MUT >= 1) {
       im0 = lds4(sH + 3 * G::PLAIN_F);
