@@ -199,11 +199,10 @@ class PerfectMagneticConductor(BaseBoundary):
 
 @dataclass
 class BlochBoundary(BaseBoundary):
-    """Periodic boundary = ``BlochBoundary(k=0)`` (``bloch.py``).
-
-    Only the real ``k = 0`` case is on the hot path; a non-zero Bloch vector needs complex fields
-    ("next") and is rejected by the plan compiler.
-    """
+    """``objects/boundaries/bloch.py``: ``F(x + L) = F(x) exp(i k L)``.  A zero Bloch vector is the plain
+    periodic boundary; a non-zero component along this boundary's axis needs
+    complex fields (``initialization.py:581-596``), which the kernels run as two real systems whose
+    wrapped ghost planes are mixed with the phase (``fdtdx_b200/bloch.py``)."""
 
     bloch_vector: tuple[float, float, float] = (0.0, 0.0, 0.0)
 
@@ -213,7 +212,20 @@ class BlochBoundary(BaseBoundary):
 
     @property
     def needs_complex_fields(self) -> bool:
-        return any(k != 0.0 for k in self.bloch_vector)
+        """``bloch.py:31-38``: only the component along this boundary's axis matters."""
+        return self.bloch_vector[self.axis] != 0.0
+
+    def get_bloch_phase(self, volume_shape, config):
+        """``bloch.py:135-155``: ``exp(i k_axis L)`` as complex64, ``L`` = physical extent of the axis.
+        jnp evaluates the weakly typed ``1j * k * L`` in float32, so the angle is rounded first."""
+        k = self.bloch_vector[self.axis]
+        if config.has_nonuniform_grid:
+            edges = np.asarray(config.resolved_grid.edges(self.axis), dtype=np.float32)
+            L = np.float32(edges[volume_shape[self.axis]] - edges[0])
+        else:
+            L = volume_shape[self.axis] * config.uniform_spacing()
+        theta = np.float32(k * L)
+        return np.complex64(complex(np.cos(theta), np.sin(theta)))
 
 
 PeriodicBoundary = BlochBoundary
@@ -224,11 +236,13 @@ def boundary_objects_from_config(
     config,
     types: dict[str, str] | str = "pml",
     thickness: int = 10,
+    bloch_vector: tuple[float, float, float] = (0.0, 0.0, 0.0),
 ) -> list[BaseBoundary]:
     """Build the six boundary objects of a box (stands in for the reference's
     ``BoundaryConfig`` + ``boundary_objects_from_config``, ``objects/boundaries/initialization.py``).
 
-    ``types`` maps "min_x".."max_z" to "pml" | "periodic" | "pec" | "pmc" (or one string for all).
+    ``types`` maps "min_x".."max_z" to "pml" | "periodic" | "bloch" | "pec" | "pmc" (or one string for all);
+    "bloch" faces carry ``bloch_vector`` (rad/m).
     """
     names = ["min_x", "max_x", "min_y", "max_y", "min_z", "max_z"]
     if isinstance(types, str):
@@ -246,6 +260,8 @@ def boundary_objects_from_config(
             out.append(PerfectlyMatchedLayer(**kw).place_on_grid(config))
         elif kind == "periodic":
             out.append(BlochBoundary(**kw))
+        elif kind == "bloch":
+            out.append(BlochBoundary(bloch_vector=tuple(float(v) for v in bloch_vector), **kw))
         elif kind == "pec":
             out.append(PerfectElectricConductor(**kw))
         elif kind == "pmc":

@@ -137,6 +137,7 @@ class SimulationConfig:
     courant_factor: float = 0.99
     gradient_config: GradientConfig | None = None
     symmetry: tuple[int, int, int] = (0, 0, 0)
+    use_complex_fields: bool | None = None  # None: complex iff a Bloch boundary has k != 0 (initialization.py:581-596)
 
     def aset(self, name: str, value: Any) -> "SimulationConfig":
         return replace(self, **{name: value})

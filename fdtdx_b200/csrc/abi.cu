@@ -110,6 +110,9 @@ struct FdtdxPlan {
   int hprev_nbox = 0;
   int hprev_box[FDTDX_MAX_HPBOX][4];  // {x0, x1, y0, y1}: rows the detectors active at that step read
   int detv_xcl = 4;
+  // Bloch axes with k != 0: this plan is one of the two real systems of a complex run
+  bool bloch = false;
+  float bloch_c[3] = {1.f, 1.f, 1.f}, bloch_s[3] = {0.f, 0.f, 0.f};
 };
 
 extern "C" const char* fdtdx_b200_last_error(void) { return g_err.c_str(); }
@@ -419,6 +422,16 @@ extern "C" int fdtdx_b200_halo_bind(FdtdxPlan* p, int has_lo, int has_hi) {
   return FDTDX_OK;
 }
 
+extern "C" int fdtdx_b200_set_bloch(FdtdxPlan* p, int enable, const double cos_kL[3], const double sin_kL[3]) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  p->bloch = enable != 0;
+  for (int a = 0; a < 3; ++a) {
+    p->bloch_c[a] = (enable && cos_kL) ? (float)cos_kL[a] : 1.0f;
+    p->bloch_s[a] = (enable && sin_kL) ? (float)sin_kL[a] : 0.0f;
+  }
+  return FDTDX_OK;
+}
+
 extern "C" int fdtdx_b200_bind(FdtdxPlan* p, int slot, int index, void* ptr) {
   if (!p || slot < 0 || slot >= FDTDX_SLOT_COUNT || index < 0 || index >= MAX_IDX)
     return fail(FDTDX_EINVAL, "bind: bad slot/index");
@@ -599,6 +612,12 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     if (!P.c1 || !P.c2 || !P.c3 || (p->has_c4 && !P.c4)) return fail(FDTDX_EUNBOUND, "dispersive coefficients must be bound");
     P.c_cs = (p->coeff_tier == 1) ? 0 : N;
   }
+  if (p->bloch) {
+    P.bE = (const float*)p->slots[FDTDX_SLOT_BLOCH_E][0];
+    P.bH = (const float*)p->slots[FDTDX_SLOT_BLOCH_H][0];
+    if (!P.bE || !P.bH) return fail(FDTDX_EUNBOUND, "BLOCH_E / BLOCH_H (the partner system's fields) must be bound");
+    for (int a = 0; a < 3; ++a) { P.bc[a] = p->bloch_c[a]; P.bs[a] = p->bloch_s[a]; }
+  }
   P.haloH = (const float*)p->slots[FDTDX_SLOT_HALO_H_LO][0];
   P.haloE = (const float*)p->slots[FDTDX_SLOT_HALO_E_HI][0];
   P.haloH_cs = P.haloE_cs = (long long)p->ny * p->nz;
@@ -752,7 +771,7 @@ static bool tma_wanted(const FdtdxPlan* p) {
 }
 // The staged kernels cover 128-bit-capable grids whose y / z halos are zero (PML, PEC, PMC faces).
 static bool can_tma(const FdtdxPlan* p, const StepParams& P, bool v4) {
-  if (!v4 || !tma_wanted(p) || p->wrap[1] || p->wrap[2]) return false;
+  if (!v4 || !tma_wanted(p) || p->wrap[1] || p->wrap[2] || p->bloch) return false;  // Bloch ghosts are mixed at the wrap sites of the marching kernels
   if ((long long)p->nz * p->ny * 4 >= (1LL << 40) || p->ny < 1) return false;
   return encode_tiled_fn() != nullptr;
 }
@@ -928,6 +947,11 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
   G.eps_tier = p->eps_tier;
   G.mu_tier = p->mu_tier;
   G.inv_mu_scalar = (float)p->inv_mu_scalar;
+  if (p->bloch) {
+    G.Ep = (const float*)p->slots[FDTDX_SLOT_BLOCH_E][0];
+    G.Hp = (const float*)p->slots[FDTDX_SLOT_BLOCH_H][0];
+    for (int a = 0; a < 3; ++a) { G.bc[a] = p->bloch_c[a]; G.bs[a] = p->bloch_s[a]; }
+  }
 }
 
 // Upload the detector descriptors (with the currently bound state pointers) for the batched launches.
@@ -1486,69 +1510,79 @@ extern "C" int fdtdx_b200_run_forward(FdtdxPlan* p, int t0, int n, int record_de
   return FDTDX_OK;
 }
 
-extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int record_detectors, int reset_fields,
-                                      void* stream) {
+extern "C" int fdtdx_b200_run_reverse_phase(FdtdxPlan* p, int t, int phase, int record_detectors, int reset_fields, void* stream) {
   if (!p) return fail(FDTDX_EINVAL, "null plan");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = finalize(p);
   if (rc) return rc;
-  for (int t = t_from - 1; t > t_from - 1 - n; --t) {
-    if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "reverse time step outside [0, T)");
-    if (!p->has_rec) return fail(FDTDX_EINVAL, "Need recorder to record boundaries");
-    if ((p->halo_lo || p->halo_hi) && !p->peer_mode)
-      return fail(FDTDX_EUNSUPPORTED, "run_reverse on an x-sharded plan needs the peer-memory halo (peer_attach)");
-    if (!p->pmls.empty()) {
-      RecDev R;
-      if ((rc = make_rec(p, R))) return rc;
-      GridDev G;
-      make_grid(p, G);
-      long long fmax = 0;
-      for (int q = 0; q < R.n_planes; ++q) {
-        const RecPlane& pl = R.planes[q];
-        fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
-      }
-      if ((rc = peer_fence_begin(p, st))) return rc;
-      if (R.n_planes > 0) {
-        dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
-        launch_pdl(rec_replay_kernel, g, dim3(256), st, R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, (int)p->replay_a[t],
-                   (int)p->replay_b[t], p->replay_w[t]);
-        p->launches++;
-        CUDA_TRY(cudaGetLastError());
-      }
-      if ((rc = peer_fence_end(p, st))) return rc;
+  if (t < 0 || t >= p->T) return fail(FDTDX_EINVAL, "reverse time step outside [0, T)");
+  if (!p->has_rec) return fail(FDTDX_EINVAL, "Need recorder to record boundaries");
+  if ((p->halo_lo || p->halo_hi) && !p->peer_mode)
+    return fail(FDTDX_EUNSUPPORTED, "run_reverse on an x-sharded plan needs the peer-memory halo (peer_attach)");
+  if (phase == 0) {  // add_interfaces (update.py:1181-1222)
+    if (p->pmls.empty()) return FDTDX_OK;
+    RecDev R;
+    if ((rc = make_rec(p, R))) return rc;
+    GridDev G;
+    make_grid(p, G);
+    long long fmax = 0;
+    for (int q = 0; q < R.n_planes; ++q) {
+      const RecPlane& pl = R.planes[q];
+      fmax = std::max(fmax, 3LL * (pl.hi[0] - pl.lo[0]) * (pl.hi[1] - pl.lo[1]) * (pl.hi[2] - pl.lo[2]));
     }
-    if (record_detectors && (rc = detectors_gather(p, t, true, st))) return rc;
-    if ((rc = step_H(p, t, 0, true, st))) return rc;
-    if ((rc = step_E(p, t, 0, true, st))) return rc;
-    if (reset_fields && !p->pmls.empty()) {
-      BoxList B;
-      B.n = 0;
-      long long nmax = 0;
-      const int nn[3] = {p->nx, p->ny, p->nz};
-      for (const PmlHost& h : p->pmls) {
-        for (int a = 0; a < 3; ++a) { B.lo[B.n][a] = 0; B.hi[B.n][a] = nn[a]; }
-        int lo = h.lo, hi = h.hi;
-        if (h.axis == 0) {  // this rank's part of an x slab
-          lo = std::max(lo - p->xoff, 0); hi = std::min(hi - p->xoff, p->nx);
-          if (hi <= lo) continue;
-        }
-        B.lo[B.n][h.axis] = lo; B.hi[B.n][h.axis] = hi;
-        nmax = std::max(nmax, (long long)(hi - lo) * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
-        B.n++;
-      }
-      GridDev G;
-      make_grid(p, G);
-      if ((rc = peer_fence_begin(p, st))) return rc;
-      if (B.n > 0) {
-        dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
-        launch_pdl(reset_pml_kernel, g, dim3(256), st, B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
-        p->launches++;
-        CUDA_TRY(cudaGetLastError());
-      }
-      if ((rc = peer_fence_end(p, st))) return rc;
+    if ((rc = peer_fence_begin(p, st))) return rc;
+    if (R.n_planes > 0) {
+      dim3 g((unsigned)std::min<long long>((fmax + 255) / 256, 1024), 2 * R.n_planes);
+      launch_pdl(rec_replay_kernel, g, dim3(256), st, R, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz, (int)p->replay_a[t],
+                 (int)p->replay_b[t], p->replay_w[t]);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
     }
-    if (record_detectors && (rc = detectors_sample(p, t, true, st))) return rc;
+    return peer_fence_end(p, st);
   }
+  if (phase == 1) return record_detectors ? detectors_gather(p, t, true, st) : FDTDX_OK;
+  if (phase == 2) return step_H(p, t, 0, true, st);
+  if (phase == 3) return step_E(p, t, 0, true, st);
+  if (phase == 4) {  // apply_field_reset in every PML slab (backward.py:117-122)
+    if (!reset_fields || p->pmls.empty()) return FDTDX_OK;
+    BoxList B;
+    B.n = 0;
+    long long nmax = 0;
+    const int nn[3] = {p->nx, p->ny, p->nz};
+    for (const PmlHost& h : p->pmls) {
+      for (int a = 0; a < 3; ++a) { B.lo[B.n][a] = 0; B.hi[B.n][a] = nn[a]; }
+      int lo = h.lo, hi = h.hi;
+      if (h.axis == 0) {  // this rank's part of an x slab
+        lo = std::max(lo - p->xoff, 0); hi = std::min(hi - p->xoff, p->nx);
+        if (hi <= lo) continue;
+      }
+      B.lo[B.n][h.axis] = lo; B.hi[B.n][h.axis] = hi;
+      nmax = std::max(nmax, (long long)(hi - lo) * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
+      B.n++;
+    }
+    GridDev G;
+    make_grid(p, G);
+    if ((rc = peer_fence_begin(p, st))) return rc;
+    if (B.n > 0) {
+      dim3 g((unsigned)std::min<long long>((nmax + 255) / 256, 4096), B.n);
+      launch_pdl(reset_pml_kernel, g, dim3(256), st, B, (float*)G.E, (float*)G.H, p->nx, p->ny, p->nz);
+      p->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    return peer_fence_end(p, st);
+  }
+  if (phase == 5) return record_detectors ? detectors_sample(p, t, true, st) : FDTDX_OK;
+  return fail(FDTDX_EINVAL, "run_reverse_phase: phase must be 0..5");
+}
+
+extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int record_detectors, int reset_fields,
+                                      void* stream) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  for (int t = t_from - 1; t > t_from - 1 - n; --t)
+    for (int phase = 0; phase < 6; ++phase) {
+      int rc = fdtdx_b200_run_reverse_phase(p, t, phase, record_detectors, reset_fields, stream);
+      if (rc) return rc;
+    }
   return FDTDX_OK;
 }
 

@@ -26,6 +26,10 @@ struct GridDev {
   int eps_tier, mu_tier;  // 1 | 3 | 9 (mu: 0 = scalar)
   float inv_mu_scalar;
   const float* w[3];  // cell widths per axis (global indexing for x) or nullptr on a uniform grid
+  // Bloch axes with k != 0 (two real systems, see StepParams::bH): partner arrays and (cos, +-sin)
+  const float* Ep;
+  const float* Hp;
+  float bc[3], bs[3];
 };
 
 struct DetDev {
@@ -66,14 +70,31 @@ struct DetDev {
 template <bool CHK>
 __device__ __forceinline__ float grid_at_t(const GridDev& G, const float* F, int c, int x, int y, int z);
 __device__ __forceinline__ float grid_at(const GridDev& G, const float* F, int c, int x, int y, int z) {
-  if (x < 0) { if (G.wrap[0]) x += G.nx; else return 0.0f; }
-  if (x >= G.nx) { if (G.wrap[0]) x -= G.nx; else return 0.0f; }
-  if (y < 0) { if (G.wrap[1]) y += G.ny; else return 0.0f; }
-  if (y >= G.ny) { if (G.wrap[1]) y -= G.ny; else return 0.0f; }
-  if (z < 0) { if (G.wrap[2]) z += G.nz; else return 0.0f; }
-  if (z >= G.nz) { if (G.wrap[2]) z -= G.nz; else return 0.0f; }
+  int side[3] = {0, 0, 0};  // -1: low-side ghost (x conj(phase)), +1: high-side ghost (x phase)
+  if (x < 0) { if (G.wrap[0]) { x += G.nx; side[0] = -1; } else return 0.0f; }
+  if (x >= G.nx) { if (G.wrap[0]) { x -= G.nx; side[0] = 1; } else return 0.0f; }
+  if (y < 0) { if (G.wrap[1]) { y += G.ny; side[1] = -1; } else return 0.0f; }
+  if (y >= G.ny) { if (G.wrap[1]) { y -= G.ny; side[1] = 1; } else return 0.0f; }
+  if (z < 0) { if (G.wrap[2]) { z += G.nz; side[2] = -1; } else return 0.0f; }
+  if (z >= G.nz) { if (G.wrap[2]) { z -= G.nz; side[2] = 1; } else return 0.0f; }
   const long long N = (long long)G.nx * G.ny * G.nz;
-  return F[c * N + ((long long)x * G.ny + y) * G.nz + z];
+  const long long idx = c * N + ((long long)x * G.ny + y) * G.nz + z;
+  float a = F[idx];
+  if (G.Ep != nullptr && (side[0] | side[1] | side[2])) {
+    // Bloch ghost: the pad corrections of the wrapped axes are applied one after the other (bloch.py:61-96)
+    const float* Fp = (F == G.E) ? G.Ep : ((F == G.H) ? G.Hp : nullptr);
+    if (Fp != nullptr) {
+      float b = Fp[idx];
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        if (side[ax] == 0) continue;
+        const float cc = G.bc[ax], ss = (side[ax] < 0) ? G.bs[ax] : -G.bs[ax];
+        const float na = a * cc + b * ss, nb = b * cc - a * ss;
+        a = na; b = nb;
+      }
+    }
+  }
+  return a;
 }
 
 // _backward_edge_average (curl.py:42-83)

@@ -117,6 +117,14 @@ struct StepParams {
   int peer_total;
   int* peer_err;          // set to 1 when a wait gave up (neighbour stalled): results are invalid
   int z_reverse;          // E step: blockIdx.z counts chunks from the high-x end, so the boundary chunk runs last
+  // Bloch-periodic axes with a non-zero wave vector (bloch.py:61-96, complex fields): the run is two
+  // real systems (Re, Im) stepped side by side.  A wrapped ghost value on the LOW side of axis a is
+  // F_ghost = F[N-1] * conj(phase): self * bc[a] + partner * bs[a]; on the HIGH side F[0] * phase:
+  // self * bc[a] - partner * bs[a], where (bc, bs) = (cos, sin) of k_a * L_a for the Re system and
+  // (cos, -sin) for the Im system, and bH / bE are the partner system's H / E arrays (nullptr: plain wrap).
+  const float* bH;
+  const float* bE;
+  float bc[3], bs[3];
   // Forward H half-step on a step where a large exact-interpolation detector is on: the kernel also
   // stores the H it loaded (H before this update = H_prev of update.py:1088) into this (3,Nx,Ny,Nz)
   // scratch, so the detector pass needs no separate H_prev copy (det_volume.cuh).  nullptr: off.
@@ -177,6 +185,14 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const Vec<V>& r, cons
     for (int e = 0; e < V; ++e)
       if (e < nv) p[e * FDTDX_ES] = r.v[e];
   }
+}
+// Bloch ghost value: self * c + partner * s (see StepParams::bH)
+template <int V>
+__device__ __forceinline__ Vec<V> bloch_mix(const Vec<V>& a, const Vec<V>& b, const float c, const float s) {
+  Vec<V> r;
+#pragma unroll
+  for (int e = 0; e < V; ++e) r.v[e] = a.v[e] * c + b.v[e] * s;
+  return r;
 }
 template <int V>
 __device__ __forceinline__ Vec<V> zerov() {

@@ -746,8 +746,13 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     hy_im = ldv<V>(pH + N - plane, nv);
     hz_im = ldv<V>(pH + 2 * N - plane, nv);
   } else if (P.x_lo_mode == 1) {
-    hy_im = ldv<V>(P.H + N + (long long)(P.nx - 1) * plane + row, nv);
-    hz_im = ldv<V>(P.H + 2 * N + (long long)(P.nx - 1) * plane + row, nv);
+    const long long o = (long long)(P.nx - 1) * plane + row;
+    hy_im = ldv<V>(P.H + N + o, nv);
+    hz_im = ldv<V>(P.H + 2 * N + o, nv);
+    if (P.bH != nullptr) {  // Bloch ghost plane: H[nx-1] * conj(phase_x)
+      hy_im = bloch_mix<V>(hy_im, ldv<V>(P.bH + N + o, nv), P.bc[0], P.bs[0]);
+      hz_im = bloch_mix<V>(hz_im, ldv<V>(P.bH + 2 * N + o, nv), P.bc[0], P.bs[0]);
+    }
   } else if (P.x_lo_mode == 2) {
     hy_im = ldv<V>(P.haloH + row, nv);
     hz_im = ldv<V>(P.haloH + P.haloH_cs + row, nv);
@@ -763,6 +768,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
     if (jm_ok) {
       hx_jm = ldv<V>(pH + djm, nv);
       hz_jm = ldv<V>(pH + 2 * N + djm, nv);
+      if (P.bH != nullptr && j == 0) {  // Bloch ghost row: H[ny-1] * conj(phase_y)
+        const float* q = P.bH + (pH - P.H) + djm;
+        hx_jm = bloch_mix<V>(hx_jm, ldv<V>(q, nv), P.bc[1], P.bs[1]);
+        hz_jm = bloch_mix<V>(hz_jm, ldv<V>(q + 2 * N, nv), P.bc[1], P.bs[1]);
+      }
     } else {
       hx_jm = zerov<V>();
       hz_jm = zerov<V>();
@@ -809,6 +819,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
       if (lane == 0) {
         hx_kmv.v[0] = km_ok ? pH[dkm] : 0.0f;
         hy_kmv.v[0] = km_ok ? pH[N + dkm] : 0.0f;
+        if (P.bH != nullptr && k0 == 0 && km_ok) {  // Bloch ghost column: H[nz-1] * conj(phase_z)
+          const float* q = P.bH + (pH - P.H) + dkm;
+          hx_kmv.v[0] = hx_kmv.v[0] * P.bc[2] + q[0] * P.bs[2];
+          hy_kmv.v[0] = hy_kmv.v[0] * P.bc[2] + q[N] * P.bs[2];
+        }
       }
     } else {
       float hx_l = __shfl_up_sync(wmask, hx.v[V - 1], 1);
@@ -816,6 +831,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
       if (lane == 0) {
         hx_l = km_ok ? pH[dkm] : 0.0f;
         hy_l = km_ok ? pH[N + dkm] : 0.0f;
+        if (P.bH != nullptr && k0 == 0 && km_ok) {  // Bloch ghost column: H[nz-1] * conj(phase_z)
+          const float* q = P.bH + (pH - P.H) + dkm;
+          hx_l = hx_l * P.bc[2] + q[0] * P.bs[2];
+          hy_l = hy_l * P.bc[2] + q[N] * P.bs[2];
+        }
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -928,6 +948,10 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     } else if (P.x_hi_mode == 1) {
       ey_n = ldv<V>(P.E + N + row, nv);
       ez_n = ldv<V>(P.E + 2 * N + row, nv);
+      if (P.bE != nullptr) {  // Bloch ghost plane: E[0] * phase_x
+        ey_n = bloch_mix<V>(ey_n, ldv<V>(P.bE + N + row, nv), P.bc[0], -P.bs[0]);
+        ez_n = bloch_mix<V>(ez_n, ldv<V>(P.bE + 2 * N + row, nv), P.bc[0], -P.bs[0]);
+      }
     } else if (P.x_hi_mode == 2) {
       ey_n = ldv<V>(P.haloE + row, nv);
       ez_n = ldv<V>(P.haloE + P.haloE_cs + row, nv);
@@ -939,6 +963,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
     if (jp_ok) {
       ex_jp = ldv<V>(pE + djp, nv);
       ez_jp = ldv<V>(pE + 2 * N + djp, nv);
+      if (P.bE != nullptr && j == ny - 1) {  // Bloch ghost row: E[0] * phase_y
+        const float* q = P.bE + (pE - P.E) + djp;
+        ex_jp = bloch_mix<V>(ex_jp, ldv<V>(q, nv), P.bc[1], -P.bs[1]);
+        ez_jp = bloch_mix<V>(ez_jp, ldv<V>(q + 2 * N, nv), P.bc[1], -P.bs[1]);
+      }
     } else {
       ex_jp = zerov<V>();
       ez_jp = zerov<V>();
@@ -982,6 +1011,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
         if (kn >= nz) {
           ex_kpv.v[e] = P.wrap[2] ? pE[-k0] : 0.0f;
           ey_kpv.v[e] = P.wrap[2] ? pE[N - k0] : 0.0f;
+          if (P.bE != nullptr && P.wrap[2]) {  // Bloch ghost column: E[0] * phase_z
+            const float* q = P.bE + (pE - P.E) - k0;
+            ex_kpv.v[e] = ex_kpv.v[e] * P.bc[2] - q[0] * P.bs[2];
+            ey_kpv.v[e] = ey_kpv.v[e] * P.bc[2] - q[N] * P.bs[2];
+          }
         } else if (e == V - 1 && lane == 31) {
           ex_kpv.v[e] = pE[kn - k0];
           ey_kpv.v[e] = pE[N + kn - k0];
@@ -993,6 +1027,11 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_H_kernel(const
       if (last_lane) {
         ex_r = kp_ok ? pE[dkp] : 0.0f;
         ey_r = kp_ok ? pE[N + dkp] : 0.0f;
+        if (P.bE != nullptr && k0 + V >= nz && kp_ok) {  // Bloch ghost column: E[0] * phase_z
+          const float* q = P.bE + (pE - P.E) + dkp;
+          ex_r = ex_r * P.bc[2] - q[0] * P.bs[2];
+          ey_r = ey_r * P.bc[2] - q[N] * P.bs[2];
+        }
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {

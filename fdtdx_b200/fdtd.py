@@ -35,8 +35,12 @@ def get_plan(arrays: ArrayContainer, objects: ObjectContainer, config: Simulatio
     mu = arrays.inv_permeabilities
     # the cache entry keeps the config alive (Plan.config), so its id cannot be recycled while the
     # entry exists; entries whose config is a different object are never returned
+    from fdtdx_b200.bloch import ComplexPlan, is_complex_run
+
+    cplx = is_complex_run(arrays)
     key = (
         id(config),
+        cplx,
         arrays.fields.E.device.index,
         tuple(arrays.inv_permittivities.shape),
         tuple(mu.shape) if hasattr(mu, "shape") else float(mu),
@@ -49,7 +53,8 @@ def get_plan(arrays: ArrayContainer, objects: ObjectContainer, config: Simulatio
     if plan is not None and plan.config is not config:
         plan = None
     if plan is None:
-        plan = Plan(objects, config, arrays)
+        # complex fields (Bloch k != 0, initialization.py:581-596): two lock-stepped real systems
+        plan = ComplexPlan(objects, config, arrays) if cplx else Plan(objects, config, arrays)
         cache[key] = plan
     plan.bind(arrays)
     return plan

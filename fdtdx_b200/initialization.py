@@ -113,12 +113,20 @@ def init_arrays(
 ) -> ArrayContainer:
     """Allocate the step's arrays with the reference's layouts (``initialization.py:552-842``)."""
     shape = objects.volume.grid_shape
-    E = np.zeros((3, *shape), _f32)
-    H = np.zeros((3, *shape), _f32)
+    # complex-valued fields only when a Bloch boundary carries a non-zero wave vector (initialization.py:581-596)
+    needs_complex = any(getattr(b, "needs_complex_fields", False) for b in objects.boundary_objects)
+    use_complex = needs_complex if config.use_complex_fields is None else bool(config.use_complex_fields)
+    if needs_complex and not use_complex:
+        raise ValueError(
+            "use_complex_fields=False but Bloch boundaries with non-zero wave vector are present. These require complex-valued fields."
+        )
+    fdt = np.complex64 if use_complex else _f32
+    E = np.zeros((3, *shape), fdt)
+    H = np.zeros((3, *shape), fdt)
     psi_E, psi_H = {}, {}
     for pml in objects.pml_objects:
-        psi_E[pml.name] = (np.zeros(pml.grid_shape, _f32), np.zeros(pml.grid_shape, _f32))
-        psi_H[pml.name] = (np.zeros(pml.grid_shape, _f32), np.zeros(pml.grid_shape, _f32))
+        psi_E[pml.name] = (np.zeros(pml.grid_shape, fdt), np.zeros(pml.grid_shape, fdt))
+        psi_H[pml.name] = (np.zeros(pml.grid_shape, fdt), np.zeros(pml.grid_shape, fdt))
     det_states = {d.name: d.init_state() for d in objects.detectors}
     rec_state = None
     gc = config.gradient_config
@@ -131,7 +139,9 @@ def init_arrays(
             for fs in ("E", "H"):
                 shp = (rec._latent_array_size, 3, *pml.interface_grid_shape())
                 if rec.dtype_code == 0:
-                    data[f"{pml.name}_{fs}"] = np.zeros(shp, _f32)
+                    data[f"{pml.name}_{fs}"] = np.zeros(shp, fdt)
+                elif use_complex:
+                    raise NotImplementedError("DtypeConversion of complex (Bloch) interface recordings")
                 else:
                     from fdtdx_b200.container import _TorchLeaf
 

@@ -77,8 +77,11 @@ def _profile_params(profile, wave_character):
 class Plan:
     """Owns one ``FdtdxPlan*``.  ``x_range`` restricts the plan to an x-slab (multi-GPU)."""
 
-    def __init__(self, objects, config, arrays, x_range: tuple[int, int] | None = None, halo=(False, False)):
+    def __init__(self, objects, config, arrays, x_range: tuple[int, int] | None = None, halo=(False, False), bloch_role: str | None = None):
         self.lib = _lib.lib()
+        # bloch_role "re" / "im": this plan is one of the two real systems of a complex (Bloch k != 0) run
+        # (fdtdx_b200/bloch.py); the Im system carries no sources (a real injection enters the real part)
+        self.bloch_role = bloch_role
         self.objects, self.config = objects, config
         shape = objects.volume.grid_shape
         self.global_shape = shape
@@ -93,7 +96,7 @@ class Plan:
         # multiple of 4, the extra cells are kept at zero by all-component PEC+PMC walls (so they are the
         # zero halo the z-max face would see anyway), a z-max CPML slab is extended over them with zero
         # coefficients, and the caller's arrays are copied in before / out after every run call.
-        self.pad = 0 if (x_range is not None or any(halo)) else self._z_padding(objects, config, arrays, nz)
+        self.pad = 0 if (x_range is not None or any(halo) or bloch_role is not None) else self._z_padding(objects, config, arrays, nz)
         self.nz_true = nz
         nz = nz + self.pad
         self._shadow = {}
@@ -108,8 +111,8 @@ class Plan:
         wrap = [False, False, False]
         for b in objects.boundary_objects:
             if b.uses_wrap_padding:
-                if getattr(b, "needs_complex_fields", False):
-                    raise NotImplementedError("Bloch boundaries with k != 0 need complex fields (out of scope)")
+                if getattr(b, "needs_complex_fields", False) and bloch_role is None:
+                    raise ValueError("Bloch boundaries with k != 0 need complex fields: pass a container whose E / H are complex64")
                 wrap[b.axis] = True
         if any(s != 0 for s in config.symmetry):
             raise NotImplementedError("config.symmetry is outside the hot-path scope (setup-time domain reduction)")
@@ -140,8 +143,18 @@ class Plan:
         )
         self.h = h
         self._add_boundaries()
-        self._add_sources()
+        if bloch_role != "im":
+            self._add_sources()
         self._add_detectors()
+        if bloch_role is not None:
+            if x_range is not None or any(halo):
+                raise NotImplementedError("complex (Bloch) runs on x-sharded plans")
+            cs, sn = [1.0, 1.0, 1.0], [0.0, 0.0, 0.0]
+            for b in objects.boundary_objects:
+                if getattr(b, "needs_complex_fields", False):
+                    ph = b.get_bloch_phase(shape, config)
+                    cs[b.axis], sn[b.axis] = float(np.real(ph)), float(np.imag(ph)) * (1.0 if bloch_role == "re" else -1.0)
+            check(self.lib.fdtdx_b200_set_bloch(self.h, 1, (C.c_double * 3)(*cs), (C.c_double * 3)(*sn)))
         self._set_recorder()
         self.n_poles = 0
         if arrays.dispersive_c1 is not None:
@@ -364,7 +377,7 @@ class Plan:
             # large exact regions (videos, volume reductions, whole cross-sections): row-marching kernels
             # with 128-bit accesses instead of one thread per cell (csrc/det_volume.cuh)
             ext = [h_ - l_ for l_, h_ in zip(lo, hi)]
-            if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0":
+            if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0" and self.bloch_role is None:
                 surface_only = (isinstance(det, EnergyDetector) and det.as_slices and not det.use_mean) or isinstance(det, ClosedSurfacePoyntingFluxDetector)
                 if not surface_only:  # three planes / the box shell only: O(surface) work already
                     flags |= _lib.DETF_VOLUME
@@ -571,6 +584,13 @@ class Plan:
         self._sync_in()
         check(self.lib.fdtdx_b200_run_forward_phase(self.h, int(t), int(phase), int(record_detectors), int(record_boundaries), int(simulate_boundaries), self._stream()))
         self._sync_out()
+
+    def run_reverse_phase(self, t: int, phase: int, record_detectors: bool, reset_fields: bool):
+        check(self.lib.fdtdx_b200_run_reverse_phase(self.h, int(t), int(phase), int(record_detectors), int(reset_fields), self._stream()))
+
+    def bind_bloch_partner(self, E, H):
+        self._bind(_lib.SLOT_BLOCH_E, 0, E)
+        self._bind(_lib.SLOT_BLOCH_H, 0, H)
 
     def run_reverse(self, t_from: int, n: int, record_detectors: bool, reset_fields: bool):
         self.set_tensor_direction(True)

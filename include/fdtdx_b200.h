@@ -79,7 +79,9 @@ enum FdtdxSlot {
   FDTDX_SLOT_GRAD_C2 = 34,
   FDTDX_SLOT_GRAD_C3 = 35,
   FDTDX_SLOT_GRAD_C4 = 36,
-  FDTDX_SLOT_COUNT = 37
+  FDTDX_SLOT_BLOCH_E = 37,   /* complex (Bloch k != 0) runs: E of the partner system (Re <-> Im), bloch.py:61-96 */
+  FDTDX_SLOT_BLOCH_H = 38,
+  FDTDX_SLOT_COUNT = 39
 };
 
 enum FdtdxBoundaryKind { FDTDX_WALL_PEC = 0, FDTDX_WALL_PMC = 1 };
@@ -171,6 +173,12 @@ int fdtdx_b200_plan_set_recorder(FdtdxPlan* plan, int dtype, int n_slots, const 
 int fdtdx_b200_plan_set_dispersion(FdtdxPlan* plan, int n_poles, int coeff_tier, int has_c4);
 /* x-slab neighbours: 0 = domain edge (zero / local wrap), 1 = halo buffer bound. */
 int fdtdx_b200_halo_bind(FdtdxPlan* plan, int has_lo_neighbour, int has_hi_neighbour);
+/* BlochBoundary.apply_pad_correction (objects/boundaries/bloch.py:61-96) for a non-zero Bloch vector.  The
+ * complex fields run as two real systems (Re, Im), one plan each; every wrapped ghost value mixes the
+ * system's own field with its partner's (FDTDX_SLOT_BLOCH_E / _H): low side F[N-1] * conj(phase) =
+ * self * cos[a] + partner * sin[a], high side F[0] * phase = self * cos[a] - partner * sin[a].  Pass
+ * (cos, sin) of k_a * L_a for the Re system and (cos, -sin) for the Im system; enable = 0 turns it off. */
+int fdtdx_b200_set_bloch(FdtdxPlan* plan, int enable, const double cos_kL[3], const double sin_kL[3]);
 
 int fdtdx_b200_bind(FdtdxPlan* plan, int slot, int index, void* device_ptr);
 
@@ -197,6 +205,10 @@ int fdtdx_b200_run_reverse(FdtdxPlan* plan, int t_from, int n, int record_detect
 /* n iterations of the reversible_fdtd backward loop (fdtd/fdtd.py:215-251 body_fn): one reverse
  * step, then the VJP of one forward step at the reconstructed state, accumulating
  * GRAD_INV_EPS / GRAD_INV_MU and carrying COT_E/COT_H/COT_PSI_*. */
+/* One phase of the reversed step t (backward.py:62-135), for callers that interleave two plans (the Re / Im
+ * systems of a complex run): 0 replay the recorded interfaces, 1 copy H for the inverse detectors, 2
+ * update_H_reverse, 3 update_E_reverse, 4 field reset in the PML (if reset_fields), 5 inverse detectors. */
+int fdtdx_b200_run_reverse_phase(FdtdxPlan* plan, int t, int phase, int record_detectors, int reset_fields, void* stream);
 int fdtdx_b200_run_adjoint(FdtdxPlan* plan, int t_from, int n, void* stream);
 /* VJP of ONE forward step t at the state that is currently bound (E_t, H_t, psi_t), without the
  * time-reversed reconstruction: the building block of the checkpointed gradient

@@ -57,6 +57,13 @@ def get_wrap_padding_axes(objects) -> tuple[bool, bool, bool]:
     return tuple(wrap)
 
 
+def _C(x):
+    """Cast to the field dtype: float32, or complex64 for the complex fields of a Bloch run with
+    k != 0 (initialization.py:581-596)."""
+    x = np.asarray(x)
+    return x.astype(np.complex64) if np.iscomplexobj(x) else x.astype(F)
+
+
 def pad_fields(fields: np.ndarray, periodic_axes) -> np.ndarray:
     padded = fields
     for i, periodic in enumerate(periodic_axes):
@@ -74,9 +81,19 @@ def pad_fields_for_boundaries(fields, objects, config) -> np.ndarray:
             idx = [slice(None)] * 4
             idx[axis + 1] = slice(0, 1)
             padded[tuple(idx)] = 0
+    # BlochBoundary.apply_pad_correction (bloch.py:61-96): the ghost plane that wrapped from the far
+    # side is multiplied by conj(phase) on the '-' face and by phase on the '+' face
+    shape = objects.volume.grid_shape
     for b in objects.boundary_objects:
         if isinstance(b, BlochBoundary) and b.needs_complex_fields:
-            raise NotImplementedError("complex Bloch fields are out of scope (SURVEY 8 f3)")
+            phase = b.get_bloch_phase(shape, config)
+            idx = [slice(None)] * 4
+            if b.direction == "-":
+                idx[b.axis + 1] = 0
+                padded[tuple(idx)] = (padded[tuple(idx)] * np.conj(phase)).astype(np.complex64)
+            else:
+                idx[b.axis + 1] = -1
+                padded[tuple(idx)] = (padded[tuple(idx)] * phase).astype(np.complex64)
     return padded
 
 
@@ -150,7 +167,7 @@ def curl_E(config, E_pad, psi_H, objects, simulate_boundaries: bool):
         comps[i][gs] += -c1
         comps[j][gs] += c2
         psi_new[pml.name] = (p1n, p2n)
-    return np.stack(comps, axis=0).astype(F), psi_new
+    return _C(np.stack(comps, axis=0)), psi_new
 
 
 def curl_H(config, H_pad, psi_E, objects, simulate_boundaries: bool):
@@ -185,7 +202,7 @@ def curl_H(config, H_pad, psi_E, objects, simulate_boundaries: bool):
         comps[i][gs] += -c1
         comps[j][gs] += c2
         psi_new[pml.name] = (p1n, p2n)
-    return np.stack(comps, axis=0).astype(F), psi_new
+    return _C(np.stack(comps, axis=0)), psi_new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -519,7 +536,7 @@ def update_E(time_step: int, arrays: ArrayContainer, objects, config, simulate_b
             arrays = arrays.aset("fields->dispersive_P_curr", P_hat.astype(F))
         E = _tensor_apply(E_old, curl, A, B, objects, config, "E", +1.0)
 
-    E = np.array(E, dtype=F)
+    E = _C(np.array(E))
     E = _apply_sources(E, arrays, objects, config, time_step, "E", inverse=False)
     E = apply_boundary_post_E_update(E, objects)
     return arrays.aset("fields->E", E)
@@ -556,7 +573,7 @@ def update_E_reverse(time_step: int, arrays: ArrayContainer, objects, config) ->
     else:
         A, B = _update_matrices_cached(inv_eps, sigma_E, config.courant_number, eta0, reverse=True)
         E = _tensor_apply(E, curl, A, B, objects, config, "E", -1.0)
-    E = apply_boundary_post_E_update(np.array(E, dtype=F), objects)
+    E = apply_boundary_post_E_update(_C(np.array(E)), objects)
     return arrays.aset("fields->E", E)
 
 
@@ -581,7 +598,7 @@ def update_H(time_step: int, arrays: ArrayContainer, objects, config, simulate_b
     else:
         A, B = _update_matrices_cached(inv_mu, sigma_H, config.courant_number, 1 / eta0)
         H = _tensor_apply(arrays.fields.H, curl, A, B, objects, config, "H", -1.0)
-    H = np.array(H, dtype=F)
+    H = _C(np.array(H))
     H = _apply_sources(H, arrays, objects, config, time_step, "H", inverse=False)
     H = apply_boundary_post_H_update(H, objects)
     return arrays.aset("fields->H", H)
@@ -607,7 +624,7 @@ def update_H_reverse(time_step: int, arrays: ArrayContainer, objects, config) ->
     else:
         A, B = _update_matrices_cached(inv_mu, sigma_H, config.courant_number, 1 / eta0, reverse=True)
         H = _tensor_apply(H, curl, A, B, objects, config, "H", +1.0)
-    H = apply_boundary_post_H_update(np.array(H, dtype=F), objects)
+    H = apply_boundary_post_H_update(_C(np.array(H)), objects)
     return arrays.aset("fields->H", H)
 
 
@@ -649,7 +666,7 @@ def interpolate_fields(E_pad, H_pad, config=None, region_slice=None):
     hi_x = bea(Hz[1:-1, 1:-1, 2:], Hz[:-2, 1:-1, 2:], 0)
     hi_xy = bea(hi_x, bea(Hz[1:-1, :-2, 2:], Hz[:-2, :-2, 2:], 0), 1)
     Hz_i = (lo_xy + hi_xy) / F(2.0)
-    return np.stack([Ex_i, Ey_i, Ez_i]).astype(F), np.stack([Hx_i, Hy_i, Hz_i]).astype(F)
+    return _C(np.stack([Ex_i, Ey_i, Ez_i])), _C(np.stack([Hx_i, Hy_i, Hz_i]))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -684,6 +701,9 @@ def _sum0(x):
 
 
 def compute_poynting_flux(E, H):
+    if np.iscomplexobj(E) or np.iscomplexobj(H):  # jnp.cross(E, conj(H)) (metrics.py:99-117); callers take .real
+        H = np.conj(H)
+        return np.stack([E[1] * H[2] - E[2] * H[1], E[2] * H[0] - E[0] * H[2], E[0] * H[1] - E[1] * H[0]], axis=0).real.astype(F)
     return np.stack(
         [E[1] * H[2] - E[2] * H[1], E[2] * H[0] - E[0] * H[2], E[0] * H[1] - E[1] * H[0]], axis=0
     ).astype(F)
@@ -831,7 +851,7 @@ def update_detector_states(time_step: int, arrays: ArrayContainer, objects, conf
 # ----------------------------------------------------------------------------------------------
 def _cast_to_rec(x: np.ndarray, recorder):
     if recorder.dtype_code == REC_F32:
-        return x.astype(F)
+        return _C(x)
     import torch
 
     return _TorchLeaf(torch.from_numpy(np.ascontiguousarray(x)).to(recorder.torch_dtype()))
@@ -842,13 +862,13 @@ def _cast_from_rec(x) -> np.ndarray:
         import torch
 
         return x.t.to(torch.float32).numpy()
-    return np.asarray(x, dtype=F)
+    return _C(x)
 
 
 def _rec_get(buf, idx: int) -> np.ndarray:
     if isinstance(buf, _TorchLeaf):
         return _cast_from_rec(_TorchLeaf(buf.t[idx]))
-    return buf[idx].astype(F)
+    return _C(buf[idx])
 
 
 def _rec_set(buf, idx: int, val: np.ndarray, recorder):
