@@ -20,8 +20,8 @@ LIB_PATH = os.environ.get("FDTDX_B200_LIB") or os.path.join(os.path.dirname(os.p
     SLOT_E_ALT, SLOT_H_ALT, SLOT_TENSOR_A_E, SLOT_TENSOR_B_E, SLOT_TENSOR_A_H, SLOT_TENSOR_B_H,
     SLOT_HALO_H_LO, SLOT_HALO_E_HI, SLOT_GRAD_INV_EPS, SLOT_GRAD_INV_MU, SLOT_COT_E, SLOT_COT_H,
     SLOT_COT_PSI_E, SLOT_COT_PSI_H, SLOT_COT_DET, SLOT_COT_P, SLOT_COT_P_PREV, SLOT_GRAD_C1, SLOT_GRAD_C2, SLOT_GRAD_C3,
-    SLOT_GRAD_C4, SLOT_BLOCH_E, SLOT_BLOCH_H, SLOT_COUNT,
-) = range(40)
+    SLOT_GRAD_C4, SLOT_BLOCH_E, SLOT_BLOCH_H, SLOT_DET_XLO_E, SLOT_DET_XLO_H, SLOT_DET_XLO_HPREV, SLOT_COUNT,
+) = range(43)
 
 DET_FIELD, DET_ENERGY, DET_POYNTING, DET_PHASOR = 0, 1, 2, 3
 DETF_EXACT, DETF_INVERSE, DETF_REDUCE, DETF_SLICES, DETF_SLICE_MEAN, DETF_KEEP_ALL, DETF_NEGATIVE, DETF_VOLUME, DETF_CLOSED = 1, 2, 4, 8, 16, 32, 64, 128, 256
@@ -34,7 +34,7 @@ EXPORTS = [
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
     "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_peer_detach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
     "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
-    "fdtdx_b200_plan_source_set_quadrature", "fdtdx_b200_peer_status", "fdtdx_b200_set_bloch", "fdtdx_b200_run_reverse_phase",
+    "fdtdx_b200_plan_source_set_quadrature", "fdtdx_b200_peer_status", "fdtdx_b200_set_bloch", "fdtdx_b200_run_reverse_phase", "fdtdx_b200_plan_detector_set_wsum",
 ]
 
 _p = C.c_void_p
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_plan_set_dispersion.argtypes = [_p, _i, _i, _i]
     L.fdtdx_b200_halo_bind.argtypes = [_p, _i, _i]
     L.fdtdx_b200_set_bloch.argtypes = [_p, _i, _dp, _dp]
+    L.fdtdx_b200_plan_detector_set_wsum.argtypes = [_p, _i, _d]
     L.fdtdx_b200_run_reverse_phase.argtypes = [_p, _i, _i, _i, _i, _p]
     L.fdtdx_b200_bind.argtypes = [_p, _i, _i, _p]
     L.fdtdx_b200_run_forward.argtypes = [_p, _i, _i, _i, _i, _i, _p]

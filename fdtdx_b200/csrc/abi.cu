@@ -79,6 +79,7 @@ struct FdtdxPlan {
   // dispersion
   int n_poles = 0, coeff_tier = 1, has_c4 = 0;
   int halo_lo = 0, halo_hi = 0;
+  bool halo_lo_planned = false;  // x_offset > 0: a lower neighbour rank exists (known at plan_create, before halo_bind)
   void* slots[FDTDX_SLOT_COUNT][MAX_IDX];
   std::vector<void*> owned;
   bool finalized = false;
@@ -143,6 +144,7 @@ extern "C" int fdtdx_b200_plan_create(FdtdxPlan** out, int nx, int ny, int nz, i
   p->eps_tier = eps_tier; p->mu_tier = mu_tier; p->sigE_tier = sigma_e_tier; p->sigH_tier = sigma_h_tier;
   p->inv_mu_scalar = inv_mu_scalar;
   for (int a = 0; a < 3; ++a) p->wrap[a] = wrap ? wrap[a] : 0;
+  p->halo_lo_planned = (nx != nx_global) && (x_offset > 0 || p->wrap[0]);
   memset(p->slots, 0, sizeof(p->slots));
   p->metric = (sB != nullptr && sB[0] != nullptr);
   const int n[3] = {nx, ny, nz};
@@ -329,9 +331,11 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
   if (p->nx != p->nxg) {
     // x-sharded: the region and its co-location stencil (x-1) must lie inside this slab; detectors
     // straddling a slab edge would need an extra E-plane exchange - not built yet.
-    const int need_lo = (flags & DET_EXACT) ? 1 : 0;
-    if (d.lo[0] < need_lo || d.hi[0] > p->nx)
-      return fail(FDTDX_EUNSUPPORTED, "detector region (plus stencil) must lie inside one x-slab");
+    // the caller passes this rank's part of the region; an exact-interpolation detector that starts on
+    // plane 0 of a slab with a lower neighbour reads that neighbour's last plane from the DET_XLO_* buffers
+    // (on the first slab of a non-periodic axis plane -1 is the zero halo, as on an unsharded grid)
+    if (d.lo[0] < 0 || d.hi[0] > p->nx)
+      return fail(FDTDX_EUNSUPPORTED, "detector region must be clipped to this rank's x-slab");
   }
   d.ncomp = 0;
   for (int c = 0; c < 6; ++c) d.ncomp += (comp_mask >> c) & 1;
@@ -397,6 +401,13 @@ extern "C" int fdtdx_b200_plan_add_detector(FdtdxPlan* p, int kind, const int lo
   p->dets.push_back(h);
   p->dets_dirty = true;
   return (int)p->dets.size() - 1;
+}
+
+extern "C" int fdtdx_b200_plan_detector_set_wsum(FdtdxPlan* p, int detector_index, double weight_sum) {
+  if (!p || detector_index < 0 || detector_index >= (int)p->dets.size()) return fail(FDTDX_EINVAL, "detector_set_wsum: bad detector index");
+  p->dets[detector_index].d.wsum = (float)weight_sum;
+  p->dets_dirty = true;
+  return FDTDX_OK;
 }
 
 extern "C" int fdtdx_b200_plan_set_recorder(FdtdxPlan* p, int dtype, int n_slots, const int32_t* slot_of_time,
@@ -947,6 +958,12 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
   G.eps_tier = p->eps_tier;
   G.mu_tier = p->mu_tier;
   G.inv_mu_scalar = (float)p->inv_mu_scalar;
+  if (p->halo_lo) {
+    G.xlo_E = (const float*)p->slots[FDTDX_SLOT_DET_XLO_E][0];
+    G.xlo_H = (const float*)p->slots[FDTDX_SLOT_DET_XLO_H][0];
+    G.xlo_Hp = (const float*)p->slots[FDTDX_SLOT_DET_XLO_HPREV][0];
+    if (!G.xlo_E || !G.xlo_H || !G.xlo_Hp) G.xlo_E = G.xlo_H = G.xlo_Hp = nullptr;
+  }
   if (p->bloch) {
     G.Ep = (const float*)p->slots[FDTDX_SLOT_BLOCH_E][0];
     G.Hp = (const float*)p->slots[FDTDX_SLOT_BLOCH_H][0];
@@ -985,6 +1002,9 @@ static int sync_dets(FdtdxPlan* p, cudaStream_t st) {
     for (int k = 0; k < 4; ++k)
       if (st[k] != d.state[k]) { d.state[k] = st[k]; changed = true; }
     if (!d.state[0]) return fail(FDTDX_EUNBOUND, "detector state must be bound");
+    if (p->halo_lo && (d.flags & DET_EXACT) && d.lo[0] == 0 &&
+        (!p->slots[FDTDX_SLOT_DET_XLO_E][0] || !p->slots[FDTDX_SLOT_DET_XLO_H][0] || !p->slots[FDTDX_SLOT_DET_XLO_HPREV][0]))
+      return fail(FDTDX_EUNBOUND, "a detector starts on plane 0 of this x-slab: DET_XLO_E / _H / _HPREV (the lower neighbour's last plane) must be bound");
     {
       const void* eh[3] = {p->slots[FDTDX_SLOT_E][0], p->slots[FDTDX_SLOT_H][0], d.hprev_full};
       bool vol = p->dets[di].volume;
@@ -1035,6 +1055,7 @@ static int detectors_gather(FdtdxPlan* p, int t, bool inverse, cudaStream_t st) 
   if (rc) return rc;
   GridDev G;
   make_grid(p, G);
+  G.xlo_H = G.xlo_Hp;  // this pass copies H BEFORE the H update: the neighbour plane delivered for that instant
   bool any_generic = false, any_volume = false;
   long long vol_rows = 0;
   std::vector<std::array<int, 4>> boxes;

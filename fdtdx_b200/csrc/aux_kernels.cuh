@@ -30,6 +30,11 @@ struct GridDev {
   const float* Ep;
   const float* Hp;
   float bc[3], bs[3];
+  // x-slab sharding: plane x0-1 of the lower neighbour rank, (3,ny,nz) each, for detector stencils at local
+  // x = 0 (E, H of this step; H before this step's H update) - nullptr: halo rule (zero / wrap)
+  const float* xlo_E;
+  const float* xlo_H;
+  const float* xlo_Hp;
 };
 
 struct DetDev {
@@ -71,7 +76,17 @@ template <bool CHK>
 __device__ __forceinline__ float grid_at_t(const GridDev& G, const float* F, int c, int x, int y, int z);
 __device__ __forceinline__ float grid_at(const GridDev& G, const float* F, int c, int x, int y, int z) {
   int side[3] = {0, 0, 0};  // -1: low-side ghost (x conj(phase)), +1: high-side ghost (x phase)
-  if (x < 0) { if (G.wrap[0]) { x += G.nx; side[0] = -1; } else return 0.0f; }
+  if (x < 0) {
+    const float* X = (F == G.E) ? G.xlo_E : ((F == G.H) ? G.xlo_H : nullptr);
+    if (X != nullptr) {  // the lower neighbour rank's last plane
+      if (y < 0) { if (G.wrap[1]) y += G.ny; else return 0.0f; }
+      if (y >= G.ny) { if (G.wrap[1]) y -= G.ny; else return 0.0f; }
+      if (z < 0) { if (G.wrap[2]) z += G.nz; else return 0.0f; }
+      if (z >= G.nz) { if (G.wrap[2]) z -= G.nz; else return 0.0f; }
+      return X[((long long)c * G.ny + y) * G.nz + z];
+    }
+    if (G.wrap[0]) { x += G.nx; side[0] = -1; } else return 0.0f;
+  }
   if (x >= G.nx) { if (G.wrap[0]) { x -= G.nx; side[0] = 1; } else return 0.0f; }
   if (y < 0) { if (G.wrap[1]) { y += G.ny; side[1] = -1; } else return 0.0f; }
   if (y >= G.ny) { if (G.wrap[1]) { y -= G.ny; side[1] = 1; } else return 0.0f; }

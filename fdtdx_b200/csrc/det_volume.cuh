@@ -186,11 +186,22 @@ __global__ void __launch_bounds__(256, 2)
       if (rx == rx0) {
         long long dx = -plane;
         bool x_zero = false;
-        if (x == 0) { if (G.wrap[0]) dx = (long long)(G.nx - 1) * plane; else x_zero = true; }
-        const RowLd l_exm = ld(E0, o_c + dx, x_zero, true);
-        const RowLd n_hym = ld(H1, o_c + dx, x_zero, false), p_hym = ld(P1, o_c + dx, x_zero, false);
-        const RowLd n_zmc = ld(H2, o_c + dx, x_zero, true), p_zmc = ld(P2, o_c + dx, x_zero, true);
-        const RowLd n_zmm = ld(H2, o_c + dx + dy, x_zero || y_zero, true), p_zmm = ld(P2, o_c + dx + dy, x_zero || y_zero, true);
+        // plane x-1: the previous plane of this array, the wrap plane, the zero halo - or, at the low edge of
+        // an x-slab, the neighbour rank's last plane delivered in the (3,ny,nz) xlo buffers
+        const float *Ex_m = E0 + o_c, *Hy_m = H1 + o_c, *Hz_m = H2 + o_c, *Py_m = P1 + o_c, *Pz_m = P2 + o_c;
+        if (x == 0) {
+          if (G.xlo_E != nullptr) {
+            const long long o_x = (long long)y * G.nz + z0;
+            Ex_m = G.xlo_E + o_x; Hy_m = G.xlo_H + plane + o_x; Hz_m = G.xlo_H + 2 * plane + o_x;
+            Py_m = G.xlo_Hp + plane + o_x; Pz_m = G.xlo_Hp + 2 * plane + o_x;
+            dx = 0;
+          } else if (G.wrap[0]) dx = (long long)(G.nx - 1) * plane;
+          else x_zero = true;
+        }
+        const RowLd l_exm = ld(Ex_m, dx, x_zero, true);
+        const RowLd n_hym = ld(Hy_m, dx, x_zero, false), p_hym = ld(Py_m, dx, x_zero, false);
+        const RowLd n_zmc = ld(Hz_m, dx, x_zero, true), p_zmc = ld(Pz_m, dx, x_zero, true);
+        const RowLd n_zmm = ld(Hz_m, dx + dy, x_zero || y_zero, true), p_zmm = ld(Pz_m, dx + dy, x_zero || y_zero, true);
         exm = row_finish(l_exm, true, own_tail);
         hy_m = detv_hbar(row_finish(p_hym, false, false), row_finish(n_hym, false, false));
         hz_mc = detv_hbar(row_finish(p_zmc, true, own_tail), row_finish(n_zmc, true, own_tail));

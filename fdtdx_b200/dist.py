@@ -44,12 +44,55 @@ def neighbours(rank: int, world: int, periodic_x: bool) -> tuple[int | None, int
     return lo, hi
 
 
-def shard_arrays(arrays, objects, x_range, device=None):
+def _state_x_axis(det, local, key):
+    """Axis of a detector-state array (time axis included) that runs along the region's x extent, or None
+    for states without one (volume reductions, the YZ slice plane)."""
+    g = det._shape_dtype_single_time_step()[key][0]
+    l = local._shape_dtype_single_time_step()[key][0]
+    diff = [i for i, (a, b) in enumerate(zip(g, l)) if a != b]
+    return None if not diff else diff[0] + 1
+
+
+def merge_detector_states(objects, config, bounds, states_per_rank):
+    """Whole-region detector states from the per-rank parts of an x-sharded run (``bounds``: the ranks'
+    ``(x0, x1)``; ``states_per_rank``: their ``detector_states`` dicts as NumPy arrays).  Region-shaped
+    states are concatenated along x; sums over the region (Poynting / energy ``reduce_volume``, weighted
+    means normalised by the global weight sum) add up; the YZ mean of an energy slice set is the
+    plane-count-weighted mean of the ranks' means (one reduction after the run)."""
+    import numpy as np
+
+    from fdtdx_b200.detectors import EnergyDetector
+    from fdtdx_b200.plan import clip_detector
+
+    out = {}
+    for det in objects.detectors:
+        dlo, dhi = det.grid_slice_tuple[0]
+        parts = [(r, clip_detector(det, x0, x1, config)) for r, (x0, x1) in enumerate(bounds) if dhi > x0 and dlo < x1]
+        if len(parts) == 1:
+            out[det.name] = {k: np.asarray(v) for k, v in states_per_rank[parts[0][0]][det.name].items()}
+            continue
+        merged = {}
+        for key in states_per_rank[parts[0][0]][det.name]:
+            ax = _state_x_axis(det, parts[0][1], key)
+            vals = [np.asarray(states_per_rank[r][det.name][key]) for r, _ in parts]
+            if ax is not None:
+                merged[key] = np.concatenate(vals, axis=ax)
+            elif isinstance(det, EnergyDetector) and det.as_slices and det.use_mean and key == "YZ Plane":
+                ex = float(dhi - dlo)
+                merged[key] = sum(v * np.float32((loc.grid_slice_tuple[0][1] - loc.grid_slice_tuple[0][0]) / ex) for v, (_, loc) in zip(vals, parts)).astype(vals[0].dtype)
+            else:
+                merged[key] = sum(vals[1:], vals[0]).astype(vals[0].dtype)
+        out[det.name] = merged
+    return out
+
+
+def shard_arrays(arrays, objects, x_range, device=None, config=None):
     """This rank's x-slab of a whole-grid (NumPy) ``ArrayContainer`` - what the reference's
     ``NamedSharding`` on the x axis gives every device (``fdtd/initialization.py:598-611``,
     ``interfaces/state.py:72-78``): fields, materials, ADE arrays and y / z CPML psi are sliced on x; an x
-    CPML slab, an x interface plane of the recorder and a detector state stay with the rank that owns
-    their planes (detectors must not straddle a slab edge).  ``device``: move to that torch device."""
+    CPML slab and an x interface plane of the recorder stay with the rank that owns their planes; a
+    detector whose region straddles a slab edge keeps, on every rank, the state of its part of the region
+    (needs ``config``; ``merge_detector_states`` puts them back together).  ``device``: move to that torch device."""
     import numpy as np
 
     from fdtdx_b200.container import ArrayContainer, FieldState, RecordingState, _TorchLeaf
@@ -81,7 +124,23 @@ def shard_arrays(arrays, objects, x_range, device=None):
         if hi <= x0 or lo >= x1:
             continue
         if lo < x0 or hi > x1:
-            raise NotImplementedError(f"detector {d.name!r} straddles the slab edge at x = {x0 if lo < x0 else x1}")
+            if config is None:
+                raise NotImplementedError(f"detector {d.name!r} straddles the slab edge at x = {x0 if lo < x0 else x1}: pass config to shard_arrays")
+            from fdtdx_b200.plan import clip_detector
+
+            local = clip_detector(d, x0, x1, config)
+            a, b = max(lo, x0) - lo, min(hi, x1) - lo
+            st = {}
+            for key, v in arrays.detector_states[d.name].items():
+                ax = _state_x_axis(d, local, key)
+                if ax is None:
+                    st[key] = np.zeros_like(v) if (a > 0) else np.array(v)  # sums: the whole-region value counts once
+                else:
+                    idx = [slice(None)] * v.ndim
+                    idx[ax] = slice(a, b)
+                    st[key] = np.ascontiguousarray(v[tuple(idx)])
+            det[d.name] = st
+            continue
         det[d.name] = arrays.detector_states[d.name]
     rec = None
     if arrays.recording_state is not None:
@@ -151,6 +210,22 @@ class SlabRunner:
         self.plan.bind(arrays)
         E, H = arrays.fields.E, arrays.fields.H
         ny, nz = E.shape[2], E.shape[3]
+        # Exact-interpolation detectors whose region continues across a slab edge read plane x-1 of the lower
+        # neighbour (co-location stencil, curl.py:86-224): on the steps they are on, that plane of H (before
+        # the H update), E and H (after) travels to the upper neighbour
+        x0, x1 = x_range
+        nxg = objects.volume.grid_shape[0]
+        crosses = lambda d, X: d.exact_interpolation and d.grid_slice_tuple[0][0] < X < d.grid_slice_tuple[0][1]
+        wraps = lambda d: periodic_x and d.exact_interpolation and d.grid_slice_tuple[0][0] == 0  # x-1 of plane 0 wraps to the last rank
+        self.det_from_lo = [d for d in objects.detectors if has_lo and (crosses(d, x0) or (x0 == 0 and wraps(d)))]
+        self.det_to_hi = [d for d in objects.detectors if has_hi and (crosses(d, x1) or (x1 == nxg and wraps(d)))]
+        if self.det_from_lo or self.det_to_hi:
+            mk3 = lambda: torch.zeros((3, ny, nz), dtype=torch.float32, device=E.device)
+            self.xlo_E, self.xlo_H, self.xlo_Hp, self.send3a, self.send3b = mk3(), mk3(), mk3(), mk3(), mk3()
+            if self.det_from_lo:
+                self.plan._bind(_lib.SLOT_DET_XLO_E, 0, self.xlo_E)
+                self.plan._bind(_lib.SLOT_DET_XLO_H, 0, self.xlo_H)
+                self.plan._bind(_lib.SLOT_DET_XLO_HPREV, 0, self.xlo_Hp)
         mk = lambda: torch.zeros((2, ny, nz), dtype=torch.float32, device=E.device)
         self.haloH, self.haloE, self.sendH, self.sendE = mk(), mk(), mk(), mk()
         if has_lo:
@@ -217,14 +292,40 @@ class SlabRunner:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(self.plan.lib.fdtdx_b200_run_half_range(self.plan.h, int(t), int(which), int(x_begin), int(x_end), int(simulate), st))
 
-    def step(self, t: int, record_detectors: bool = False):
+    def _det_halo_on(self, t: int, record_detectors: bool, inverse: bool = False):
+        on = lambda ds: record_detectors and any(bool(d._is_on_at_time_step_arr[t]) and bool(d.inverse) == inverse for d in ds)
+        return on(self.det_from_lo), on(self.det_to_hi)
+
+    def _det_halo(self, t: int, record_detectors: bool, before_H: bool):
+        """Plane x-1 for the straddling detectors that are on at step t: H before the H update, or E and H
+        after it, from every rank to its upper neighbour (the same on/off tables on both sides of an edge)."""
+        recv, send = self._det_halo_on(t, record_detectors)
+        if not (recv or send):
+            return
+        E, H = self.arrays.fields.E, self.arrays.fields.H
+        if before_H:
+            if send:
+                self.send3a.copy_(H[:, -1])
+            self.hx.exchange(self.send3a if send else None, self.xlo_Hp if recv else None, None, None)
+        else:
+            if send:
+                self.send3a.copy_(E[:, -1])
+                self.send3b.copy_(H[:, -1])
+            self.hx.exchange(self.send3a if send else None, self.xlo_E if recv else None, None, None)
+            self.hx.exchange(self.send3b if send else None, self.xlo_H if recv else None, None, None)
+
+    def step(self, t: int, record_detectors: bool = False, record_boundaries: bool = False):
         import torch
 
         E, H = self.arrays.fields.E, self.arrays.fields.H
         if self.peer:
+            self._det_halo(t, record_detectors, True)
             for phase in range(3):
-                self.plan.run_forward_phase(t, phase, record_detectors, False, True)
+                if phase == 2:
+                    self._det_halo(t, record_detectors, False)
+                self.plan.run_forward_phase(t, phase, record_detectors, record_boundaries, True)
             return
+        self._det_halo(t, record_detectors, True)
         xc = self.plan.xchunk_hint()
         if self.side is None:
             self.sendH.copy_(H[1:3, -1])
@@ -254,16 +355,42 @@ class SlabRunner:
             self._range(t, 1, 0, last)
             main.wait_stream(self.side)
             self._range(t, 1, last, self.nx)
+        self._det_halo(t, record_detectors, False)
         self.plan.run_forward_phase(t, 2, record_detectors, False, True)
 
     def run(self, t0: int, n: int, record_detectors: bool = False, record_boundaries: bool = False):
-        if self.peer:  # one asynchronous submission for the whole run
-            self.plan.run_forward(t0, n, record_detectors, record_boundaries, True)
+        if self.peer:
+            # one asynchronous submission per stretch of steps on which no straddling detector is on; the
+            # steps in between are issued phase by phase around the detector-plane exchange
+            t, end = int(t0), int(t0) + int(n)
+            while t < end:
+                m = 0
+                while t + m < end and not any(self._det_halo_on(t + m, record_detectors)):
+                    m += 1
+                if m:
+                    self.plan.run_forward(t, m, record_detectors, record_boundaries, True)
+                    t += m
+                else:
+                    self.step(t, record_detectors, record_boundaries)
+                    t += 1
             return
         if record_boundaries:
             raise NotImplementedError("interface recording on slabs runs on the peer-memory halo")
         for t in range(t0, t0 + n):
             self.step(t, record_detectors)
+
+    def gather_detector_states(self, group=None):
+        """Whole-region detector states on every rank (``merge_detector_states``) - the one reduction after
+        the run that SURVEY section 8e allows."""
+        import torch.distributed as dist
+
+        mine = {d: {k: v.detach().cpu().numpy() for k, v in st.items()} for d, st in self.arrays.detector_states.items()}
+        if self.world == 1:
+            return mine
+        x0 = self.plan.x0
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, ((x0, self.plan.x1), mine), group=group)
+        return merge_detector_states(self.objects, self.config, [b for b, _ in everyone], [s for _, s in everyone])
 
     def run_reverse(self, t_from: int, n: int, record_detectors: bool = False, reset_fields: bool = True):
         """``full_backward`` on this rank's slab (``backward.py:18-135``): interface replay, reverse H and
@@ -271,4 +398,6 @@ class SlabRunner:
         asynchronous submission; needs the peer-memory halo."""
         if not self.peer:
             raise NotImplementedError("the time-reversed pass on slabs runs on the peer-memory halo")
+        if record_detectors and any(d.inverse for d in self.det_from_lo + self.det_to_hi):
+            raise NotImplementedError("inverse detectors straddling a slab edge in the time-reversed pass")
         self.plan.run_reverse(t_from, n, record_detectors, reset_fields)

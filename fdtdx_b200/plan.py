@@ -55,6 +55,31 @@ def metric_scales(config, axis: int):
     return (_f32(ref) / wb).astype(_f32), (_f32(ref) / w).astype(_f32)
 
 
+def clip_detector(det, x0: int, x1: int, config):
+    """This rank's part of a detector whose region straddles an x-slab edge (sources,
+    detectors and PML slabs are clipped to each rank's slab): a shallow copy over the clipped region with
+    its weight tables recomputed; ``_global`` keeps the whole-region object (global normalisations,
+    state merging in ``dist.merge_detector_states``).  Returns ``det`` itself when nothing is cut."""
+    import copy
+
+    dlo, dhi = det.grid_slice_tuple[0]
+    lo, hi = max(dlo, x0), min(dhi, x1)
+    if (lo, hi) == (dlo, dhi):
+        return det
+    if isinstance(det, (ClosedSurfacePhasorPoyntingFluxDetector, ClosedSurfacePoyntingFluxDetector)) or type(det).__name__ in ("ModeOverlapDetector", "PhasorPoyntingFluxDetector"):
+        raise NotImplementedError(f"detector {det.name!r} ({type(det).__name__}) straddles the slab edge at x = {x0 if dlo < x0 else x1}")
+    c = copy.copy(det)
+    if isinstance(det, PoyntingFluxDetector):
+        c.fixed_propagation_axis = det.propagation_axis  # not re-inferred from the clipped shape
+    c.grid_slice_tuple = ((lo, hi), det.grid_slice_tuple[1], det.grid_slice_tuple[2])
+    c.place_on_grid(config)
+    if isinstance(det, EnergyDetector) and det._slice_indices is not None:
+        gi = dlo + det._slice_indices[0]  # the fixed-x plane lives on exactly one rank
+        c._slice_indices = (gi - lo if lo <= gi < hi else -1, det._slice_indices[1], det._slice_indices[2])
+    c._global = det
+    return c
+
+
 def _profile_params(profile, wave_character):
     p = [0.0] * 8
     signal = None
@@ -312,7 +337,12 @@ class Plan:
                     faces.append((key, self._add_detector(face)))
                 self.det_faces[det.name] = faces
                 continue
-            self.det_index[det.name] = self._add_detector(det)
+            local = clip_detector(det, self.x0, self.x1, cfg)
+            di = self._add_detector(local)
+            self.det_index[det.name] = di
+            if local is not det and getattr(det, "reduce_volume", False) and isinstance(det, (FieldDetector, PhasorDetector)):
+                # weighted mean over the WHOLE region: every rank divides its partial sum by the global weight sum
+                check(self.lib.fdtdx_b200_plan_detector_set_wsum(self.h, di, float(np.sum(det._cached_cell_volume_weights, dtype=np.float64))))
 
     def _add_detector(self, det) -> int:
         cfg = self.config

@@ -81,7 +81,13 @@ enum FdtdxSlot {
   FDTDX_SLOT_GRAD_C4 = 36,
   FDTDX_SLOT_BLOCH_E = 37,   /* complex (Bloch k != 0) runs: E of the partner system (Re <-> Im), bloch.py:61-96 */
   FDTDX_SLOT_BLOCH_H = 38,
-  FDTDX_SLOT_COUNT = 39
+  /* x-sharded plans whose detectors straddle the low slab edge: plane x0-1 of the lower neighbour,
+   * (3,ny,nz) each - E and H after this step's updates, and H before its H update (the co-location
+   * stencil of curl.py:86-224 reads x-1) */
+  FDTDX_SLOT_DET_XLO_E = 39,
+  FDTDX_SLOT_DET_XLO_H = 40,
+  FDTDX_SLOT_DET_XLO_HPREV = 41,
+  FDTDX_SLOT_COUNT = 42
 };
 
 enum FdtdxBoundaryKind { FDTDX_WALL_PEC = 0, FDTDX_WALL_PMC = 1 };
@@ -167,6 +173,9 @@ int fdtdx_b200_plan_add_detector(FdtdxPlan* plan, int kind, const int lo[3], con
 
 /* Recorder (interfaces/recorder.py:70-199, time_filter.py:139-257, modules.py:98-161):
  * slot_of_time[t] (-1 = not stored), replay_a/b/w[t] for reconstruction; dtype enum FdtdxRecDtype. */
+/* x-sharded plans: the detector's region is this rank's part only, but a weighted mean (reduce_volume of
+ * field / phasor detectors, detector.py:108) divides by the weight sum of the WHOLE region. */
+int fdtdx_b200_plan_detector_set_wsum(FdtdxPlan* plan, int detector_index, double weight_sum);
 int fdtdx_b200_plan_set_recorder(FdtdxPlan* plan, int dtype, int n_slots, const int32_t* slot_of_time,
                                  const int32_t* replay_a, const int32_t* replay_b, const float* replay_w);
 /* ADE dispersion (update.py:316-350): n_poles, coefficient component tier (1|3), c4 present. */

@@ -96,6 +96,51 @@ for rec_name, modules in (("f32", []), ("every3+bf16", [fx.LinearReconstructEver
         print(f"[rank {rank}] recorder + full_backward on slabs: peer-memory halo unavailable, skipped", flush=True)
         good = os.environ.get("FDTDX_B200_PEER_FAIL") is not None
     ok = ok and good
+# ---- detectors straddling slab edges: every rank samples its part of the region, the
+# co-location stencil at a slab's first plane reads the lower neighbour's last plane (exchanged on the
+# steps the detector is on), and one merge after the run rebuilds the whole-region states
+from fdtdx_b200.dist import merge_detector_states  # noqa: E402,F401
+
+nxs = 16 * world
+for halo, overlap in (("peer", False), ("nccl", True)):
+    objects, arrays_np, cfg = build_scene(shape=(nxs, 14, 36), thickness=4, source="plane_z", time=5e-15, eps_tier=3)
+    wc = fx.WaveCharacter(wavelength=0.8e-6)
+    dets = [
+        fx.EnergyDetector(name="video", grid_slice_tuple=((0, nxs), (0, 14), (0, 36)), as_slices=True, switch=fx.OnOffSwitch(interval=3)),   # row-marching kernels, YZ mean over ranks
+        fx.EnergyDetector(name="cube", grid_slice_tuple=((3, nxs - 2), (2, 12), (1, 35))),                                                  # row-marching, region-shaped
+        fx.FieldDetector(name="block", grid_slice_tuple=((5, nxs - 5), (3, 11), (4, 20)), switch=fx.OnOffSwitch(interval=2)),               # generic kernels
+        fx.FieldDetector(name="fmean", grid_slice_tuple=((2, nxs - 3), (2, 12), (5, 30)), reduce_volume=True, components=("Ex", "Hz")),       # weighted mean, global weight sum
+        fx.EnergyDetector(name="etot", grid_slice_tuple=((0, nxs), (0, 14), (0, 36)), reduce_volume=True),
+        fx.PoyntingFluxDetector(name="flux", grid_slice_tuple=((0, nxs), (0, 14), (28, 29)), direction="+"),                                # z-normal plane across all ranks
+        fx.PhasorDetector(name="ph", grid_slice_tuple=((1, nxs - 1), (7, 8), (2, 34)), wave_characters=(wc,)),                              # y-normal plane across all ranks
+        fx.EnergyDetector(name="fixed", grid_slice_tuple=((0, nxs), (0, 14), (0, 36)), as_slices=True, x_slice=(nxs // 2 + 3) * 50e-9, y_slice=3 * 50e-9, z_slice=9 * 50e-9),
+    ]
+    objects, arrays_np, _, cfg, _ = fx.place_objects(list(objects.object_list) + dets, cfg, inv_permittivities=arrays_np.inv_permittivities)
+    T = cfg.time_steps_total
+    x0, x1 = slab_bounds(nxs, world, rank)
+    arrays = shard_arrays(arrays_np, objects, (x0, x1), dev, config=cfg)
+    runner = SlabRunner(objects, cfg, arrays, (x0, x1), rank, world, overlap=overlap, halo=halo)
+    runner.run(0, T, record_detectors=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    merged = runner.gather_detector_states()
+    st = fx.run_fdtd(arrays_np.to_torch(dev), objects, cfg)
+    torch.cuda.synchronize()
+    dE = float((arrays.fields.E - st[1].fields.E[:, x0:x1]).abs().max())
+    good = dE == 0.0
+    for d, stt in st[1].detector_states.items():
+        for k, v in stt.items():
+            ref = v.cpu().numpy()
+            got = merged[d][k]
+            exact = d in ("cube", "block", "ph", "fixed") or (d == "video" and k != "YZ Plane")
+            err = float(np.abs(got - ref).max()) / max(float(np.abs(ref).max()), 1e-30)
+            fine = (err == 0.0) if exact else (err <= 2e-6)
+            good = good and fine and got.shape == ref.shape and float(np.abs(ref).max()) > 0
+            if rank == 0:
+                print(f"  straddling {d}/{k} halo={halo}: max rel err {err:.2e} {'(bit-exact)' if exact else ''} {'OK' if fine else 'MISMATCH'}", flush=True)
+    print(f"[rank {rank}] straddling detectors halo={halo}{'' if runner.peer or halo != 'peer' else ' (fell back to nccl)'}: fields max|dE|={dE:.3e} {'OK' if good else 'MISMATCH'}", flush=True)
+    objects.__dict__.pop("_plan_cache", None)
+    ok = ok and good
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -121,3 +121,50 @@ def test_array_container_reset_and_aset():
     assert np.array_equal(r.inv_permittivities, eps) and arrays.fields.E.any()
     r2 = r.aset("fields->E", np.ones_like(r.fields.E))
     assert r2.fields.E.all() and not r.fields.E.any()
+
+
+def test_straddling_detector_states_shard_and_merge_round_trip():
+    """a detector whose region crosses x-slab edges keeps, per rank, the state of its
+    part of the region; ``merge_detector_states`` rebuilds the whole-region arrays (concatenation on x, sums
+    for volume reductions, plane-count-weighted mean for the YZ mean of an energy slice set)."""
+    import numpy as np
+
+    import fdtdx_b200 as fx
+    from fdtdx_b200.dist import merge_detector_states, shard_arrays, slab_bounds
+    from fdtdx_b200.plan import clip_detector
+    from scenes import build_scene
+
+    nxs, world = 24, 3
+    objects, arrays, cfg = build_scene(shape=(nxs, 6, 8), thickness=2, time=3e-15)
+    wc = fx.WaveCharacter(wavelength=0.8e-6)
+    dets = [
+        fx.EnergyDetector(name="video", grid_slice_tuple=((0, nxs), (0, 6), (0, 8)), as_slices=True),
+        fx.EnergyDetector(name="cube", grid_slice_tuple=((3, nxs - 2), (1, 5), (1, 7))),
+        fx.FieldDetector(name="fmean", grid_slice_tuple=((2, nxs - 3), (1, 5), (1, 7)), reduce_volume=True, components=("Ex", "Hz")),
+        fx.PoyntingFluxDetector(name="flux", grid_slice_tuple=((0, nxs), (0, 6), (5, 6)), direction="+"),
+        fx.PhasorDetector(name="ph", grid_slice_tuple=((1, nxs - 1), (3, 4), (1, 7)), wave_characters=(wc,)),
+        fx.EnergyDetector(name="fixed", grid_slice_tuple=((0, nxs), (0, 6), (0, 8)), as_slices=True, x_slice=13 * 50e-9, y_slice=2 * 50e-9, z_slice=3 * 50e-9),
+        fx.FieldDetector(name="inside", grid_slice_tuple=((9, 15), (1, 5), (1, 7))),
+    ]
+    objects, arrays, _, cfg, _ = fx.place_objects(list(objects.object_list) + dets, cfg, inv_permittivities=arrays.inv_permittivities)
+    rng = np.random.default_rng(0)
+    for st in arrays.detector_states.values():
+        for k, v in st.items():
+            v[...] = rng.standard_normal(v.shape).astype(v.dtype)
+    bounds = [slab_bounds(nxs, world, r) for r in range(world)]
+    parts = [shard_arrays(arrays, objects, b, config=cfg).detector_states for b in bounds]
+    # per-rank parts have the clipped shapes; the fixed-x plane of "fixed" lives on one rank only
+    assert parts[1]["cube"]["energy"].shape[1] == 8 and parts[0]["cube"]["energy"].shape[1] == 5
+    assert [clip_detector(objects["fixed"], *b, cfg)._slice_indices[0] for b in bounds] == [-1, objects["fixed"]._slice_indices[0] - 8, -1]
+    assert "inside" in parts[1] and "inside" not in parts[0]
+    # mean over x of the YZ plane: emulate what each rank's kernel writes (the mean over ITS planes)
+    merged = merge_detector_states(objects, cfg, bounds, parts)
+    for d, st in arrays.detector_states.items():
+        for k, v in st.items():
+            if d == "video" and k == "YZ Plane":
+                continue  # parts hold the global value on rank 0 and zeros elsewhere: a weighted mean of those is not the identity
+            np.testing.assert_allclose(merged[d][k], v, rtol=1e-6, atol=1e-7, err_msg=f"{d}/{k}")
+    per_rank = [{"video": {"YZ Plane": np.full((1, 6, 8), float(r + 1), np.float32), **{k: p["video"][k] for k in ("XY Plane", "XZ Plane")}}} for r, p in enumerate(parts)]
+    full = [{**p, **q} for p, q in zip(parts, per_rank)]
+    yz = merge_detector_states(objects, cfg, bounds, full)["video"]["YZ Plane"]
+    np.testing.assert_allclose(yz, 2.0, rtol=1e-6)  # (1 + 2 + 3) * 8 / 24
