@@ -694,6 +694,8 @@ struct alignas(64) TmaSet {
 cudaError_t fdtdx_dispatch_E4_tma(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
                                   cudaStream_t st);
 cudaError_t fdtdx_dispatch_H4_tma(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
+cudaError_t fdtdx_dispatch_E4_tma_konly(const StepParams& P, const TmaSet& M, int t, int pm, bool rev, bool met, dim3 g, cudaStream_t st);
+cudaError_t fdtdx_dispatch_H4_tma_konly(const StepParams& P, const TmaSet& M, int t, int pm, bool rev, bool met, dim3 g, cudaStream_t st);
 // 64-cell tile rows, two rows per warp: thin grids (Nz <= 64)
 cudaError_t fdtdx_dispatch_E4_tma64(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
                                     cudaStream_t st);

@@ -316,7 +316,8 @@ __global__ void tensor_apply_kernel(const TensorParams P, const int t) {
 // phase 2, four cells per thread with 128-bit accesses (uniform grid, Nz % 4 == 0, aligned buffers):
 // same samples and the same summation order as tensor_apply_kernel / t_avg.  Sources are applied
 // afterwards by tensor_inject_kernel (O(surface)); blockDim (32, 8), grid (z tiles, y tiles, x planes).
-template <bool IS_E>
+// HAS_A = false: no conductivity, A is the identity (fdtd/misc.py:88-96) and the field averages are not needed
+template <bool IS_E, bool HAS_A>
 __global__ void __launch_bounds__(256) tensor_apply4_kernel(const TensorParams P) {
   constexpr int V = 4;
   const int k0 = (blockIdx.x * 32 + threadIdx.x) * V;
@@ -361,20 +362,21 @@ __global__ void __launch_bounds__(256) tensor_apply4_kernel(const TensorParams P
       const int sl = IS_E ? +1 : -1, scn = IS_E ? -1 : +1;
       const int lx = (r == 0) * sl, ly = (r == 1) * sl, lz = (r == 2) * sl;
       const int cx = (q == 0) * scn, cy = (q == 1) * scn, cz = (q == 2) * scn;
-      const Vec<V> f10 = ldsh(P.F_in, q, lx, ly, lz), f01 = ldsh(P.F_in, q, cx, cy, cz), f11 = ldsh(P.F_in, q, lx + cx, ly + cy, lz + cz);
       const Vec<V> k10 = ldsh(P.K, q, lx, ly, lz), k01 = ldsh(P.K, q, cx, cy, cz), k11 = ldsh(P.K, q, lx + cx, ly + cy, lz + cz);
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        fa[q].v[e] = (((F0[q].v[e] + f10.v[e]) + f01.v[e]) + f11.v[e]) / 4.0f;
-        ka[q].v[e] = (((K0[q].v[e] + k10.v[e]) + k01.v[e]) + k11.v[e]) / 4.0f;
+      for (int e = 0; e < V; ++e) ka[q].v[e] = (((K0[q].v[e] + k10.v[e]) + k01.v[e]) + k11.v[e]) / 4.0f;
+      if (HAS_A) {
+        const Vec<V> f10 = ldsh(P.F_in, q, lx, ly, lz), f01 = ldsh(P.F_in, q, cx, cy, cz), f11 = ldsh(P.F_in, q, lx + cx, ly + cy, lz + cz);
+#pragma unroll
+        for (int e = 0; e < V; ++e) fa[q].v[e] = (((F0[q].v[e] + f10.v[e]) + f01.v[e]) + f11.v[e]) / 4.0f;
       }
     }
     Vec<V> b0 = ldv<V>(P.B + (long long)(3 * r + 0) * N + cell0), b1 = ldv<V>(P.B + (long long)(3 * r + 1) * N + cell0), b2 = ldv<V>(P.B + (long long)(3 * r + 2) * N + cell0);
     Vec<V> a0, a1, a2;
-    if (P.A) { a0 = ldv<V>(P.A + (long long)(3 * r + 0) * N + cell0); a1 = ldv<V>(P.A + (long long)(3 * r + 1) * N + cell0); a2 = ldv<V>(P.A + (long long)(3 * r + 2) * N + cell0); }
+    if (HAS_A) { a0 = ldv<V>(P.A + (long long)(3 * r + 0) * N + cell0); a1 = ldv<V>(P.A + (long long)(3 * r + 1) * N + cell0); a2 = ldv<V>(P.A + (long long)(3 * r + 2) * N + cell0); }
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const float t1 = P.A ? (a0.v[e] * fa[0].v[e] + a1.v[e] * fa[1].v[e]) + a2.v[e] * fa[2].v[e] : fa[r].v[e];
+      const float t1 = HAS_A ? (a0.v[e] * fa[0].v[e] + a1.v[e] * fa[1].v[e]) + a2.v[e] * fa[2].v[e] : fa[r].v[e];
       const float t2 = (b0.v[e] * ka[0].v[e] + b1.v[e] * ka[1].v[e]) + b2.v[e] * ka[2].v[e];
       out[r].v[e] = plus ? (t1 + t2) : (t1 - t2);
     }

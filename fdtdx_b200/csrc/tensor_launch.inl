@@ -69,10 +69,23 @@ static int tensor_step(FdtdxPlan* p, int t, int simulate, bool rev, bool is_E, c
     StepParams Q = S;
     if (is_E) { Q.H = const_cast<float*>(T.F_other); Q.E = T.K; }
     else { Q.E = const_cast<float*>(T.F_other); Q.H = T.K; }
-    dim3 b(32, p->rows);
-    dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
-    if (is_E) fdtdx_dispatch_E4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
-    else fdtdx_dispatch_H4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
+    Q.n_src = 0;
+    if (can_tma(p, Q, true) && tma_tz(p) == 128) {
+      // TMA-staged curl-only kernel: three halo tiles of the other field per plane, K stored with 128-bit writes
+      TmaSet M;
+      memset(&M, 0, sizeof(M));
+      if ((rc = get_tmap(p, T.F_other, 3, p->nx, 0, &M.fld_halo))) return rc;
+      M.fld_plain = M.mat_plain = M.xhalo = M.fld_halo;  // not read in curl-only mode
+      Q.xchunk = tma_chunk(p, Q);
+      dim3 g((p->nz + 127) / 128, (p->ny + FDTDX_TMA_R - 1) / FDTDX_TMA_R, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+      if (is_E) CUDA_TRY(fdtdx_dispatch_E4_tma_konly(Q, M, t, pml_mode(p, Q), rev, p->metric, g, st));
+      else CUDA_TRY(fdtdx_dispatch_H4_tma_konly(Q, M, t, pml_mode(p, Q), rev, p->metric, g, st));
+    } else {
+      dim3 b(32, p->rows);
+      dim3 g((p->nz + 127) / 128, (p->ny + p->rows - 1) / p->rows, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
+      if (is_E) fdtdx_dispatch_E4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
+      else fdtdx_dispatch_H4_konly(Q, t, pml_mode(p, Q), rev, p->metric, g, b, st);
+    }
   } else {
     tensor_curl_kernel<<<blocks, 256, 0, st>>>(T);
   }
@@ -80,8 +93,8 @@ static int tensor_step(FdtdxPlan* p, int t, int simulate, bool rev, bool is_E, c
     TensorParams T2 = T;
     T2.n_src = 0;
     dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, p->nx);
-    if (is_E) tensor_apply4_kernel<true><<<g, b, 0, st>>>(T2);
-    else tensor_apply4_kernel<false><<<g, b, 0, st>>>(T2);
+    if (is_E) { if (T2.A) tensor_apply4_kernel<true, true><<<g, b, 0, st>>>(T2); else tensor_apply4_kernel<true, false><<<g, b, 0, st>>>(T2); }
+    else { if (T2.A) tensor_apply4_kernel<false, true><<<g, b, 0, st>>>(T2); else tensor_apply4_kernel<false, false><<<g, b, 0, st>>>(T2); }
     if (!rev) {
       for (size_t si = 0; si < p->srcs.size(); ++si) {
         const SrcDev& d = p->srcs[si].d;

@@ -72,3 +72,42 @@ cudaError_t fdtdx_dispatch_E4_tma(const StepParams& P, const TmaSet& M, int t, i
   if (tier == 1) return rev ? launch_E2<1, true>(P, M, t, pm, sig, ade, met, g, st) : launch_E2<1, false>(P, M, t, pm, sig, ade, met, g, st);
   return rev ? launch_E2<3, true>(P, M, t, pm, sig, ade, met, g, st) : launch_E2<3, false>(P, M, t, pm, sig, ade, met, g, st);
 }
+
+#if FDTDX_TZ_SEL == 128
+// curl-only mode (phase 1 of the full-tensor tier): K = curl + CPML correction, written to P.E
+template <bool REV, bool MET, int PM>
+static cudaError_t go_E_konly(const StepParams& P, const TmaSet& M, int t, dim3 g, cudaStream_t st) {
+  constexpr int R = FDTDX_TMA_R, S = FDTDX_TMA_S, TZ = FDTDX_TZ_SEL;
+  constexpr int smem = tma_smem_bytes<R, TZ, 1, S>();
+  auto k = yee_E_tma<1, REV, false, false, MET, PM, R, S, TZ, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g;
+  cfg.blockDim = dim3(32, R);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 0;  // the neighbours of this launch are plain launches
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, P, M, t);
+}
+template <bool REV, bool MET>
+static cudaError_t konly_pm_E(const StepParams& P, const TmaSet& M, int t, int pm, dim3 g, cudaStream_t st) {
+  if (pm == 0) return go_E_konly<REV, MET, 0>(P, M, t, g, st);
+  if (pm == 1) return go_E_konly<REV, MET, 1>(P, M, t, g, st);
+  return go_E_konly<REV, MET, 2>(P, M, t, g, st);
+}
+cudaError_t fdtdx_dispatch_E4_tma_konly(const StepParams& P, const TmaSet& M, int t, int pm, bool rev, bool met, dim3 g, cudaStream_t st) {
+  if (rev) return met ? konly_pm_E<true, true>(P, M, t, pm, g, st) : konly_pm_E<true, false>(P, M, t, pm, g, st);
+  return met ? konly_pm_E<false, true>(P, M, t, pm, g, st) : konly_pm_E<false, false>(P, M, t, pm, g, st);
+}
+#endif

@@ -258,19 +258,22 @@ struct PmlT {
 // E half-step, TMA-staged.  blockDim = (32, R).
 // Stage layout: [Hx halo][Hy halo][Hz halo][Ex][Ey][Ez][inv_eps x TIER]; halo tile origin (k0-4, j0-1).
 // ------------------------------------------------------------------------------------------------
-template <int TIER, int R, int TZ>
+template <int TIER, int R, int TZ, bool KONLY = false>
 __device__ __forceinline__ void tma_issue_E(const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i) {
   using G = TmaGeom<R, TZ>;
-  mbar_expect_tx(full, 3 * G::HALO_RAW + (3 + TIER) * G::PLAIN_B);
+  mbar_expect_tx(full, KONLY ? 3 * G::HALO_RAW : 3 * G::HALO_RAW + (3 + TIER) * G::PLAIN_B);
 #pragma unroll
   for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G::HALO_B, &M.fld_halo, kt0 - 4, j0 - 1, i, c, full);
+  if (KONLY) return;  // curl-only mode: neither the field being updated nor its material is read
 #pragma unroll
   for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G::HALO_B + c * G::PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
 #pragma unroll
   for (int c = 0; c < TIER; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
 }
 
-template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, int R, int S, int TZ>
+// KONLY: write the curl (with its CPML correction) instead of updating E - phase 1 of the full-tensor tier
+// (tensor_kernels.cuh): only the three halo tiles of H are staged; P.E is the curl scratch.
+template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, int R, int S, int TZ, bool KONLY = false>
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_E_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
@@ -327,13 +330,13 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   // register queue below reads it, and its H half-step must have finished reading E[0] before this CTA
   // overwrites it
   if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
-  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+  if (!KONLY && REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_E<V, TIER>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1
-    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R, TZ>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
+    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R, TZ, KONLY>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
   }
   if (j0 + warp * WR >= ny) return;
 
@@ -417,15 +420,17 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     hz_im = hz;
     FDTDX_TCPML_BLOCK(psiE, aE, bE, kE)
     const float* sE = sb + 3 * G::HALO_F + op;
-    const Vec<V> ex = lds4(sE), ey = lds4(sE + G::PLAIN_F), ez = lds4(sE + 2 * G::PLAIN_F);
-    const Vec<V> ie0 = lds4(sE + 3 * G::PLAIN_F);
-    Vec<V> ie1, ie2;
-    if (TIER == 3) {
-      ie1 = lds4(sE + 4 * G::PLAIN_F);
-      ie2 = lds4(sE + 5 * G::PLAIN_F);
-    } else {
-      ie1 = ie0;
-      ie2 = ie0;
+    Vec<V> ex, ey, ez, ie0, ie1, ie2;
+    if (!KONLY) {
+      ex = lds4(sE); ey = lds4(sE + G::PLAIN_F); ez = lds4(sE + 2 * G::PLAIN_F);
+      ie0 = lds4(sE + 3 * G::PLAIN_F);
+      if (TIER == 3) {
+        ie1 = lds4(sE + 4 * G::PLAIN_F);
+        ie2 = lds4(sE + 5 * G::PLAIN_F);
+      } else {
+        ie1 = ie0;
+        ie2 = ie0;
+      }
     }
     // all operands of this plane are in registers: the last warp to get here refills the stage
     __syncwarp();
@@ -433,17 +438,21 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S < ic1) tma_issue_E<TIER, R, TZ>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
+        if (i + S < ic1) tma_issue_E<TIER, R, TZ, KONLY>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
       }
     }
     if (++s == S) { s = 0; ph ^= 1; }
 
-    const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
     Vec<V> o3[3];
-    material_update_E<V, REV, SIG, ADE>(P, N, cell0, lane_ok, V, Eo3, K3, ie3, sg3, o3);
+    if (KONLY) {
+      o3[0] = Kx; o3[1] = Ky; o3[2] = Kz;
+    } else {
+      const Vec<V> Eo3[3] = {ex, ey, ez}, K3[3] = {Kx, Ky, Kz}, ie3[3] = {ie0, ie1, ie2};
+      material_update_E<V, REV, SIG, ADE>(P, N, cell0, lane_ok, V, Eo3, K3, ie3, sg3, o3);
+    }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
     // PEC walls (pec.py:70-77)
-    if (P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
+    if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[0] && i < P.wall_x1[0]) wall_mask<V>(P, 0, i, j, k0, o0, o1, o2);
     if (lane_ok) {
       stv<V>(pE, o0);
       stv<V>(pE + N, o1);
@@ -452,7 +461,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     pE += plane;
     cell0 += plane;
   }
-  if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
+  if (!KONLY && !REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_E<V, TIER>(P, t, false, ic0, ic1, j, k0);
   if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, 0xffffffffu);
 }
 #endif  // !FDTDX_BUILD_H
@@ -463,17 +472,19 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 // halo tile origin (k0, j0): row +1 is the j+1 neighbour, column +4.. the k+1 neighbour; the x+1
 // neighbour plane is the next ring stage (one extra Ey,Ez stage is loaded after the last plane).
 // ------------------------------------------------------------------------------------------------
-template <int MUT, int R, int TZ>
+template <int MUT, int R, int TZ, bool KONLY = false>
 __device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i, int ic1) {
   using G = TmaGeom<R, TZ>;
   if (i < ic1) {
-    mbar_expect_tx(full, 3 * G::HALO_RAW + (3 + MUT) * G::PLAIN_B);
+    mbar_expect_tx(full, KONLY ? 3 * G::HALO_RAW : 3 * G::HALO_RAW + (3 + MUT) * G::PLAIN_B);
 #pragma unroll
     for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G::HALO_B, &M.fld_halo, kt0, j0, i, c, full);
+    if (!KONLY) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G::HALO_B + c * G::PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
+      for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G::HALO_B + c * G::PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
 #pragma unroll
-    for (int c = 0; c < MUT; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
+      for (int c = 0; c < MUT; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
+    }
   } else {
     // Ey, Ez of the plane after the chunk: in-domain plane, wrap plane, neighbour-rank halo, or
     // (coordinate nx, out of bounds) the zero halo
@@ -494,7 +505,7 @@ __device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M
   }
 }
 
-template <int MUT, bool REV, bool SIG, bool MET, int PM, int R, int S, int TZ>
+template <int MUT, bool REV, bool SIG, bool MET, int PM, int R, int S, int TZ, bool KONLY = false>
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_H_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
@@ -544,14 +555,14 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   // x-slab neighbour over NVLink: its E[0] plane of this step must be final before the extra ring stage
   // loads it, and its E half-step must have finished reading H[nx-1] before this CTA overwrites it
   if (P.peer_wait != nullptr && peer_cta) peer_wait_cta(P);
-  if (REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
+  if (!KONLY && REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) {
     src_pass_H<V, MUT>(P, t, true, ic0, ic1, j, k0);
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1 (plane ic1 is the Ey,Ez-only stage)
     for (int s = 0; s < S && ic0 + s <= ic1; ++s)
-      tma_issue_H<MUT, R, TZ>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
+      tma_issue_H<MUT, R, TZ, KONLY>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
   }
   if (j0 + warp * WR >= ny) return;
 
@@ -622,15 +633,16 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     FDTDX_TCPML_BLOCK(psiH, aH, bH, kH)
     const float* sH = sb + 3 * G::HALO_F + op;
-    const Vec<V> hx = lds4(sH), hy = lds4(sH + G::PLAIN_F), hz = lds4(sH + 2 * G::PLAIN_F);
-    if (!REV && P.hprev_out != nullptr && lane_ok && hprev_wanted(P, i, j)) {  // H_prev for the detector pass
+    Vec<V> hx, hy, hz;
+    if (!KONLY) { hx = lds4(sH); hy = lds4(sH + G::PLAIN_F); hz = lds4(sH + 2 * G::PLAIN_F); }
+    if (!KONLY && !REV && P.hprev_out != nullptr && lane_ok && hprev_wanted(P, i, j)) {  // H_prev for the detector pass
       float* hp = P.hprev_out + cell0;
       stv<V>(hp, hx);
       stv<V>(hp + N, hy);
       stv<V>(hp + 2 * N, hz);
     }
     Vec<V> im0, im1, im2;
-    if (MUT >= 1) {
+    if (!KONLY && MUT >= 1) {
       im0 = lds4(sH + 3 * G::PLAIN_F);
       if (MUT == 3) {
         im1 = lds4(sH + 4 * G::PLAIN_F);
@@ -645,7 +657,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S <= ic1) tma_issue_H<MUT, R, TZ>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
+        if (i + S <= ic1) tma_issue_H<MUT, R, TZ, KONLY>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
       }
     }
     s = sn;
@@ -658,11 +670,15 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       for (int e = 0; e < V; ++e) im3[0].v[e] = P.inv_mu_scalar;
       im3[1] = im3[0]; im3[2] = im3[0];
     }
-    const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
     Vec<V> o3[3];
-    material_update_H<V, REV, SIG>(P, cell0, lane_ok, V, Ho3, K3, im3, sg3, o3);
+    if (KONLY) {
+      o3[0] = Kx; o3[1] = Ky; o3[2] = Kz;
+    } else {
+      const Vec<V> Ho3[3] = {hx, hy, hz}, K3[3] = {Kx, Ky, Kz};
+      material_update_H<V, REV, SIG>(P, cell0, lane_ok, V, Ho3, K3, im3, sg3, o3);
+    }
     Vec<V>&o0 = o3[0], &o1 = o3[1], &o2 = o3[2];
-    if (P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
+    if (!KONLY && P.n_walls > 0 && i >= P.wall_x0[1] && i < P.wall_x1[1]) wall_mask<V>(P, 1, i, j, k0, o0, o1, o2);
     if (lane_ok) {
       stv<V>(pH, o0);
       stv<V>(pH + N, o1);
@@ -672,7 +688,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     cell0 += plane;
   }
   // the extra Ey,Ez stage was consumed as the "next plane" of the last iteration; nothing to release
-  if (!REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
+  if (!KONLY && !REV && P.n_src > 0 && P.src_inline && lane_ok && ic0 < P.src_x1 && ic1 > P.src_x0) src_pass_H<V, MUT>(P, t, false, ic0, ic1, j, k0);
   if (P.peer_signal != nullptr && peer_cta) peer_signal_warp(P, 0xffffffffu);
 }
 #endif  // !FDTDX_BUILD_E
