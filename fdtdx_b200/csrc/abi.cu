@@ -112,6 +112,7 @@ struct FdtdxPlan {
   int hprev_box[FDTDX_MAX_HPBOX][4];  // {x0, x1, y0, y1}: rows the detectors active at that step read
   int detv_xcl = 4;
   // Bloch axes with k != 0: this plan is one of the two real systems of a complex run
+  int sym[3] = {0, 0, 0}, mirror[3] = {0, 0, 0};  // config.symmetry (see GridDev::sym)
   bool bloch = false;
   float bloch_c[3] = {1.f, 1.f, 1.f}, bloch_s[3] = {0.f, 0.f, 0.f};
 };
@@ -433,6 +434,17 @@ extern "C" int fdtdx_b200_halo_bind(FdtdxPlan* p, int has_lo, int has_hi) {
   return FDTDX_OK;
 }
 
+extern "C" int fdtdx_b200_set_symmetry(FdtdxPlan* p, const int symmetric_axes[3], const int electric_wall_axes[3]) {
+  if (!p) return fail(FDTDX_EINVAL, "null plan");
+  for (int a = 0; a < 3; ++a) {
+    p->sym[a] = (symmetric_axes && symmetric_axes[a]) ? 1 : 0;
+    p->mirror[a] = (p->sym[a] && electric_wall_axes && electric_wall_axes[a]) ? 1 : 0;
+  }
+  if ((p->sym[0] | p->sym[1] | p->sym[2]) && (p->eps_tier == 9 || p->mu_tier == 9 || p->sigE_tier == 9 || p->sigH_tier == 9 || p->nx != p->nxg))
+    return fail(FDTDX_EUNSUPPORTED, "config.symmetry with full-tensor media or on x-sharded plans");
+  return FDTDX_OK;
+}
+
 extern "C" int fdtdx_b200_set_bloch(FdtdxPlan* p, int enable, const double cos_kL[3], const double sin_kL[3]) {
   if (!p) return fail(FDTDX_EINVAL, "null plan");
   p->bloch = enable != 0;
@@ -535,7 +547,8 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
   P.nx = p->nx; P.ny = p->ny; P.nz = p->nz;
   const long long N = (long long)p->nx * p->ny * p->nz;
   for (int a = 0; a < 3; ++a) P.wrap[a] = p->wrap[a];
-  P.x_lo_mode = p->halo_lo ? 2 : (p->wrap[0] ? 1 : 0);
+  for (int a = 0; a < 3; ++a) P.sym[a] = p->sym[a];
+  P.x_lo_mode = p->halo_lo ? 2 : ((p->wrap[0] && !p->sym[0]) ? 1 : 0);
   P.x_hi_mode = p->halo_hi ? 2 : (p->wrap[0] ? 1 : 0);
   P.cour = (float)p->courant; P.eta0 = (float)kEta0; P.inv_mu_scalar = (float)p->inv_mu_scalar; P.dt = (float)p->dt;
   // full-tensor tiers ping-pong their field between the primary and the ALT buffer
@@ -950,7 +963,7 @@ static void make_grid(const FdtdxPlan* p, GridDev& G) {
   memset(&G, 0, sizeof(G));
   G.nx = p->nx; G.ny = p->ny; G.nz = p->nz; G.x_offset = p->xoff;
   const long long N = (long long)p->nx * p->ny * p->nz;
-  for (int a = 0; a < 3; ++a) { G.wrap[a] = p->wrap[a]; G.w[a] = p->d_w[a]; }
+  for (int a = 0; a < 3; ++a) { G.wrap[a] = p->wrap[a]; G.w[a] = p->d_w[a]; G.sym[a] = p->sym[a]; G.mirror[a] = p->mirror[a]; }
   G.E = (const float*)p->slots[p->e_parity ? FDTDX_SLOT_E_ALT : FDTDX_SLOT_E][0];
   G.H = (const float*)p->slots[p->h_parity ? FDTDX_SLOT_H_ALT : FDTDX_SLOT_H][0];
   G.eps = (const float*)p->slots[FDTDX_SLOT_INV_EPS][0];

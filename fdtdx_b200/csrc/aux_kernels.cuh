@@ -35,6 +35,10 @@ struct GridDev {
   const float* xlo_E;
   const float* xlo_H;
   const float* xlo_Hp;
+  // config.symmetry: sym[a] - the min-side halo of axis a is never wrapped (update.py:121-125); mirror[a] - an
+  // electric symmetry wall sits on the min face, and the detector stencil reads the parity-weighted mirror
+  // partner there instead of the zero halo (pad_fields_with_symmetry_mirror, update.py:139-198)
+  int sym[3], mirror[3];
 };
 
 struct DetDev {
@@ -76,6 +80,37 @@ template <bool CHK>
 __device__ __forceinline__ float grid_at_t(const GridDev& G, const float* F, int c, int x, int y, int z);
 __device__ __forceinline__ float grid_at(const GridDev& G, const float* F, int c, int x, int y, int z) {
   int side[3] = {0, 0, 0};  // -1: low-side ghost (x conj(phase)), +1: high-side ghost (x phase)
+  if (G.sym[0] | G.sym[1] | G.sym[2]) {
+    // symmetric axes: index -1 maps per axis to its mirror partner (electric wall: parity * the first cell for a
+    // component sampled half a cell off the plane, the second for one sampled on it) or to the zero halo
+    const bool isE = (F == G.E);
+    int p[3] = {x, y, z};
+    const int n[3] = {G.nx, G.ny, G.nz};
+    float par = 1.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (p[a] < 0 && G.sym[a]) {
+        if (!G.mirror[a] || !(isE || F == G.H)) return 0.0f;
+        const bool normal = (c == a);
+        const bool on_plane = isE ? !normal : normal;      // component_sits_on_plane
+        par = (isE ? normal : !normal) ? par : -par;        // field_component_parity, wall = -1
+        p[a] = on_plane ? 1 : 0;
+        if (p[a] >= n[a]) return 0.0f;
+      }
+    }
+    if (p[0] != x || p[1] != y || p[2] != z) {
+      x = p[0]; y = p[1]; z = p[2];
+      // the remaining out-of-range coordinates follow the ordinary halo rule
+      if (x < 0) { if (G.wrap[0]) x += G.nx; else return 0.0f; }
+      if (x >= G.nx) { if (G.wrap[0]) x -= G.nx; else return 0.0f; }
+      if (y < 0) { if (G.wrap[1]) y += G.ny; else return 0.0f; }
+      if (y >= G.ny) { if (G.wrap[1]) y -= G.ny; else return 0.0f; }
+      if (z < 0) { if (G.wrap[2]) z += G.nz; else return 0.0f; }
+      if (z >= G.nz) { if (G.wrap[2]) z -= G.nz; else return 0.0f; }
+      const long long Ns = (long long)G.nx * G.ny * G.nz;
+      return par * F[c * Ns + ((long long)x * G.ny + y) * G.nz + z];
+    }
+  }
   if (x < 0) {
     const float* X = (F == G.E) ? G.xlo_E : ((F == G.H) ? G.xlo_H : nullptr);
     if (X != nullptr) {  // the lower neighbour rank's last plane

@@ -60,6 +60,7 @@ struct SrcDev {
 struct StepParams {
   int nx, ny, nz;
   int wrap[3];
+  int sym[3];  // config.symmetry axis: the MIN-side halo is never wrapped (update.py:121-125); the far side still is
   int x_lo_mode, x_hi_mode;  // 0 zero halo, 1 local wrap, 2 neighbour halo buffer
   float cour, eta0, inv_mu_scalar, dt;
   float* E;

@@ -722,9 +722,9 @@ static __global__ void __launch_bounds__(256, FDTDX_MIN_CTAS) yee_E_kernel(const
   // neighbour offsets (in elements) relative to this thread's first cell; *_ok false = zero halo
   bool jm_ok = true, km_ok = true;
   long long djm = -(long long)nz;
-  if (j == 0) { if (P.wrap[1]) djm = (long long)(ny - 1) * nz; else jm_ok = false; }
+  if (j == 0) { if (P.wrap[1] && !P.sym[1]) djm = (long long)(ny - 1) * nz; else jm_ok = false; }
   int dkm = -1;
-  if (k0 == 0) { if (P.wrap[2]) dkm = nz - 1; else km_ok = false; }
+  if (k0 == 0) { if (P.wrap[2] && !P.sym[2]) dkm = nz - 1; else km_ok = false; }
 
   const bool lane_ok = true;  // inactive lanes have already left
   FDTDX_CPML_SETUP(psiE, aE, bE, kE)

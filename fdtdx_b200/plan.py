@@ -139,8 +139,10 @@ class Plan:
                 if getattr(b, "needs_complex_fields", False) and bloch_role is None:
                     raise ValueError("Bloch boundaries with k != 0 need complex fields: pass a container whose E / H are complex64")
                 wrap[b.axis] = True
-        if any(s != 0 for s in config.symmetry):
-            raise NotImplementedError("config.symmetry is outside the hot-path scope (setup-time domain reduction)")
+        # config.symmetry (the reduced half-domain itself is built at setup time, fdtd/symmetry.py - out of scope):
+        # the step's part is the one-sided halo rule of update.py:121-125 and the detector mirror of :139-198
+        self.sym = [int(s != 0) for s in config.symmetry]
+        self.mirror = [int(config.symmetry[a] == -1 and any(getattr(b, "_is_symmetry_wall", False) and b.axis == a for b in objects.boundary_objects)) for a in range(3)]
         self.wrap = wrap
         sB = sF = widths = None
         if config.has_nonuniform_grid:
@@ -167,6 +169,10 @@ class Plan:
             )
         )
         self.h = h
+        if any(self.sym):
+            if x_range is not None or bloch_role is not None:
+                raise NotImplementedError("config.symmetry on x-sharded or complex (Bloch) plans")
+            check(self.lib.fdtdx_b200_set_symmetry(self.h, _iarr(self.sym), _iarr(self.mirror)))
         self._add_boundaries()
         if bloch_role != "im":
             self._add_sources()
@@ -407,7 +413,7 @@ class Plan:
             # large exact regions (videos, volume reductions, whole cross-sections): row-marching kernels
             # with 128-bit accesses instead of one thread per cell (csrc/det_volume.cuh)
             ext = [h_ - l_ for l_, h_ in zip(lo, hi)]
-            if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0" and self.bloch_role is None:
+            if det.exact_interpolation and ext[2] >= 32 and ext[0] * ext[1] * ext[2] >= 4096 and os.environ.get("FDTDX_B200_DET_VOLUME", "1") != "0" and self.bloch_role is None and not any(self.sym):
                 surface_only = (isinstance(det, EnergyDetector) and det.as_slices and not det.use_mean) or isinstance(det, ClosedSurfacePoyntingFluxDetector)
                 if not surface_only:  # three planes / the box shell only: O(surface) work already
                     flags |= _lib.DETF_VOLUME
@@ -636,6 +642,8 @@ class Plan:
         cotangents; gradients accumulate into ``grad_inv_eps`` / ``grad_inv_mu``."""
         import torch
 
+        if any(self.sym):
+            raise NotImplementedError("gradients with config.symmetry (the adjoint kernels transpose the two-sided halo rule)")
         self.bind(arrays)
         self._bind_z(_lib.SLOT_COT_E, 0, cot_E, torch.float32, None, True)
         self._bind_z(_lib.SLOT_COT_H, 0, cot_H, torch.float32, None, True)

@@ -182,6 +182,10 @@ int fdtdx_b200_plan_set_recorder(FdtdxPlan* plan, int dtype, int n_slots, const 
 int fdtdx_b200_plan_set_dispersion(FdtdxPlan* plan, int n_poles, int coeff_tier, int has_c4);
 /* x-slab neighbours: 0 = domain edge (zero / local wrap), 1 = halo buffer bound. */
 int fdtdx_b200_halo_bind(FdtdxPlan* plan, int has_lo_neighbour, int has_hi_neighbour);
+/* config.symmetry (fdtd/update.py:92-198): on a symmetric axis the min-side halo is never wrapped (:121-125);
+ * where an electric symmetry wall sits on the min face, the detector co-location stencil reads the
+ * parity-weighted mirror partner instead of the zero halo (pad_fields_with_symmetry_mirror, :139-198). */
+int fdtdx_b200_set_symmetry(FdtdxPlan* plan, const int symmetric_axes[3], const int electric_wall_axes[3]);
 /* BlochBoundary.apply_pad_correction (objects/boundaries/bloch.py:61-96) for a non-zero Bloch vector.  The
  * complex fields run as two real systems (Re, Im), one plan each; every wrapped ghost value mixes the
  * system's own field with its partner's (FDTDX_SLOT_BLOCH_E / _H): low side F[N-1] * conj(phase) =

@@ -97,6 +97,46 @@ def pad_fields_for_boundaries(fields, objects, config) -> np.ndarray:
     return padded
 
 
+def field_component_parity(field_type: str, component: int, axis: int, wall: int) -> int:
+    """core/physics/symmetry.py: mirror parity of a component across a plane normal to ``axis``
+    (wall -1: PEC / electric, +1: PMC / magnetic)."""
+    normal = component == axis
+    if wall == -1:
+        return (1 if normal else -1) if field_type == "E" else (-1 if normal else 1)
+    if wall == 1:
+        return (-1 if normal else 1) if field_type == "E" else (1 if normal else -1)
+    raise ValueError(f"wall must be -1 (PEC) or +1 (PMC), got {wall}")
+
+
+def mirror_pairs_on_plane(field_type: str, component: int, axis: int, wall: int) -> bool:
+    """core/physics/symmetry.py: an electric plane sits on the tangential-E node row, so components
+    sampled there (E tangential, H normal) pair as m +- j; everything else is a plain flip."""
+    sits = (component != axis) if field_type == "E" else (component == axis)
+    return wall == -1 and sits
+
+
+def pad_fields_with_symmetry_mirror(fields, objects, config, field_type: str) -> np.ndarray:
+    """update.py:139-198: the halo of every *electric* ``config.symmetry`` plane holds the parity-weighted
+    mirror partner (detector co-location stencil only; the field updates never see it)."""
+    padded = pad_fields_for_boundaries(fields, objects, config)
+    for b in objects.boundary_objects:
+        if not getattr(b, "_is_symmetry_wall", False):
+            continue
+        axis = b.axis
+        wall = config.symmetry[axis]
+        if wall != -1:
+            continue
+        for component in range(3):
+            parity = field_component_parity(field_type, component, axis, wall)
+            src = 2 if mirror_pairs_on_plane(field_type, component, axis, wall) else 1
+            tgt_i = [slice(None)] * 3
+            src_i = [slice(None)] * 3
+            tgt_i[axis] = slice(0, 1)
+            src_i[axis] = slice(src, src + 1)
+            padded[(component, *tgt_i)] = parity * padded[(component, *src_i)]
+    return padded
+
+
 # ----------------------------------------------------------------------------------------------
 # curl + CPML  (core/physics/curl.py:10-39, 227-397; perfectly_matched_layer.py:138-190)
 # ----------------------------------------------------------------------------------------------
@@ -828,8 +868,8 @@ def update_detector_states(time_step: int, arrays: ArrayContainer, objects, conf
         else:
             if full is None:
                 full = interpolate_fields(
-                    pad_fields_for_boundaries(E, objects, config),
-                    pad_fields_for_boundaries((H_prev + H) / F(2), objects, config),
+                    pad_fields_with_symmetry_mirror(E, objects, config, "E"),
+                    pad_fields_with_symmetry_mirror((H_prev + H) / F(2), objects, config, "H"),
                     config=config,
                 )
             E_reg, H_reg = full[0][(slice(None), *gs)], full[1][(slice(None), *gs)]
