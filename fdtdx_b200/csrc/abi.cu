@@ -113,6 +113,7 @@ struct FdtdxPlan {
   int detv_xcl = 4;
   // Bloch axes with k != 0: this plan is one of the two real systems of a complex run
   int sym[3] = {0, 0, 0}, mirror[3] = {0, 0, 0};  // config.symmetry (see GridDev::sym)
+  int zpad = 0;  // the last zpad z cells are padding of the caller's grid (plan.py): recorder planes keep the true Nz
   bool bloch = false;
   float bloch_c[3] = {1.f, 1.f, 1.f}, bloch_s[3] = {0.f, 0.f, 0.f};
 };
@@ -431,6 +432,12 @@ extern "C" int fdtdx_b200_plan_set_dispersion(FdtdxPlan* p, int n_poles, int coe
 extern "C" int fdtdx_b200_halo_bind(FdtdxPlan* p, int has_lo, int has_hi) {
   if (!p) return fail(FDTDX_EINVAL, "halo_bind: null plan");
   p->halo_lo = has_lo; p->halo_hi = has_hi;
+  return FDTDX_OK;
+}
+
+extern "C" int fdtdx_b200_set_z_padding(FdtdxPlan* p, int pad_cells) {
+  if (!p || pad_cells < 0 || pad_cells >= p->nz) return fail(FDTDX_EINVAL, "set_z_padding: bad argument");
+  p->zpad = pad_cells;
   return FDTDX_OK;
 }
 
@@ -1208,7 +1215,7 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
       if (cell < 0 || cell >= p->nx) continue;
     }
     RecPlane& pl = R.planes[R.n_planes++];
-    const int n[3] = {p->nx, p->ny, p->nz};
+    const int n[3] = {p->nx, p->ny, p->nz - p->zpad};  // the recorder buffers are shaped by the caller's (unpadded) grid
     for (int a = 0; a < 3; ++a) { pl.lo[a] = 0; pl.hi[a] = n[a]; }
     pl.lo[h.axis] = cell; pl.hi[h.axis] = cell + 1;
     pl.data[0] = p->slots[FDTDX_SLOT_REC_DATA][2 * q + 0];

@@ -169,6 +169,8 @@ class Plan:
             )
         )
         self.h = h
+        if self.pad:
+            check(self.lib.fdtdx_b200_set_z_padding(self.h, self.pad))
         if any(self.sym):
             if x_range is not None or bloch_role is not None:
                 raise NotImplementedError("config.symmetry on x-sharded or complex (Bloch) plans")
@@ -207,10 +209,11 @@ class Plan:
 
         if nz % 4 == 0 or os.environ.get("FDTDX_B200_PAD_Z", "1") == "0":
             return 0
-        if config.gradient_config is not None or arrays.recording_state is not None:
-            # the interface recorder's buffers are shaped by the true Nz, and on the small grids where
-            # gradients are typically taken the padded pass measured slower (135x135x75: 0.70 vs 0.49
-            # ms per backward step); gradient runs keep the ragged kernels
+        gc = config.gradient_config
+        if gc is not None and gc.method == "checkpointed":
+            # that driver steps one call at a time; the shadow copies around every call would dominate
+            return 0
+        if os.environ.get("FDTDX_B200_PAD_Z_GRAD", "1") == "0" and (gc is not None or arrays.recording_state is not None):
             return 0
         if arrays.dispersive_c1 is not None or arrays.fields.dispersive_P_curr is not None:
             return 0

@@ -182,6 +182,9 @@ int fdtdx_b200_plan_set_recorder(FdtdxPlan* plan, int dtype, int n_slots, const 
 int fdtdx_b200_plan_set_dispersion(FdtdxPlan* plan, int n_poles, int coeff_tier, int has_c4);
 /* x-slab neighbours: 0 = domain edge (zero / local wrap), 1 = halo buffer bound. */
 int fdtdx_b200_halo_bind(FdtdxPlan* plan, int has_lo_neighbour, int has_hi_neighbour);
+/* The plan's grid carries pad_cells extra z cells beyond the caller's Nz (kept at zero by walls; host side:
+ * plan.py::_z_padding): interface-recorder planes (interfaces/recorder.py) keep the caller's Nz. */
+int fdtdx_b200_set_z_padding(FdtdxPlan* plan, int pad_cells);
 /* config.symmetry (fdtd/update.py:92-198): on a symmetric axis the min-side halo is never wrapped (:121-125);
  * where an electric symmetry wall sits on the min face, the detector co-location stencil reads the
  * parity-weighted mirror partner instead of the zero halo (pad_fields_with_symmetry_mirror, :139-198). */
