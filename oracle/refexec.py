@@ -476,3 +476,30 @@ class _Objects:
 def to_jarr(arrays):
     """ArrayContainer of NumPy leaves -> the same container with JArr leaves (functional ``.at``)."""
     return arrays.map_arrays(lambda a: _narrow(np.array(a)) if isinstance(a, np.ndarray) else a)
+
+
+def reference_pml_tables(ref: Reference, host_pml, config) -> dict:
+    """CPML coefficient tables from the reference's own ``PerfectlyMatchedLayer.place_on_grid`` body
+    (perfectly_matched_layer.py:97-136, profiles :231-303), run on an instance of the executed class whose user
+    fields (axis, direction, slice, sigma/kappa/alpha start/end/order) come from ``host_pml``."""
+    RefPML = ref.modules["fdtdx.objects.boundaries.perfectly_matched_layer"].PerfectlyMatchedLayer
+    _Any.place_on_grid = lambda self, *a, **k: self  # SimulationObject.place_on_grid: sets slice + config, which Inst serves
+
+    class Inst(RefPML):
+        def __getattribute__(self, name):
+            if name == "_config":
+                return config
+            if name == "_grid_slice_tuple":
+                return host_pml.grid_slice_tuple
+            try:
+                v = object.__getattribute__(self, name)
+            except AttributeError:
+                return getattr(host_pml, name)
+            return getattr(host_pml, name) if v is _Any else v
+
+        def aset(self, name, value, **kw):
+            object.__setattr__(self, name, value)
+            return self
+
+    inst = RefPML.place_on_grid(object.__new__(Inst), host_pml.grid_slice_tuple, config, None)
+    return {k: np.asarray(getattr(inst, k)) for k in ("pml_a_E", "pml_b_E", "inv_kappa_E", "pml_a_H", "pml_b_H", "inv_kappa_H")}

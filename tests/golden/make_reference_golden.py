@@ -162,6 +162,49 @@ def extra_reference(ref):
     return out
 
 
+PML_CASES = [(nonuni, kappa) for nonuni in (False, True) for kappa in (False, True)]
+
+
+def _pml_hosts(nonuni, kappa):
+    """Fresh host PML objects (user fields only; sigma_end left to be derived) of a 14x12x18 scene, 5-cell slabs."""
+    import fdtdx_b200 as fx
+    from scenes import build_scene
+
+    objects, _, cfg = build_scene(shape=(14, 12, 18), thickness=5, nonuniform=nonuni)
+    hosts = []
+    for pml in objects.pml_objects:
+        h = fx.PerfectlyMatchedLayer(name=pml.name, grid_slice_tuple=pml.grid_slice_tuple, axis=pml.axis, direction=pml.direction)
+        if kappa:
+            h.kappa_end = 4.0
+        hosts.append(h)
+    return hosts, cfg
+
+
+def pml_tables_reference(ref):
+    """CPML a / b / 1/kappa tables (E and H side) from the reference's own place_on_grid body."""
+    from oracle import refexec
+
+    out = {}
+    for nonuni, kappa in PML_CASES:
+        hosts, cfg = _pml_hosts(nonuni, kappa)
+        for h in hosts:
+            for k, v in refexec.reference_pml_tables(ref, h, cfg).items():
+                out[f"pml_tables/nonuniform={int(nonuni)},kappa={int(kappa)}/{h.name}/{k}"] = v
+    return out
+
+
+def pml_tables_host():
+    """The same tables from this repo's host mirror (fdtdx_b200/boundaries.py) - what oracle AND kernels consume."""
+    out = {}
+    for nonuni, kappa in PML_CASES:
+        hosts, cfg = _pml_hosts(nonuni, kappa)
+        for h in hosts:
+            h.place_on_grid(cfg)
+            for k in ("pml_a_E", "pml_b_E", "inv_kappa_E", "pml_a_H", "pml_b_H", "inv_kappa_H"):
+                out[f"pml_tables/nonuniform={int(nonuni)},kappa={int(kappa)}/{h.name}/{k}"] = np.asarray(getattr(h, k))
+    return out
+
+
 def extra_oracle():
     from oracle import yee
     from scenes import build_scene, seed_fields
@@ -193,6 +236,7 @@ def main():
         out.update(run_reference(ref, name))
         print(f"{name}: done", flush=True)
     out.update(extra_reference(ref))
+    out.update(pml_tables_reference(ref))
     np.savez_compressed(PATH, **out)
     print(f"wrote {PATH}: {len(out)} arrays, {os.path.getsize(PATH) / 1e6:.2f} MB")
 

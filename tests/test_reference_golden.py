@@ -50,6 +50,20 @@ def test_oracle_pure_functions_match_reference_source():
         _close(k, out[k], GOLD[k], 1e-6)
 
 
+def test_host_cpml_tables_match_reference_place_on_grid():
+    """The CPML a / b / 1/kappa tables are built once by fdtdx_b200/boundaries.py and consumed by BOTH the oracle and
+    the kernels, so a CUDA-vs-oracle test cannot see a wrong table.  Here they are compared with the tables the
+    reference's own ``PerfectlyMatchedLayer.place_on_grid`` body produced (uniform / stretched grid, kappa 1 / graded
+    to 4, all six faces): float32-identical up to 1 ulp."""
+    host = G.pml_tables_host()
+    keys = [k for k in GOLD.files if k.startswith("pml_tables/")]
+    assert sorted(keys) == sorted(host) and len(keys) == 4 * 6 * 6
+    for k in keys:
+        a, b = host[k].reshape(-1), GOLD[k].reshape(-1)
+        assert a.shape == b.shape and a.dtype == np.float32
+        np.testing.assert_allclose(a, b, rtol=2e-7, atol=0, err_msg=k)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/fdtdx"), reason="reference sources not present (GPU box)")
 def test_fixtures_are_what_the_reference_source_produces():
     """Guards the committed fixtures: three scenes re-executed from the reference's files."""
