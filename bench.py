@@ -41,13 +41,14 @@ def _peaks():
 
 
 def _csrc_sha():
-    """sha256 (first 16 hex) over the kernel sources, in name order: ties profiles/traffic.json to the code."""
+    """sha256 (first 16 hex) over the sources of the staged half-step kernels (yee_E_tma / yee_H_tma and the
+    bodies they share with the marching kernels), in name order: ties profiles/traffic.json to the code."""
     import hashlib
 
     d = os.path.join(ROOT, "fdtdx_b200", "csrc")
     h = hashlib.sha256()
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".inl", ".h")):
+        if name in ("common.cuh", "tma_cfg.h", "yee_kernels.cuh", "yee_tma.cuh", "yee_E4t.cu", "yee_H4t.cu"):
             with open(os.path.join(d, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
