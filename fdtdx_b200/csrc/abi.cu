@@ -102,6 +102,10 @@ struct FdtdxPlan {
   std::map<std::tuple<const void*, int, int>, CUtensorMap> tmaps;  // (base, components, box kind) -> map
   float* d_K = nullptr;  // tensor path: curl scratch (3,N)
   float *d_Etmp = nullptr, *d_Htmp = nullptr, *d_lamHx = nullptr, *d_ld = nullptr;  // adjoint scratch
+  // fused adjoint kernel: second set of psi-cotangent buffers per half-step kind ([0] H, [1] E; index 2*q+w as
+  // COT_PSI_*) and which set currently holds the value (1: the plan-owned one; copied back at the end of run_adjoint)
+  std::vector<float*> d_cotpsi_alt[2];
+  int cotpsi_parity[2] = {0, 0};
   double* d_energy_partial = nullptr;  // total_energy: per-block partial sums
   bool adjoint_exact = false;          // run_adjoint_exact: VJP at the bound state, no reverse step
   // row-marching detector kernels (det_volume.cuh): plan-wide H_prev scratch in the layout of H, the
@@ -1629,6 +1633,42 @@ extern "C" int fdtdx_b200_run_reverse(FdtdxPlan* p, int t_from, int n, int recor
   return FDTDX_OK;
 }
 
+static bool adj_fused_wanted() {
+  const char* e = getenv("FDTDX_B200_ADJ_FUSED");  // 0: the two-kernel form (adj_local4 + adj_gather4) everywhere
+  return !(e && e[0] == '0');
+}
+static int adj_fused_xchunk() {
+  const char* e = getenv("FDTDX_B200_ADJ_XC");
+  return e ? atoi(e) : 0;
+}
+static bool adj_interleave_wanted() {
+  const char* e = getenv("FDTDX_B200_ADJ_INTERLEAVE");  // 0: reverse step, then recompute the step into scratch
+  return !(e && e[0] == '0');
+}
+static size_t pml_slab_cells(const FdtdxPlan* p, const PmlHost& h) {
+  int lo = h.lo, hi = h.hi;
+  if (h.axis == 0) { lo = std::max(lo - p->xoff, 0); hi = std::min(hi - p->xoff, p->nx); }
+  const long long len = std::max(hi - lo, 0);
+  const long long nn[3] = {p->nx, p->ny, p->nz};
+  return (size_t)(len * nn[(h.axis + 1) % 3] * nn[(h.axis + 2) % 3]);
+}
+// the fused adjoint kernel leaves the psi cotangents in the plan-owned partner buffers after an odd number of
+// half-steps: bring them home (the caller reads the bound buffers)
+static int adj_cotpsi_home(FdtdxPlan* p, cudaStream_t st) {
+  for (int kind = 0; kind < 2; ++kind) {
+    if (!p->cotpsi_parity[kind]) continue;
+    const int cot_slot = kind ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H;
+    for (size_t q = 0; q < p->pmls.size(); ++q)
+      for (int w = 0; w < 2; ++w) {
+        float* bound = (float*)p->slots[cot_slot][2 * q + w];
+        if (bound && p->d_cotpsi_alt[kind].size() > 2 * q + w)
+          CUDA_TRY(cudaMemcpyAsync(bound, p->d_cotpsi_alt[kind][2 * q + w], pml_slab_cells(p, p->pmls[q]) * 4, cudaMemcpyDeviceToDevice, st));
+      }
+    p->cotpsi_parity[kind] = 0;
+  }
+  return FDTDX_OK;
+}
+
 static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const float* F, const float* G, float* lamF, float* lamG,
                         const float* lam_extra, cudaStream_t st) {
   AdjParams A;
@@ -1647,10 +1687,15 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
     A.sig = S.sigH; A.sig_cs = S.sigH_cs;
     A.g_mat = (p->mu_tier > 0) ? (float*)p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr;
   }
+  const int kind = is_E ? 1 : 0;
+  const int cot_slot = is_E ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H;
   for (size_t q = 0; q < p->pmls.size(); ++q) {
     const PmlHost& h = p->pmls[q];
-    for (int w = 0; w < 2; ++w)
-      A.lam_psi[h.axis][h.dir][w] = (float*)p->slots[is_E ? FDTDX_SLOT_COT_PSI_E : FDTDX_SLOT_COT_PSI_H][2 * q + w];
+    for (int w = 0; w < 2; ++w) {
+      float* bound = (float*)p->slots[cot_slot][2 * q + w];
+      const bool alt = bound && p->cotpsi_parity[kind] && p->d_cotpsi_alt[kind].size() > 2 * q + w;
+      A.lam_psi[h.axis][h.dir][w] = alt ? p->d_cotpsi_alt[kind][2 * q + w] : bound;
+    }
   }
   A.n_walls = S.n_walls; A.walls = S.walls;
   if (is_E && p->n_poles > 0) {
@@ -1667,6 +1712,61 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
   const void* ptrs[] = {F, G, lamF, lamG, lam_extra, A.ld, A.mat, A.sig, A.g_mat, A.sc[2]};
   for (const void* q : ptrs)
     if (q && !aligned16(q)) v4 = false;
+  // Single-pass form (adj_fused4_kernel): whenever lambda' is left as it is by the half-step's transpose, or only
+  // masked by PEC / PMC walls - no conductivity, no ADE, no extra input cotangent.
+  int walls_kind = 0;
+  for (const WallDev& wl : p->walls) walls_kind += (wl.kind == (is_E ? 0 : 1)) ? 1 : 0;
+  // the fused kernel takes one z-slab side per 4-cell group: keep degenerate grids (both z slabs in one group) off it
+  const AxisPmlDev& zs = A.pml[2];
+  const bool z_mixed = zs.lo_len > 0 && zs.hi_start < p->nz && zs.hi_start <= ((zs.lo_len - 1) / 4) * 4 + 3;
+  const bool fused = v4 && adj_fused_wanted() && !A.sig && !lam_extra && A.n_poles == 0 && walls_kind <= FDTDX_ADJ_MAXW && !z_mixed;
+  if (fused) {
+    // ping-pong partner of every bound psi-cotangent buffer (a neighbour's re-evaluation reads the old value)
+    std::vector<float*>& alt = p->d_cotpsi_alt[kind];
+    if (alt.size() < 2 * p->pmls.size()) {
+      alt.assign(2 * p->pmls.size(), nullptr);
+      for (size_t q = 0; q < p->pmls.size(); ++q) {
+        int rcq;
+        for (int w = 0; w < 2; ++w)
+          if ((rcq = to_device<float>(p, nullptr, pml_slab_cells(p, p->pmls[q]), &alt[2 * q + w]))) return rcq;
+      }
+    }
+    for (size_t q = 0; q < p->pmls.size(); ++q) {
+      const PmlHost& h = p->pmls[q];
+      for (int w = 0; w < 2; ++w) {
+        float* bound = (float*)p->slots[cot_slot][2 * q + w];
+        A.lam_psi_new[h.axis][h.dir][w] = !bound ? nullptr : (p->cotpsi_parity[kind] ? bound : alt[2 * q + w]);
+      }
+    }
+    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + 7) / 8);  // per 8 rows
+    int xc = adj_fused_xchunk();
+    if (xc <= 0) xc = (int)std::max<long long>(4, std::min<long long>(16, (long long)p->nx * tiles / (148 * 2 * 3)));
+    A.xchunk = std::min(xc, p->nx);
+    const bool grad = A.g_mat != nullptr;
+    const bool met = A.sc[0] || A.sc[1] || A.sc[2];
+    dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, (p->nx + A.xchunk - 1) / A.xchunk);
+    A.psi_vec = 1;
+    for (int a = 0; a < 2; ++a)
+      for (int sd = 0; sd < 2; ++sd)
+        for (int w = 0; w < 2; ++w) {
+          const void* ps[] = {A.lam_psi[a][sd][w], A.lam_psi_new[a][sd][w], is_E ? A.pml[a].psiE[sd][w] : A.pml[a].psiH[sd][w]};
+          for (const void* q : ps)
+            if (q && !aligned16(q)) A.psi_vec = 0;
+        }
+    // one pass for the cotangents, then (when a material gradient is wanted) one for g += lambda_in . (+-c K)
+#define GO(IE, MT) do { \
+      if (met) adj_fused4_kernel<IE, MT, true, 8><<<g, b, 0, st>>>(A); else adj_fused4_kernel<IE, MT, false, 8><<<g, b, 0, st>>>(A); \
+      if (grad) { if (met) adj_grad4_kernel<IE, MT, true, 8><<<g, b, 0, st>>>(A); else adj_grad4_kernel<IE, MT, false, 8><<<g, b, 0, st>>>(A); } \
+    } while (0)
+    if (is_E) { if (A.mat_tier == 3) GO(true, 3); else GO(true, 1); }
+    else { if (A.mat_tier == 0) GO(false, 0); else if (A.mat_tier == 1) GO(false, 1); else GO(false, 3); }
+#undef GO
+    p->launches += grad ? 1 : 0;
+    p->cotpsi_parity[kind] ^= 1;
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return FDTDX_OK;
+  }
   if (v4) {
     dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, p->nx);
     if (is_E) { adj_local4_kernel<true><<<g, b, 0, st>>>(A); adj_gather4_kernel<true><<<g, b, 0, st>>>(A); }
@@ -1701,41 +1801,93 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_lamHx))) return rc;
     if ((rc = to_device<float>(p, nullptr, (size_t)6 * N, &p->d_ld))) return rc;
   }
+  // Reversible mode, interleaved (default): the reversed step is split around the two transposes, so every
+  // state a transpose needs is in the field arrays at the moment it runs and nothing is recomputed -
+  //   replay interfaces -> [keep H_{t+1} for the detector cotangents] -> reverse H (H := H_t) ->
+  //   detector + H half-step transposes (E_{t+1}, H_t) -> reverse E (E := E_t) -> E half-step transpose (E_t, H_t).
+  // E_{t+1} / H_{t+1} are then the reconstructed values instead of a re-run of the forward step from (E_t, H_t)
+  // with the frozen psi: identical outside the CPML slabs up to rounding, and inside them the reference's
+  // reversible gradient is reconstruction noise either way (tests compare outside the slabs).
+  // FDTDX_B200_ADJ_INTERLEAVE=0 and the exact mode use the reverse-then-recompute order.
+  const bool interleave = !p->adjoint_exact && adj_interleave_wanted();
+  // does the H half-step transpose run fused (then the detector H_prev cotangent is added afterwards, box by box)?
+  int pmc_walls = 0;
+  for (const WallDev& wl : p->walls) pmc_walls += (wl.kind == 1) ? 1 : 0;
+  const AxisPmlDev& zsl = p->axis[2];
+  const bool z_mixed = zsl.lo_len > 0 && zsl.hi_start < p->nz && zsl.hi_start <= ((zsl.lo_len - 1) / 4) * 4 + 3;
+  const bool fusedH = adj_fused_wanted() && (p->nz % 4 == 0) && p->sigH_tier == 0 && pmc_walls <= FDTDX_ADJ_MAXW && !z_mixed;
+  bool fusedH_checked = false;
   for (int t = t_from - 1; t > t_from - 1 - n; --t) {
     if (t < 0) break;  // the reference's extra t = -1 iteration (fdtd.py:253-260) starts from the zero state; skipped
-    // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False);
-    //     exact mode: the caller has bound the stored state of step t instead
-    if (!p->adjoint_exact && (rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
-    StepParams S;
-    if ((rc = make_params(p, S, 1))) return rc;
-    float* E = S.E;
-    float* H = S.H;
-    // (2) recompute E_{t+1}, H_{t+1} from the reconstructed state without touching psi.  The staged
-    // kernels write straight into the scratch buffers; the marching kernels update in place, so their
-    // input is copied first.
-    StepParams F1 = S;
-    F1.psi_store = 0;
-    F1.p_store = 0;
-    StepParams F2;
-    if (can_tma(p, S, can_vec4(p, S))) {
-      F1.E_out = p->d_Etmp;
-      if ((rc = launch_E(p, F1, t, false, st))) return rc;
-      F2 = F1;
-      F2.E = p->d_Etmp;
-      F2.E_out = nullptr;
-      F2.H_out = p->d_Htmp;
-      if ((rc = launch_H(p, F2, t, false, st))) return rc;
-    } else {
-      CUDA_TRY(cudaMemcpyAsync(p->d_Etmp, E, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
-      F1.E = p->d_Etmp;
-      if ((rc = launch_E(p, F1, t, false, st))) return rc;
-      F2 = F1;
-      F2.H = p->d_Htmp;
-      if ((rc = launch_H(p, F2, t, false, st))) return rc;
+    bool any_on = false;
+    for (size_t di = 0; di < p->dets.size(); ++di) {
+      DetHost& h = p->dets[di];
+      if ((h.d.flags & DET_INVERSE) || !h.on[t]) continue;
+      for (int k = 0; k < 4; ++k) any_on = any_on || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
     }
+    // Energy / Poynting cotangents are linearised at E_{t+1}, H_{t+1}: where such a detector reaches into a CPML
+    // slab the reference's re-run of the step (frozen psi) and the reconstructed fields differ by more than
+    // rounding, so the steps on which one is on (with a cotangent) keep the reverse-then-recompute order.
+    bool interleave_t = interleave;
+    for (size_t di = 0; interleave_t && di < p->dets.size(); ++di) {
+      DetHost& h = p->dets[di];
+      if ((h.d.flags & DET_INVERSE) || !h.on[t] || !(h.d.kind == 1 || h.d.kind == 2)) continue;
+      bool any_cot = false;
+      for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
+      if (!any_cot) continue;
+      for (const PmlHost& m : p->pmls) {
+        const int lo = m.lo - (m.axis == 0 ? p->xoff : 0), hi = m.hi - (m.axis == 0 ? p->xoff : 0);
+        if (h.d.lo[m.axis] - 1 < hi && h.d.hi[m.axis] + 1 > lo) interleave_t = false;
+      }
+    }
+    StepParams S;
+    const float* E1;  // E_{t+1}
+    const float* H1;  // H_{t+1}
+    if (interleave_t) {
+      if ((rc = fdtdx_b200_run_reverse_phase(p, t, 0, 0, 0, stream))) return rc;
+      if ((rc = make_params(p, S, 1))) return rc;
+      if (any_on) CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, S.H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+      if ((rc = fdtdx_b200_run_reverse_phase(p, t, 2, 0, 0, stream))) return rc;
+      E1 = S.E;
+      H1 = p->d_Htmp;
+    } else {
+      // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False);
+      //     exact mode: the caller has bound the stored state of step t instead
+      if (!p->adjoint_exact && (rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
+      if ((rc = make_params(p, S, 1))) return rc;
+      // (2) recompute E_{t+1}, H_{t+1} from the reconstructed state without touching psi.  The staged
+      // kernels write straight into the scratch buffers; the marching kernels update in place, so their
+      // input is copied first.
+      StepParams F1 = S;
+      F1.psi_store = 0;
+      F1.p_store = 0;
+      StepParams F2;
+      if (can_tma(p, S, can_vec4(p, S))) {
+        F1.E_out = p->d_Etmp;
+        if ((rc = launch_E(p, F1, t, false, st))) return rc;
+        F2 = F1;
+        F2.E = p->d_Etmp;
+        F2.E_out = nullptr;
+        F2.H_out = p->d_Htmp;
+        if ((rc = launch_H(p, F2, t, false, st))) return rc;
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(p->d_Etmp, S.E, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(p->d_Htmp, S.H, (size_t)3 * N * 4, cudaMemcpyDeviceToDevice, st));
+        F1.E = p->d_Etmp;
+        if ((rc = launch_E(p, F1, t, false, st))) return rc;
+        F2 = F1;
+        F2.H = p->d_Htmp;
+        if ((rc = launch_H(p, F2, t, false, st))) return rc;
+      }
+      E1 = p->d_Etmp;
+      H1 = p->d_Htmp;
+    }
+    float* E = S.E;
+    float* H = S.H;  // H_t
     // (3) detector cotangents at step t
     bool any_det = false;
+    std::vector<std::array<int, 6>> boxes;  // per detector: the box its H_prev cotangents were scattered into
+    const int nn[3] = {p->nx, p->ny, p->nz};
     for (size_t di = 0; di < p->dets.size(); ++di) {
       DetHost& h = p->dets[di];
       if ((h.d.flags & DET_INVERSE) || !h.on[t]) continue;
@@ -1745,18 +1897,28 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
         if (!any_cot) continue;
       }
       if (h.d.flags & DET_CLOSED) return fail(FDTDX_EUNSUPPORTED, "run_adjoint: closed-surface Poynting detectors have no adjoint kernel yet");
-      if (!any_det) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
+      // two-kernel form: the scratch is consumed whole, so it is zeroed whole; fused form: it is kept zero
+      // outside the boxes by adj_box_add_clear_kernel
+      if (!any_det && !fusedH) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
       any_det = true;
+      std::array<int, 6> bx;
+      for (int a = 0; a < 3; ++a) {  // the stencil reaches one cell down in x, y and one up in z (+ wrap)
+        int lo = h.d.lo[a] - 1, hi = h.d.hi[a] + 1;
+        if (p->wrap[a] && (lo < 0 || hi > nn[a])) { lo = 0; hi = nn[a]; }
+        bx[2 * a] = std::max(lo, 0);
+        bx[2 * a + 1] = std::min(hi, nn[a]);
+      }
+      boxes.push_back(bx);
       GridDev G;
       make_grid(p, G);
-      G.E = p->d_Etmp;
+      G.E = E1;
       G.H = H;  // H_prev gather reads the step's input H
       if (h.d.flags & DET_EXACT) {
         const long long hn = 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1) * (h.d.hi[2] - h.d.lo[2] + 1);
         det_gather_hprev_kernel<<<(int)std::min<long long>((hn + 255) / 256, 148 * 16), 256, 0, st>>>(G, h.d);
         p->launches++;
       }
-      G.H = p->d_Htmp;
+      G.H = H1;
       DetAdj A;
       for (int k = 0; k < 4; ++k) A.cot[k] = (const float*)p->slots[FDTDX_SLOT_COT_DET][4 * di + k];
       A.lamE = lamE; A.lamH = lamH; A.lamHprev = p->d_lamHx;
@@ -1770,11 +1932,34 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
       CUDA_TRY(cudaGetLastError());
     }
     // (4) H half-step transpose: lambda_H' -> lambda_H_in, accumulates into lambda_E'
-    if ((rc = adjoint_half(p, S, false, H, p->d_Etmp, lamH, lamE, any_det ? p->d_lamHx : nullptr, st))) return rc;
+    if (fusedH && !fusedH_checked) {  // same alignment test as adjoint_half's (only matters before any scatter happened)
+      const void* ptrs[] = {H, E1, lamH, lamE, S.mu, p->mu_tier > 0 ? p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr, p->d_sF[2]};
+      for (const void* q : ptrs)
+        if (q && !aligned16(q)) return fail(FDTDX_EINVAL, "run_adjoint: unaligned operands with a multiple-of-4 Nz (set FDTDX_B200_ADJ_FUSED=0)");
+      fusedH_checked = true;
+    }
+    if ((rc = adjoint_half(p, S, false, H, E1, lamH, lamE, (any_det && !fusedH) ? p->d_lamHx : nullptr, st))) return rc;
+    if (any_det && fusedH) {  // lambda_H_in += the detectors' H_prev cotangent (same addition, after the kernel)
+      for (const auto& bx : boxes) {  // overlapping boxes: the first launch adds and clears the overlap, the next one sees zeros
+        const int ex = bx[1] - bx[0], ey = bx[3] - bx[2], ez = bx[5] - bx[4];
+        if (ex <= 0 || ey <= 0 || ez <= 0) continue;
+        const long long nb = 3LL * ex * ey * ez;
+        adj_box_add_clear_kernel<<<(unsigned)std::min<long long>((nb + 255) / 256, 148 * 16), 256, 0, st>>>(lamH, p->d_lamHx, p->nx, p->ny, p->nz, bx[0], bx[2], bx[4], ex,
+                                                                                                          ey, ez);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
+    }
+    if (interleave_t) {
+      if ((rc = fdtdx_b200_run_reverse_phase(p, t, 3, 0, 0, stream))) return rc;
+      if ((rc = make_params(p, S, 1))) return rc;
+      E = S.E;
+      H = S.H;
+    }
     // (5) E half-step transpose: lambda_E' -> lambda_E_in, accumulates into lambda_H_in
     if ((rc = adjoint_half(p, S, true, E, H, lamE, lamH, nullptr, st))) return rc;
   }
-  return FDTDX_OK;
+  return adj_cotpsi_home(p, st);
 }
 
 extern "C" int fdtdx_b200_run_adjoint_exact(FdtdxPlan* p, int t, void* stream) {

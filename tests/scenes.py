@@ -49,7 +49,7 @@ def build_scene(
     mu_tier=0,
     nonuniform=False,
     source=None,          # None | "plane_x" | "plane_y" | "plane_z" | "dipole" | "pulse" | "gated" | "table"
-    detectors=(),         # names from: field, field_reduce, energy, energy_slices, energy_pos, energy_reduce, poynting, poynting_full, poynting_all, phasor, phasor_reduce, raw_field, inverse_energy
+    detectors=(),         # names from: field, field_reduce, energy, energy_slices, energy_pos, energy_reduce, poynting, poynting_interior, energy_interior, poynting_full, poynting_all, phasor, phasor_reduce, raw_field, inverse_energy
     recorder=None,
     poles=0,
     c4=False,
@@ -137,6 +137,8 @@ def build_scene(
         "energy_reduce": lambda: fx.EnergyDetector(name="energy_reduce", grid_slice_tuple=full, reduce_volume=True),
         "inverse_energy": lambda: fx.EnergyDetector(name="inverse_energy", grid_slice_tuple=full, as_slices=True, inverse=True, switch=fx.OnOffSwitch(interval=3)),
         "poynting": lambda: fx.PoyntingFluxDetector(name="poynting", grid_slice_tuple=plane, direction="+"),
+        "poynting_interior": lambda: fx.PoyntingFluxDetector(name="poynting_interior", grid_slice_tuple=((off + 1, nx - off - 1), (off + 1, ny - off - 1), (nz - off - 3, nz - off - 2)), direction="+"),
+        "energy_interior": lambda: fx.EnergyDetector(name="energy_interior", grid_slice_tuple=((off + 1, nx - off - 1), (off + 1, ny - off - 1), (off + 1, nz - off - 1)), reduce_volume=True),
         "poynting_full": lambda: fx.PoyntingFluxDetector(name="poynting_full", grid_slice_tuple=xplane, direction="-", reduce_volume=False),
         "poynting_all": lambda: fx.PoyntingFluxDetector(name="poynting_all", grid_slice_tuple=inner, direction="+", keep_all_components=True, fixed_propagation_axis=2),
         "phasor": lambda: fx.PhasorDetector(name="phasor", grid_slice_tuple=xplane, wave_characters=(wc, fx.WaveCharacter(wavelength=1.0e-6))),

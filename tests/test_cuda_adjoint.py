@@ -264,3 +264,71 @@ def test_checkpointed_gradient_through_dispersive_media(name):
         gk, gk_ref = getattr(dev, "dispersive_" + k).grad.cpu().numpy(), co[k].grad.numpy()
         assert np.abs(gk_ref).max() > 0
         assert rel_l2(gk, gk_ref) <= 1e-4, f"d loss / d {k} rel-L2 {rel_l2(gk, gk_ref)}"
+
+
+FUSED_CASES = {
+    # two z tiles (128 + 8 cells), three y tiles, several x chunks; CPML on every face
+    "pml_two_ztiles": dict(source="plane_z", detectors=("poynting", "phasor", "field_reduce"), time=3e-15, shape=(24, 19, 136), thickness=4),
+    "pml_kappa_diag_mu": dict(source="plane_z", detectors=("poynting", "field"), eps_tier=3, mu_tier=3, kappa=True, time=3e-15, shape=(16, 14, 20), thickness=4),
+    "periodic": dict(boundaries="periodic", source="plane_z", detectors=("field", "phasor"), time=3e-15),
+    "nonuniform_mixed_walls": dict(source="dipole", detectors=("poynting_all", "phasor_reduce", "raw_field"), nonuniform=True, time=3e-15, shape=(14, 12, 16),
+                                   boundaries={"min_x": "pec", "max_x": "pmc", "min_y": "periodic", "max_y": "periodic", "min_z": "pec", "max_z": "pmc"}),
+    "pml_energy_slices": dict(source="plane_z", detectors=("energy_reduce", "poynting_full", "energy_slices"), time=3e-15, shape=(16, 14, 20), thickness=4),
+}
+
+
+def _grad_with_env(kw, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rec = fx.Recorder(modules=[])
+    objects, arrays, cfg = build_scene(recorder=rec, **kw)
+    dev = arrays.to_torch("cuda")
+    dev.inv_permittivities.requires_grad_(True)
+    has_mu = isinstance(arrays.inv_permeabilities, np.ndarray)
+    if has_mu:
+        dev.inv_permeabilities.requires_grad_(True)
+    _, out = fx.run_fdtd(dev, objects, cfg)
+    _loss(out.detector_states, out.fields.E).backward()
+    torch.cuda.synchronize()
+    return dev.inv_permittivities.grad.cpu().numpy(), (dev.inv_permeabilities.grad.cpu().numpy() if has_mu else None)
+
+
+@pytest.mark.parametrize("name", list(FUSED_CASES))
+def test_fused_adjoint_kernel_matches_two_kernel_form(name, monkeypatch):
+    """adj_fused4_kernel (one x-marching pass, derivative cotangents re-evaluated at the neighbours) follows the
+    arithmetic and summation order of adj_local4 + adj_gather4: same gradients up to the order of the detector
+    kernels' atomic scatters (<= 1e-6)."""
+    kw = FUSED_CASES[name]
+    g0, m0 = _grad_with_env(kw, {"FDTDX_B200_ADJ_FUSED": "0", "FDTDX_B200_ADJ_INTERLEAVE": "1"}, monkeypatch)
+    g1, m1 = _grad_with_env(kw, {"FDTDX_B200_ADJ_FUSED": "1", "FDTDX_B200_ADJ_INTERLEAVE": "1", "FDTDX_B200_ADJ_XC": "4"}, monkeypatch)
+    assert np.abs(g0).max() > 0
+    err = rel_l2(g1, g0)
+    print(f"[{name}] fused vs two-kernel adjoint: d/d inv_eps rel-L2 {err:.2e}, max |delta| {np.abs(g1 - g0).max():.2e}")
+    assert err <= 1e-6
+    if m0 is not None:
+        assert rel_l2(m1, m0) <= 1e-6
+
+
+INTERLEAVE_CASES = {
+    # nonlinear detectors (Poynting, energy) strictly inside the CPML slabs: every step runs interleaved
+    "pml_interior_poynting_energy": dict(source="plane_z", detectors=("poynting_interior", "energy_interior", "phasor"), time=3e-15, shape=(24, 19, 136), thickness=4),
+    "pml_diag_mu_interior": dict(source="plane_z", detectors=("poynting_interior", "field"), eps_tier=3, mu_tier=3, time=3e-15, shape=(18, 18, 24), thickness=4),
+    # a Poynting plane that crosses the slabs: the steps it is on keep the reverse-then-recompute order
+    "pml_poynting_across_slabs": FUSED_CASES["pml_two_ztiles"],
+    "periodic": FUSED_CASES["periodic"],
+}
+
+
+@pytest.mark.parametrize("name", list(INTERLEAVE_CASES))
+def test_interleaved_backward_matches_reverse_then_recompute(name, monkeypatch):
+    """The interleaved backward iteration (reverse H -> transposes of the detectors and the H half-step -> reverse E ->
+    transpose of the E half-step) uses the reconstructed E(t+1), H(t+1) where the reverse-then-recompute order re-runs
+    the forward step: same gradient outside the CPML slabs up to the rounding of one reversed step."""
+    kw = INTERLEAVE_CASES[name]
+    g0, _ = _grad_with_env(kw, {"FDTDX_B200_ADJ_FUSED": "0", "FDTDX_B200_ADJ_INTERLEAVE": "0"}, monkeypatch)
+    g1, _ = _grad_with_env(kw, {"FDTDX_B200_ADJ_FUSED": "1", "FDTDX_B200_ADJ_INTERLEAVE": "1"}, monkeypatch)
+    th = kw.get("thickness", 0) + 1 if kw.get("boundaries") != "periodic" else 0
+    sl = (slice(None),) * 4 if th == 0 else (slice(None), *(slice(th, -th),) * 3)
+    err = rel_l2(g1[sl], g0[sl])
+    print(f"[{name}] interleaved vs reverse-then-recompute: rel-L2 {err:.2e} outside the slabs")
+    assert err <= 2e-5
