@@ -828,7 +828,13 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
     const int tzc = tma_tz(p), rtc = FDTDX_TMA_R * (128 / tzc);
     const long long tiles = (long long)((p->nz + tzc - 1) / tzc) * ((p->ny + rtc - 1) / rtc);
     const long long nxr = P.x_end - P.x_begin;
-    if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
+    if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 4 && pml_mode(p, P) == 1) {
+      // Small grid on the masked-psi path (odd-position z slabs, e.g. the z-padded C4 grid): CTAs that sit in the
+      // slabs run several times longer than interior ones, and with about one wave of CTAs the launch lasts as long
+      // as the slowest of them.  Very short chunks let the hardware scheduler balance the load: measured on
+      // (135,135,76), B200 (scripts/small_grid_sweep.py): 78.0 us/step at 8 planes, 65.2 at 4, 58.9 at 2.
+      xc = 2;
+    } else if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
       double best = -1.0;
       for (int c = 10; c >= 5; --c) {
         const long long ctas = tiles * ((nxr + c - 1) / c);

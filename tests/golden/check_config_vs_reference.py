@@ -83,6 +83,9 @@ def main():
                 v = np.asarray(a.detector_states["Energy Video"][key])[:, ::2, ::2]
                 extra[f"video_{key[:2]}"] = np.ascontiguousarray(v[t_pick(v.shape[0])])
                 extra[f"video_{key[:2]}_norm"] = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2)))  # of the sub-sampled frames
+        if which == "c4":
+            for n, k in (("out flux", "out_flux"), ("in flux", "in_flux")):
+                extra[k] = np.asarray(a.detector_states[n]["poynting_flux"])
         np.savez_compressed(os.path.join(HERE, f"cfg_{which}_refsrc.npz"), fwd_E=sub(E), fwd_H=sub(H), fwd_E_norm=field_norms(E), fwd_H_norm=field_norms(H), **extra)
         lines.append(f"[{which.upper()}] fwd E (every 4th cell): rel-L2 {rel_l2(sub(E), g['fwd_E']):.3e}")
         lines.append(f"[{which.upper()}] fwd H (every 4th cell): rel-L2 {rel_l2(sub(H), g['fwd_H']):.3e}")
@@ -93,9 +96,8 @@ def main():
                 v = np.asarray(st[key])
                 lines.append(f"[C1] video {key} norm of every frame: rel-L2 {rel_l2(np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2))), g[f'video_{key[:2]}_norm']):.3e}")
         else:
-            for n, k in (("out flux", "flux_out"), ("in flux", "flux_in")):
-                if k in g.files:
-                    lines.append(f"[C4] {n} series: rel-L2 {rel_l2(np.asarray(a.detector_states[n]['poynting_flux']), g[k]):.3e}")
+            for n, k in (("out flux", "out_flux"), ("in flux", "in_flux")):
+                lines.append(f"[C4] {n} series: rel-L2 {rel_l2(extra[k], g[k]):.3e}")
     lines.append(f"# ({time.time() - t0:.0f} s on the CPU)")
     report(lines)
 
