@@ -1902,7 +1902,6 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
         for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
         if (!any_cot) continue;
       }
-      if (h.d.flags & DET_CLOSED) return fail(FDTDX_EUNSUPPORTED, "run_adjoint: closed-surface Poynting detectors have no adjoint kernel yet");
       // two-kernel form: the scratch is consumed whole, so it is zeroed whole; fused form: it is kept zero
       // outside the boxes by adj_box_add_clear_kernel
       if (!any_det && !fusedH) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));

@@ -534,6 +534,11 @@ __global__ void det_adjoint_kernel(const GridDev G, const DetDev D, const DetAdj
   const int ry = (int)((cell / ez) % ey);
   const int rx = (int)(cell / ((long long)ez * ey));
   const int x = D.lo[0] + rx, y = D.lo[1] + ry, z = D.lo[2] + rz;
+  if (D.flags & DET_CLOSED) {  // only the shell of a closed surface is sampled (det_sample_body)
+    const bool fx = ((D.aux >> 0) & 1) && (rx == 0 || rx == ex - 1), fy = ((D.aux >> 1) & 1) && (ry == 0 || ry == ey - 1);
+    const bool fz = ((D.aux >> 2) & 1) && (rz == 0 || rz == ez - 1);
+    if (!fx && !fy && !fz) return;
+  }
   float Es[3], Hs[3];
   colocate(G, D, x, y, z, Es, Hs);
   const int slot = D.arr_idx[t];
@@ -588,7 +593,17 @@ __global__ void det_adjoint_kernel(const GridDev G, const DetDev D, const DetAdj
   } else {
     float g[3] = {0.f, 0.f, 0.f};
     const float sg = (D.flags & DET_NEGATIVE) ? -1.0f : 1.0f;
-    if (D.flags & DET_KEEP_ALL) {
+    if (D.flags & DET_CLOSED) {
+      // state[slot] = sum over shell cells of (+S_a area on the max face, -S_a area on the min face), metrics.py:120-160
+      const int r3[3] = {rx, ry, rz}, e3[3] = {ex, ey, ez};
+      for (int a = 0; a < 3; ++a) {
+        if (!((D.aux >> a) & 1)) continue;
+        float coef = 0.0f;
+        if (r3[a] == e3[a] - 1) coef += 1.0f;
+        if (r3[a] == 0) coef -= 1.0f;
+        g[a] = sg * (A.cot[0][slot] * coef * D.weights[a * n + cell]);
+      }
+    } else if (D.flags & DET_KEEP_ALL) {
       for (int c = 0; c < 3; ++c)
         g[c] = sg * ((D.flags & DET_REDUCE) ? A.cot[0][(long long)slot * 3 + c] * D.weights[c * n + cell] : A.cot[0][((long long)slot * 3 + c) * n + cell]);
     } else {
