@@ -34,7 +34,7 @@ EXPORTS = [
     "fdtdx_b200_run_forward_phase", "fdtdx_b200_run_reverse", "fdtdx_b200_run_adjoint",
     "fdtdx_b200_get_parity", "fdtdx_b200_set_parity", "fdtdx_b200_launch_count", "fdtdx_b200_set_tuning", "fdtdx_b200_set_tma", "fdtdx_b200_peer_export", "fdtdx_b200_peer_attach", "fdtdx_b200_peer_detach", "fdtdx_b200_total_energy", "fdtdx_b200_run_adjoint_exact",
     "fdtdx_b200_run_forward_host", "fdtdx_b200_run_half_range", "fdtdx_b200_get_xchunk",
-    "fdtdx_b200_plan_source_set_quadrature", "fdtdx_b200_peer_status", "fdtdx_b200_set_bloch", "fdtdx_b200_run_reverse_phase", "fdtdx_b200_plan_detector_set_wsum", "fdtdx_b200_set_symmetry", "fdtdx_b200_set_z_padding",
+    "fdtdx_b200_plan_source_set_quadrature", "fdtdx_b200_peer_status", "fdtdx_b200_set_bloch", "fdtdx_b200_run_reverse_phase", "fdtdx_b200_plan_detector_set_wsum", "fdtdx_b200_set_symmetry", "fdtdx_b200_set_z_padding", "fdtdx_b200_plan_pml_set_true_range",
 ]
 
 _p = C.c_void_p
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
     L.fdtdx_b200_set_bloch.argtypes = [_p, _i, _dp, _dp]
     L.fdtdx_b200_set_symmetry.argtypes = [_p, _ip, _ip]
     L.fdtdx_b200_set_z_padding.argtypes = [_p, _i]
+    L.fdtdx_b200_plan_pml_set_true_range.argtypes = [_p, _i, _i, _i]
     L.fdtdx_b200_plan_detector_set_wsum.argtypes = [_p, _i, _d]
     L.fdtdx_b200_run_reverse_phase.argtypes = [_p, _i, _i, _i, _i, _p]
     L.fdtdx_b200_bind.argtypes = [_p, _i, _i, _p]

@@ -38,6 +38,7 @@ static const double kEta0 = (4e-7 * M_PI) * 299792458.0;
 
 struct PmlHost {
   int axis, dir, lo, hi, kappa_one;
+  int lo_true, hi_true;  // the reference's slab (recorder interface plane, field reset); [lo, hi) may be a padded superset
   std::vector<float> aE, bE, kE, aH, bH, kH;
 };
 struct SrcHost {
@@ -180,6 +181,15 @@ extern "C" int fdtdx_b200_plan_destroy(FdtdxPlan* p) {
   return FDTDX_OK;
 }
 
+extern "C" int fdtdx_b200_plan_pml_set_true_range(FdtdxPlan* p, int index, int lo, int hi) {
+  if (!p || index < 0 || index >= (int)p->pmls.size()) return fail(FDTDX_EINVAL, "pml_set_true_range: bad slab index");
+  PmlHost& h = p->pmls[index];
+  if (lo < h.lo || hi > h.hi || hi <= lo) return fail(FDTDX_EINVAL, "pml_set_true_range: the true slab must lie inside the registered one");
+  h.lo_true = lo;
+  h.hi_true = hi;
+  return FDTDX_OK;
+}
+
 extern "C" int fdtdx_b200_plan_add_pml(FdtdxPlan* p, int axis, int direction, int lo, int hi, const float* a_E,
                                        const float* b_E, const float* inv_kappa_E, const float* a_H,
                                        const float* b_H, const float* inv_kappa_H, int kappa_is_one) {
@@ -190,6 +200,7 @@ extern "C" int fdtdx_b200_plan_add_pml(FdtdxPlan* p, int axis, int direction, in
   if (direction == 1 && hi != ng[axis]) return fail(FDTDX_EUNSUPPORTED, "add_pml: a '+' slab must end at the domain edge");
   PmlHost h;
   h.axis = axis; h.dir = direction; h.lo = lo; h.hi = hi; h.kappa_one = kappa_is_one;
+  h.lo_true = lo; h.hi_true = hi;
   const int L = hi - lo;
   h.aE.assign(a_E, a_E + L); h.bE.assign(b_E, b_E + L);
   h.aH.assign(a_H, a_H + L); h.bH.assign(b_H, b_H + L);
@@ -724,10 +735,39 @@ cudaError_t fdtdx_dispatch_H4_tma_konly(const StepParams& P, const TmaSet& M, in
 cudaError_t fdtdx_dispatch_E4_tma64(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
                                     cudaStream_t st);
 cudaError_t fdtdx_dispatch_H4_tma64(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
+// flat tiles: any other row length up to 124 cells (the CTA's threads laid over (row, z quad) pairs)
+cudaError_t fdtdx_dispatch_E4_tmaf(const StepParams& P, const TmaSet& M, int t, int tier, int pm, bool rev, bool sig, bool ade, bool met, dim3 g,
+                                   cudaStream_t st);
+cudaError_t fdtdx_dispatch_H4_tmaf(const StepParams& P, const TmaSet& M, int t, int mt, int pm, bool rev, bool sig, bool met, dim3 g, cudaStream_t st);
 static int tma_tz(const FdtdxPlan* p) {
   const char* e = getenv("FDTDX_B200_TMA_TZ");
   if (e && (atoi(e) == 64 || atoi(e) == 128)) return atoi(e);
   return p->nz <= 64 ? 64 : 128;
+}
+// z quads per row when the half-steps run with flat tiles (0: the 64- / 128-cell tile rows).  FDTDX_B200_TMA_FLAT=0
+// or an explicit FDTDX_B200_TMA_TZ turn it off.
+static int tma_flat_lz(const FdtdxPlan* p) {
+  const char* e = getenv("FDTDX_B200_TMA_FLAT");
+  if (e && e[0] == '0') return 0;
+  const char* tz = getenv("FDTDX_B200_TMA_TZ");
+  if (tz && (atoi(tz) == 64 || atoi(tz) == 128)) return 0;
+  if (p->nz % 4 != 0) return 0;
+  const int lz = p->nz / 4;
+  return (lz >= 5 && lz <= 31 && lz != 16) ? lz : 0;
+}
+// tile row length / rows per CTA tile of the staged half-steps
+static void tma_tile(const FdtdxPlan* p, int lz, int* tz, int* rt) {
+  if (lz > 0) { *tz = 4 * lz; *rt = (FDTDX_TMA_R * 32) / lz; }
+  else { *tz = tma_tz(p); *rt = FDTDX_TMA_R * (128 / *tz); }
+}
+// warps of one x chunk that own rows (the in-kernel peer ordering counts their arrivals)
+static int tma_active_warps(const FdtdxPlan* p, int lz, int gx) {
+  int tz, rt;
+  tma_tile(p, lz, &tz, &rt);
+  const int lanes = tz / 4;
+  int n = 0;
+  for (int j0 = 0; j0 < p->ny; j0 += rt) n += std::min(FDTDX_TMA_R, (std::min(rt, p->ny - j0) * lanes + 31) / 32);
+  return gx * n;
 }
 
 // 0: no CPML slab on this rank; 1: scalar z-slab accesses; 2: 128-bit z-slab accesses
@@ -760,9 +800,10 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // kind 0: halo box (TZ+4, R+1), kind 1: plain box (TZ, R).  Arrays are (C, nx, ny, nz) float32.
-static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind, CUtensorMap* out) {
-  const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
-  auto key = std::make_tuple(base, comps * 4 + (nx == p->nx ? 0 : 1), kind);
+static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind, CUtensorMap* out, int lz = 0) {
+  int tz, rt;
+  tma_tile(p, lz, &tz, &rt);
+  auto key = std::make_tuple(base, comps * 4 + (nx == p->nx ? 0 : 1) + 64 * lz, kind);
   auto it = p->tmaps.find(key);
   if (it != p->tmaps.end()) { *out = it->second; return FDTDX_OK; }
   EncodeTiledFn enc = encode_tiled_fn();
@@ -781,15 +822,16 @@ static int get_tmap(FdtdxPlan* p, const void* base, int comps, int nx, int kind,
 }
 
 // (2, ny, nz)-shaped view with an arbitrary component stride (packed staging buffer or a peer field array)
-static int get_xhalo_tmap(FdtdxPlan* p, const void* base, long long comp_stride, CUtensorMap* out) {
-  auto key = std::make_tuple(base, (int)(comp_stride % 2147483647LL), 2);
+static int get_xhalo_tmap(FdtdxPlan* p, const void* base, long long comp_stride, CUtensorMap* out, int lz = 0) {
+  auto key = std::make_tuple(base, (int)(comp_stride % 2147483647LL), 2 + 4 * lz);
   auto it = p->tmaps.find(key);
   if (it != p->tmaps.end()) { *out = it->second; return FDTDX_OK; }
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(FDTDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)p->nz, (cuuint64_t)p->ny, 2, 1};
   const cuuint64_t strides[3] = {(cuuint64_t)p->nz * 4, (cuuint64_t)comp_stride * 4, (cuuint64_t)comp_stride * 8};
-  const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+  int tz, rt;
+  tma_tile(p, lz, &tz, &rt);
   const cuuint32_t box[4] = {(cuuint32_t)(tz + 4), (cuuint32_t)(rt + 1), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap m;
@@ -825,21 +867,21 @@ static int tma_chunk(const FdtdxPlan* p, const StepParams& P) {
     xc = 8;
     // Mid-size grids run only a few waves of the 148 x 2 resident CTAs: pick the chunk length in 5..10
     // whose CTA count wastes the least of its last wave (large grids: no effect).
-    const int tzc = tma_tz(p), rtc = FDTDX_TMA_R * (128 / tzc);
+    int tzc, rtc;
+    tma_tile(p, tma_flat_lz(p), &tzc, &rtc);
     const long long tiles = (long long)((p->nz + tzc - 1) / tzc) * ((p->ny + rtc - 1) / rtc);
     const long long nxr = P.x_end - P.x_begin;
-    if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 4 && pml_mode(p, P) == 1) {
-      // Small grid on the masked-psi path (odd-position z slabs, e.g. the z-padded C4 grid): CTAs that sit in the
-      // slabs run several times longer than interior ones, and with about one wave of CTAs the launch lasts as long
-      // as the slowest of them.  Very short chunks let the hardware scheduler balance the load: measured on
-      // (135,135,76), B200 (scripts/small_grid_sweep.py): 78.0 us/step at 8 planes, 65.2 at 4, 58.9 at 2.
-      xc = 2;
-    } else if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
+    if (tiles * ((nxr + 7) / 8) < 148LL * 2 * 12) {
+      // Score = fill of the last wave, discounted when the whole launch is about one wave: then every SM runs its two
+      // CTAs in lock step, nothing overlaps their ring fill / drain, and the launch lasts as long as its slowest
+      // (CPML-heavy) CTA, whereas several waves of short chunks let the hardware scheduler balance the load.
+      // Measured on B200 (scripts/small_grid_sweep.py): C4 grid (135,135,76) 67.4 us/step at 7 planes per CTA,
+      // 55.9 at 2; C1 grid 120^3 45.3 at 7 (one full wave), 47.2 at 2.
       double best = -1.0;
-      for (int c = 10; c >= 5; --c) {
+      for (int c = 10; c >= 2; --c) {
         const long long ctas = tiles * ((nxr + c - 1) / c);
         const long long waves = (ctas + 148 * 2 - 1) / (148 * 2);
-        const double eff = (double)ctas / (double)(waves * 148 * 2) - 0.004 * std::abs(c - 8);
+        const double eff = (double)ctas / (double)(waves * 148 * 2) * (1.0 - 0.12 / (double)waves) - 0.004 * std::abs(c - 8);
         if (eff > best) { best = eff; xc = c; }
       }
     }
@@ -914,16 +956,20 @@ static int launch_E(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     TmaSet M;
     memset(&M, 0, sizeof(M));
     int rc;
-    if ((rc = get_tmap(p, P.H, 3, p->nx, 0, &M.fld_halo))) return rc;
-    if ((rc = get_tmap(p, P.E, 3, p->nx, 1, &M.fld_plain))) return rc;
-    if ((rc = get_tmap(p, P.eps, p->eps_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain))) return rc;
+    const int lz = tma_flat_lz(p);
+    if ((rc = get_tmap(p, P.H, 3, p->nx, 0, &M.fld_halo, lz))) return rc;
+    if ((rc = get_tmap(p, P.E, 3, p->nx, 1, &M.fld_plain, lz))) return rc;
+    if ((rc = get_tmap(p, P.eps, p->eps_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain, lz))) return rc;
     M.xhalo = M.fld_halo;
     StepParams Q = P;
     Q.xchunk = tma_chunk(p, P);
-    const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+    Q.flat_lz = lz;
+    int tz, rt;
+    tma_tile(p, lz, &tz, &rt);
     dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
-    Q.peer_total = (int)g.x * ((p->ny + 128 / tz - 1) / (128 / tz));  // warps of one x chunk that own rows
-    if (tz == 64) CUDA_TRY(fdtdx_dispatch_E4_tma64(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
+    Q.peer_total = tma_active_warps(p, lz, (int)g.x);  // warps of one x chunk that own rows
+    if (lz > 0) CUDA_TRY(fdtdx_dispatch_E4_tmaf(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
+    else if (tz == 64) CUDA_TRY(fdtdx_dispatch_E4_tma64(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
     else CUDA_TRY(fdtdx_dispatch_E4_tma(Q, M, t, p->eps_tier, pml_mode(p, P), rev, sig, ade, met, g, st));
   } else {
     // register-marching kernels, four cells per thread: 128-bit accesses (E4) or, on ragged rows, four
@@ -950,18 +996,22 @@ static int launch_H(FdtdxPlan* p, const StepParams& P, int t, bool rev, cudaStre
     TmaSet M;
     memset(&M, 0, sizeof(M));
     int rc;
-    if ((rc = get_tmap(p, P.E, 3, p->nx, 0, &M.fld_halo))) return rc;
-    if ((rc = get_tmap(p, P.H, 3, p->nx, 1, &M.fld_plain))) return rc;
+    const int lz = tma_flat_lz(p);
+    if ((rc = get_tmap(p, P.E, 3, p->nx, 0, &M.fld_halo, lz))) return rc;
+    if ((rc = get_tmap(p, P.H, 3, p->nx, 1, &M.fld_plain, lz))) return rc;
     M.mat_plain = M.fld_plain;
-    if (p->mu_tier > 0 && (rc = get_tmap(p, P.mu, p->mu_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain))) return rc;
+    if (p->mu_tier > 0 && (rc = get_tmap(p, P.mu, p->mu_tier == 1 ? 1 : 3, p->nx, 1, &M.mat_plain, lz))) return rc;
     M.xhalo = M.fld_halo;
-    if (P.x_hi_mode == 2 && (rc = get_xhalo_tmap(p, P.haloE, P.haloE_cs, &M.xhalo))) return rc;
+    if (P.x_hi_mode == 2 && (rc = get_xhalo_tmap(p, P.haloE, P.haloE_cs, &M.xhalo, lz))) return rc;
     StepParams Q = P;
     Q.xchunk = tma_chunk(p, P);
-    const int tz = tma_tz(p), rt = FDTDX_TMA_R * (128 / tz);
+    Q.flat_lz = lz;
+    int tz, rt;
+    tma_tile(p, lz, &tz, &rt);
     dim3 g((p->nz + tz - 1) / tz, (p->ny + rt - 1) / rt, (Q.x_end - Q.x_begin + Q.xchunk - 1) / Q.xchunk);
-    Q.peer_total = (int)g.x * ((p->ny + 128 / tz - 1) / (128 / tz));
-    if (tz == 64) CUDA_TRY(fdtdx_dispatch_H4_tma64(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
+    Q.peer_total = tma_active_warps(p, lz, (int)g.x);
+    if (lz > 0) CUDA_TRY(fdtdx_dispatch_H4_tmaf(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
+    else if (tz == 64) CUDA_TRY(fdtdx_dispatch_H4_tma64(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
     else CUDA_TRY(fdtdx_dispatch_H4_tma(Q, M, t, p->mu_tier, pml_mode(p, P), rev, p->sigH_tier > 0, p->metric, g, st));
   } else {
     dim3 b(32, p->rows);
@@ -1219,7 +1269,7 @@ static int make_rec(FdtdxPlan* p, RecDev& R) {
     const PmlHost& h = p->pmls[q];
     // x-sharded plans (interfaces/state.py:72-78 shards every recorder array on x): a y / z interface
     // plane is this rank's x-slice of it, an x interface plane lives on the rank that owns that plane
-    int cell = (h.dir == 1) ? h.lo : h.hi - 1;  // boundary.py:134-144
+    int cell = (h.dir == 1) ? h.lo_true : h.hi_true - 1;  // boundary.py:134-144
     if (h.axis == 0) {
       cell -= p->xoff;
       if (cell < 0 || cell >= p->nx) continue;
@@ -1604,7 +1654,7 @@ extern "C" int fdtdx_b200_run_reverse_phase(FdtdxPlan* p, int t, int phase, int 
     const int nn[3] = {p->nx, p->ny, p->nz};
     for (const PmlHost& h : p->pmls) {
       for (int a = 0; a < 3; ++a) { B.lo[B.n][a] = 0; B.hi[B.n][a] = nn[a]; }
-      int lo = h.lo, hi = h.hi;
+      int lo = h.lo_true, hi = h.hi_true;  // the reference's slab, not a padded superset of it
       if (h.axis == 0) {  // this rank's part of an x slab
         lo = std::max(lo - p->xoff, 0); hi = std::min(hi - p->xoff, p->nx);
         if (hi <= lo) continue;

@@ -9,10 +9,10 @@ mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC ${FDTDX_NVCC_EXTRA:-}"
 pids=()
-for u in abi yee_E4 yee_E1 yee_H4 yee_H1 yee_E4t yee_H4t yee_E4t64 yee_H4t64; do
+for u in abi yee_E4 yee_E1 yee_H4 yee_H1 yee_E4t yee_H4t yee_E4t64 yee_H4t64 yee_E4tf yee_H4tf; do
   "$NVCC" $FLAGS -c "$HERE/$u.cu" -o "$OBJ/$u.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ/abi.o" "$OBJ/yee_E4.o" "$OBJ/yee_E1.o" "$OBJ/yee_H4.o" "$OBJ/yee_H1.o" "$OBJ/yee_E4t.o" "$OBJ/yee_H4t.o" "$OBJ/yee_E4t64.o" "$OBJ/yee_H4t64.o"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ/abi.o" "$OBJ/yee_E4.o" "$OBJ/yee_E1.o" "$OBJ/yee_H4.o" "$OBJ/yee_H1.o" "$OBJ/yee_E4t.o" "$OBJ/yee_H4t.o" "$OBJ/yee_E4t64.o" "$OBJ/yee_H4t64.o" "$OBJ/yee_E4tf.o" "$OBJ/yee_H4tf.o"
 echo "built $OUT"

@@ -104,6 +104,7 @@ struct StepParams {
   const float* haloE;
   long long haloH_cs, haloE_cs;
   int xchunk;
+  int flat_lz;         // staged kernels with flat tiles (yee_tma.cuh, TmaRt): z quads per row (Nz / 4); 0 otherwise
   int x_begin, x_end;  // plane range of this launch (sub-ranges let the halo exchange overlap)
   // Peer-memory halo (x-slab sharding, neighbour arrays mapped over NVLink): producer / consumer order
   // with the neighbour rank is kept INSIDE the half-step kernel.  Only the CTAs of the boundary chunk

@@ -18,15 +18,16 @@ static cudaError_t go_E(const StepParams& P, const TmaSet& M, int t, dim3 g, cud
   // variants run a 2-deep ring (78 KB, two CTAs per SM)
   constexpr int R = FDTDX_TMA_R, S = (TIER == 3) ? 2 : FDTDX_TMA_S;
   constexpr int TZ = FDTDX_TZ_SEL;
-  constexpr int smem = tma_smem_bytes<R, TZ, TIER, S>();
+  // flat tiles (TZ == 0): the geometry, and with it the shared-memory size, follows the row length of the grid
+  const int smem = TZ > 0 ? tma_smem_bytes<R, (TZ > 0 ? TZ : 128), TIER, S>() : tma_smem_bytes_flat<R>(P.flat_lz, TIER, S);
   auto k = yee_E_tma<TIER, REV, SIG, ADE, MET, PM, R, S, TZ>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_smem = smem;
   }
   // programmatic dependent launch: this grid may begin while the previous kernel of the stream drains
   cudaLaunchConfig_t cfg = {};

@@ -50,6 +50,37 @@ struct TmaGeom {
   static constexpr int PLAIN_B = TZ * RT * 4;
   static constexpr int HALO_F = HALO_B / 4, PLAIN_F = PLAIN_B / 4;
 };
+// Run-time tile geometry.  TZ > 0: the compile-time shapes above (every member folds to a constant).  TZ == 0
+// ("flat" tiles, grids whose rows are neither 64 nor 128 cells: Nz = 4 * lz, 5 <= lz <= 31): a tile row is the whole
+// z extent, the CTA's 256 threads are laid over (row, z quad) pairs in row-major order - thread t owns quad t % lz
+// of row t / lz - so RT = 256 / lz rows keep (almost) every lane busy whatever the row length (Nz = 68: 255 of 256
+// lanes instead of 17 of 32).  The z neighbour across a lane that is not the adjacent quad of the same row (first /
+// last quad of a row, first / last lane of a warp) is read from the staged tile instead of by shuffle.
+struct TmaRt {
+  int TZ, LZ, RT, HZ, HALO_RAW, HALO_B, PLAIN_B, HALO_F, PLAIN_F;
+};
+template <int R, int TZ>
+__host__ __device__ __forceinline__ TmaRt tma_geometry(const int flat_lz) {
+  TmaRt g;
+  if (TZ > 0) {
+    using G = TmaGeom<R, (TZ > 0 ? TZ : 128)>;
+    g.TZ = TZ; g.LZ = TZ / 4; g.RT = G::RT; g.HZ = G::HZ; g.HALO_RAW = G::HALO_RAW; g.HALO_B = G::HALO_B; g.PLAIN_B = G::PLAIN_B;
+  } else {
+    g.LZ = flat_lz; g.TZ = 4 * flat_lz; g.RT = (R * 32) / flat_lz; g.HZ = g.TZ + 4;
+    g.HALO_RAW = g.HZ * (g.RT + 1) * 4;
+    g.HALO_B = (g.HALO_RAW + 127) / 128 * 128;
+    g.PLAIN_B = (g.TZ * g.RT * 4 + 127) / 128 * 128;  // tile slots stay 128-byte aligned; the TMA writes TZ * RT * 4 bytes
+  }
+  g.HALO_F = g.HALO_B / 4;
+  g.PLAIN_F = g.PLAIN_B / 4;
+  return g;
+}
+// dynamic shared memory of a flat-tile launch (host side)
+template <int R>
+inline int tma_smem_bytes_flat(const int flat_lz, const int nmat, const int S) {
+  const TmaRt g = tma_geometry<R, 0>(flat_lz);
+  return S * (3 * g.HALO_B + (3 + nmat) * g.PLAIN_B) + FDTDX_TMA_TAIL_F * 4;
+}
 template <int R, int TZ, int NMAT, int S>
 constexpr int tma_smem_bytes() {
   // stages, full barriers, arrival counters (padded to 16 B), z-slab coefficient tables, per-plane x scale
@@ -211,8 +242,8 @@ struct PmlT {
     }                                                                                                                  \
     if (PM == 2) {                                                                                                     \
       if (L.zh0 || L.zh1) {                                                                                            \
-        const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZ + zl * V);                                  \
-        const Vec<V> kz = lds4(ztab + 2 * TZ + zl * V);                                                                  \
+        const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZE + zl * V);                                  \
+        const Vec<V> kz = lds4(ztab + 2 * TZE + zl * V);                                                                  \
         float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                          \
         float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                          \
         if (L.zh0) {                                                                                                   \
@@ -243,8 +274,8 @@ struct PmlT {
         }                                                                                                              \
       }                                                                                                                \
     } else if (L.zm) {                                                                                                 \
-      const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZ + zl * V);                                    \
-      const Vec<V> kz = lds4(ztab + 2 * TZ + zl * V);                                                                    \
+      const Vec<V> az = lds4(ztab + zl * V), bz = lds4(ztab + TZE + zl * V);                                    \
+      const Vec<V> kz = lds4(ztab + 2 * TZE + zl * V);                                                                    \
       float* q1 = pz.PSI[L.zside][0] + ((long long)i * L.zstride + L.zoff);                                            \
       float* q2 = pz.PSI[L.zside][1] + ((long long)i * L.zstride + L.zoff);                                            \
       const bool k1 = pz.kappa_one;                                                                                    \
@@ -259,16 +290,17 @@ struct PmlT {
 // Stage layout: [Hx halo][Hy halo][Hz halo][Ex][Ey][Ez][inv_eps x TIER]; halo tile origin (k0-4, j0-1).
 // ------------------------------------------------------------------------------------------------
 template <int TIER, int R, int TZ, bool KONLY = false>
-__device__ __forceinline__ void tma_issue_E(const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i) {
-  using G = TmaGeom<R, TZ>;
-  mbar_expect_tx(full, KONLY ? 3 * G::HALO_RAW : 3 * G::HALO_RAW + (3 + TIER) * G::PLAIN_B);
+__device__ __forceinline__ void tma_issue_E(const TmaRt& G, const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i) {
+  // bytes the TMA engine delivers: whole boxes, out-of-bounds parts included (flat tiles: TZ * RT * 4, not the padded slot)
+  const int plain_raw = G.TZ * G.RT * 4;
+  mbar_expect_tx(full, KONLY ? 3 * G.HALO_RAW : 3 * G.HALO_RAW + (3 + TIER) * plain_raw);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G::HALO_B, &M.fld_halo, kt0 - 4, j0 - 1, i, c, full);
+  for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G.HALO_B, &M.fld_halo, kt0 - 4, j0 - 1, i, c, full);
   if (KONLY) return;  // curl-only mode: neither the field being updated nor its material is read
 #pragma unroll
-  for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G::HALO_B + c * G::PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
+  for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G.HALO_B + c * G.PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
 #pragma unroll
-  for (int c = 0; c < TIER; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
+  for (int c = 0; c < TIER; ++c) tma_load_4d(dst + 3 * G.HALO_B + (3 + c) * G.PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
 }
 
 // KONLY: write the curl (with its CPML correction) instead of updating E - phase 1 of the full-tensor tier
@@ -277,20 +309,26 @@ template <int TIER, bool REV, bool SIG, bool ADE, bool MET, int PM, int R, int S
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_E_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
-  using G = TmaGeom<R, TZ>;
-  constexpr int HZ = G::HZ, WR = G::WR, LZ = TZ / 4;  // lanes per row
-  constexpr int STAGE_F = 3 * G::HALO_F + (3 + TIER) * G::PLAIN_F;
+  constexpr bool FLAT = (TZ == 0);
+  const TmaRt G = tma_geometry<R, TZ>(P.flat_lz);
+  const int HZ = G.HZ, LZ = G.LZ, TZE = G.TZ;  // halo row pitch, lanes per row, tile row length
+  const int STAGE_F = 3 * G.HALO_F + (3 + TIER) * G.PLAIN_F;
   const int lane = threadIdx.x, warp = threadIdx.y;
-  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * G::RT;
-  const int zl = lane % LZ, trow = warp * WR + lane / LZ;  // z lane inside the row, row inside the tile
+  const int kt0 = blockIdx.x * TZE, j0 = blockIdx.y * G.RT;
+  // z lane inside the row, row inside the tile (flat tiles: the CTA's threads in row-major (row, quad) order)
+  const int tid = warp * 32 + lane;
+  const int trow = FLAT ? tid / LZ : warp * (32 / LZ) + lane / LZ;
+  const int zl = FLAT ? tid - trow * LZ : lane % LZ;
   const int nz = P.nz, ny = P.ny;
   const int ic0 = P.x_begin + (P.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const bool peer_cta = (ic0 == 0);  // the chunk that reads the low neighbour's H plane and owns E[0]
   const int j = j0 + trow;
   const int k0 = kt0 + zl * V;
-  const bool lane_ok = (j < ny) && (k0 < nz);
-  const int n_act = min(R, (ny - j0 + WR - 1) / WR);  // warps that own a row (the others leave before the loop)
+  const bool lane_ok = (trow < G.RT) && (j < ny) && (k0 < nz);
+  const int rows_here = min(G.RT, ny - j0);                      // rows of this tile inside the grid
+  const int n_act = min(R, (rows_here * LZ + 31) / 32);          // warps that own a row (the others leave before the loop)
+  const bool z_first = (zl == 0) || (FLAT && lane == 0);         // k-1 neighbour not in the previous lane: read the staged tile
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
   int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
@@ -302,8 +340,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   // griddepcontrol.wait below touches only constant tables and shared memory.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
-  for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
-    const int tb = q / TZ, k = kt0 + (q - tb * TZ);
+  for (int q = warp * 32 + lane; q < 3 * TZE; q += R * 32) {
+    const int tb = q / TZE, k = kt0 + (q - tb * TZE);
     float v = 0.0f;
     if (PM > 0 && k < nz) {
       v = (tb == 0) ? P.pml[2].aE[k] : (tb == 1) ? P.pml[2].bE[k] : P.pml[2].kE[k];
@@ -336,9 +374,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   }
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1
-    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R, TZ, KONLY>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
+    for (int s = 0; s < S && ic0 + s < ic1; ++s) tma_issue_E<TIER, R, TZ, KONLY>(G, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s);
   }
-  if (j0 + warp * WR >= ny) return;
+  if (warp >= n_act) return;
 
   // ---------------- consumers ----------------
   const long long plane = (long long)ny * nz;
@@ -370,7 +408,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
   }
   const int oh = (trow + 1) * HZ + 4 + zl * V;  // own cells inside a halo tile
-  const int op = trow * TZ + zl * V;            // own cells inside a plain tile
+  const int op = trow * TZE + zl * V;           // own cells inside a plain tile
 
   int s = 0;
   uint32_t ph = 0;
@@ -382,14 +420,14 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     mbar_wait(bar_full + s * 8, ph);
     const float* sb = fdtdx_tma_smem + s * STAGE_F;
     const float* sHx = sb + oh;
-    const float* sHy = sb + G::HALO_F + oh;
-    const float* sHz = sb + 2 * G::HALO_F + oh;
+    const float* sHy = sb + G.HALO_F + oh;
+    const float* sHz = sb + 2 * G.HALO_F + oh;
     const Vec<V> hx = lds4(sHx), hy = lds4(sHy), hz = lds4(sHz);
     const Vec<V> hx_jm = lds4(sHx - HZ), hz_jm = lds4(sHz - HZ);
     // z-neighbour (k-1) of the first element: last element of the previous lane / the tile's pad column
     float hx_l = __shfl_up_sync(0xffffffffu, hx.v[V - 1], 1);
     float hy_l = __shfl_up_sync(0xffffffffu, hy.v[V - 1], 1);
-    if (zl == 0) {
+    if (z_first) {
       hx_l = sHx[-1];
       hy_l = sHy[-1];
     }
@@ -419,14 +457,14 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     hy_im = hy;
     hz_im = hz;
     FDTDX_TCPML_BLOCK(psiE, aE, bE, kE)
-    const float* sE = sb + 3 * G::HALO_F + op;
+    const float* sE = sb + 3 * G.HALO_F + op;
     Vec<V> ex, ey, ez, ie0, ie1, ie2;
     if (!KONLY) {
-      ex = lds4(sE); ey = lds4(sE + G::PLAIN_F); ez = lds4(sE + 2 * G::PLAIN_F);
-      ie0 = lds4(sE + 3 * G::PLAIN_F);
+      ex = lds4(sE); ey = lds4(sE + G.PLAIN_F); ez = lds4(sE + 2 * G.PLAIN_F);
+      ie0 = lds4(sE + 3 * G.PLAIN_F);
       if (TIER == 3) {
-        ie1 = lds4(sE + 4 * G::PLAIN_F);
-        ie2 = lds4(sE + 5 * G::PLAIN_F);
+        ie1 = lds4(sE + 4 * G.PLAIN_F);
+        ie2 = lds4(sE + 5 * G.PLAIN_F);
       } else {
         ie1 = ie0;
         ie2 = ie0;
@@ -438,7 +476,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S < ic1) tma_issue_E<TIER, R, TZ, KONLY>(M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
+        if (i + S < ic1) tma_issue_E<TIER, R, TZ, KONLY>(G, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S);
       }
     }
     if (++s == S) { s = 0; ph ^= 1; }
@@ -473,34 +511,33 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 // neighbour plane is the next ring stage (one extra Ey,Ez stage is loaded after the last plane).
 // ------------------------------------------------------------------------------------------------
 template <int MUT, int R, int TZ, bool KONLY = false>
-__device__ __forceinline__ void tma_issue_H(const StepParams& P, const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i, int ic1) {
-  using G = TmaGeom<R, TZ>;
+__device__ __forceinline__ void tma_issue_H(const TmaRt& G, const StepParams& P, const TmaSet& M, uint32_t dst, uint32_t full, int kt0, int j0, int i, int ic1) {
   if (i < ic1) {
-    mbar_expect_tx(full, KONLY ? 3 * G::HALO_RAW : 3 * G::HALO_RAW + (3 + MUT) * G::PLAIN_B);
+    mbar_expect_tx(full, KONLY ? 3 * G.HALO_RAW : 3 * G.HALO_RAW + (3 + MUT) * (G.TZ * G.RT * 4));
 #pragma unroll
-    for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G::HALO_B, &M.fld_halo, kt0, j0, i, c, full);
+    for (int c = 0; c < 3; ++c) tma_load_4d(dst + c * G.HALO_B, &M.fld_halo, kt0, j0, i, c, full);
     if (!KONLY) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G::HALO_B + c * G::PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
+      for (int c = 0; c < 3; ++c) tma_load_4d(dst + 3 * G.HALO_B + c * G.PLAIN_B, &M.fld_plain, kt0, j0, i, c, full);
 #pragma unroll
-      for (int c = 0; c < MUT; ++c) tma_load_4d(dst + 3 * G::HALO_B + (3 + c) * G::PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
+      for (int c = 0; c < MUT; ++c) tma_load_4d(dst + 3 * G.HALO_B + (3 + c) * G.PLAIN_B, &M.mat_plain, kt0, j0, i, c, full);
     }
   } else {
     // Ey, Ez of the plane after the chunk: in-domain plane, wrap plane, neighbour-rank halo, or
     // (coordinate nx, out of bounds) the zero halo
-    mbar_expect_tx(full, 2 * G::HALO_RAW);
+    mbar_expect_tx(full, 2 * G.HALO_RAW);
     if (i < P.nx || P.x_hi_mode == 0) {
-      tma_load_4d(dst + G::HALO_B, &M.fld_halo, kt0, j0, i, 1, full);
-      tma_load_4d(dst + 2 * G::HALO_B, &M.fld_halo, kt0, j0, i, 2, full);
+      tma_load_4d(dst + G.HALO_B, &M.fld_halo, kt0, j0, i, 1, full);
+      tma_load_4d(dst + 2 * G.HALO_B, &M.fld_halo, kt0, j0, i, 2, full);
     } else if (P.x_hi_mode == 1) {
-      tma_load_4d(dst + G::HALO_B, &M.fld_halo, kt0, j0, 0, 1, full);
-      tma_load_4d(dst + 2 * G::HALO_B, &M.fld_halo, kt0, j0, 0, 2, full);
+      tma_load_4d(dst + G.HALO_B, &M.fld_halo, kt0, j0, 0, 1, full);
+      tma_load_4d(dst + 2 * G.HALO_B, &M.fld_halo, kt0, j0, 0, 2, full);
     } else {
       // the neighbour's stores were observed through an acquire load in the generic proxy (peer_wait_cta
       // + CTA barrier); order them before this async-proxy read
       asm volatile("fence.proxy.async;" ::: "memory");
-      tma_load_4d(dst + G::HALO_B, &M.xhalo, kt0, j0, 0, 0, full);
-      tma_load_4d(dst + 2 * G::HALO_B, &M.xhalo, kt0, j0, 1, 0, full);
+      tma_load_4d(dst + G.HALO_B, &M.xhalo, kt0, j0, 0, 0, full);
+      tma_load_4d(dst + 2 * G.HALO_B, &M.xhalo, kt0, j0, 1, 0, full);
     }
   }
 }
@@ -509,20 +546,25 @@ template <int MUT, bool REV, bool SIG, bool MET, int PM, int R, int S, int TZ, b
 __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     yee_H_tma(const __grid_constant__ StepParams P, const __grid_constant__ TmaSet M, const int t) {
   constexpr int V = 4;
-  using G = TmaGeom<R, TZ>;
-  constexpr int HZ = G::HZ, WR = G::WR, LZ = TZ / 4;  // lanes per row
-  constexpr int STAGE_F = 3 * G::HALO_F + (3 + MUT) * G::PLAIN_F;
+  constexpr bool FLAT = (TZ == 0);
+  const TmaRt G = tma_geometry<R, TZ>(P.flat_lz);
+  const int HZ = G.HZ, LZ = G.LZ, TZE = G.TZ;  // halo row pitch, lanes per row, tile row length
+  const int STAGE_F = 3 * G.HALO_F + (3 + MUT) * G.PLAIN_F;
   const int lane = threadIdx.x, warp = threadIdx.y;
-  const int kt0 = blockIdx.x * TZ, j0 = blockIdx.y * G::RT;
-  const int zl = lane % LZ, trow = warp * WR + lane / LZ;  // z lane inside the row, row inside the tile
+  const int kt0 = blockIdx.x * TZE, j0 = blockIdx.y * G.RT;
+  const int tid = warp * 32 + lane;
+  const int trow = FLAT ? tid / LZ : warp * (32 / LZ) + lane / LZ;  // row inside the tile, z lane inside the row
+  const int zl = FLAT ? tid - trow * LZ : lane % LZ;
   const int nz = P.nz, ny = P.ny;
   const int ic0 = P.x_begin + blockIdx.z * P.xchunk;
   const int ic1 = min(ic0 + P.xchunk, P.x_end);
   const bool peer_cta = (ic1 == P.nx);  // the chunk that reads the high neighbour's E plane and owns H[nx-1]
   const int j = j0 + trow;
   const int k0 = kt0 + zl * V;
-  const bool lane_ok = (j < ny) && (k0 < nz);
-  const int n_act = min(R, (ny - j0 + WR - 1) / WR);
+  const bool lane_ok = (trow < G.RT) && (j < ny) && (k0 < nz);
+  const int rows_here = min(G.RT, ny - j0);
+  const int n_act = min(R, (rows_here * LZ + 31) / 32);
+  const bool z_last = (zl == LZ - 1) || (FLAT && lane == 31);  // k+1 neighbour not in the next lane: read the staged tile
   const uint32_t sbase = smem_u32(fdtdx_tma_smem);
   const uint32_t bar_full = sbase + S * STAGE_F * 4;
   int* const arrivals = reinterpret_cast<int*>(fdtdx_tma_smem + S * STAGE_F + FDTDX_TMA_TAIL_ARR);
@@ -531,8 +573,8 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // CTA-constant tables: z-slab CPML coefficients of this tile and the x metric scale of this chunk
-  for (int q = warp * 32 + lane; q < 3 * TZ; q += R * 32) {
-    const int tb = q / TZ, k = kt0 + (q - tb * TZ);
+  for (int q = warp * 32 + lane; q < 3 * TZE; q += R * 32) {
+    const int tb = q / TZE, k = kt0 + (q - tb * TZE);
     float v = 0.0f;
     if (PM > 0 && k < nz) {
       v = (tb == 0) ? P.pml[2].aH[k] : (tb == 1) ? P.pml[2].bH[k] : P.pml[2].kH[k];
@@ -562,9 +604,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   __syncthreads();
   if (warp == 0 && lane == 0) {  // ring fill: planes ic0 .. ic0+S-1 (plane ic1 is the Ey,Ez-only stage)
     for (int s = 0; s < S && ic0 + s <= ic1; ++s)
-      tma_issue_H<MUT, R, TZ, KONLY>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
+      tma_issue_H<MUT, R, TZ, KONLY>(G, P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, ic0 + s, ic1);
   }
-  if (j0 + warp * WR >= ny) return;
+  if (warp >= n_act) return;
 
   // ---------------- consumers ----------------
   const long long plane = (long long)ny * nz;
@@ -581,7 +623,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   long long cell0 = (long long)ic0 * plane + row;
   float* pH = (P.H_out ? P.H_out : P.H) + cell0;
   const int oh = trow * HZ + zl * V;
-  const int op = trow * TZ + zl * V;
+  const int op = trow * TZE + zl * V;
 
   int s = 0;
   uint32_t ph = 0;
@@ -595,19 +637,19 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     mbar_wait(bar_full + s * 8, ph);
     const float* sb = fdtdx_tma_smem + s * STAGE_F;
     const float* sEx = sb + oh;
-    const float* sEy = sb + G::HALO_F + oh;
-    const float* sEz = sb + 2 * G::HALO_F + oh;
+    const float* sEy = sb + G.HALO_F + oh;
+    const float* sEz = sb + 2 * G.HALO_F + oh;
     const Vec<V> ex = lds4(sEx), ey = lds4(sEy), ez = lds4(sEz);
     const Vec<V> ex_jp = lds4(sEx + HZ), ez_jp = lds4(sEz + HZ);
     float ex_r = __shfl_down_sync(0xffffffffu, ex.v[0], 1);
     float ey_r = __shfl_down_sync(0xffffffffu, ey.v[0], 1);
-    if (zl == LZ - 1) {
+    if (z_last) {
       ex_r = sEx[V];
       ey_r = sEy[V];
     }
     mbar_wait(bar_full + sn * 8, phn);
     const float* sbn = fdtdx_tma_smem + sn * STAGE_F;
-    const Vec<V> ey_n = lds4(sbn + G::HALO_F + oh), ez_n = lds4(sbn + 2 * G::HALO_F + oh);
+    const Vec<V> ey_n = lds4(sbn + G.HALO_F + oh), ez_n = lds4(sbn + 2 * G.HALO_F + oh);
     float sFx = 1.0f;
     if (MET) sFx = xs[i - ic0];
     Vec<V> Kx, Ky, Kz;
@@ -632,9 +674,9 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       dyFz.v[e] = dyEz; dzFy.v[e] = dzEy; dzFx.v[e] = dzEx;
     }
     FDTDX_TCPML_BLOCK(psiH, aH, bH, kH)
-    const float* sH = sb + 3 * G::HALO_F + op;
+    const float* sH = sb + 3 * G.HALO_F + op;
     Vec<V> hx, hy, hz;
-    if (!KONLY) { hx = lds4(sH); hy = lds4(sH + G::PLAIN_F); hz = lds4(sH + 2 * G::PLAIN_F); }
+    if (!KONLY) { hx = lds4(sH); hy = lds4(sH + G.PLAIN_F); hz = lds4(sH + 2 * G.PLAIN_F); }
     if (!KONLY && !REV && P.hprev_out != nullptr && lane_ok && hprev_wanted(P, i, j)) {  // H_prev for the detector pass
       float* hp = P.hprev_out + cell0;
       stv<V>(hp, hx);
@@ -643,10 +685,10 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
     }
     Vec<V> im0, im1, im2;
     if (!KONLY && MUT >= 1) {
-      im0 = lds4(sH + 3 * G::PLAIN_F);
+      im0 = lds4(sH + 3 * G.PLAIN_F);
       if (MUT == 3) {
-        im1 = lds4(sH + 4 * G::PLAIN_F);
-        im2 = lds4(sH + 5 * G::PLAIN_F);
+        im1 = lds4(sH + 4 * G.PLAIN_F);
+        im2 = lds4(sH + 5 * G.PLAIN_F);
       } else {
         im1 = im0;
         im2 = im0;
@@ -657,7 +699,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
       __threadfence_block();
       if (atomicAdd(&arrivals[s], 1) == n_act - 1) {
         arrivals[s] = 0;
-        if (i + S <= ic1) tma_issue_H<MUT, R, TZ, KONLY>(P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
+        if (i + S <= ic1) tma_issue_H<MUT, R, TZ, KONLY>(G, P, M, sbase + s * STAGE_F * 4, bar_full + s * 8, kt0, j0, i + S, ic1);
       }
     }
     s = sn;

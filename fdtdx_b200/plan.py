@@ -233,6 +233,7 @@ class Plan:
     # ------------------------------------------------------------------ tables
     def _add_boundaries(self):
         self.pml_index = {}
+        self._zext = {}  # z-padded layout: cells added before / after each z slab's psi rows (pre, post)
         order = [p.axis for p in self.objects.pml_objects]
         if order != sorted(order):
             raise NotImplementedError("PML objects must be listed in axis order (x, y, z) - the CPML corrections are applied in that order")
@@ -246,15 +247,24 @@ class Plan:
             for i in (2, 5):
                 if t[i].size == 1:
                     t[i] = np.full(hi - lo, t[i][0], _f32)
-            if self.pad and pml.axis == 2 and pml.direction == "+":
-                # the slab swallows the padded cells with a = b = 1/kappa - 1 = 0 (psi stays 0, no correction)
-                t = [np.ascontiguousarray(np.concatenate([x, np.zeros(self.pad, _f32)])) for x in t]
-                hi = hi + self.pad
+            lo_true, hi_true = lo, hi
+            if self.pad and pml.axis == 2:
+                # z slabs of the padded layout are registered as supersets whose extra cells have a = b = 0 and
+                # 1/kappa = 1 (psi stays 0, the correction is an exact zero): the z-max slab swallows the padded
+                # cells, and a slab whose inner edge sits on an odd cell grows by one interior cell so that the
+                # kernels can move its psi as aligned 64-bit halves (the unmasked CPML path of the staged kernels)
+                pre, post = (lo % 2, self.pad) if pml.direction == "+" else (0, hi % 2)
+                ext = lambda x, one: np.ascontiguousarray(np.concatenate([np.full(pre, one, _f32), x, np.full(post, one, _f32)]))
+                t = [ext(x, 1.0 if i in (2, 5) else 0.0) for i, x in enumerate(t)]
+                lo, hi = lo - pre, hi + post
+                self._zext[pml.name] = (pre, post)
             idx = check(
                 self.lib.fdtdx_b200_plan_add_pml(
                     self.h, pml.axis, 1 if pml.direction == "+" else 0, lo, hi, *[_fptr(x) for x in t], int(pml.kappa_is_one)
                 )
             )
+            if (lo, hi) != (lo_true, hi_true):
+                check(self.lib.fdtdx_b200_plan_pml_set_true_range(self.h, idx, lo_true, min(hi_true, hi)))
             self.pml_index[pml.name] = idx
         for b in self.objects.boundary_objects:
             if isinstance(b, (PerfectElectricConductor, PerfectMagneticConductor)):
@@ -467,13 +477,16 @@ class Plan:
         self._bound.append(t)
         check(self.lib.fdtdx_b200_bind(self.h, slot, index, C.c_void_p(t.data_ptr())))
 
-    def _bind_z(self, slot: int, index: int, t, dtype, shape, state: bool, fill: float = 0.0):
+    def _bind_z(self, slot: int, index: int, t, dtype, shape, state: bool, fill: float = 0.0, pre: int = 0, post: int | None = None):
         """Bind an array whose last axis runs along z.  Without padding: the array itself.  With padding:
-        a plan-owned shadow whose last axis is longer by the z padding; ``state`` arrays are copied back
-        after every run call, constants (materials) only copied in."""
+        a plan-owned shadow whose last axis is longer (``pre`` cells in front, ``post`` - default: the z padding -
+        behind); ``state`` arrays are copied back after every run call, constants (materials) only copied in."""
         import torch
 
         if not self.pad:
+            return self._bind(slot, index, t, dtype, shape)
+        post = self.pad if post is None else post
+        if pre == 0 and post == 0:
             return self._bind(slot, index, t, dtype, shape)
         if dtype is not None and t.dtype != dtype:
             raise ValueError(f"buffer dtype {t.dtype} != expected {dtype}")
@@ -482,21 +495,21 @@ class Plan:
         n = t.shape[-1]
         key = (slot, index)
         sh = self._shadow.get(key)
-        want = (*t.shape[:-1], n + self.pad)
-        if sh is None or tuple(sh[1].shape) != want or sh[1].device != t.device:
-            sh = [t, torch.full(want, fill, dtype=t.dtype, device=t.device), n, state]
+        want = (*t.shape[:-1], pre + n + post)
+        if sh is None or tuple(sh[1].shape) != want or sh[1].device != t.device or sh[4] != pre:
+            sh = [t, torch.full(want, fill, dtype=t.dtype, device=t.device), n, state, pre]
             self._shadow[key] = sh
         sh[0], sh[3] = t, state
         self._bind(slot, index, sh[1], dtype)
 
     def _sync_in(self):
-        for t, buf, n, _ in self._shadow.values():
-            buf[..., :n].copy_(t)
+        for t, buf, n, _, pre in self._shadow.values():
+            buf[..., pre:pre + n].copy_(t)
 
     def _sync_out(self):
-        for t, buf, n, state in self._shadow.values():
+        for t, buf, n, state, pre in self._shadow.values():
             if state:
-                t.copy_(buf[..., :n])
+                t.copy_(buf[..., pre:pre + n])
 
     def bind(self, arrays):
         import torch
@@ -517,11 +530,12 @@ class Plan:
             q = self.pml_index[pml.name]
             if pml.name not in arrays.fields.psi_E:
                 continue  # slab lives on another rank
+            # x / y slabs run along the padded z axis; z slabs are thicker by their (pre, post) extension
+            pre, post = self._zext.get(pml.name, (0, None)) if pml.axis == 2 else (0, None)
             for w in range(2):
-                if self.pad and (pml.axis != 2 or pml.direction == "+"):
-                    # x / y slabs run along the padded z axis; the z-max slab is thicker by the padding
-                    self._bind_z(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32, None, True)
-                    self._bind_z(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32, None, True)
+                if self.pad:
+                    self._bind_z(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32, None, True, pre=pre, post=post)
+                    self._bind_z(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32, None, True, pre=pre, post=post)
                 else:
                     self._bind(_lib.SLOT_PSI_E, 2 * q + w, arrays.fields.psi_E[pml.name][w], f32)
                     self._bind(_lib.SLOT_PSI_H, 2 * q + w, arrays.fields.psi_H[pml.name][w], f32)
@@ -671,8 +685,8 @@ class Plan:
                     if key not in self._cot_psi:
                         # plan-owned cotangent of psi, in the layout the kernels see (z-padded where psi is)
                         shp = list(src[pml.name][w].shape)
-                        if self.pad and (pml.axis != 2 or pml.direction == "+"):
-                            shp[-1] += self.pad
+                        if self.pad:
+                            shp[-1] += sum(self._zext.get(pml.name, (0, 0))) if pml.axis == 2 else self.pad
                         self._cot_psi[key] = torch.zeros(shp, dtype=torch.float32, device=src[pml.name][w].device)
                     self._bind(slot, 2 * q + w, self._cot_psi[key])
         for det in self.objects.detectors:

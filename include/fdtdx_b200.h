@@ -127,6 +127,11 @@ int fdtdx_b200_plan_add_pml(FdtdxPlan* plan, int axis, int direction, int lo, in
                             const float* a_E, const float* b_E, const float* inv_kappa_E,
                             const float* a_H, const float* b_H, const float* inv_kappa_H,
                             int kappa_is_one);
+/* A slab may be registered as a superset [lo,hi) of the reference's slab whose extra cells carry zero
+ * coefficients (a = b = 0, 1/kappa = 1: no correction) - the z-padded layout of ragged grids aligns slab starts
+ * that way.  This names the reference's own range [lo_true,hi_true) of slab `index`, which still positions the
+ * recorder's interface plane (boundary.py:117-144) and the field reset of the reversed pass (backward.py:117-122). */
+int fdtdx_b200_plan_pml_set_true_range(FdtdxPlan* plan, int index, int lo_true, int hi_true);
 /* PEC / PMC wall (pec.py:70-77, pmc.py:63-76): zero the two tangential comps on box [lo,hi). */
 int fdtdx_b200_plan_add_wall(FdtdxPlan* plan, int kind, int axis, const int lo[3], const int hi[3]);
 

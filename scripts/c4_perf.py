@@ -17,7 +17,7 @@ shape = objects.volume.grid_shape
 cells = float(np.prod(shape))
 dev = arrays.to_torch("cuda")
 dev.inv_permittivities.requires_grad_(True)
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", "3"))):
     dev.inv_permittivities.grad = None
     torch.cuda.synchronize(); t0 = time.perf_counter()
     _, out = fx.run_fdtd(dev, objects, cfg)

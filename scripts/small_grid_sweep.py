@@ -17,7 +17,7 @@ for name in ("c1", "c4"):
     e0.record(); plan.run_forward(6, n, False, False, True); e1.record(); torch.cuda.synchronize()
     print(f"  {name}: {e0.elapsed_time(e1) / n * 1e3:.1f} us/step", flush=True)
 ''' % (ROOT, ROOT)
-variants = [{"FDTDX_B200_TMA_XCHUNK": str(c)} for c in (int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "2,3,4,6,7,8").split(","))]
+variants = [{}] + [{"FDTDX_B200_TMA_XCHUNK": str(c)} for c in (int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "2,3,4,6,7,8").split(","))]
 for v in variants:
     print(v or "default", flush=True)
     env = dict(os.environ); env.update(v)
