@@ -1587,7 +1587,7 @@ extern "C" int fdtdx_b200_total_energy(FdtdxPlan* p, float* d_out, void* stream)
   make_grid(p, G);
   if (!G.E || !G.H || !G.eps) return fail(FDTDX_EUNBOUND, "E, H and INV_EPS must be bound");
   if (!p->d_energy_partial && (rc = to_device<double>(p, nullptr, FDTDX_ENERGY_BLOCKS, &p->d_energy_partial))) return rc;
-  energy_partial_kernel<<<FDTDX_ENERGY_BLOCKS, 256, 0, st>>>(G, p->d_energy_partial);
+  energy_partial_kernel<<<FDTDX_ENERGY_BLOCKS, 256, 0, st>>>(G, p->d_energy_partial, p->zpad);
   energy_final_kernel<<<1, 256, 0, st>>>(p->d_energy_partial, FDTDX_ENERGY_BLOCKS, d_out);
   p->launches += 2;
   CUDA_TRY(cudaGetLastError());

@@ -704,10 +704,12 @@ __global__ void halo_pack_kernel(const float* F, float* out, int nx, int ny, int
 // is deterministic; stage 2 (one block) folds the per-block partials and writes one float.
 // ------------------------------------------------------------------------------------------------
 #define FDTDX_ENERGY_BLOCKS (148 * 4)
-__global__ void __launch_bounds__(256) energy_partial_kernel(const GridDev G, double* __restrict__ partial) {
+// zpad: the last zpad cells of every z row are padding of the caller's grid (zero fields, zero inv_eps): not part of the sum
+__global__ void __launch_bounds__(256) energy_partial_kernel(const GridDev G, double* __restrict__ partial, const int zpad) {
   const long long N = (long long)G.nx * G.ny * G.nz;
   double acc = 0.0;
   for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < N; cell += (long long)gridDim.x * blockDim.x) {
+    if (zpad > 0 && (int)(cell % G.nz) >= G.nz - zpad) continue;
     float eE[3], eH[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

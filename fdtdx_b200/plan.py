@@ -118,7 +118,7 @@ class Plan:
         self._keep = []  # host arrays must stay alive until the C call returns; kept for safety
         # Ragged rows (Nz % 4 != 0) cannot use 128-bit accesses or TMA tensor maps (16-byte strides).
         # For forward-only runs the plan then works on z-padded shadow copies: Nz is rounded up to a
-        # multiple of 4, the extra cells are kept at zero by all-component PEC+PMC walls (so they are the
+        # multiple of 4, the extra cells stay at zero because their shadow inv_eps is zero (so they are the
         # zero halo the z-max face would see anyway), a z-max CPML slab is extended over them with zero
         # coefficients, and the caller's arrays are copied in before / out after every run call.
         self.pad = 0 if (x_range is not None or any(halo) or bloch_role is not None) else self._z_padding(objects, config, arrays, nz)
@@ -272,10 +272,9 @@ class Plan:
                 lo = [s[0] for s in b.grid_slice_tuple]
                 hi = [s[1] for s in b.grid_slice_tuple]
                 check(self.lib.fdtdx_b200_plan_add_wall(self.h, kind, b.axis, _iarr(lo), _iarr(hi)))
-        if self.pad:
-            gs = self.global_shape
-            for kind in (0, 1):  # axis 3: no component is normal to the wall, so all three are zeroed
-                check(self.lib.fdtdx_b200_plan_add_wall(self.h, kind, 3, _iarr([0, 0, self.nz_true]), _iarr([gs[0], gs[1], self.nz_true + self.pad])))
+        # z-padded layout: the padded cells stay at zero without any mask - their shadow inv_eps is 0 (bind), so the E
+        # update adds c * K * 0 to a zero field, and with E = 0 there (and beyond, the zero halo) every difference the H
+        # update of a padded cell takes vanishes.  They are therefore exactly the zero halo of the z-max face.
 
     def _switch_tables(self, src):
         if src.uses_default_switch:
@@ -519,7 +518,7 @@ class Plan:
         L = self.local_shape
         self._bind_z(_lib.SLOT_E, 0, arrays.fields.E, f32, (3, *L), True)
         self._bind_z(_lib.SLOT_H, 0, arrays.fields.H, f32, (3, *L), True)
-        self._bind_z(_lib.SLOT_INV_EPS, 0, arrays.inv_permittivities, f32, (self.eps_tier, *L), False, fill=1.0)
+        self._bind_z(_lib.SLOT_INV_EPS, 0, arrays.inv_permittivities, f32, (self.eps_tier, *L), False, fill=0.0)  # 0: padded cells never move
         if self.mu_is_array:
             self._bind_z(_lib.SLOT_INV_MU, 0, arrays.inv_permeabilities, f32, (self.mu_tier, *L), False, fill=1.0)
         if self.sigE_tier:
