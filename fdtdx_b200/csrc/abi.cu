@@ -1697,6 +1697,10 @@ static int adj_fused_xchunk() {
   const char* e = getenv("FDTDX_B200_ADJ_XC");
   return e ? atoi(e) : 0;
 }
+static bool adj_flat_wanted() {
+  const char* e = getenv("FDTDX_B200_ADJ_FLAT");  // 0: a warp per row also on thin grids
+  return !(e && e[0] == '0');
+}
 static bool adj_interleave_wanted() {
   const char* e = getenv("FDTDX_B200_ADJ_INTERLEAVE");  // 0: reverse step, then recompute the step into scratch
   return !(e && e[0] == '0');
@@ -1794,13 +1798,17 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
         A.lam_psi_new[h.axis][h.dir][w] = !bound ? nullptr : (p->cotpsi_parity[kind] ? bound : alt[2 * q + w]);
       }
     }
-    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + 7) / 8);  // per 8 rows
+    // thin rows (Nz <= 124): the CTA's threads laid over (row, z quad) pairs, 256 / lz rows per CTA
+    const int flz = (adj_flat_wanted() && p->nz / 4 >= 5 && p->nz / 4 <= 31) ? p->nz / 4 : 0;
+    const int rt = flz ? 256 / flz : 8;
+    A.flat_lz = flz;
+    const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + rt - 1) / rt);
     int xc = adj_fused_xchunk();
     if (xc <= 0) xc = (int)std::max<long long>(4, std::min<long long>(16, (long long)p->nx * tiles / (148 * 2 * 3)));
     A.xchunk = std::min(xc, p->nx);
     const bool grad = A.g_mat != nullptr;
     const bool met = A.sc[0] || A.sc[1] || A.sc[2];
-    dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, (p->nx + A.xchunk - 1) / A.xchunk);
+    dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + rt - 1) / rt, (p->nx + A.xchunk - 1) / A.xchunk);
     A.psi_vec = 1;
     for (int a = 0; a < 2; ++a)
       for (int sd = 0; sd < 2; ++sd)

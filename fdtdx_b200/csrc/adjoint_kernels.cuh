@@ -38,6 +38,7 @@ struct AdjParams {
   float* lam_psi[3][2][2];  // cotangent of psi per axis / side / which (same shapes as psi) or nullptr
   float* lam_psi_new[3][2][2];  // fused kernel only: where the updated psi cotangents go (ping-pong partner of lam_psi)
   int xchunk;                   // fused kernel only: x planes per CTA
+  int flat_lz;                  // fused kernels only: thin rows (Nz = 4 * flat_lz <= 124) - threads laid over (row, z quad) pairs; 0: warp = row
   int psi_vec;                  // fused kernel only: every psi / psi-cotangent buffer is 16-byte aligned (128-bit rows)
   float* lamF;         // in: cotangent of the updated field; out: cotangent of the input field
   float* lamG;         // cotangent of the other field (accumulated by the gather)
@@ -839,11 +840,18 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_FUSED_MIN_CTAS) adj_fused
     s_zk[q] = c.ck;
   }
   __syncthreads();
+  // thread -> (row, z quad): a warp per row, or (thin rows, flat_lz quads each) the CTA's threads in row-major order
+  // over 256 / flat_lz rows, so that rows shorter than 128 cells still fill the lanes (yee_tma.cuh, TmaRt)
   const int lane = threadIdx.x;
-  const int k0 = (blockIdx.x * 32 + lane) * V;
-  const int y = blockIdx.y * ROWS + threadIdx.y;
-  if (y >= P.ny) return;  // whole warp; no CTA-wide barrier after this point
-  const bool active = k0 < P.nz;
+  const int lz = P.flat_lz;
+  const int tid = threadIdx.y * 32 + lane;
+  const int trow = lz ? tid / lz : (int)threadIdx.y;
+  const int rt = lz ? (32 * ROWS) / lz : ROWS;
+  const int k0 = lz ? (tid - trow * lz) * V : (blockIdx.x * 32 + lane) * V;
+  const bool row_ok = trow < rt && (int)blockIdx.y * rt + trow < P.ny;
+  if (__ballot_sync(0xffffffffu, row_ok) == 0) return;  // no CTA-wide barrier after this point
+  const int y = min((int)blockIdx.y * rt + trow, P.ny - 1);
+  const bool active = row_ok && k0 < P.nz;
   const long long plane = (long long)P.ny * P.nz, N = plane * P.nx;
   const long long row0 = (long long)y * P.nz + k0;
   const int c0 = blockIdx.z * P.xchunk, c1 = min(c0 + P.xchunk, P.nx);
@@ -878,7 +886,7 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_FUSED_MIN_CTAS) adj_fused
     }
   }
   // the cell across the tile edge in the gather direction
-  const bool a_edge = IS_E ? (lane == 31 || k0 + V >= P.nz) : (lane == 0);
+  const bool a_edge = IS_E ? (lane == 31 || k0 + V >= P.nz) : (lane == 0 || k0 == 0);  // the adjacent lane is not the adjacent quad
   int kza = IS_E ? k0 + V : k0 - 1;
   bool kza_ok = active;
   if (kza < 0) { if (P.wrap[2]) kza = P.nz - 1; else kza_ok = false; }
@@ -1178,10 +1186,15 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_GRAD_MIN_CTAS) adj_grad4_
   }
   __syncthreads();
   const int lane = threadIdx.x;
-  const int k0 = (blockIdx.x * 32 + lane) * V;
-  const int y = blockIdx.y * ROWS + threadIdx.y;
-  if (y >= P.ny) return;
-  const bool active = k0 < P.nz;
+  const int lz = P.flat_lz;  // thread -> (row, z quad) as in adj_fused4_kernel
+  const int tid = threadIdx.y * 32 + lane;
+  const int trow = lz ? tid / lz : (int)threadIdx.y;
+  const int rt = lz ? (32 * ROWS) / lz : ROWS;
+  const int k0 = lz ? (tid - trow * lz) * V : (blockIdx.x * 32 + lane) * V;
+  const bool row_ok = trow < rt && (int)blockIdx.y * rt + trow < P.ny;
+  if (__ballot_sync(0xffffffffu, row_ok) == 0) return;
+  const int y = min((int)blockIdx.y * rt + trow, P.ny - 1);
+  const bool active = row_ok && k0 < P.nz;
   const long long plane = (long long)P.ny * P.nz, N = plane * P.nx;
   const long long row0 = (long long)y * P.nz + k0;
   const int c0 = blockIdx.z * P.xchunk, c1 = min(c0 + P.xchunk, P.nx);
@@ -1198,7 +1211,7 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_GRAD_MIN_CTAS) adj_grad4_
 #pragma unroll
   for (int e = 0; e < V; ++e) scz_h.v[e] = 1.0f;
   if (MET && P.sc[2] && active) scz_h = ldv<V>(P.sc[2] + k0);
-  const bool p_edge = IS_E ? (lane == 0) : (lane == 31 || k0 + V >= P.nz);
+  const bool p_edge = IS_E ? (lane == 0 || k0 == 0) : (lane == 31 || k0 + V >= P.nz);
   int kzp = IS_E ? k0 - 1 : k0 + V;
   bool kzp_ok = active && p_edge;
   if (kzp < 0) { if (P.wrap[2]) kzp = P.nz - 1; else kzp_ok = false; }
