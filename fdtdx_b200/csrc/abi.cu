@@ -752,8 +752,18 @@ static int tma_flat_lz(const FdtdxPlan* p) {
   const char* tz = getenv("FDTDX_B200_TMA_TZ");
   if (tz && (atoi(tz) == 64 || atoi(tz) == 128)) return 0;
   if (p->nz % 4 != 0) return 0;
-  const int lz = p->nz / 4;
-  return (lz >= 5 && lz <= 31 && lz != 16) ? lz : 0;
+  // Rows of up to 124 cells are one flat tile; longer rows that are not a multiple of 128 cells are cut into
+  // nt equal flat tiles (Nz = 136: two tiles of 17 quads instead of 128 + 8 cells) when that keeps clearly more
+  // lanes busy than 128-cell tile rows would.
+  const int q = p->nz / 4;                       // z quads per row
+  const int nt = (q + 30) / 31;                  // tiles of at most 31 quads
+  const int lz = (q + nt - 1) / nt;
+  if (lz < 5 || lz > 31) return 0;
+  if (nt == 1) return lz != 16 ? lz : 0;         // 64-cell rows: the two-rows-per-warp instantiation
+  const int rt = (FDTDX_TMA_R * 32) / lz;
+  const double flat_eff = (double)q / (double)(lz * nt) * ((double)(lz * rt) / (FDTDX_TMA_R * 32.0));
+  const double std_eff = (double)p->nz / (128.0 * ((p->nz + 127) / 128));
+  return flat_eff > std_eff + 0.05 ? lz : 0;
 }
 // tile row length / rows per CTA tile of the staged half-steps
 static void tma_tile(const FdtdxPlan* p, int lz, int* tz, int* rt) {
