@@ -15,6 +15,7 @@ dist.init_process_group("nccl", device_id=dev)
 ok = True
 for name, build, steps in (
     ("box", lambda xr: W.build_box((32 * world, 40, 64), device=dev, x_range=xr, thickness=6), 40),
+    ("box_flat_tiles", lambda xr: W.build_box((24 * world, 45, 72), device=dev, x_range=xr, thickness=6), 40),  # 18-quad rows: flat tiles, 14 rows per CTA
     ("coupler", lambda xr: W.build_coupler(5, device=dev, n_copies=world, x_range=xr), 60),
 ):
     objects, arrays_full, cfg = build(None)

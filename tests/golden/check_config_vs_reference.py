@@ -1,6 +1,6 @@
 """Config-faithful runs of the REFERENCE'S OWN SOURCE (oracle/refexec.py) against the oracle's config goldens.
 
-    python tests/golden/check_config_vs_reference.py c3a | c1 | c4 [max_steps]     (this container only; minutes)
+    python tests/golden/check_config_vs_reference.py c3a | c1 | c3b | c4     (this container only; minutes)
 
 Steps a BASELINE config at its real grid with the reference's ``update_E`` / ``update_H`` / ``update_detector_states``
 executed from /root/reference under the NumPy ``jax.numpy`` stand-in, and compares with ``tests/golden/cfg_*.npz``
@@ -69,7 +69,7 @@ def main():
                             pulse_trace_A=np.asarray(a.detector_states["pulse_trace_A"]["fields"]), pulse_trace_B=np.asarray(a.detector_states["pulse_trace_B"]["fields"]))
         scale = float(np.linalg.norm(g["mid_E"].astype(np.float64)))
         lines.append(f"[C3a] final E: |ref - oracle| / |E(mid)| = {float(np.linalg.norm(np.asarray(a.fields.E, np.float64) - g['fwd_E'])) / scale:.3e}")
-    elif which in ("c1", "c4"):
+    elif which in ("c1", "c4", "c3b"):
         for t in range(T):
             a = step(ref, robj, cfg, a, t)
             if t % 25 == 0:
@@ -86,6 +86,9 @@ def main():
         if which == "c4":
             for n, k in (("out flux", "out_flux"), ("in flux", "in_flux")):
                 extra[k] = np.asarray(a.detector_states[n]["poynting_flux"])
+        if which == "c3b":
+            v = np.asarray(a.detector_states["Electric Field Video"]["fields"])
+            extra["video_norm"] = np.sqrt((v.astype(np.float64).reshape(v.shape[0], -1) ** 2).sum(axis=1))
         np.savez_compressed(os.path.join(HERE, f"cfg_{which}_refsrc.npz"), fwd_E=sub(E), fwd_H=sub(H), fwd_E_norm=field_norms(E), fwd_H_norm=field_norms(H), **extra)
         lines.append(f"[{which.upper()}] fwd E (every 4th cell): rel-L2 {rel_l2(sub(E), g['fwd_E']):.3e}")
         lines.append(f"[{which.upper()}] fwd H (every 4th cell): rel-L2 {rel_l2(sub(H), g['fwd_H']):.3e}")
@@ -95,9 +98,11 @@ def main():
             for key in ("XY Plane", "XZ Plane", "YZ Plane"):
                 v = np.asarray(st[key])
                 lines.append(f"[C1] video {key} norm of every frame: rel-L2 {rel_l2(np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2))), g[f'video_{key[:2]}_norm']):.3e}")
-        else:
+        elif which == "c4":
             for n, k in (("out flux", "out_flux"), ("in flux", "in_flux")):
                 lines.append(f"[C4] {n} series: rel-L2 {rel_l2(extra[k], g[k]):.3e}")
+        else:
+            lines.append(f"[C3b] Ey video norm of every frame: rel-L2 {rel_l2(extra['video_norm'][1:], g['video_norm'][1:]):.3e}")
     lines.append(f"# ({time.time() - t0:.0f} s on the CPU)")
     report(lines)
 
