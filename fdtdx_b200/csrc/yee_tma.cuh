@@ -387,7 +387,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   float sBy = 1.0f;
   Vec<V> sBz;
   if (MET) {
-    sBy = P.sB[1][j];
+    sBy = lane_ok ? P.sB[1][j] : 1.0f;  // lanes of a partly filled warp may sit past the last row
     sBz = lane_ok ? ldv<V>(P.sB[2] + k0) : zerov<V>();
   }
   long long cell0 = (long long)ic0 * plane + row;  // this thread's first cell of the current plane
@@ -617,7 +617,7 @@ __global__ void __maxnreg__(FDTDX_TMA_MAXREG)
   float sFy = 1.0f;
   Vec<V> sFz;
   if (MET) {
-    sFy = P.sF[1][j];
+    sFy = lane_ok ? P.sF[1][j] : 1.0f;
     sFz = lane_ok ? ldv<V>(P.sF[2] + k0) : zerov<V>();
   }
   long long cell0 = (long long)ic0 * plane + row;
