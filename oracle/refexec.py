@@ -326,6 +326,8 @@ class Reference:
             "FieldDetector": ("fdtdx.objects.detectors.field", "FieldDetector"),
             "PoyntingFluxDetector": ("fdtdx.objects.detectors.poynting_flux", "PoyntingFluxDetector"),
             "PhasorDetector": ("fdtdx.objects.detectors.phasor", "PhasorDetector"),
+            # objects/detectors/mode.py: ModeOverlapDetector(PhasorDetector) keeps PhasorDetector.update (its overlap integral is post-run)
+            "ModeOverlapDetector": ("fdtdx.objects.detectors.phasor", "PhasorDetector"),
             "TFSFPlaneSource": ("fdtdx.objects.sources.tfsf", "TFSFPlaneSource"),
             "PointDipoleSource": ("fdtdx.objects.sources.dipole", "PointDipoleSource"),
             "SingleFrequencyProfile": ("fdtdx.objects.sources.profile", "SingleFrequencyProfile"),

@@ -1,6 +1,6 @@
 """Config-faithful runs of the REFERENCE'S OWN SOURCE (oracle/refexec.py) against the oracle's config goldens.
 
-    python tests/golden/check_config_vs_reference.py c3a | c1 | c3b | c4     (this container only; minutes)
+    python tests/golden/check_config_vs_reference.py c3a | c1 | c2 | c3b | c4     (this container only; minutes)
 
 Steps a BASELINE config at its real grid with the reference's ``update_E`` / ``update_H`` / ``update_detector_states``
 executed from /root/reference under the NumPy ``jax.numpy`` stand-in, and compares with ``tests/golden/cfg_*.npz``
@@ -69,6 +69,19 @@ def main():
                             pulse_trace_A=np.asarray(a.detector_states["pulse_trace_A"]["fields"]), pulse_trace_B=np.asarray(a.detector_states["pulse_trace_B"]["fields"]))
         scale = float(np.linalg.norm(g["mid_E"].astype(np.float64)))
         lines.append(f"[C3a] final E: |ref - oracle| / |E(mid)| = {float(np.linalg.norm(np.asarray(a.fields.E, np.float64) - g['fwd_E'])) / scale:.3e}")
+    elif which == "c2":
+        # the bench scene at cells-per-lambda 6: the first C2_MID steps (pulse inside the coupling section)
+        from make_config_golden import C2_MID
+
+        for t in range(C2_MID):
+            a = step(ref, robj, cfg, a, t)
+            if t % 100 == 0:
+                print(f"step {t}/{C2_MID} {time.time() - t0:.0f}s", flush=True)
+        E, H = np.asarray(a.fields.E), np.asarray(a.fields.H)
+        np.savez_compressed(os.path.join(HERE, "cfg_c2_refsrc.npz"), mid_E=sub(E), mid_H=sub(H), mid_E_norm=field_norms(E), mid_H_norm=field_norms(H))
+        lines.append(f"[C2] E at step {C2_MID} (every 4th cell): rel-L2 {rel_l2(sub(E), g['mid_E']):.3e}")
+        lines.append(f"[C2] H at step {C2_MID} (every 4th cell): rel-L2 {rel_l2(sub(H), g['mid_H']):.3e}")
+        lines.append(f"[C2] |E| per component at step {C2_MID}: rel-L2 {rel_l2(field_norms(E), g['mid_E_norm']):.3e}")
     elif which in ("c1", "c4", "c3b"):
         for t in range(T):
             a = step(ref, robj, cfg, a, t)
