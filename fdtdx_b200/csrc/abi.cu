@@ -1707,6 +1707,10 @@ static int adj_fused_xchunk() {
   const char* e = getenv("FDTDX_B200_ADJ_XC");
   return e ? atoi(e) : 0;
 }
+static bool adj_async_wanted() {
+  const char* e = getenv("FDTDX_B200_ADJ_ASYNC");  // 0: the fused kernel loads each plane directly instead of staging the next one with cp.async
+  return !(e && e[0] == '0');
+}
 static bool adj_flat_wanted() {
   const char* e = getenv("FDTDX_B200_ADJ_FLAT");  // 0: a warp per row also on thin grids
   return !(e && e[0] == '0');
@@ -1828,13 +1832,26 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
             if (q && !aligned16(q)) A.psi_vec = 0;
         }
     // one pass for the cotangents, then (when a material gradient is wanted) one for g += lambda_in . (+-c K)
+    const bool use_async = adj_async_wanted();
+#define GO_F(IE, MT, ME) do { \
+      if (use_async) { \
+        auto k = adj_fused4_kernel<IE, MT, ME, 8, true>; \
+        constexpr int smem = 2 * adj_stage_vecs<MT>() * 256 * 16; \
+        static bool attr_set = false; \
+        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
+        k<<<g, b, smem, st>>>(A); \
+      } else { \
+        adj_fused4_kernel<IE, MT, ME, 8, false><<<g, b, 0, st>>>(A); \
+      } \
+    } while (0)
 #define GO(IE, MT) do { \
-      if (met) adj_fused4_kernel<IE, MT, true, 8><<<g, b, 0, st>>>(A); else adj_fused4_kernel<IE, MT, false, 8><<<g, b, 0, st>>>(A); \
+      if (met) GO_F(IE, MT, true); else GO_F(IE, MT, false); \
       if (grad) { if (met) adj_grad4_kernel<IE, MT, true, 8><<<g, b, 0, st>>>(A); else adj_grad4_kernel<IE, MT, false, 8><<<g, b, 0, st>>>(A); } \
     } while (0)
     if (is_E) { if (A.mat_tier == 3) GO(true, 3); else GO(true, 1); }
     else { if (A.mat_tier == 0) GO(false, 0); else if (A.mat_tier == 1) GO(false, 1); else GO(false, 3); }
 #undef GO
+#undef GO_F
     p->launches += grad ? 1 : 0;
     p->cotpsi_parity[kind] ^= 1;
     p->launches += 1;

@@ -812,8 +812,28 @@ __device__ __forceinline__ void adj_acc2(float& acc, const float sh, const float
   }
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): the data of the NEXT plane travels while this plane is computed
+__device__ __forceinline__ void adj_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void adj_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void adj_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ Vec<4> adj_lds4(const float4* p) {
+  const float4 t = *p;
+  Vec<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+// vectors a thread stages per plane: lambda' (3), material (0 | 1 | 3), y-neighbour lambda' (2) and material (0 | 1 | 2), lamG (3)
+template <int MT>
+__host__ __device__ constexpr int adj_stage_vecs() { return 3 + (MT == 3 ? 3 : MT) + 2 + (MT == 3 ? 2 : MT) + 3; }
+extern __shared__ __align__(16) float4 adj_stage_smem[];
+
 // MT: material tier of this half-step (0 scalar, 1, 3); MET: non-uniform grid (metric scales); ROWS: rows (warps) per CTA.
-template <bool IS_E, int MT, bool MET, int ROWS>
+// ASYNC: every thread stages its own operands of plane i+1 in shared memory with cp.async while it computes plane i
+// (two stages of adj_stage_vecs<MT>() x 16 B per thread; no barrier - a thread only ever reads what it staged itself).
+template <bool IS_E, int MT, bool MET, int ROWS, bool ASYNC>
 __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_FUSED_MIN_CTAS) adj_fused4_kernel(const AdjParams P) {
   constexpr int V = 4;
   constexpr int s = IS_E ? +1 : -1;  // the gather looks this way (transpose of the backward / forward difference)
@@ -1009,6 +1029,34 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_FUSED_MIN_CTAS) adj_fused
 
   long long off = (long long)xfirst * plane + row0;
   const long long doff = IS_E ? -plane : plane;
+  constexpr int NV = adj_stage_vecs<MT>(), NM = (MT == 3 ? 3 : MT), NMY = (MT == 3 ? 2 : MT);
+  auto slot = [&](const int st, const int v) -> float4* { return adj_stage_smem + ((st * NV + v) * (32 * ROWS) + tid); };
+  // stage this thread's operands of the plane at offset o (same guards as the direct loads below)
+  auto stage_plane = [&](const int st, const long long o) {
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) adj_cp_async16(slot(st, c), P.lamF + c * N + o);
+      if (MT == 1) adj_cp_async16(slot(st, 3), P.mat + o);
+      if (MT == 3) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) adj_cp_async16(slot(st, 3 + c), P.mat + (long long)c * P.mat_cs + o);
+      }
+      if (yok) {
+        const long long on = o - row0 + rown;
+        adj_cp_async16(slot(st, 3 + NM), P.lamF + 2 * N + on);
+        adj_cp_async16(slot(st, 4 + NM), P.lamF + on);
+        if (MT == 1) adj_cp_async16(slot(st, 5 + NM), P.mat + on);
+        if (MT == 3) {
+          adj_cp_async16(slot(st, 5 + NM), P.mat + 2 * P.mat_cs + on);
+          adj_cp_async16(slot(st, 6 + NM), P.mat + on);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) adj_cp_async16(slot(st, 5 + NM + NMY + c), P.lamG + c * N + o);
+    }
+    adj_cp_commit();
+  };
+  if (ASYNC) stage_plane(0, off);
   for (int it = 0; it < nplanes; ++it, off += doff) {
     const int x = IS_E ? xfirst - it : xfirst + it;
     const float scx_h = (MET && P.sc[0]) ? P.sc[0][x] : 1.0f;
@@ -1028,7 +1076,35 @@ __global__ void __launch_bounds__(32 * ROWS, FDTDX_ADJ_FUSED_MIN_CTAS) adj_fused
 #pragma unroll
     for (int c = 0; c < 3; ++c) { lamv[c] = zerov<V>(); mq[c] = zerov<V>(); og[c] = zerov<V>(); }
     lny[0] = lny[1] = mny[0] = mny[1] = zerov<V>();
-    if (active) {
+    if (ASYNC) {
+      const int st = it & 1;
+      if (it + 1 < nplanes) {  // the next plane's operands start travelling now; this plane's group is the older one
+        stage_plane(st ^ 1, off + doff);
+        adj_cp_wait<1>();
+      } else {
+        adj_cp_wait<0>();
+      }
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lamv[c] = adj_lds4(slot(st, c));
+        if (MT == 0) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) mq[0].v[e] = P.mat_scalar;
+        } else {
+          mq[0] = adj_lds4(slot(st, 3));
+        }
+        if (MT == 3) { mq[1] = adj_lds4(slot(st, 4)); mq[2] = adj_lds4(slot(st, 5)); }
+        else { mq[1] = mq[0]; mq[2] = mq[0]; }
+        if (yok) {
+          lny[0] = adj_lds4(slot(st, 3 + NM));
+          lny[1] = adj_lds4(slot(st, 4 + NM));
+          if (MT == 0) mny[0] = mq[0]; else mny[0] = adj_lds4(slot(st, 5 + NM));
+          mny[1] = (MT == 3) ? adj_lds4(slot(st, 6 + NM)) : mny[0];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) og[c] = adj_lds4(slot(st, 5 + NM + NMY + c));
+      }
+    } else if (active) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         lamv[c] = ldv<V>(P.lamF + c * N + off);
