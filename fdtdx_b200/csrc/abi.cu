@@ -107,6 +107,10 @@ struct FdtdxPlan {
   // COT_PSI_*) and which set currently holds the value (1: the plan-owned one; copied back at the end of run_adjoint)
   std::vector<float*> d_cotpsi_alt[2];
   int cotpsi_parity[2] = {0, 0};
+  // the detectors' cotangent kernels of one step are independent (atomic scatters): they run side by side on two
+  // plan-owned streams forked from / joined to the caller's stream
+  cudaStream_t adj_side[2] = {nullptr, nullptr};
+  cudaEvent_t adj_fork = nullptr, adj_join[2] = {nullptr, nullptr};
   double* d_energy_partial = nullptr;  // total_energy: per-block partial sums
   bool adjoint_exact = false;          // run_adjoint_exact: VJP at the bound state, no reverse step
   // row-marching detector kernels (det_volume.cuh): plan-wide H_prev scratch in the layout of H, the
@@ -177,6 +181,11 @@ extern "C" int fdtdx_b200_plan_destroy(FdtdxPlan* p) {
   if (p) for (auto& kv : p->ipc_open) cudaIpcCloseMemHandle(kv.second);
   if (!p) return FDTDX_OK;
   for (void* q : p->owned) cudaFree(q);
+  for (int k = 0; k < 2; ++k) {
+    if (p->adj_side[k]) cudaStreamDestroy(p->adj_side[k]);
+    if (p->adj_join[k]) cudaEventDestroy(p->adj_join[k]);
+  }
+  if (p->adj_fork) cudaEventDestroy(p->adj_fork);
   delete p;
   return FDTDX_OK;
 }
@@ -1707,6 +1716,10 @@ static int adj_fused_xchunk() {
   const char* e = getenv("FDTDX_B200_ADJ_XC");
   return e ? atoi(e) : 0;
 }
+static bool adj_det_streams_wanted() {
+  const char* e = getenv("FDTDX_B200_ADJ_DET_STREAMS");  // 0: the detectors' cotangent kernels run one after the other
+  return !(e && e[0] == '0');
+}
 static bool adj_async_wanted() {
   const char* e = getenv("FDTDX_B200_ADJ_ASYNC");  // 0: the fused kernel loads each plane directly instead of staging the next one with cp.async
   return !(e && e[0] == '0');
@@ -1979,17 +1992,34 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
     bool any_det = false;
     std::vector<std::array<int, 6>> boxes;  // per detector: the box its H_prev cotangents were scattered into
     const int nn[3] = {p->nx, p->ny, p->nz};
+    std::vector<size_t> active;
     for (size_t di = 0; di < p->dets.size(); ++di) {
       DetHost& h = p->dets[di];
       if ((h.d.flags & DET_INVERSE) || !h.on[t]) continue;
-      {  // a detector is skipped only when none of its state leaves carries a cotangent
-        bool any_cot = false;
-        for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
-        if (!any_cot) continue;
+      // a detector is skipped only when none of its state leaves carries a cotangent
+      bool any_cot = false;
+      for (int k = 0; k < 4; ++k) any_cot = any_cot || p->slots[FDTDX_SLOT_COT_DET][4 * di + k] != nullptr;
+      if (any_cot) active.push_back(di);
+    }
+    // two-kernel form: the scratch is consumed whole, so it is zeroed whole; fused form: it is kept zero
+    // outside the boxes by adj_box_add_clear_kernel
+    if (!active.empty() && !fusedH) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
+    const bool fork = active.size() > 1 && adj_det_streams_wanted();
+    if (fork) {
+      if (!p->adj_fork) {
+        CUDA_TRY(cudaEventCreateWithFlags(&p->adj_fork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+          CUDA_TRY(cudaStreamCreateWithFlags(&p->adj_side[k], cudaStreamNonBlocking));
+          CUDA_TRY(cudaEventCreateWithFlags(&p->adj_join[k], cudaEventDisableTiming));
+        }
       }
-      // two-kernel form: the scratch is consumed whole, so it is zeroed whole; fused form: it is kept zero
-      // outside the boxes by adj_box_add_clear_kernel
-      if (!any_det && !fusedH) CUDA_TRY(cudaMemsetAsync(p->d_lamHx, 0, (size_t)3 * N * 4, st));
+      CUDA_TRY(cudaEventRecord(p->adj_fork, st));
+      for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(p->adj_side[k], p->adj_fork, 0));
+    }
+    for (size_t ai = 0; ai < active.size(); ++ai) {
+      const size_t di = active[ai];
+      DetHost& h = p->dets[di];
+      cudaStream_t ds = fork ? p->adj_side[ai % 2] : st;
       any_det = true;
       std::array<int, 6> bx;
       for (int a = 0; a < 3; ++a) {  // the stencil reaches one cell down in x, y and one up in z (+ wrap)
@@ -2005,7 +2035,7 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
       G.H = H;  // H_prev gather reads the step's input H
       if (h.d.flags & DET_EXACT) {
         const long long hn = 3LL * (h.d.hi[0] - h.d.lo[0] + 1) * (h.d.hi[1] - h.d.lo[1] + 1) * (h.d.hi[2] - h.d.lo[2] + 1);
-        det_gather_hprev_kernel<<<(int)std::min<long long>((hn + 255) / 256, 148 * 16), 256, 0, st>>>(G, h.d);
+        det_gather_hprev_kernel<<<(int)std::min<long long>((hn + 255) / 256, 148 * 16), 256, 0, ds>>>(G, h.d);
         p->launches++;
       }
       G.H = H1;
@@ -2017,10 +2047,15 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
       A.g_mu = (p->mu_tier > 0) ? (float*)p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr;
       A.mu_tier = p->mu_tier;
       const long long dn = (long long)(h.d.hi[0] - h.d.lo[0]) * (h.d.hi[1] - h.d.lo[1]) * (h.d.hi[2] - h.d.lo[2]);
-      det_adjoint_kernel<<<(unsigned)((dn + 127) / 128), 128, 0, st>>>(G, h.d, A, t);
+      det_adjoint_kernel<<<(unsigned)((dn + 127) / 128), 128, 0, ds>>>(G, h.d, A, t);
       p->launches++;
       CUDA_TRY(cudaGetLastError());
     }
+    if (fork)
+      for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaEventRecord(p->adj_join[k], p->adj_side[k]));
+        CUDA_TRY(cudaStreamWaitEvent(st, p->adj_join[k], 0));
+      }
     // (4) H half-step transpose: lambda_H' -> lambda_H_in, accumulates into lambda_E'
     if (fusedH && !fusedH_checked) {  // same alignment test as adjoint_half's (only matters before any scatter happened)
       const void* ptrs[] = {H, E1, lamH, lamE, S.mu, p->mu_tier > 0 ? p->slots[FDTDX_SLOT_GRAD_INV_MU][0] : nullptr, p->d_sF[2]};
