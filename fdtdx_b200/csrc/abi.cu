@@ -1871,6 +1871,14 @@ static int adjoint_half(FdtdxPlan* p, const StepParams& S, bool is_E, const floa
     CUDA_TRY(cudaGetLastError());
     return FDTDX_OK;
   }
+  // two-kernel form: the six derivative cotangents go through a 6 N scratch (allocated on first use only - the fused
+  // kernels never touch it)
+  if (!p->d_ld) {
+    int rcl = to_device<float>(p, nullptr, (size_t)6 * N, &p->d_ld);
+    if (rcl) return rcl;
+    if (!aligned16(p->d_ld)) v4 = false;
+  }
+  A.ld = p->d_ld;
   if (v4) {
     dim3 b(32, 8), g((p->nz + 127) / 128, (p->ny + 7) / 8, p->nx);
     if (is_E) { adj_local4_kernel<true><<<g, b, 0, st>>>(A); adj_gather4_kernel<true><<<g, b, 0, st>>>(A); }
@@ -1899,11 +1907,9 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
   float* lamE = (float*)p->slots[FDTDX_SLOT_COT_E][0];
   float* lamH = (float*)p->slots[FDTDX_SLOT_COT_H][0];
   if (!lamE || !lamH || !p->slots[FDTDX_SLOT_GRAD_INV_EPS][0]) return fail(FDTDX_EUNBOUND, "COT_E, COT_H and GRAD_INV_EPS must be bound");
-  if (!p->d_Etmp) {
-    if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_Etmp))) return rc;
+  if (!p->d_Htmp) {  // scratch of the interleaved iteration; the re-run order adds a copy of E on first use
     if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_Htmp))) return rc;
     if ((rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_lamHx))) return rc;
-    if ((rc = to_device<float>(p, nullptr, (size_t)6 * N, &p->d_ld))) return rc;
   }
   // Reversible mode, interleaved (default): the reversed step is split around the two transposes, so every
   // state a transpose needs is in the field arrays at the moment it runs and nothing is recomputed -
@@ -1955,6 +1961,7 @@ extern "C" int fdtdx_b200_run_adjoint(FdtdxPlan* p, int t_from, int n, void* str
       E1 = S.E;
       H1 = p->d_Htmp;
     } else {
+      if (!p->d_Etmp && (rc = to_device<float>(p, nullptr, (size_t)3 * N, &p->d_Etmp))) return rc;
       // (1) reconstruct the state at t (backward.py:62-135, record_detectors=False, reset_fields=False);
       //     exact mode: the caller has bound the stored state of step t instead
       if (!p->adjoint_exact && (rc = fdtdx_b200_run_reverse(p, t + 1, 1, 0, 0, stream))) return rc;
