@@ -61,3 +61,4 @@ def __getattr__(name):
 
         return getattr(_fdtd, name)
     raise AttributeError(name)
+from fdtdx_b200.symmetry import unfold_array, unfold_detector_states, unfold_fields  # noqa: E402,F401
