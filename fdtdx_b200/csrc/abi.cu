@@ -698,7 +698,9 @@ static int make_params(FdtdxPlan* p, StepParams& P, int simulate) {
     // one-plane re-read at each chunk start stays below ~3 % of the traffic
     const long long tiles = (long long)((p->nz + 127) / 128) * ((p->ny + p->rows - 1) / p->rows);
     long long want = (148LL * 2 * 16 + tiles - 1) / tiles;  // >= ~16 waves at 2 resident CTAs per SM
-    xc = (int)std::max(16LL, std::min<long long>(32, p->nx / std::max(1LL, want)));
+    // small grids (about a wave of CTAs): shorter chunks balance the load better than they cost in re-read planes
+    // (C3b 120^3, periodic x / y: 112 us/step at 16 planes per CTA, 95 at 8 - scripts/c3b_perf.py)
+    xc = (int)std::max(8LL, std::min<long long>(32, p->nx / std::max(1LL, want)));
   }
   P.xchunk = std::min(xc, p->nx);
   P.x_begin = 0;
